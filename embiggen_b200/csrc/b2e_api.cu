@@ -1,0 +1,514 @@
+// C ABI of the engine (include/b2e.h): handle management, K1 CSR upload, K3 alias table,
+// the chunked walk -> SGD pipeline on two streams, and the host-buffer entry points.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+using namespace b2e;
+
+static thread_local std::string g_last_error;
+
+static int fail(int status, const std::string &message) {
+    g_last_error = message;
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(B2E_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+#define REQUIRE_HANDLE(h)                                                                    \
+    do {                                                                                     \
+        if (!(h)) return fail(B2E_ERR_INVALID, "null handle");                               \
+        CUDA_TRY(cudaSetDevice((h)->cfg.device));                                            \
+    } while (0)
+
+extern "C" const char *b2e_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b2e_abi_version(void) { return B2E_ABI_VERSION; }
+
+// integer accept thresholds (DESIGN.md "second-order accept test")
+static void thresholds(float return_weight, float explore_weight, unsigned long long out[3]) {
+    const double w[3] = {(double)return_weight, 1.0, (double)explore_weight};
+    const double wmax = std::max(w[0], std::max(w[1], w[2]));
+    for (int i = 0; i < 3; ++i) {
+        if (w[i] >= wmax) {
+            out[i] = 4294967296ull;
+        } else {
+            const double t = floor(w[i] / wmax * 4294967296.0);
+            out[i] = t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t;
+        }
+    }
+}
+
+extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
+    if (!config || !out) return fail(B2E_ERR_INVALID, "null argument");
+    if (config->struct_size != sizeof(b2e_config))
+        return fail(B2E_ERR_INVALID, "b2e_config.struct_size does not match this library (ABI mismatch)");
+    const b2e_config &c = *config;
+    if (c.model > B2E_CBOW) return fail(B2E_ERR_INVALID, "model must be 0 (SkipGram) or 1 (CBOW)");
+    if (c.embedding_size == 0 || c.embedding_size > 512)
+        return fail(B2E_ERR_INVALID, "embedding_size must be in [1, 512]");
+    if (c.walk_length < 2 || c.walk_length > 65535)
+        return fail(B2E_ERR_INVALID, "walk_length must be in [2, 65535]");
+    if (c.window_size == 0 || c.window_size > 64)
+        return fail(B2E_ERR_INVALID, "window_size must be in [1, 64]");
+    if (c.number_of_negative_samples > 31)
+        return fail(B2E_ERR_INVALID, "number_of_negative_samples must be at most 31");
+    if (c.iterations == 0) return fail(B2E_ERR_INVALID, "iterations must be positive");
+    if (!(c.return_weight > 0.0f) || !(c.explore_weight > 0.0f))
+        return fail(B2E_ERR_INVALID, "return_weight and explore_weight must be strictly positive");
+    if (!(c.clipping_value > 0.0f)) return fail(B2E_ERR_INVALID, "clipping_value must be positive");
+    if (!(c.negative_sampling_exponent >= 0.0f))
+        return fail(B2E_ERR_INVALID, "negative_sampling_exponent must be non-negative");
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2E_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (c.device < 0 || c.device >= count) return fail(B2E_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10)
+        return fail(B2E_ERR_CUDA, "this library is built for sm_100a (Blackwell) only");
+
+    b2e_handle *h = new (std::nothrow) b2e_handle();
+    if (!h) return fail(B2E_ERR_INVALID, "out of host memory");
+    h->cfg = c;
+    h->sm_count = prop.multiProcessorCount;
+    h->row_stride = (c.embedding_size + 3u) / 4u * 4u;
+    thresholds(c.return_weight, c.explore_weight, h->thr);
+    h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
+    for (int s = 0; s < 2; ++s) {
+        if (cudaEventCreateWithFlags(&h->walk_done[s], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->train_done[s], cudaEventDisableTiming) != cudaSuccess) {
+            b2e_destroy(h);
+            return fail(B2E_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+    if (cudaStreamCreateWithFlags(&h->walk_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->train_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&h->d_counters, sizeof(DeviceCounters)) != cudaSuccess ||
+        cudaMemset(h->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) {
+        b2e_destroy(h);
+        return fail(B2E_ERR_CUDA, "stream / counter allocation failed");
+    }
+    h->own_streams = true;
+    *out = h;
+    return B2E_OK;
+}
+
+static void free_graph(b2e_handle *h) {
+    cudaFree(h->d_indptr); h->d_indptr = nullptr;
+    cudaFree(h->d_indices); h->d_indices = nullptr;
+    cudaFree(h->d_sources); h->d_sources = nullptr;
+    cudaFree(h->d_alias); h->d_alias = nullptr;
+    cudaFree(h->d_t0); h->d_t0 = nullptr;
+    cudaFree(h->d_t1); h->d_t1 = nullptr;
+    for (int s = 0; s < 2; ++s) { cudaFree(h->d_walks[s]); h->d_walks[s] = nullptr; }
+}
+
+extern "C" void b2e_destroy(b2e_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    free_graph(h);
+    cudaFree(h->d_counters);
+    for (int s = 0; s < 2; ++s) {
+        if (h->walk_done[s]) cudaEventDestroy(h->walk_done[s]);
+        if (h->train_done[s]) cudaEventDestroy(h->train_done[s]);
+    }
+    if (h->own_streams) {
+        if (h->walk_stream) cudaStreamDestroy(h->walk_stream);
+        if (h->train_stream) cudaStreamDestroy(h->train_stream);
+    }
+    delete h;
+}
+
+// K3: Vose alias table over deg^alpha, built on the host while the CSR copy is in flight.
+static double degree_weight(uint64_t deg, double alpha) {
+    if (deg == 0) return 0.0;
+    const double d = (double)deg;
+    if (alpha == 0.0) return 1.0;
+    if (alpha == 1.0) return d;
+    if (alpha == 0.5) return sqrt(d);
+    if (alpha == 0.75) return sqrt(sqrt(d * d * d));
+    return pow(d, alpha);
+}
+
+static bool build_alias(const int64_t *indptr, uint64_t n, double alpha, std::vector<uint32_t> &thr,
+                        std::vector<uint32_t> &alias) {
+    std::vector<double> scaled(n);
+    std::vector<uint32_t> small, large;
+    small.reserve(n);
+    large.reserve(n);
+    double total = 0.0;
+    for (uint64_t i = 0; i < n; ++i) {
+        scaled[i] = degree_weight((uint64_t)(indptr[i + 1] - indptr[i]), alpha);
+        total += scaled[i];
+    }
+    if (!(total > 0.0)) return false;
+    thr.assign(n, 0xFFFFFFFFu);
+    alias.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        scaled[i] = scaled[i] * (double)n / total;
+        alias[i] = (uint32_t)i;
+        if (scaled[i] < 1.0) small.push_back((uint32_t)i); else large.push_back((uint32_t)i);
+    }
+    while (!small.empty() && !large.empty()) {
+        const uint32_t s = small.back(); small.pop_back();
+        const uint32_t l = large.back(); large.pop_back();
+        const double t = floor(scaled[s] * 4294967296.0);
+        thr[s] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        alias[s] = l;
+        scaled[l] = (scaled[l] + scaled[s]) - 1.0;
+        if (scaled[l] < 1.0) small.push_back(l); else large.push_back(l);
+    }
+    return true;
+}
+
+extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
+                            uint64_t n, uint64_t nnz) {
+    REQUIRE_HANDLE(h);
+    if (!indptr || (!indices && nnz)) return fail(B2E_ERR_INVALID, "null CSR pointer");
+    if (n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
+    if (n >= 0xFFFFFFFFull) return fail(B2E_ERR_INVALID, "node ids must fit 32 bits");
+    if (nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
+    if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
+        return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
+    const b2e_config &c = h->cfg;
+    CUDA_TRY(cudaDeviceSynchronize());
+    free_graph(h);
+    h->n = n;
+    h->nnz = nnz;
+
+    // start the big copies first, do the host-side derivations underneath them
+    CUDA_TRY(cudaMalloc(&h->d_indptr, (n + 1) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&h->d_indices, nnz * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpyAsync(h->d_indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                             h->walk_stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                             h->walk_stream));
+
+    std::vector<uint32_t> sources;
+    sources.reserve(n);
+    for (uint64_t v = 0; v < n; ++v) {
+        if (indptr[v + 1] < indptr[v]) return fail(B2E_ERR_INVALID, "indptr must be non-decreasing");
+        if (indptr[v + 1] > indptr[v]) sources.push_back((uint32_t)v);
+    }
+    h->n_src = sources.size();
+    CUDA_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, h->walk_stream));
+
+    h->h_alias_thr.clear();
+    h->h_alias_idx.clear();
+    if (c.use_scale_free_distribution) {
+        if (!build_alias(indptr, n, (double)c.negative_sampling_exponent, h->h_alias_thr, h->h_alias_idx))
+            return fail(B2E_ERR_INVALID, "alias table: total weight is zero");
+        std::vector<uint2> packed(n);
+        for (uint64_t i = 0; i < n; ++i) packed[i] = make_uint2(h->h_alias_thr[i], h->h_alias_idx[i]);
+        CUDA_TRY(cudaMalloc(&h->d_alias, n * sizeof(uint2)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_alias, packed.data(), n * sizeof(uint2), cudaMemcpyHostToDevice,
+                                 h->walk_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `packed` dies here
+    }
+
+    CUDA_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
+
+    const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
+    uint64_t cap = c.chunk_walks ? c.chunk_walks : (1ull << 20);
+    cap = std::max<uint64_t>(1, std::min(cap, per_epoch));
+    h->chunk_cap = cap;
+    for (int s = 0; s < 2; ++s)
+        CUDA_TRY(cudaMalloc(&h->d_walks[s], cap * c.walk_length * sizeof(uint32_t)));
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    return B2E_OK;
+}
+
+extern "C" uint64_t b2e_number_of_sources(const b2e_handle *h) { return h ? h->n_src : 0; }
+extern "C" uint64_t b2e_row_stride(const b2e_handle *h) { return h ? h->row_stride : 0; }
+extern "C" uint64_t b2e_launch_count(const b2e_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int b2e_chunk_capacity(const b2e_handle *h, uint64_t *walks) {
+    if (!h || !walks) return fail(B2E_ERR_INVALID, "null argument");
+    *walks = h->chunk_cap;
+    return B2E_OK;
+}
+
+extern "C" int b2e_set_streams(b2e_handle *h, void *walk_stream, void *train_stream) {
+    REQUIRE_HANDLE(h);
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (h->own_streams) {
+        cudaStreamDestroy(h->walk_stream);
+        cudaStreamDestroy(h->train_stream);
+        h->own_streams = false;
+    }
+    h->walk_stream = (cudaStream_t)walk_stream;
+    h->train_stream = (cudaStream_t)train_stream;
+    return B2E_OK;
+}
+
+static int require_graph(b2e_handle *h) {
+    if (!h->d_indptr) return fail(B2E_ERR_STATE, "b2e_load_csr must be called first");
+    return B2E_OK;
+}
+
+extern "C" int b2e_init_tables(b2e_handle *h, uint64_t seed) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    CUDA_TRY(launch_init_tables(h->d_t0, h->d_t1, h->n, h->cfg.embedding_size, h->row_stride, seed,
+                                h->train_stream));
+    ++h->launches;
+    return B2E_OK;
+}
+
+static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                     uint64_t walk_id_stride, uint32_t *d_out, cudaStream_t stream) {
+    WalkParams p;
+    p.indptr = h->d_indptr;
+    p.indices = h->d_indices;
+    p.sources = h->d_sources;
+    p.n_src = h->n_src;
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    p.first_walk = first_walk;
+    p.n_walks = n_walks;
+    p.walk_id_stride = walk_id_stride;
+    p.walk_length = h->cfg.walk_length;
+    p.thr_return = h->thr[0];
+    p.thr_common = h->thr[1];
+    p.thr_explore = h->thr[2];
+    p.out = d_out;
+    p.counters = h->d_counters;
+    CUDA_TRY(launch_walks(p, h->second_order, stream));
+    if (n_walks) ++h->launches;
+    return B2E_OK;
+}
+
+extern "C" int b2e_walk_chunk(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                              uint64_t walk_id_stride, uint32_t slot) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (slot > 1) return fail(B2E_ERR_INVALID, "slot must be 0 or 1");
+    if (n_walks > h->chunk_cap) return fail(B2E_ERR_INVALID, "n_walks exceeds the chunk capacity");
+    if (walk_id_stride == 0) return fail(B2E_ERR_INVALID, "walk_id_stride must be positive");
+    if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
+    // the slot may still be read by the SGD kernel of two chunks ago
+    CUDA_TRY(cudaStreamWaitEvent(h->walk_stream, h->train_done[slot], 0));
+    if (int rc = walk_into(h, seed, first_walk, n_walks, walk_id_stride, h->d_walks[slot], h->walk_stream))
+        return rc;
+    CUDA_TRY(cudaEventRecord(h->walk_done[slot], h->walk_stream));
+    h->slot_first[slot] = first_walk;
+    h->slot_count[slot] = n_walks;
+    h->slot_stride[slot] = walk_id_stride;
+    return B2E_OK;
+}
+
+static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learning_rate) {
+    const b2e_config &c = h->cfg;
+    TrainParams p;
+    p.walks = h->d_walks[slot];
+    p.first_walk = h->slot_first[slot];
+    p.n_walks = h->slot_count[slot];
+    p.walk_id_stride = h->slot_stride[slot];
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    p.n = (uint32_t)h->n;
+    p.walk_length = c.walk_length;
+    p.window = c.window_size;
+    p.negatives = c.number_of_negative_samples;
+    p.row_stride = h->row_stride;
+    p.clip = c.clipping_value;
+    p.lr = learning_rate;
+    p.inv_scale = 1.0f / sqrtf((float)c.embedding_size);
+    p.use_alias = c.use_scale_free_distribution ? 1u : 0u;
+    p.normalize_lr = c.normalize_learning_rate_by_degree ? 1u : 0u;
+    p.scale_dot = c.scale_by_sqrt_dim ? 1u : 0u;
+    p.alias = h->d_alias;
+    p.indptr = h->d_indptr;
+    p.t0 = h->d_t0;
+    p.t1 = h->d_t1;
+    p.counters = h->d_counters;
+    CUDA_TRY(launch_train(p, c.model, c.deterministic != 0, h->sm_count, h->train_stream));
+    if (p.n_walks) ++h->launches;
+    return B2E_OK;
+}
+
+extern "C" int b2e_train_chunk(b2e_handle *h, uint64_t seed, uint32_t slot, float learning_rate) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (slot > 1) return fail(B2E_ERR_INVALID, "slot must be 0 or 1");
+    CUDA_TRY(cudaStreamWaitEvent(h->train_stream, h->walk_done[slot], 0));
+    if (int rc = train_slot(h, seed, slot, learning_rate)) return rc;
+    CUDA_TRY(cudaEventRecord(h->train_done[slot], h->train_stream));
+    return B2E_OK;
+}
+
+extern "C" int b2e_train_host_walks(b2e_handle *h, uint64_t seed, const uint32_t *walks,
+                                    uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                                    float learning_rate) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!walks) return fail(B2E_ERR_INVALID, "null walks");
+    if (n_walks > h->chunk_cap) return fail(B2E_ERR_INVALID, "n_walks exceeds the chunk capacity");
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
+    CUDA_TRY(cudaMemcpy(h->d_walks[0], walks, n_walks * h->cfg.walk_length * sizeof(uint32_t),
+                        cudaMemcpyHostToDevice));
+    h->slot_first[0] = first_walk;
+    h->slot_count[0] = n_walks;
+    h->slot_stride[0] = walk_id_stride;
+    if (int rc = train_slot(h, seed, 0, learning_rate)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
+    return B2E_OK;
+}
+
+extern "C" int b2e_sync(b2e_handle *h) {
+    REQUIRE_HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
+    return B2E_OK;
+}
+
+extern "C" int b2e_walks(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                         uint64_t walk_id_stride, uint32_t *out) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!out && n_walks) return fail(B2E_ERR_INVALID, "null output buffer");
+    if (walk_id_stride == 0) return fail(B2E_ERR_INVALID, "walk_id_stride must be positive");
+    if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
+    if (int rc = b2e_sync(h)) return rc;
+    const uint32_t L = h->cfg.walk_length;
+    uint64_t done = 0;
+    while (done < n_walks) {
+        const uint64_t count = std::min(h->chunk_cap, n_walks - done);
+        if (int rc = walk_into(h, seed, first_walk + done * walk_id_stride, count, walk_id_stride,
+                               h->d_walks[0], h->walk_stream))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + done * L, h->d_walks[0], count * L * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, h->walk_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+        done += count;
+    }
+    return B2E_OK;
+}
+
+extern "C" int b2e_device_tables(b2e_handle *h, void **table0, void **table1) {
+    if (!h || !table0 || !table1) return fail(B2E_ERR_INVALID, "null argument");
+    if (int rc = require_graph(h)) return rc;
+    *table0 = h->d_t0;
+    *table1 = h->d_t1;
+    return B2E_OK;
+}
+
+extern "C" int b2e_export_tables(b2e_handle *h, float *table0, float *table1) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!table0 || !table1) return fail(B2E_ERR_INVALID, "null output buffer");
+    if (int rc = b2e_sync(h)) return rc;
+    const size_t width = h->cfg.embedding_size * sizeof(float);
+    const size_t pitch = h->row_stride * sizeof(float);
+    CUDA_TRY(cudaMemcpy2D(table0, width, h->d_t0, pitch, width, h->n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy2D(table1, width, h->d_t1, pitch, width, h->n, cudaMemcpyDeviceToHost));
+    return B2E_OK;
+}
+
+extern "C" int b2e_import_tables(b2e_handle *h, const float *table0, const float *table1) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!table0 || !table1) return fail(B2E_ERR_INVALID, "null input buffer");
+    if (int rc = b2e_sync(h)) return rc;
+    const size_t width = h->cfg.embedding_size * sizeof(float);
+    const size_t pitch = h->row_stride * sizeof(float);
+    CUDA_TRY(cudaMemset(h->d_t0, 0, h->n * pitch));
+    CUDA_TRY(cudaMemset(h->d_t1, 0, h->n * pitch));
+    CUDA_TRY(cudaMemcpy2D(h->d_t0, pitch, table0, width, width, h->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy2D(h->d_t1, pitch, table1, width, width, h->n, cudaMemcpyHostToDevice));
+    return B2E_OK;
+}
+
+extern "C" int b2e_export_alias(b2e_handle *h, uint32_t *threshold, uint32_t *alias) {
+    if (!h || !threshold || !alias) return fail(B2E_ERR_INVALID, "null argument");
+    if (h->h_alias_thr.empty()) return fail(B2E_ERR_STATE, "no alias table (uniform negatives or no graph)");
+    memcpy(threshold, h->h_alias_thr.data(), h->n * sizeof(uint32_t));
+    memcpy(alias, h->h_alias_idx.data(), h->n * sizeof(uint32_t));
+    return B2E_OK;
+}
+
+extern "C" int b2e_counters_read(b2e_handle *h, b2e_counters *out) {
+    REQUIRE_HANDLE(h);
+    if (!out) return fail(B2E_ERR_INVALID, "null argument");
+    if (int rc = b2e_sync(h)) return rc;
+    DeviceCounters c;
+    CUDA_TRY(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->walk_steps = c.walk_steps;
+    out->walk_trials = c.walk_trials;
+    out->walk_searches = c.walk_searches;
+    out->pairs = c.pairs;
+    out->targets = c.targets;
+    out->loss_sum = c.loss_sum;
+    return B2E_OK;
+}
+
+extern "C" int b2e_counters_reset(b2e_handle *h) {
+    REQUIRE_HANDLE(h);
+    if (int rc = b2e_sync(h)) return rc;
+    CUDA_TRY(cudaMemset(h->d_counters, 0, sizeof(DeviceCounters)));
+    return B2E_OK;
+}
+
+// The whole path: init, then per epoch walk chunk k+1 on the walk stream while the SGD
+// kernel consumes chunk k on the train stream (two walk buffers, event-ordered).
+extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table1, float *epoch_loss) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!table0 || !table1) return fail(B2E_ERR_INVALID, "null output buffer");
+    if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
+    const b2e_config &c = h->cfg;
+    if (int rc = b2e_init_tables(h, seed)) return rc;
+    const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
+    float lr = c.learning_rate;
+    uint64_t chunk_index = 0;
+    for (uint32_t epoch = 0; epoch < c.epochs; ++epoch) {
+        if (int rc = b2e_counters_reset(h)) return rc;
+        const uint64_t base = (uint64_t)epoch * per_epoch;
+        uint64_t issued = 0;
+        // prime the pipeline with the first chunk, then keep one walk chunk ahead of the SGD
+        uint64_t count = std::min(h->chunk_cap, per_epoch);
+        if (int rc = b2e_walk_chunk(h, seed, base, count, 1, chunk_index & 1)) return rc;
+        issued = count;
+        while (true) {
+            const uint32_t slot = chunk_index & 1;
+            if (issued < per_epoch) {
+                const uint64_t next = std::min(h->chunk_cap, per_epoch - issued);
+                if (int rc = b2e_walk_chunk(h, seed, base + issued, next, 1, slot ^ 1)) return rc;
+                issued += next;
+                if (int rc = b2e_train_chunk(h, seed, slot, lr)) return rc;
+                ++chunk_index;
+            } else {
+                if (int rc = b2e_train_chunk(h, seed, slot, lr)) return rc;
+                ++chunk_index;
+                break;
+            }
+        }
+        b2e_counters counters;
+        if (int rc = b2e_counters_read(h, &counters)) return rc;
+        if (epoch_loss) epoch_loss[epoch] = counters.pairs ? (float)(counters.loss_sum / (double)counters.pairs) : 0.0f;
+        lr = lr * c.learning_rate_decay;
+    }
+    // role order of the reference: [central, contextual]; for CBOW the table scored against
+    // the centre node is the output table
+    if (c.model == B2E_CBOW) return b2e_export_tables(h, table1, table0);
+    return b2e_export_tables(h, table0, table1);
+}

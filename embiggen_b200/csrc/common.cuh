@@ -1,0 +1,107 @@
+// Shared device helpers and the handle layout of the B200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b2e.h"
+
+namespace b2e {
+
+// Philox stream tags (top byte of counter word 3); the normative layout is in DESIGN.md.
+constexpr uint32_t TAG_WALK1 = 1u;  // first-order steps, 4 per block
+constexpr uint32_t TAG_WALK2 = 2u;  // second-order trials, 2 per block
+constexpr uint32_t TAG_NEG = 3u;    // negative draws
+constexpr uint32_t TAG_INIT0 = 4u;  // table 0 initialisation
+constexpr uint32_t TAG_INIT1 = 5u;  // table 1 initialisation
+constexpr uint32_t MAX_TRIALS = 1u << 20;
+constexpr uint32_t PAD = B2E_PAD_TOKEN;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                               uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+struct DeviceCounters {
+    unsigned long long walk_steps;
+    unsigned long long walk_trials;
+    unsigned long long walk_searches;
+    unsigned long long pairs;
+    unsigned long long targets;
+    double loss_sum;
+    unsigned long long work_counter;  // dynamic walk fetch of the SGD kernels
+};
+
+struct WalkParams {
+    const int64_t *indptr;
+    const uint32_t *indices;
+    const uint32_t *sources;
+    uint64_t n_src;
+    uint32_t seed_lo, seed_hi;
+    uint64_t first_walk, n_walks, walk_id_stride;
+    uint32_t walk_length;
+    unsigned long long thr_return, thr_common, thr_explore;
+    uint32_t *out;
+    DeviceCounters *counters;
+};
+
+struct TrainParams {
+    const uint32_t *walks;
+    uint64_t first_walk, n_walks, walk_id_stride;
+    uint32_t seed_lo, seed_hi;
+    uint32_t n;
+    uint32_t walk_length, window, negatives;
+    uint32_t row_stride;  // floats, multiple of 4
+    float clip, lr, inv_scale;
+    uint32_t use_alias, normalize_lr, scale_dot;
+    const uint2 *alias;  // {threshold, alias} per node
+    const int64_t *indptr;
+    float *t0, *t1;
+    DeviceCounters *counters;
+};
+
+cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
+cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
+                               uint32_t row_stride, uint64_t seed, cudaStream_t stream);
+cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
+                         cudaStream_t stream);
+cudaError_t launch_pack_rows(const float *src, float *dst, uint64_t n, uint32_t embedding_size,
+                             uint32_t row_stride, bool strip, cudaStream_t stream);
+
+}  // namespace b2e
+
+struct b2e_handle {
+    b2e_config cfg;
+    int sm_count = 0;
+    uint64_t n = 0, nnz = 0, n_src = 0;
+    uint32_t row_stride = 0;
+    int64_t *d_indptr = nullptr;
+    uint32_t *d_indices = nullptr;
+    uint32_t *d_sources = nullptr;
+    uint2 *d_alias = nullptr;
+    float *d_t0 = nullptr, *d_t1 = nullptr;
+    uint32_t *d_walks[2] = {nullptr, nullptr};
+    uint64_t chunk_cap = 0;
+    uint64_t slot_first[2] = {0, 0}, slot_count[2] = {0, 0}, slot_stride[2] = {1, 1};
+    cudaEvent_t walk_done[2] = {nullptr, nullptr}, train_done[2] = {nullptr, nullptr};
+    cudaStream_t walk_stream = nullptr, train_stream = nullptr;
+    bool own_streams = false;
+    b2e::DeviceCounters *d_counters = nullptr;
+    unsigned long long thr[3] = {0, 0, 0};
+    bool second_order = false;
+    uint64_t launches = 0;
+    std::vector<uint32_t> h_alias_thr, h_alias_idx;
+};

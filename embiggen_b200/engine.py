@@ -1,0 +1,255 @@
+"""Host-side driver above the C ABI: the object that stands where the reference holds its
+``ensmallen.models.SkipGram / CBOW`` instance
+(/root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:65-69, used at :99).
+
+PyTorch appears only as plumbing for the multi-GPU path (``torch.distributed`` over NCCL and
+a zero-copy tensor view of the device tables); every kernel is in ``libb2e.so``.
+"""
+import ctypes
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2EConfig, B2ECounters, MODEL_IDS, check
+
+
+class _DeviceArray:
+    """Exposes a raw device pointer through ``__cuda_array_interface__``."""
+
+    def __init__(self, pointer: int, shape: Tuple[int, ...], typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {
+            "shape": shape, "typestr": typestr, "data": (pointer, False), "version": 2,
+        }
+
+
+def pairs_per_walk(walk_length: int, window_size: int) -> int:
+    """P(L, w) = 2wL - w(w+1): positives of a border-trimmed window."""
+    w = min(window_size, walk_length - 1)
+    return 2 * w * walk_length - w * (w + 1)
+
+
+class Engine:
+    """One engine = one ``b2e_handle`` on one GPU."""
+
+    def __init__(self, model: str, embedding_size: int = 100, epochs: int = 30,
+                 walk_length: int = 128, iterations: int = 10, window_size: int = 5,
+                 number_of_negative_samples: int = 10, clipping_value: float = 6.0,
+                 return_weight: float = 1.0, explore_weight: float = 1.0,
+                 learning_rate: float = 0.01, learning_rate_decay: float = 0.9,
+                 negative_sampling_exponent: float = 0.75,
+                 use_scale_free_distribution: bool = True,
+                 normalize_learning_rate_by_degree: bool = False,
+                 scale_by_sqrt_dim: bool = False, deterministic: bool = False,
+                 chunk_walks: int = 0, device: int = 0):
+        self._lib = _lib.load()
+        self._handle = ctypes.c_void_p()
+        self.model = model.lower()
+        if self.model not in MODEL_IDS:
+            raise ValueError(f"Unknown model {model!r}; expected 'SkipGram' or 'CBOW'.")
+        self.config = B2EConfig(
+            struct_size=ctypes.sizeof(B2EConfig), model=MODEL_IDS[self.model],
+            embedding_size=embedding_size, epochs=epochs, walk_length=walk_length,
+            iterations=iterations, window_size=window_size,
+            number_of_negative_samples=number_of_negative_samples,
+            clipping_value=clipping_value, return_weight=return_weight,
+            explore_weight=explore_weight, learning_rate=learning_rate,
+            learning_rate_decay=learning_rate_decay,
+            negative_sampling_exponent=negative_sampling_exponent,
+            use_scale_free_distribution=int(bool(use_scale_free_distribution)),
+            normalize_learning_rate_by_degree=int(bool(normalize_learning_rate_by_degree)),
+            scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), deterministic=int(bool(deterministic)),
+            chunk_walks=chunk_walks, device=device,
+        )
+        check(self._lib.b2e_create(ctypes.byref(self.config), ctypes.byref(self._handle)))
+        self.n = 0
+        self._keepalive = None
+
+    # ---- lifetime ----
+    def close(self) -> None:
+        if self._handle:
+            self._lib.b2e_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *_):
+        self.close()
+
+    # ---- K1 ----
+    def load_csr(self, indptr: np.ndarray, indices: np.ndarray) -> None:
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        if indptr.ndim != 1 or indptr.shape[0] < 2:
+            raise ValueError("The provided graph is empty.")
+        n, nnz = indptr.shape[0] - 1, indices.shape[0]
+        check(self._lib.b2e_load_csr(self._handle, indptr.ctypes.data, indices.ctypes.data, n, nnz))
+        self.n = n
+
+    @property
+    def number_of_sources(self) -> int:
+        return int(self._lib.b2e_number_of_sources(self._handle))
+
+    @property
+    def row_stride(self) -> int:
+        return int(self._lib.b2e_row_stride(self._handle))
+
+    @property
+    def chunk_capacity(self) -> int:
+        out = ctypes.c_uint64()
+        check(self._lib.b2e_chunk_capacity(self._handle, ctypes.byref(out)))
+        return int(out.value)
+
+    @property
+    def walks_per_epoch(self) -> int:
+        return self.config.iterations * self.number_of_sources
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b2e_launch_count(self._handle))
+
+    # ---- whole path, host buffers (single GPU) ----
+    def fit(self, seed: int, table0: Optional[np.ndarray] = None,
+            table1: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray, List[float]]:
+        """Returns ([central, contextual] role-ordered tables, per-epoch mean pair loss)."""
+        shape = (self.n, self.config.embedding_size)
+        t0 = np.empty(shape, dtype=np.float32) if table0 is None else table0
+        t1 = np.empty(shape, dtype=np.float32) if table1 is None else table1
+        for t in (t0, t1):
+            if t.shape != shape or t.dtype != np.float32 or not t.flags.c_contiguous:
+                raise ValueError(f"Output tables must be C-contiguous float32 of shape {shape}.")
+        losses = np.zeros(max(1, self.config.epochs), dtype=np.float32)
+        check(self._lib.b2e_fit(self._handle, seed, t0.ctypes.data, t1.ctypes.data,
+                                losses.ctypes.data))
+        return t0, t1, [float(x) for x in losses[: self.config.epochs]]
+
+    # ---- K2 parity/debug export ----
+    def walks(self, seed: int, first_walk: int, n_walks: int, walk_id_stride: int = 1) -> np.ndarray:
+        out = np.empty((n_walks, self.config.walk_length), dtype=np.uint32)
+        check(self._lib.b2e_walks(self._handle, seed, first_walk, n_walks, walk_id_stride,
+                                  out.ctypes.data))
+        return out
+
+    # ---- stepping API ----
+    def set_streams(self, walk_stream, train_stream) -> None:
+        """Accepts ``torch.cuda.Stream`` objects or raw ``cudaStream_t`` integers."""
+        self._keepalive = (walk_stream, train_stream)
+        handles = [getattr(s, "cuda_stream", s) for s in (walk_stream, train_stream)]
+        check(self._lib.b2e_set_streams(self._handle, ctypes.c_void_p(handles[0]),
+                                        ctypes.c_void_p(handles[1])))
+
+    def init_tables(self, seed: int) -> None:
+        check(self._lib.b2e_init_tables(self._handle, seed))
+
+    def walk_chunk(self, seed: int, first_walk: int, n_walks: int, walk_id_stride: int = 1,
+                   slot: int = 0) -> None:
+        check(self._lib.b2e_walk_chunk(self._handle, seed, first_walk, n_walks, walk_id_stride, slot))
+
+    def train_chunk(self, seed: int, slot: int, learning_rate: float) -> None:
+        check(self._lib.b2e_train_chunk(self._handle, seed, slot, learning_rate))
+
+    def train_host_walks(self, seed: int, walks: np.ndarray, learning_rate: float,
+                         first_walk: int = 0, walk_id_stride: int = 1) -> None:
+        walks = np.ascontiguousarray(walks, dtype=np.uint32)
+        if walks.ndim != 2 or walks.shape[1] != self.config.walk_length:
+            raise ValueError("walks must have shape (n_walks, walk_length).")
+        check(self._lib.b2e_train_host_walks(self._handle, seed, walks.ctypes.data, first_walk,
+                                             walks.shape[0], walk_id_stride, learning_rate))
+
+    def sync(self) -> None:
+        check(self._lib.b2e_sync(self._handle))
+
+    def export_tables(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Raw (input table T0, output table T1), padding stripped."""
+        shape = (self.n, self.config.embedding_size)
+        t0, t1 = np.empty(shape, dtype=np.float32), np.empty(shape, dtype=np.float32)
+        check(self._lib.b2e_export_tables(self._handle, t0.ctypes.data, t1.ctypes.data))
+        return t0, t1
+
+    def import_tables(self, t0: np.ndarray, t1: np.ndarray) -> None:
+        shape = (self.n, self.config.embedding_size)
+        t0 = np.ascontiguousarray(t0, dtype=np.float32)
+        t1 = np.ascontiguousarray(t1, dtype=np.float32)
+        if t0.shape != shape or t1.shape != shape:
+            raise ValueError(f"Tables must have shape {shape}.")
+        check(self._lib.b2e_import_tables(self._handle, t0.ctypes.data, t1.ctypes.data))
+
+    def export_alias(self) -> Tuple[np.ndarray, np.ndarray]:
+        thr, alias = np.empty(self.n, dtype=np.uint32), np.empty(self.n, dtype=np.uint32)
+        check(self._lib.b2e_export_alias(self._handle, thr.ctypes.data, alias.ctypes.data))
+        return thr, alias
+
+    def counters(self) -> dict:
+        out = B2ECounters()
+        check(self._lib.b2e_counters_read(self._handle, ctypes.byref(out)))
+        return out.as_dict()
+
+    def reset_counters(self) -> None:
+        check(self._lib.b2e_counters_reset(self._handle))
+
+    def device_tables(self):
+        """Zero-copy torch views (n x row_stride float32) of the two device tables."""
+        import torch
+        p0, p1 = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._lib.b2e_device_tables(self._handle, ctypes.byref(p0), ctypes.byref(p1)))
+        shape = (self.n, self.row_stride)
+        device = f"cuda:{self.config.device}"
+        return tuple(torch.as_tensor(_DeviceArray(p.value, shape), device=device) for p in (p0, p1))
+
+    # ---- data-parallel path: start nodes sharded, tables averaged by NCCL all-reduce ----
+    def fit_distributed(self, seed: int, sync_interval: int = 4, process_group=None
+                        ) -> Tuple[np.ndarray, np.ndarray, List[float]]:
+        """Every rank holds the CSR and both tables; rank r walks ids = r mod world_size.
+
+        Tables are averaged (all-reduce, AVG) every ``sync_interval`` chunks and at each epoch
+        end.  Returns role-ordered tables like :meth:`fit` (identical on every rank).
+        """
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        cfg = self.config
+        tables = self.device_tables()
+        self.init_tables(seed)  # identical on every rank (counter-based init)
+        per_epoch = self.walks_per_epoch
+        chunk = self.chunk_capacity * world  # global walks per step, chunk_capacity per rank
+        lr = np.float32(cfg.learning_rate)
+        losses = []
+
+        def average():
+            self.sync()
+            for t in tables:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=process_group)
+            torch.cuda.synchronize(cfg.device)
+
+        for epoch in range(cfg.epochs):
+            self.reset_counters()
+            base = epoch * per_epoch
+            done, index = 0, 0
+            while done < per_epoch:
+                count = min(chunk, per_epoch - done)
+                mine = (count - rank + world - 1) // world if count > rank else 0
+                slot = index & 1
+                self.walk_chunk(seed, base + done + rank, mine, world, slot)
+                self.train_chunk(seed, slot, float(lr))
+                done += count
+                index += 1
+                if sync_interval and index % sync_interval == 0 and done < per_epoch:
+                    average()
+            average()
+            c = self.counters()
+            stats = torch.tensor([c["loss_sum"], float(c["pairs"])], dtype=torch.float64,
+                                 device=f"cuda:{cfg.device}")
+            dist.all_reduce(stats, group=process_group)
+            losses.append(float(stats[0] / max(float(stats[1]), 1.0)))
+            lr = np.float32(lr * np.float32(cfg.learning_rate_decay))
+        t0, t1 = self.export_tables()
+        if self.model == "cbow":
+            t0, t1 = t1, t0
+        return t0, t1, losses

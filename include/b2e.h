@@ -1,0 +1,146 @@
+/*
+ * include/b2e.h -- C ABI of the B200-native Node2Vec/DeepWalk SkipGram & CBOW engine.
+ *
+ * This is the drop-in boundary for ONE path of monarch-initiative/embiggen: what
+ * `ensmallen.models.SkipGram / CBOW` do below the PyO3 call at
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:99
+ * (`self._model.fit_transform(graph)`), constructed at node2vec.py:65-69 from the
+ * kwargs declared in .../node2vec_skipgram.py:9-146.  The reference's own FFI is PyO3
+ * (process-internal, Rust objects); a replacement binds these entry points instead
+ * (ctypes stub in INTEGRATION.md).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative b2e_status, never aborts; b2e_last_error() gives the thread-local message the
+ * Python shim turns into ValueError / RuntimeError (reference error behaviour:
+ * .../abstract_embedding_model.py:114-166).  The caller owns host buffers; the library
+ * owns device memory for the lifetime of a handle.  There is no CPU fallback: without a
+ * CUDA device b2e_create fails with B2E_ERR_CUDA.
+ */
+#ifndef B2E_H
+#define B2E_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2E_ABI_VERSION 1
+#define B2E_PAD_TOKEN 0xFFFFFFFFu /* walk token after a dead end (directed graphs only) */
+
+typedef enum {
+    B2E_OK = 0,
+    B2E_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+    B2E_ERR_CUDA = -2,    /* CUDA runtime failure, device missing, out of memory */
+    B2E_ERR_STATE = -3    /* call order violated (e.g. fit before load_csr) */
+} b2e_status;
+
+typedef enum { B2E_SKIPGRAM = 0, B2E_CBOW = 1 } b2e_model;
+
+/*
+ * Mirrors the constructor kwargs of Node2VecSkipGramEnsmallen / Node2VecCBOWEnsmallen
+ * (.../node2vec_skipgram.py:9-35, node2vec_cbow.py) that reach the native engine.
+ * DeepWalk = return_weight == explore_weight == 1 (.../deepwalk_skipgram.py:6-139).
+ */
+typedef struct {
+    uint32_t struct_size; /* sizeof(b2e_config), ABI check */
+    uint32_t model;       /* b2e_model */
+    uint32_t embedding_size;
+    uint32_t epochs;
+    uint32_t walk_length;
+    uint32_t iterations;
+    uint32_t window_size;
+    uint32_t number_of_negative_samples;
+    float clipping_value;
+    float return_weight;  /* 1/p */
+    float explore_weight; /* 1/q */
+    float learning_rate;
+    float learning_rate_decay;
+    float negative_sampling_exponent;           /* alias table over deg^alpha; north_star: 0.75 */
+    uint32_t use_scale_free_distribution;       /* 0 => uniform negatives */
+    uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre) */
+    uint32_t scale_by_sqrt_dim;                 /* score = dot / sqrt(D) */
+    uint32_t deterministic; /* 1: one warp trains walks in ascending id order (bit-exact) */
+    uint32_t chunk_walks;   /* walks per walk->SGD chunk, 0 = automatic */
+    int32_t device;         /* CUDA device ordinal */
+} b2e_config;
+
+/* Event counters accumulated on the device (roofline accounting). */
+typedef struct {
+    uint64_t walk_steps;    /* sampled transitions */
+    uint64_t walk_trials;   /* second-order proposals */
+    uint64_t walk_searches; /* adjacency checks that needed a binary search */
+    uint64_t pairs;         /* (centre, context) positives trained */
+    uint64_t targets;       /* target rows scored (positive + valid negatives) */
+    double loss_sum;        /* sum of pair losses since the last b2e_reset_counters */
+} b2e_counters;
+
+typedef struct b2e_handle b2e_handle;
+
+const char *b2e_last_error(void);
+int b2e_abi_version(void);
+
+int b2e_create(const b2e_config *config, b2e_handle **out);
+void b2e_destroy(b2e_handle *handle);
+
+/*
+ * K1: copy GRAPE's sorted neighbour arrays into HBM once.  indptr has n + 1 entries
+ * (0 followed by get_cumulative_node_degrees(), .../pecanpy_embedders/node2vec.py:144-148),
+ * indices has nnz sorted-per-row destination ids (get_directed_destination_node_ids(), :161).
+ * Host pointers.  Also derives the start-node list (degree > 0) and the alias table (K3).
+ */
+int b2e_load_csr(b2e_handle *handle, const int64_t *indptr, const uint32_t *indices,
+                 uint64_t n, uint64_t nnz);
+
+uint64_t b2e_number_of_sources(const b2e_handle *handle);
+uint64_t b2e_row_stride(const b2e_handle *handle); /* floats per table row on the device */
+
+/*
+ * The whole path, host buffers in and out: replaces `model.fit_transform(graph)`
+ * (node2vec.py:99).  table0 / table1 receive n x embedding_size float32, row-major, in
+ * [central, contextual] role order like the reference; epoch_loss (may be NULL) receives
+ * `epochs` mean pair losses.  The seed is read here, not at create time.
+ */
+int b2e_fit(b2e_handle *handle, uint64_t seed, float *table0, float *table1, float *epoch_loss);
+
+/*
+ * K2, parity/debug export: walks with ids first_walk + i * walk_id_stride, i < n_walks,
+ * row-major [n_walks][walk_length] uint32 into a host buffer.
+ */
+int b2e_walks(b2e_handle *handle, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+              uint64_t walk_id_stride, uint32_t *out);
+
+/* ---- stepping API (device-resident; used by the host driver, multi-GPU and bench) ---- */
+
+/* Streams are cudaStream_t handles (e.g. torch.cuda.Stream().cuda_stream); NULL = default. */
+int b2e_set_streams(b2e_handle *handle, void *walk_stream, void *train_stream);
+int b2e_init_tables(b2e_handle *handle, uint64_t seed);
+/* walks for one chunk into device buffer `slot` (0 or 1), asynchronous on the walk stream */
+int b2e_walk_chunk(b2e_handle *handle, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                   uint64_t walk_id_stride, uint32_t slot);
+/* K4/K5 over the walks in `slot`, asynchronous on the train stream, ordered after the walk */
+int b2e_train_chunk(b2e_handle *handle, uint64_t seed, uint32_t slot, float learning_rate);
+/* train on caller-provided host walks (parity tests feed the oracle's walks) */
+int b2e_train_host_walks(b2e_handle *handle, uint64_t seed, const uint32_t *walks,
+                         uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                         float learning_rate);
+int b2e_sync(b2e_handle *handle);
+
+/* device pointers of the two tables (n x row_stride float32) for NCCL averaging by the host */
+int b2e_device_tables(b2e_handle *handle, void **table0, void **table1);
+int b2e_chunk_capacity(const b2e_handle *handle, uint64_t *walks);
+/* strip the row padding and copy both tables to host buffers (n x embedding_size each) */
+int b2e_export_tables(b2e_handle *handle, float *table0, float *table1);
+/* overwrite both device tables from host buffers (n x embedding_size each) */
+int b2e_import_tables(b2e_handle *handle, const float *table0, const float *table1);
+/* alias table as built for the handle (n entries each); parity/debug export */
+int b2e_export_alias(b2e_handle *handle, uint32_t *threshold, uint32_t *alias);
+
+int b2e_counters_read(b2e_handle *handle, b2e_counters *out);
+int b2e_counters_reset(b2e_handle *handle);
+/* number of kernels this handle has launched since creation */
+uint64_t b2e_launch_count(const b2e_handle *handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

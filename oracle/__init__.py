@@ -1,0 +1,262 @@
+"""ctypes binding of the CPU oracle (``oracle/liboracle.so``).
+
+TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+package; ``embiggen_b200`` never does.  PARITY UNPINNED against Ensmallen, see
+``oracle/oracle.h`` for what the oracle is pinned against instead.
+"""
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+PAD_TOKEN = 0xFFFFFFFF
+
+
+class WalkCounters(ctypes.Structure):
+    _fields_ = [
+        ("steps", ctypes.c_uint64),
+        ("trials", ctypes.c_uint64),
+        ("first_order", ctypes.c_uint64),
+        ("searches", ctypes.c_uint64),
+        ("probe_sectors", ctypes.c_uint64),
+        ("capped", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+class SgnsCfg(ctypes.Structure):
+    _fields_ = [
+        ("model", ctypes.c_uint32),
+        ("embedding_size", ctypes.c_uint32),
+        ("row_stride", ctypes.c_uint32),
+        ("walk_length", ctypes.c_uint32),
+        ("window_size", ctypes.c_uint32),
+        ("negatives", ctypes.c_uint32),
+        ("clipping_value", ctypes.c_float),
+        ("learning_rate", ctypes.c_float),
+        ("use_alias", ctypes.c_uint32),
+        ("normalize_learning_rate_by_degree", ctypes.c_uint32),
+        ("scale_by_sqrt_dim", ctypes.c_uint32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    sources = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in sources
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def _ptr(array, ctype):
+    return None if array is None else array.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        l = ctypes.CDLL(_LIB_PATH)
+        u64, u32, f32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float
+        P = ctypes.POINTER
+        l.orc_philox.restype = None
+        l.orc_philox.argtypes = [u64, u32, u32, u32, u32, P(u32)]
+        l.orc_sources.restype = u64
+        l.orc_sources.argtypes = [P(ctypes.c_int64), u64, P(u32)]
+        l.orc_thresholds.restype = None
+        l.orc_thresholds.argtypes = [f32, f32, P(u64)]
+        l.orc_walks.restype = ctypes.c_int
+        l.orc_walks.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32), u64, u64, u64, u64, u64,
+                                u32, f32, f32, P(u32), P(WalkCounters)]
+        l.orc_alias_build.restype = ctypes.c_int
+        l.orc_alias_build.argtypes = [P(ctypes.c_int64), u64, ctypes.c_double, P(u32), P(u32)]
+        l.orc_set_threads.restype = None
+        l.orc_set_threads.argtypes = [ctypes.c_int]
+        l.orc_get_threads.restype = ctypes.c_int
+        l.orc_sigmoid.restype = f32
+        l.orc_sigmoid.argtypes = [f32]
+        l.orc_dot.restype = f32
+        l.orc_dot.argtypes = [P(f32), P(f32), u32]
+        l.orc_init_tables.restype = ctypes.c_int
+        l.orc_init_tables.argtypes = [u64, u32, u32, u64, P(f32), P(f32)]
+        l.orc_train.restype = ctypes.c_int
+        l.orc_train.argtypes = [P(SgnsCfg), P(u32), u64, u64, u64, u64, u64, P(ctypes.c_int64),
+                                P(u32), P(u32), P(f32), P(f32), P(ctypes.c_double), P(u64), P(u64)]
+        _lib = l
+    return _lib
+
+
+def philox(seed: int, c0: int, c1: int, c2: int, c3: int) -> Tuple[int, int, int, int]:
+    out = (ctypes.c_uint32 * 4)()
+    lib().orc_philox(seed, c0, c1, c2, c3, out)
+    return tuple(int(x) for x in out)
+
+
+def set_threads(threads: int) -> None:
+    lib().orc_set_threads(int(threads))
+
+
+def row_stride(embedding_size: int) -> int:
+    return (int(embedding_size) + 3) // 4 * 4
+
+
+def _csr(indptr, indices):
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    return indptr, indices
+
+
+def sources(indptr) -> np.ndarray:
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    n = indptr.shape[0] - 1
+    out = np.empty(n, dtype=np.uint32)
+    count = lib().orc_sources(_ptr(indptr, ctypes.c_int64), n, _ptr(out, ctypes.c_uint32))
+    return out[:count].copy()
+
+
+def thresholds(return_weight: float, explore_weight: float) -> np.ndarray:
+    out = np.zeros(3, dtype=np.uint64)
+    lib().orc_thresholds(return_weight, explore_weight, _ptr(out, ctypes.c_uint64))
+    return out
+
+
+def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length: int,
+          return_weight: float = 1.0, explore_weight: float = 1.0, walk_id_stride: int = 1,
+          srcs: Optional[np.ndarray] = None) -> Tuple[np.ndarray, dict]:
+    indptr, indices = _csr(indptr, indices)
+    n = indptr.shape[0] - 1
+    if srcs is None:
+        srcs = sources(indptr)
+    srcs = np.ascontiguousarray(srcs, dtype=np.uint32)
+    out = np.empty((n_walks, walk_length), dtype=np.uint32)
+    counters = WalkCounters()
+    rc = lib().orc_walks(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32), n,
+                         _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
+                         walk_id_stride, walk_length, return_weight, explore_weight,
+                         _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
+    if rc != 0:
+        raise ValueError(f"orc_walks failed with status {rc}")
+    return out, counters.as_dict()
+
+
+def alias_build(indptr, alpha: float = 0.75) -> Tuple[np.ndarray, np.ndarray]:
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    n = indptr.shape[0] - 1
+    thr = np.empty(n, dtype=np.uint32)
+    alias = np.empty(n, dtype=np.uint32)
+    rc = lib().orc_alias_build(_ptr(indptr, ctypes.c_int64), n, alpha, _ptr(thr, ctypes.c_uint32),
+                               _ptr(alias, ctypes.c_uint32))
+    if rc != 0:
+        raise ValueError(f"orc_alias_build failed with status {rc}")
+    return thr, alias
+
+
+def sigmoid(x: float) -> float:
+    return float(lib().orc_sigmoid(x))
+
+
+def dot(a: np.ndarray, b: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return float(lib().orc_dot(_ptr(a, ctypes.c_float), _ptr(b, ctypes.c_float), a.shape[0]))
+
+
+def init_tables(n: int, embedding_size: int, seed: int) -> Tuple[np.ndarray, np.ndarray]:
+    stride = row_stride(embedding_size)
+    t0 = np.empty((n, stride), dtype=np.float32)
+    t1 = np.empty((n, stride), dtype=np.float32)
+    rc = lib().orc_init_tables(n, embedding_size, stride, seed, _ptr(t0, ctypes.c_float),
+                               _ptr(t1, ctypes.c_float))
+    if rc != 0:
+        raise ValueError(f"orc_init_tables failed with status {rc}")
+    return t0, t1
+
+
+def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, seed: int, n: int,
+          embedding_size: int, window_size: int, negatives: int, learning_rate: float,
+          clipping_value: float = 6.0, first_walk: int = 0, walk_id_stride: int = 1,
+          thr: Optional[np.ndarray] = None, alias: Optional[np.ndarray] = None,
+          indptr: Optional[np.ndarray] = None, normalize_learning_rate_by_degree: bool = False,
+          scale_by_sqrt_dim: bool = False) -> dict:
+    """Train in place over row-major walks; returns loss_sum / pairs / targets."""
+    walk_array = np.ascontiguousarray(walk_array, dtype=np.uint32)
+    assert t0.dtype == np.float32 and t1.dtype == np.float32
+    assert t0.flags.c_contiguous and t1.flags.c_contiguous
+    cfg = SgnsCfg(
+        model={"skipgram": 0, "cbow": 1}[model.lower()],
+        embedding_size=embedding_size,
+        row_stride=t0.shape[1],
+        walk_length=walk_array.shape[1],
+        window_size=window_size,
+        negatives=negatives,
+        clipping_value=clipping_value,
+        learning_rate=learning_rate,
+        use_alias=int(thr is not None),
+        normalize_learning_rate_by_degree=int(normalize_learning_rate_by_degree),
+        scale_by_sqrt_dim=int(scale_by_sqrt_dim),
+    )
+    if indptr is not None:
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    loss = ctypes.c_double(0.0)
+    pairs = ctypes.c_uint64(0)
+    targets = ctypes.c_uint64(0)
+    rc = lib().orc_train(ctypes.byref(cfg), _ptr(walk_array, ctypes.c_uint32), walk_array.shape[0],
+                         first_walk, walk_id_stride, seed, n, _ptr(indptr, ctypes.c_int64),
+                         _ptr(thr, ctypes.c_uint32), _ptr(alias, ctypes.c_uint32),
+                         _ptr(t0, ctypes.c_float), _ptr(t1, ctypes.c_float), ctypes.byref(loss),
+                         ctypes.byref(pairs), ctypes.byref(targets))
+    if rc != 0:
+        raise ValueError(f"orc_train failed with status {rc}")
+    return {"loss_sum": loss.value, "pairs": pairs.value, "targets": targets.value}
+
+
+def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int, iterations: int,
+        walk_length: int, window_size: int, negatives: int, learning_rate: float,
+        learning_rate_decay: float, return_weight: float = 1.0, explore_weight: float = 1.0,
+        clipping_value: float = 6.0, alpha: float = 0.75, use_scale_free_distribution: bool = True,
+        normalize_learning_rate_by_degree: bool = False, chunk_walks: int = 1 << 16):
+    """Whole path: walks + SGD for ``epochs`` epochs in ascending walk-id order.
+
+    Returns (t0, t1, epoch_mean_loss) with padded row stride.
+    """
+    indptr, indices = _csr(indptr, indices)
+    n = indptr.shape[0] - 1
+    srcs = sources(indptr)
+    thr = alias = None
+    if use_scale_free_distribution:
+        thr, alias = alias_build(indptr, alpha)
+    t0, t1 = init_tables(n, embedding_size, seed)
+    walks_per_epoch = iterations * srcs.shape[0]
+    lr = np.float32(learning_rate)
+    losses = []
+    for epoch in range(epochs):
+        loss_sum, pairs = 0.0, 0
+        done = 0
+        while done < walks_per_epoch:
+            count = min(chunk_walks, walks_per_epoch - done)
+            first = epoch * walks_per_epoch + done
+            w, _ = walks(indptr, indices, seed, first, count, walk_length, return_weight,
+                         explore_weight, srcs=srcs)
+            r = train(model, w, t0, t1, seed, n, embedding_size, window_size, negatives, float(lr),
+                      clipping_value, first_walk=first, thr=thr, alias=alias, indptr=indptr,
+                      normalize_learning_rate_by_degree=normalize_learning_rate_by_degree)
+            loss_sum += r["loss_sum"]
+            pairs += r["pairs"]
+            done += count
+        losses.append(loss_sum / max(pairs, 1))
+        lr = np.float32(lr * np.float32(learning_rate_decay))
+    return t0, t1, losses

@@ -1,0 +1,105 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE: CPU restatement of the hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (embiggen_b200/)
+ * never does.
+ *
+ * PARITY UNPINNED against Ensmallen: the reference's arithmetic for this path
+ * lives in the third-party Rust wheel `ensmallen>=0.8.94`
+ * (/root/reference/setup.py:76, call site
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:99) whose
+ * source is not vendored and which no reference test pins numerically
+ * (SURVEY.md 8c).  What this oracle IS pinned against:
+ *   - Random123 known-answer vectors for Philox4x32-10,
+ *   - the analytic node2vec transition pmf (Grover & Leskovec 2016, eq. 2)
+ *     by chi-square on small graphs,
+ *   - the target pmf deg^alpha for the alias table,
+ *   - an independent numpy restatement of the SkipGram/CBOW update
+ *     (tests/test_oracle_sgns.py) and committed fixtures in tests/golden/.
+ * Semantics of every kwarg follow the reference docstrings
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec_skipgram.py:37-119.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_PAD_TOKEN 0xFFFFFFFFu
+#define ORC_MAX_TRIALS (1u << 20)
+
+typedef struct {
+    uint64_t steps;          /* sampled transitions                                        */
+    uint64_t trials;         /* proposals drawn by second-order steps                      */
+    uint64_t first_order;    /* steps taken with the uniform (first-order) rule            */
+    uint64_t searches;       /* adjacency checks not resolved by return / bound shortcuts  */
+    uint64_t probe_sectors;  /* 32 B sectors those checks touch (SURVEY.md 8d S_probe)     */
+    uint64_t capped;         /* steps that hit ORC_MAX_TRIALS                              */
+} orc_walk_counters;
+
+/* Philox4x32-10, key = (seed lo, seed hi); exported for the known-answer tests */
+void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
+
+/* nodes with degree > 0, ascending; returns their count (out may be NULL). */
+uint64_t orc_sources(const int64_t *indptr, uint64_t n, uint32_t *out);
+
+/* thresholds of the integer accept test, SURVEY.md App. C.4 */
+void orc_thresholds(float return_weight, float explore_weight, uint64_t thr[3]);
+
+/*
+ * Walk ids are first_walk + i * walk_id_stride, i in [0, n_walks); walk id g
+ * starts at sources[g % n_src].  out is row-major [n_walks][walk_length].
+ */
+int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const uint32_t *sources,
+              uint64_t n_src, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+              uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
+              float explore_weight, uint32_t *out, orc_walk_counters *counters);
+
+/* Vose alias table over deg^alpha; thr/alias have n entries. */
+int orc_alias_build(const int64_t *indptr, uint64_t n, double alpha, uint32_t *thr,
+                    uint32_t *alias);
+
+typedef struct {
+    uint32_t model; /* 0 SkipGram, 1 CBOW */
+    uint32_t embedding_size;
+    uint32_t row_stride; /* floats per row, multiple of 4, >= embedding_size */
+    uint32_t walk_length;
+    uint32_t window_size;
+    uint32_t negatives;
+    float clipping_value;
+    float learning_rate;
+    uint32_t use_alias;                         /* 0 => uniform negatives                   */
+    uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre)                         */
+    uint32_t scale_by_sqrt_dim;                 /* dot / sqrt(D)  (P)   */
+} orc_sgns_cfg;
+
+/*
+ * threads > 1 turns orc_walks / orc_train into OpenMP loops over walks
+ * (Hogwild for the tables, like the reference engine's rayon pool).  Used
+ * only to time the CPU baseline; parity tests run with 1 (the default).
+ */
+void orc_set_threads(int threads);
+int orc_get_threads(void);
+
+float orc_sigmoid(float x);
+float orc_dot(const float *a, const float *b, uint32_t row_stride);
+
+int orc_init_tables(uint64_t n, uint32_t embedding_size, uint32_t row_stride, uint64_t seed,
+                    float *t0, float *t1);
+
+/*
+ * Sequential deterministic training over row-major walks (ascending order).
+ * loss_sum / pairs / targets are accumulated into (may be NULL).
+ */
+int orc_train(const orc_sgns_cfg *cfg, const uint32_t *walks, uint64_t n_walks,
+              uint64_t first_walk, uint64_t walk_id_stride, uint64_t seed, uint64_t n,
+              const int64_t *indptr, const uint32_t *thr, const uint32_t *alias, float *t0,
+              float *t1, double *loss_sum, uint64_t *pairs, uint64_t *targets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,151 @@
+/*
+ * oracle/walks.c -- TEST INFRASTRUCTURE: CPU reference sampler for DeepWalk /
+ * node2vec walks.  The GPU walk kernel must match it bit for bit.
+ *
+ * Follows: the p/q semantics of the reference docstrings
+ * (/root/reference/embiggen/embedders/ensmallen_embedders/node2vec_skipgram.py:58-71,
+ * return_weight = 1/p, explore_weight = 1/q), the sorted-CSR hand-off of
+ * /root/reference/embiggen/embedders/pecanpy_embedders/node2vec.py:139-163, and
+ * the rejection sampler north_star prescribes (KnightKing, SOSP'19): uniform
+ * neighbour proposal, integer accept test.  DeepWalk = both weights 1
+ * (/root/reference/embiggen/embedders/ensmallen_embedders/deepwalk_skipgram.py:6-139).
+ *
+ * The oracle always classifies a proposal the plain way (return / common /
+ * explore, full binary search); the counters additionally model the
+ * shortcuts a fast implementation may take (return test first, then
+ * lower-/upper-bound pre-decision) so that algorithmic bytes can be
+ * accounted.  Shortcuts never change a decision, which is exactly what
+ * bit-exact parity of the GPU kernel demonstrates.
+ */
+#include "oracle.h"
+#include "philox.h"
+#include <math.h>
+#include <stddef.h>
+
+void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c0, c1, c2, c3, out);
+}
+
+uint64_t orc_sources(const int64_t *indptr, uint64_t n, uint32_t *out) {
+    uint64_t count = 0;
+    for (uint64_t v = 0; v < n; ++v) {
+        if (indptr[v + 1] > indptr[v]) {
+            if (out) out[count] = (uint32_t)v;
+            ++count;
+        }
+    }
+    return count;
+}
+
+void orc_thresholds(float return_weight, float explore_weight, uint64_t thr[3]) {
+    const double w[3] = {(double)return_weight, 1.0, (double)explore_weight};
+    double wmax = w[0];
+    if (w[1] > wmax) wmax = w[1];
+    if (w[2] > wmax) wmax = w[2];
+    for (int i = 0; i < 3; ++i) {
+        if (w[i] >= wmax) {
+            thr[i] = 4294967296ull;
+        } else {
+            double t = floor(w[i] / wmax * 4294967296.0);
+            thr[i] = t >= 4294967296.0 ? 4294967296ull : (uint64_t)t;
+        }
+    }
+}
+
+/* sorted-row membership, plain lower-bound bisection */
+static int row_contains(const uint32_t *row, uint64_t len, uint32_t key) {
+    uint64_t lo = 0, hi = len;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (row[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < len && row[lo] == key;
+}
+
+static uint64_t probe_sectors(uint64_t len) {
+    /* ceil(log2(len + 1)) - 2, at least 1: the last three levels share a 32 B sector */
+    uint64_t levels = 0;
+    while (((uint64_t)1 << levels) < len + 1) ++levels;
+    return levels > 3 ? levels - 2 : 1;
+}
+
+int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const uint32_t *sources,
+              uint64_t n_src, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+              uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
+              float explore_weight, uint32_t *out, orc_walk_counters *counters) {
+    if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
+    (void)n;
+    const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+    const int second_order = !(return_weight == 1.0f && explore_weight == 1.0f);
+    uint64_t thr[3];
+    orc_thresholds(return_weight, explore_weight, thr);
+    const uint64_t thr_lo = thr[1] < thr[2] ? thr[1] : thr[2];
+    const uint64_t thr_hi = thr[1] < thr[2] ? thr[2] : thr[1];
+    uint64_t n_steps = 0, n_trials = 0, n_first = 0, n_searches = 0, n_probe = 0, n_capped = 0;
+    const int threads = orc_get_threads();
+
+#pragma omp parallel for num_threads(threads) if (threads > 1) schedule(dynamic, 256) \
+    reduction(+ : n_steps, n_trials, n_first, n_searches, n_probe, n_capped)
+    for (uint64_t i = 0; i < n_walks; ++i) {
+        orc_walk_counters c = {0, 0, 0, 0, 0, 0};
+        const uint64_t wid = first_walk + i * walk_id_stride;
+        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+        uint32_t *walk = out + i * (uint64_t)walk_length;
+        uint32_t cur = sources[wid % n_src];
+        uint32_t prev = ORC_PAD_TOKEN;
+        walk[0] = cur;
+        uint32_t rnd[4] = {0, 0, 0, 0};
+        uint32_t t = 1;
+        for (; t < walk_length; ++t) {
+            const int64_t off = indptr[cur];
+            const uint64_t deg = (uint64_t)(indptr[cur + 1] - off);
+            if (deg == 0) break;
+            uint32_t next;
+            if (!second_order || t == 1) {
+                const uint32_t s = t - 1;
+                orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, s >> 2, ORC_TAG_WALK1 << 24,
+                                  rnd);
+                next = indices[off + orc_mulhi(rnd[s & 3], (uint32_t)deg)];
+                ++c.first_order;
+            } else {
+                const int64_t poff = indptr[prev];
+                const uint64_t pdeg = (uint64_t)(indptr[prev + 1] - poff);
+                uint32_t trial = 0;
+                for (;;) {
+                    if ((trial & 1u) == 0)
+                        orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
+                                          (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
+                    const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
+                    next = indices[off + orc_mulhi(r0, (uint32_t)deg)];
+                    ++c.trials;
+                    int cls;
+                    if (next == prev) {
+                        cls = 0;
+                    } else {
+                        cls = row_contains(indices + poff, pdeg, next) ? 1 : 2;
+                        if ((uint64_t)r1 >= thr_lo && (uint64_t)r1 < thr_hi) {
+                            ++c.searches;
+                            c.probe_sectors += probe_sectors(pdeg);
+                        }
+                    }
+                    if ((uint64_t)r1 < thr[cls]) break;
+                    ++trial;
+                    if (trial >= ORC_MAX_TRIALS) { ++c.capped; break; }
+                }
+            }
+            ++c.steps;
+            walk[t] = next;
+            prev = cur;
+            cur = next;
+        }
+        for (; t < walk_length; ++t) walk[t] = ORC_PAD_TOKEN;
+        n_steps += c.steps; n_trials += c.trials; n_first += c.first_order;
+        n_searches += c.searches; n_probe += c.probe_sectors; n_capped += c.capped;
+    }
+    if (counters) {
+        counters->steps = n_steps; counters->trials = n_trials; counters->first_order = n_first;
+        counters->searches = n_searches; counters->probe_sectors = n_probe;
+        counters->capped = n_capped;
+    }
+    return 0;
+}

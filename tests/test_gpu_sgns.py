@@ -1,0 +1,144 @@
+"""SkipGram / CBOW SGD kernels against the CPU oracle, through the C ABI.
+
+Deterministic mode (one warp, ascending walk order) must reproduce the oracle's tables bit
+for bit; the Hogwild production launch is compared by tolerance (update order differs).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from embiggen_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+SEED = 42
+
+
+def run_pair(graph, model, D, L, w, K, rw, ew, n_walks, lr=0.05, deterministic=True,
+             use_alias=True, normalize=False, clip=6.0, alpha=0.75, scale=False):
+    n = graph.get_number_of_nodes()
+    walks, _ = oracle.walks(graph.indptr, graph.indices, SEED, 0, n_walks, L, rw, ew)
+    t0, t1 = oracle.init_tables(n, D, SEED)
+    thr = alias = None
+    if use_alias:
+        thr, alias = oracle.alias_build(graph.indptr, alpha)
+    stats = oracle.train(model, walks, t0, t1, SEED, n, D, w, K, lr, clip, thr=thr, alias=alias,
+                         indptr=graph.indptr, normalize_learning_rate_by_degree=normalize,
+                         scale_by_sqrt_dim=scale)
+    with Engine(model, embedding_size=D, walk_length=L, window_size=w, iterations=1,
+                number_of_negative_samples=K, return_weight=rw, explore_weight=ew,
+                clipping_value=clip, use_scale_free_distribution=use_alias,
+                negative_sampling_exponent=alpha, normalize_learning_rate_by_degree=normalize,
+                scale_by_sqrt_dim=scale, deterministic=deterministic,
+                chunk_walks=n_walks) as engine:
+        engine.load_csr(graph.indptr, graph.indices)
+        engine.init_tables(SEED)
+        init0, init1 = engine.export_tables()
+        engine.walk_chunk(SEED, 0, n_walks, 1, 0)
+        engine.train_chunk(SEED, 0, lr)
+        g0, g1 = engine.export_tables()
+        counters = engine.counters()
+        gpu_alias = engine.export_alias() if use_alias else None
+    return dict(o0=t0[:, :D], o1=t1[:, :D], g0=g0, g1=g1, init0=init0, init1=init1, stats=stats,
+                counters=counters, alias=(thr, alias), gpu_alias=gpu_alias, n=n, D=D)
+
+
+def test_init_tables_bit_exact(small_ppi):
+    for D in (5, 100, 128, 200):
+        t0, t1 = oracle.init_tables(1064, D, 1234)
+        with Engine("SkipGram", embedding_size=D) as engine:
+            engine.load_csr(small_ppi.indptr, small_ppi.indices)
+            engine.init_tables(1234)
+            g0, g1 = engine.export_tables()
+        assert np.array_equal(g0, t0[:, :D]) and np.array_equal(g1, t1[:, :D])
+        assert np.abs(g0).max() <= 0.5 / D and g0.std() > 0
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 0.75, 1.0, 0.6])
+def test_alias_table_bit_exact(rmat_graph, alpha):
+    thr, alias = oracle.alias_build(rmat_graph.indptr, alpha)
+    with Engine("SkipGram", negative_sampling_exponent=alpha) as engine:
+        engine.load_csr(rmat_graph.indptr, rmat_graph.indices)
+        g_thr, g_alias = engine.export_alias()
+    assert np.array_equal(g_thr, thr) and np.array_equal(g_alias, alias)
+
+
+@pytest.mark.parametrize("model,D,K,w", [
+    ("SkipGram", 100, 10, 4), ("CBOW", 128, 10, 4), ("SkipGram", 5, 3, 1), ("CBOW", 5, 5, 2),
+    ("SkipGram", 200, 10, 5), ("CBOW", 300, 4, 3), ("SkipGram", 64, 20, 2), ("SkipGram", 128, 0, 3),
+])
+def test_deterministic_tables_bit_exact(small_ppi, model, D, K, w):
+    r = run_pair(small_ppi, model, D, 32, w, K, 0.25, 4.0, n_walks=300)
+    assert r["counters"]["pairs"] == r["stats"]["pairs"]
+    assert r["counters"]["targets"] == r["stats"]["targets"]
+    assert np.array_equal(r["g0"], r["o0"])
+    assert np.array_equal(r["g1"], r["o1"])
+    assert not np.array_equal(r["g0"], r["init0"])
+    assert np.isclose(r["counters"]["loss_sum"], r["stats"]["loss_sum"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("model", ["SkipGram", "CBOW"])
+def test_deterministic_options(rmat_graph, model):
+    """uniform negatives, lr / degree, dot / sqrt(D), tight clipping: still bit exact."""
+    for kwargs in (dict(use_alias=False), dict(normalize=True, lr=0.5), dict(scale=True),
+                   dict(clip=0.01, lr=0.5), dict(alpha=1.0)):
+        r = run_pair(rmat_graph, model, 100, 24, 3, 7, 2.0, 0.5, n_walks=200, **kwargs)
+        assert np.array_equal(r["g0"], r["o0"]), kwargs
+        assert np.array_equal(r["g1"], r["o1"]), kwargs
+        assert r["counters"]["targets"] == r["stats"]["targets"]
+
+
+@pytest.mark.parametrize("model,D", [("SkipGram", 100), ("CBOW", 128)])
+def test_hogwild_tracks_oracle(small_ppi, model, D):
+    """Production launch (all SMs, racy updates): same pair/target counts, loss within 2 %."""
+    r = run_pair(small_ppi, model, D, 128, 4, 10, 0.25, 4.0, n_walks=2128, deterministic=False)
+    assert r["counters"]["pairs"] == r["stats"]["pairs"]
+    assert r["counters"]["targets"] == r["stats"]["targets"]
+    oracle_loss = r["stats"]["loss_sum"] / r["stats"]["pairs"]
+    gpu_loss = r["counters"]["loss_sum"] / r["counters"]["pairs"]
+    assert abs(gpu_loss - oracle_loss) <= 0.02 * oracle_loss
+    assert np.isfinite(r["g0"]).all() and np.isfinite(r["g1"]).all()
+    # embeddings agree in direction for the bulk of the nodes
+    num = (r["g0"] * r["o0"]).sum(1)
+    den = np.linalg.norm(r["g0"], axis=1) * np.linalg.norm(r["o0"], axis=1) + 1e-12
+    assert np.median(num / den) > 0.9
+
+
+def test_fit_matches_oracle_fit(small_ppi):
+    """b2e_fit (host buffers in/out, chunked pipeline) == oracle.fit in deterministic mode."""
+    kw = dict(embedding_size=20, epochs=2, iterations=1, walk_length=16, window_size=2,
+              learning_rate=0.05, learning_rate_decay=0.9, return_weight=0.25, explore_weight=4.0)
+    for model in ("SkipGram", "CBOW"):
+        o0, o1, o_loss = oracle.fit(model, small_ppi.indptr, small_ppi.indices, SEED, negatives=5,
+                                    chunk_walks=300, **kw)
+        with Engine(model, number_of_negative_samples=5, deterministic=True, chunk_walks=300,
+                    **kw) as engine:
+            engine.load_csr(small_ppi.indptr, small_ppi.indices)
+            g0, g1, g_loss = engine.fit(SEED)
+        if model == "CBOW":  # role order [central, contextual]: CBOW's central table is T1
+            g0, g1 = g1, g0
+        assert np.array_equal(g0, o0[:, :20]) and np.array_equal(g1, o1[:, :20])
+        assert np.allclose(g_loss, o_loss, rtol=1e-4)
+
+
+def test_loss_decreases_over_epochs(er_graph):
+    with Engine("SkipGram", embedding_size=32, epochs=4, iterations=2, walk_length=32,
+                window_size=3, number_of_negative_samples=5, learning_rate=0.05) as engine:
+        engine.load_csr(er_graph.indptr, er_graph.indices)
+        t0, t1, losses = engine.fit(SEED)
+    assert losses[-1] < losses[0]
+    assert np.isfinite(t0).all() and np.isfinite(t1).all()
+
+
+def test_error_paths(small_ppi):
+    with pytest.raises(ValueError):
+        Engine("SkipGram", embedding_size=0)
+    with pytest.raises(ValueError):
+        Engine("SkipGram", number_of_negative_samples=64)
+    with Engine("SkipGram") as engine:
+        with pytest.raises(RuntimeError):
+            engine.init_tables(1)  # before load_csr
+        with pytest.raises(ValueError):
+            engine.load_csr(np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint32))
+        with pytest.raises(ValueError):
+            engine.load_csr(np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.uint32))

@@ -1,0 +1,95 @@
+"""GPU walks (through the C ABI) must equal the CPU oracle's walks bit for bit."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import tiny_graphs
+from embiggen_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+PQ = [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5), (0.5, 2.0), (1.0, 3.0), (7.5, 1.0)]
+
+
+def gpu_walks(graph, seed, first, count, length, rw, ew, stride=1, chunk=0):
+    with Engine("SkipGram", walk_length=length, return_weight=rw, explore_weight=ew,
+                iterations=1, chunk_walks=chunk) as engine:
+        engine.load_csr(graph.indptr, graph.indices)
+        walks = engine.walks(seed, first, count, stride)
+        counters = engine.counters()
+    return walks, counters
+
+
+@pytest.mark.parametrize("rw,ew", PQ)
+@pytest.mark.parametrize("fixture", ["small_ppi", "er_graph", "rmat_graph"])
+def test_walks_bit_exact(request, fixture, rw, ew):
+    graph = request.getfixturevalue(fixture)
+    n_src = int((np.diff(graph.indptr) > 0).sum())
+    count = 2 * n_src + 17  # more than one iteration, ragged tail
+    expected, oc = oracle.walks(graph.indptr, graph.indices, 42, 5, count, 128, rw, ew)
+    got, gc = gpu_walks(graph, 42, 5, count, 128, rw, ew)
+    assert np.array_equal(got, expected)
+    assert gc["walk_steps"] == oc["steps"]
+    assert gc["walk_trials"] == oc["trials"]
+    assert gc["walk_searches"] == oc["searches"]
+
+
+@pytest.mark.parametrize("length", [2, 3, 4, 5, 7, 33, 130])
+def test_ragged_walk_lengths(small_ppi, length):
+    expected, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 9, 0, 777, length, 0.25, 4.0)
+    got, _ = gpu_walks(small_ppi, 9, 0, 777, length, 0.25, 4.0)
+    assert np.array_equal(got, expected)
+
+
+@pytest.mark.parametrize("name", sorted(tiny_graphs()))
+@pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (4.0, 0.25)])
+def test_edge_case_graphs(name, rw, ew):
+    graph = tiny_graphs()[name]
+    expected, _ = oracle.walks(graph.indptr, graph.indices, 3, 0, 64, 16, rw, ew)
+    got, _ = gpu_walks(graph, 3, 0, 64, 16, rw, ew)
+    assert np.array_equal(got, expected)
+    if name == "directed_dead_end":
+        assert (got == oracle.PAD_TOKEN).any()
+
+
+def test_walk_ids_shard_invariant(er_graph):
+    """Counter-based RNG: a walk id gives the same walk whatever the sharding / chunking."""
+    whole, _ = gpu_walks(er_graph, 42, 0, 4000, 64, 0.5, 2.0)
+    for world in (2, 4, 8):
+        for rank in range(world):
+            count = (4000 - rank + world - 1) // world
+            shard, _ = gpu_walks(er_graph, 42, rank, count, 64, 0.5, 2.0, stride=world, chunk=257)
+            assert np.array_equal(shard, whole[rank::world])
+
+
+def test_seed_and_64bit_walk_ids(er_graph):
+    first = (1 << 40) + 12345
+    seed = 0xDEADBEEFCAFEF00D
+    expected, _ = oracle.walks(er_graph.indptr, er_graph.indices, seed, first, 500, 32, 0.25, 4.0)
+    got, _ = gpu_walks(er_graph, seed, first, 500, 32, 0.25, 4.0)
+    assert np.array_equal(got, expected)
+    other, _ = gpu_walks(er_graph, seed + 1, first, 500, 32, 0.25, 4.0)
+    assert not np.array_equal(got, other)
+
+
+def test_full_size_properties():
+    """BASELINE-scale shape (ER 1M / 10M): every transition is an edge; start nodes cycle."""
+    from embiggen_b200.graph import erdos_renyi
+    graph = erdos_renyi(1_000_000, 10_000_000, seed=42)
+    n_src = int((np.diff(graph.indptr) > 0).sum())
+    count = 200_000
+    walks, counters = gpu_walks(graph, 42, n_src - 1000, count, 128, 1.0, 1.0)
+    assert counters["walk_steps"] == count * 127
+    sources = np.flatnonzero(np.diff(graph.indptr) > 0)
+    ids = (n_src - 1000 + np.arange(count)) % n_src
+    assert np.array_equal(walks[:, 0], sources[ids].astype(np.uint32))
+    src = walks[:, :-1].ravel().astype(np.int64)
+    dst = walks[:, 1:].ravel().astype(np.int64)
+    keys = src * graph.get_number_of_nodes() + dst
+    edge_keys = (np.repeat(np.arange(graph.get_number_of_nodes(), dtype=np.int64),
+                           np.diff(graph.indptr)) * graph.get_number_of_nodes()
+                 + graph.indices.astype(np.int64))
+    assert np.isin(keys[:2_000_000], edge_keys).all()
+    # the oracle agrees on a bounded sample of the same walks
+    expected, _ = oracle.walks(graph.indptr, graph.indices, 42, n_src - 1000, 2000, 128)
+    assert np.array_equal(walks[:2000], expected)
