@@ -56,6 +56,7 @@ def test_init_tables_bit_exact(small_ppi):
 
 @pytest.mark.parametrize("alpha", [0.0, 0.5, 0.75, 1.0, 0.6])
 def test_alias_table_bit_exact(rmat_graph, alpha):
+    alpha = float(np.float32(alpha))  # b2e_config carries the exponent as a C float
     thr, alias = oracle.alias_build(rmat_graph.indptr, alpha)
     with Engine("SkipGram", negative_sampling_exponent=alpha) as engine:
         engine.load_csr(rmat_graph.indptr, rmat_graph.indices)

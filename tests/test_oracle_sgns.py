@@ -1,0 +1,210 @@
+"""Pins the CPU oracle's alias table and SkipGram / CBOW update (CPU only, no GPU).
+
+The reference holds no numeric fixtures for this path (parity unpinned against
+Ensmallen), so the C oracle is cross-checked here against an independent float64 numpy
+restatement of the normative recipe in DESIGN.md (kwarg semantics from
+/root/reference/embiggen/embedders/ensmallen_embedders/node2vec_skipgram.py:37-119; model
+structure from /root/reference/embiggen/embedders/tensorflow_embedders/skipgram.py:28-61 and
+cbow.py:28-60) and against the closed forms the domain offers.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle
+from embiggen_b200.graph import philox4x32
+
+PAD = oracle.PAD_TOKEN
+TAG_NEG = 3
+
+
+# ---------------------------------------------------------------- alias table
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 0.75, 1.0, 0.6])
+def test_alias_table_reproduces_target_pmf(rmat_graph, alpha):
+    degrees = np.diff(rmat_graph.indptr).astype(np.float64)
+    target = np.where(degrees > 0, degrees ** alpha, 0.0)
+    target /= target.sum()
+    thr, alias = oracle.alias_build(rmat_graph.indptr, alpha)
+    n = len(degrees)
+    keep = (thr.astype(np.float64) + (thr == 0xFFFFFFFF)) / 2.0 ** 32  # 0xFFFFFFFF means "always"
+    pmf = keep / n
+    np.add.at(pmf, alias, (1.0 - keep) / n)
+    assert np.abs(pmf - target).max() < 2e-9
+    assert pmf[degrees == 0].max(initial=0.0) < 1e-9  # isolated nodes are (almost) never drawn
+
+
+def test_alias_sampling_chi_square(small_ppi):
+    thr, alias = oracle.alias_build(small_ppi.indptr, 0.75)
+    n = len(thr)
+    draws = 400_000
+    r0, r1, _, _ = philox4x32(99, np.arange(draws, dtype=np.uint64), 0, 0, 0)
+    idx = ((r0.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+    node = np.where(r1 < thr[idx], idx, alias[idx])
+    degrees = np.diff(small_ppi.indptr).astype(np.float64)
+    target = degrees ** 0.75 / (degrees ** 0.75).sum()
+    counts = np.bincount(node, minlength=n)
+    order = np.argsort(target)
+    # pool the many degree-1 nodes so every bin expects >= 50 draws
+    bins = np.array_split(order, 60)
+    observed = np.array([counts[b].sum() for b in bins])
+    expected = np.array([target[b].sum() for b in bins]) * draws
+    assert stats.chisquare(observed, expected).pvalue > 1e-3
+
+
+# ------------------------------------------------- numpy restatement of the update
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def draw_negatives(seed, wid, site, K, n, thr, alias, centre, context):
+    negs, valid = [], []
+    for k in range(K):
+        r0, r1, _, _ = philox4x32(seed, wid & 0xFFFFFFFF, wid >> 32, site, (TAG_NEG << 24) | k)
+        idx = (int(r0) * n) >> 32
+        node = idx
+        if thr is not None:
+            node = idx if int(r1) < int(thr[idx]) else int(alias[idx])
+        ok = node != centre and node != context and node not in negs
+        negs.append(node)
+        valid.append(ok)
+    return negs, valid
+
+
+def apply_targets(h, t1, targets, valid, lr, clip, scale, stats_out):
+    rows = [t1[u].copy() for u in targets]
+    acc = np.zeros_like(h)
+    for k, (u, ok) in enumerate(zip(targets, valid)):
+        if not ok:
+            continue
+        stats_out["targets"] += 1
+        f = float(h @ rows[k]) * scale
+        if abs(f) > clip:
+            continue
+        label = 1.0 if k == 0 else 0.0
+        g = (label - sigmoid(f)) * lr
+        stats_out["loss"] += np.log1p(np.exp(-f if k == 0 else f))
+        acc += g * rows[k]
+        t1[u] = rows[k] + g * h
+    return acc
+
+
+def reference_train(model, walks, t0, t1, seed, n, D, w, K, lr, clip=6.0, first_walk=0, thr=None,
+                    alias=None, indptr=None, normalize=False, scale_by_sqrt_dim=False):
+    t0, t1 = t0.astype(np.float64), t1.astype(np.float64)
+    out = {"pairs": 0, "targets": 0, "loss": 0.0}
+    scale = 1.0 / np.sqrt(D) if scale_by_sqrt_dim else 1.0
+    L = walks.shape[1]
+    for row_index, walk in enumerate(walks):
+        wid = first_walk + row_index
+        for i in range(L):
+            c = int(walk[i])
+            if c == PAD:
+                break
+            step = lr / float(indptr[c + 1] - indptr[c]) if normalize else lr
+            window = [j for j in range(max(0, i - w), min(L - 1, i + w) + 1)
+                      if j != i and int(walk[j]) != PAD and int(walk[j]) != c]
+            if model == "SkipGram":
+                h = t0[c].copy()
+                for j in window:
+                    o = int(walk[j])
+                    negs, valid = draw_negatives(seed, wid, (i << 16) | j, K, n, thr, alias, c, o)
+                    h = h + apply_targets(h, t1, [o] + negs, [True] + valid, step, clip, scale, out)
+                    out["pairs"] += 1
+                t0[c] = h
+            else:
+                if not window:
+                    continue
+                ctx = [int(walk[j]) for j in window]
+                h = t0[ctx].sum(axis=0) / len(ctx)
+                negs, valid = draw_negatives(seed, wid, (i << 16) | 0xFFFF, K, n, thr, alias, c, c)
+                acc = apply_targets(h, t1, [c] + negs, [True] + valid, step, clip, scale, out)
+                for o in ctx:
+                    t0[o] = t0[o] + acc
+                out["pairs"] += len(ctx)
+    return t0, t1, out
+
+
+CASES = [
+    ("SkipGram", 16, 5, 2, dict()),
+    ("CBOW", 16, 5, 2, dict()),
+    ("SkipGram", 7, 3, 1, dict(use_alias=False)),
+    ("CBOW", 12, 4, 3, dict(normalize=True, lr=0.5)),
+    ("SkipGram", 20, 6, 3, dict(scale_by_sqrt_dim=True, lr=0.2)),
+    ("SkipGram", 8, 10, 4, dict(clip=0.02, lr=0.5)),
+    ("CBOW", 8, 0, 2, dict()),
+]
+
+
+@pytest.mark.parametrize("model,D,K,w,options", CASES)
+def test_c_oracle_matches_numpy_restatement(small_ppi, model, D, K, w, options):
+    seed, L, n_walks, first = 17, 12, 40, 1000
+    lr = options.get("lr", 0.05)
+    clip = options.get("clip", 6.0)
+    n = small_ppi.get_number_of_nodes()
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, seed, first, n_walks, L, 0.25, 4.0)
+    thr = alias = None
+    if options.get("use_alias", True):
+        thr, alias = oracle.alias_build(small_ppi.indptr, 0.75)
+    t0, t1 = oracle.init_tables(n, D, seed)
+    # make the rows large enough for the sigmoid to leave its linear range
+    t0 *= 30.0
+    t1 *= 30.0
+    e0, e1, expected = reference_train(
+        model, walks, t0[:, :D], t1[:, :D], seed, n, D, w, K, lr, clip, first, thr, alias,
+        small_ppi.indptr, options.get("normalize", False), options.get("scale_by_sqrt_dim", False))
+    got = oracle.train(model, walks, t0, t1, seed, n, D, w, K, lr, clip, first_walk=first, thr=thr,
+                       alias=alias, indptr=small_ppi.indptr,
+                       normalize_learning_rate_by_degree=options.get("normalize", False),
+                       scale_by_sqrt_dim=options.get("scale_by_sqrt_dim", False))
+    assert got["pairs"] == expected["pairs"] and got["targets"] == expected["targets"]
+    assert got["pairs"] > 0
+    assert np.isclose(got["loss_sum"], expected["loss"], rtol=1e-5)
+    assert np.allclose(t0[:, :D], e0, rtol=0, atol=2e-6)
+    assert np.allclose(t1[:, :D], e1, rtol=0, atol=2e-6)
+    assert (t0[:, D:] == 0).all() and (t1[:, D:] == 0).all()  # row padding stays zero
+
+
+def test_pairs_per_walk_closed_form(er_graph):
+    """P(L, w) = 2wL - w(w+1) positives per walk when no token repeats inside a window."""
+    from embiggen_b200.engine import pairs_per_walk
+    n = er_graph.get_number_of_nodes()
+    for L, w in [(16, 2), (32, 4), (9, 5)]:
+        walks = np.arange(3 * L, dtype=np.uint32).reshape(3, L)  # distinct tokens
+        t0, t1 = oracle.init_tables(n, 8, 1)
+        r = oracle.train("SkipGram", walks, t0, t1, 1, n, 8, w, 2, 0.01)
+        assert r["pairs"] == 3 * pairs_per_walk(L, w)
+        t0, t1 = oracle.init_tables(n, 8, 1)
+        r = oracle.train("CBOW", walks, t0, t1, 1, n, 8, w, 2, 0.01)
+        assert r["pairs"] == 3 * pairs_per_walk(L, w)
+
+
+def test_init_tables_distribution_and_padding():
+    t0, t1 = oracle.init_tables(5000, 10, 3)
+    assert t0.shape == (5000, 12) and (t0[:, 10:] == 0).all() and (t1[:, 10:] == 0).all()
+    for t in (t0, t1):
+        values = t[:, :10].ravel().astype(np.float64) * 10
+        assert values.min() >= -0.5 and values.max() < 0.5
+        assert stats.kstest(values + 0.5, "uniform").pvalue > 1e-3
+    assert not np.array_equal(t0, t1)
+    again0, _ = oracle.init_tables(5000, 10, 3)
+    assert np.array_equal(again0, t0)
+
+
+def test_sigmoid_and_dot_primitives():
+    xs = np.linspace(-20, 20, 4001, dtype=np.float32)
+    got = np.array([oracle.sigmoid(float(x)) for x in xs])
+    assert np.abs(got - 1.0 / (1.0 + np.exp(-xs.astype(np.float64)))).max() < 2e-7
+    rng = np.random.default_rng(0)
+    for length in (4, 8, 100, 128, 300):
+        a = rng.standard_normal(length).astype(np.float32)
+        b = rng.standard_normal(length).astype(np.float32)
+        stride = (length + 3) // 4 * 4
+        pa, pb = np.zeros(stride, np.float32), np.zeros(stride, np.float32)
+        pa[:length], pb[:length] = a, b
+        assert abs(oracle.dot(pa, pb) - float(a.astype(np.float64) @ b.astype(np.float64))) < 1e-4
+
+
+def test_training_lowers_the_objective(small_ppi):
+    o0, o1, losses = oracle.fit("SkipGram", small_ppi.indptr, small_ppi.indices, 42, 16, 3, 1, 24, 3,
+                                5, 0.05, 0.9, return_weight=0.25, explore_weight=4.0)
+    assert losses[0] > losses[-1] and np.isfinite(o0).all() and np.isfinite(o1).all()

@@ -1,0 +1,165 @@
+"""Pins the CPU oracle's walk sampler (CPU only, no GPU).
+
+The reference holds no golden walks for this path, so the oracle is pinned
+against what the domain fixes: every transition is an edge, DeepWalk picks neighbours
+uniformly, and second-order transitions follow the analytic node2vec distribution
+(Grover & Leskovec 2016, eq. 2, with return_weight = 1/p and explore_weight = 1/q as in
+/root/reference/embiggen/embedders/ensmallen_embedders/node2vec_skipgram.py:58-71).
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle
+from conftest import tiny_graphs
+from embiggen_b200.graph import csr_from_edges
+
+
+def neighbours(graph, v):
+    return graph.indices[graph.indptr[v]:graph.indptr[v + 1]]
+
+
+def analytic_pmf(graph, prev, cur, rw, ew):
+    """node2vec transition pmf out of `cur` having arrived from `prev`."""
+    nv = neighbours(graph, cur)
+    np_ = set(int(x) for x in neighbours(graph, prev))
+    w = np.array([rw if x == prev else (1.0 if int(x) in np_ else ew) for x in nv], dtype=np.float64)
+    return nv, w / w.sum()
+
+
+def dense_test_graph():
+    """12 nodes: a clique of 5, a ring, chords and a pendant (all three classes occur)."""
+    src = [0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 4, 5, 6, 7, 8, 9, 10, 5, 6, 2, 11]
+    dst = [1, 2, 3, 4, 2, 3, 4, 3, 4, 4, 5, 6, 7, 8, 9, 10, 4, 8, 10, 7, 0]
+    return csr_from_edges(np.array(src), np.array(dst), 12, name="dense12")
+
+
+@pytest.mark.parametrize("fixture", ["small_ppi", "er_graph", "rmat_graph"])
+@pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
+def test_walks_follow_edges_and_start_at_sources(request, fixture, rw, ew):
+    graph = request.getfixturevalue(fixture)
+    srcs = oracle.sources(graph.indptr)
+    assert np.array_equal(srcs, np.flatnonzero(np.diff(graph.indptr) > 0).astype(np.uint32))
+    first, count, L = 3, 2 * len(srcs) + 5, 40
+    walks, counters = oracle.walks(graph.indptr, graph.indices, 11, first, count, L, rw, ew)
+    assert walks.shape == (count, L) and walks.dtype == np.uint32
+    assert np.array_equal(walks[:, 0], srcs[(first + np.arange(count)) % len(srcs)])
+    n = graph.get_number_of_nodes()
+    edge_keys = np.repeat(np.arange(n, dtype=np.int64), np.diff(graph.indptr)) * n + graph.indices
+    keys = walks[:, :-1].astype(np.int64).ravel() * n + walks[:, 1:].astype(np.int64).ravel()
+    assert np.isin(keys, edge_keys).all()
+    assert counters["steps"] == count * (L - 1) and counters["capped"] == 0
+    if rw == 1.0 and ew == 1.0:
+        assert counters["trials"] == 0 and counters["first_order"] == counters["steps"]
+    else:
+        assert counters["first_order"] == count  # only the first transition of every walk
+        assert counters["trials"] >= counters["steps"] - count
+        assert counters["searches"] <= counters["trials"]
+
+
+def test_deepwalk_is_uniform_over_neighbours():
+    graph = dense_test_graph()
+    walks, _ = oracle.walks(graph.indptr, graph.indices, 5, 0, 120_000, 2)
+    for v in (0, 4, 2):
+        nxt = walks[walks[:, 0] == v, 1]
+        nv = neighbours(graph, v)
+        counts = np.array([(nxt == x).sum() for x in nv])
+        assert counts.sum() == len(nxt) and len(nxt) > 5000
+        assert stats.chisquare(counts).pvalue > 1e-3
+
+
+@pytest.mark.parametrize("rw,ew", [(0.25, 4.0), (2.0, 0.5), (0.5, 2.0), (1.0, 3.0), (7.5, 1.0)])
+def test_second_order_transitions_match_analytic_pmf(rw, ew):
+    """chi-square of the third token given the first two against the analytic pmf."""
+    graph = dense_test_graph()
+    walks, _ = oracle.walks(graph.indptr, graph.indices, 2024, 0, 360_000, 3, rw, ew)
+    checked = 0
+    for prev, cur in [(0, 4), (4, 0), (1, 2), (5, 6), (11, 0), (2, 7), (10, 4)]:
+        sel = walks[(walks[:, 0] == prev) & (walks[:, 1] == cur), 2]
+        nv, pmf = analytic_pmf(graph, prev, cur, rw, ew)
+        counts = np.array([(sel == x).sum() for x in nv])
+        assert counts.sum() == len(sel)
+        if len(sel) < 500:
+            continue
+        assert stats.chisquare(counts, pmf * len(sel)).pvalue > 1e-3, (prev, cur)
+        checked += 1
+    assert checked >= 5
+
+
+def test_second_order_on_small_ppi_hub(small_ppi):
+    """The hub of BASELINE config C1's graph (degree 348): pooled chi-square by class."""
+    rw, ew = 0.25, 4.0
+    degrees = np.diff(small_ppi.indptr)
+    hub = int(degrees.argmax())
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 1, 0, 300_000, 3, rw, ew)
+    sel = walks[walks[:, 1] == hub]
+    observed = np.zeros(3)
+    expected = np.zeros(3)
+    for prev in np.unique(sel[:, 0]):
+        rows = sel[sel[:, 0] == prev]
+        nv, pmf = analytic_pmf(small_ppi, int(prev), hub, rw, ew)
+        np_ = set(int(x) for x in neighbours(small_ppi, int(prev)))
+        cls = np.array([0 if x == prev else (1 if int(x) in np_ else 2) for x in nv])
+        for c in range(3):
+            expected[c] += pmf[cls == c].sum() * len(rows)
+            observed[c] += np.isin(rows[:, 2], nv[cls == c]).sum()
+    keep = expected > 5
+    assert keep.sum() >= 2 and observed.sum() > 10_000
+    assert stats.chisquare(observed[keep], expected[keep] * observed[keep].sum() / expected[keep].sum()).pvalue > 1e-3
+
+
+def test_thresholds_are_exact_integer_ratios():
+    thr = oracle.thresholds(0.25, 4.0)
+    assert list(thr) == [2 ** 32 // 16, 2 ** 32 // 4, 2 ** 32]
+    thr = oracle.thresholds(2.0, 0.5)
+    assert list(thr) == [2 ** 32, 2 ** 31, 2 ** 30]
+    assert list(oracle.thresholds(1.0, 1.0)) == [2 ** 32] * 3
+
+
+def test_walk_ids_are_independent_of_batching(er_graph):
+    whole, _ = oracle.walks(er_graph.indptr, er_graph.indices, 42, 0, 3000, 24, 0.5, 2.0)
+    for world in (2, 3, 8):
+        for rank in range(world):
+            count = (3000 - rank + world - 1) // world
+            shard, _ = oracle.walks(er_graph.indptr, er_graph.indices, 42, rank, count, 24, 0.5,
+                                    2.0, walk_id_stride=world)
+            assert np.array_equal(shard, whole[rank::world])
+    tail, _ = oracle.walks(er_graph.indptr, er_graph.indices, 42, 2500, 500, 24, 0.5, 2.0)
+    assert np.array_equal(tail, whole[2500:])
+    other, _ = oracle.walks(er_graph.indptr, er_graph.indices, 43, 0, 3000, 24, 0.5, 2.0)
+    assert not np.array_equal(other, whole)
+
+
+def test_multithreaded_oracle_gives_the_same_walks(er_graph):
+    single, c1 = oracle.walks(er_graph.indptr, er_graph.indices, 7, 0, 5000, 32, 0.25, 4.0)
+    oracle.set_threads(4)
+    try:
+        multi, c4 = oracle.walks(er_graph.indptr, er_graph.indices, 7, 0, 5000, 32, 0.25, 4.0)
+    finally:
+        oracle.set_threads(1)
+    assert np.array_equal(single, multi) and c1 == c4
+
+
+@pytest.mark.parametrize("name", sorted(tiny_graphs()))
+def test_edge_case_graphs(name):
+    graph = tiny_graphs()[name]
+    for rw, ew in [(1.0, 1.0), (0.25, 4.0), (4.0, 0.25)]:
+        walks, counters = oracle.walks(graph.indptr, graph.indices, 3, 0, 64, 16, rw, ew)
+        alive = walks != oracle.PAD_TOKEN
+        assert alive[:, 0].all()
+        # PAD only ever follows PAD or a dead end
+        for row, mask in zip(walks, alive):
+            stop = int(mask.sum())
+            assert mask[:stop].all() and not mask[stop:].any()
+            if stop < 16:
+                last = int(row[stop - 1])
+                assert graph.indptr[last + 1] == graph.indptr[last]
+        if name == "directed_dead_end":
+            assert (~alive).any()
+        else:
+            assert alive.all()
+        if name == "path" and (rw, ew) == (1.0, 1.0):
+            assert (np.abs(np.diff(walks.astype(np.int64), axis=1)) == 1).all()
+        if name == "star":
+            hub_positions = walks[walks[:, 0] == 0][:, ::2]
+            assert (hub_positions == 0).all()
