@@ -1,0 +1,388 @@
+"""Node2Vec / DeepWalk SkipGram and CBOW embedders backed by the B200 engine.
+
+Host-side mirror of the reference's Ensmallen adapters: same constructor kwargs, defaults,
+``parameters()`` / ``smoke_test_parameters()`` behaviour, capability flags and
+``fit_transform(graph, return_dataframe) -> EmbeddingResult`` contract as
+
+* ``Node2VecEnsmallen``          /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:13-166
+* ``Node2VecSkipGramEnsmallen``  .../node2vec_skipgram.py:6-165
+* ``Node2VecCBOWEnsmallen``      .../node2vec_cbow.py:6-165
+* ``DeepWalkSkipGramEnsmallen``  .../deepwalk_skipgram.py:6-139
+* ``DeepWalkCBOWEnsmallen``      .../deepwalk_cbow.py:6-139
+* ``EnsmallenEmbedder``          .../ensmallen_embedder.py:9-55
+
+What stands where the reference holds ``ensmallen.models.SkipGram / CBOW`` is
+:class:`embiggen_b200.engine.Engine` (C ABI ``include/b2e.h``, hand-written sm_100a kernels).
+There is no CPU fallback: constructing an embedder without the CUDA extension and a
+Blackwell GPU raises.  ``library_name()`` is ``"B200"``; with ``library_name=None`` the
+registry keeps preferring "Ensmallen" (abstract_model.py:670-675), so registration is
+non-breaking.
+"""
+import os
+import warnings
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .embedding_api import (AbstractEmbeddingModel, AbstractModel, EmbeddingResult, abstract_class,
+                            normalize_kwargs)
+from .engine import Engine
+from .graph import as_csr
+
+_DTYPES = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
+# engine options that are not part of the reference's signature (keyword-only, defaulted)
+_B200_DEFAULTS = dict(negative_sampling_exponent=0.75, scale_by_sqrt_dim=False, deterministic=False,
+                      chunk_walks=0, sync_interval=4, device=None)
+
+
+@abstract_class
+class B200Embedder(AbstractEmbeddingModel):
+    """Counterpart of ``EnsmallenEmbedder`` (ensmallen_embedder.py:9-55)."""
+
+    def __init__(self, random_state: Optional[int] = None, embedding_size: Optional[int] = None,
+                 ring_bell: bool = False, enable_cache: bool = False):
+        super().__init__(random_state=random_state, embedding_size=embedding_size,
+                         ring_bell=ring_bell, enable_cache=enable_cache)
+
+    @classmethod
+    def task_name(cls) -> str:
+        return "Node Embedding"
+
+    @classmethod
+    def library_name(cls) -> str:
+        return "B200"
+
+    @classmethod
+    def requires_nodes_sorted_by_decreasing_node_degree(cls) -> bool:
+        return False
+
+    @classmethod
+    def is_topological(cls) -> bool:
+        return True
+
+    @staticmethod
+    def is_available() -> bool:
+        """True when libb2e.so is built and a Blackwell device is visible."""
+        try:
+            return _lib.load().b2e_device_count() > 0
+        except Exception:
+            return False
+
+
+@abstract_class
+class Node2VecB200(B200Embedder):
+    """Counterpart of ``Node2VecEnsmallen`` (node2vec.py:13-166)."""
+
+    MODELS = {
+        "DeepWalk CBOW": "CBOW",
+        "DeepWalk SkipGram": "SkipGram",
+        "Node2Vec CBOW": "CBOW",
+        "Node2Vec SkipGram": "SkipGram",
+    }
+
+    def __init__(self, embedding_size: int = 100, random_state: int = 42, ring_bell: bool = False,
+                 enable_cache: bool = False, **model_kwargs: Dict):
+        if self.model_name() not in self.MODELS:
+            raise ValueError(f"The model name {self.model_name()!r} is not in {sorted(self.MODELS)}.")
+        self._model_kwargs = normalize_kwargs(
+            self, {**model_kwargs, "embedding_size": embedding_size, "random_state": random_state})
+        embedding_size = self._model_kwargs.pop("embedding_size")
+        random_state = self._model_kwargs.pop("random_state")
+        self._check_supported(self._model_kwargs)
+        # Like the reference, which builds the Rust model here (node2vec.py:65-69), fail at
+        # construction time when the native engine cannot run.
+        _lib.load()
+        self._last_losses: List[float] = []
+        super().__init__(embedding_size=embedding_size, enable_cache=enable_cache,
+                         ring_bell=ring_bell, random_state=random_state)
+
+    @staticmethod
+    def _check_supported(kwargs: Dict[str, Any]) -> None:
+        for name in ("change_node_type_weight", "change_edge_type_weight"):
+            if kwargs.get(name, 1.0) != 1.0:
+                raise NotImplementedError(
+                    f"{name} != 1.0 (typed walks) is not implemented by the B200 engine.")
+        for name in ("normalize_by_degree", "stochastic_downsample_by_degree"):
+            if kwargs.get(name, False):
+                raise NotImplementedError(f"{name}=True is not implemented by the B200 engine.")
+        if kwargs.get("dtype", "f32") not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}, got {kwargs.get('dtype')!r}.")
+        if isinstance(kwargs.get("learning_rate"), str):
+            raise NotImplementedError("Only a numeric learning_rate is supported.")
+
+    @classmethod
+    def smoke_test_parameters(cls) -> Dict[str, Any]:
+        """Same as node2vec.py:79-87."""
+        return dict(epochs=1, embedding_size=5, window_size=1, walk_length=4, max_neighbours=10)
+
+    def parameters(self) -> Dict[str, Any]:
+        return dict(**super().parameters(), **self._model_kwargs)
+
+    def get_losses(self) -> List[float]:
+        """Mean pair loss of every epoch of the last ``fit_transform``."""
+        return list(self._last_losses)
+
+    # -- what stands where the reference calls self._model.fit_transform(graph), node2vec.py:99 --
+    def _engine_kwargs(self, device: int) -> Dict[str, Any]:
+        k = self._model_kwargs
+        return dict(
+            model=self.MODELS[self.model_name()], embedding_size=self._embedding_size,
+            epochs=k["epochs"], walk_length=k["walk_length"], iterations=k["iterations"],
+            window_size=k["window_size"],
+            number_of_negative_samples=k["number_of_negative_samples"],
+            clipping_value=k["clipping_value"], return_weight=k.get("return_weight", 1.0),
+            explore_weight=k.get("explore_weight", 1.0), learning_rate=k["learning_rate"],
+            learning_rate_decay=k["learning_rate_decay"],
+            negative_sampling_exponent=k["negative_sampling_exponent"],
+            use_scale_free_distribution=k["use_scale_free_distribution"],
+            normalize_learning_rate_by_degree=k["normalize_learning_rate_by_degree"],
+            scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
+            chunk_walks=k["chunk_walks"], device=device)
+
+    def _output_buffers(self, n: int):
+        """float32 host buffers the engine writes; .npy memory maps when paths are given
+        (node2vec_skipgram.py:86-93)."""
+        buffers = []
+        for key in ("central_nodes_embedding_path", "contextual_nodes_embedding_path"):
+            path = self._model_kwargs.get(key)
+            if path is None or self._model_kwargs["dtype"] != "f32":
+                buffers.append(np.empty((n, self._embedding_size), dtype=np.float32))
+            else:
+                buffers.append(np.lib.format.open_memmap(
+                    path, mode="w+", dtype=np.float32, shape=(n, self._embedding_size)))
+        return buffers
+
+    def _fit_transform(self, graph, return_dataframe: bool = True) -> EmbeddingResult:
+        indptr, indices, weights = as_csr(graph)
+        if weights is not None:
+            warnings.warn("The B200 engine currently walks the graph topology only: edge weights "
+                          "are ignored.")
+        # max_neighbours (approximated walks for hubs) is accepted for compatibility: the walk
+        # kernel always samples the exact transition distribution.
+        device = self._model_kwargs["device"]
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        n = indptr.shape[0] - 1
+        world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size()
+        except ImportError:
+            pass
+        # the seed is read here, not at construction: set_random_state() between holdouts takes
+        # effect (abstract_classifier_model.py:711-712)
+        seed = int(self._random_state) & 0xFFFFFFFFFFFFFFFF
+        central, contextual = self._output_buffers(n)
+        with Engine(**self._engine_kwargs(device)) as engine:
+            engine.load_csr(indptr, indices)
+            if world > 1:
+                c, x, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"])
+                central[:], contextual[:] = c, x
+            else:
+                _, _, losses = engine.fit(seed, central, contextual)
+        self._last_losses = losses
+        if self._model_kwargs["verbose"]:
+            print(f"{self.model_name()} (B200): mean pair loss per epoch "
+                  + ", ".join(f"{loss:.4f}" for loss in losses))
+        dtype = _DTYPES[self._model_kwargs["dtype"]]
+        node_embeddings = [central, contextual]
+        if dtype is not np.float32:
+            node_embeddings = [e.astype(dtype) for e in node_embeddings]
+            for e, key in zip(node_embeddings, ("central_nodes_embedding_path",
+                                                "contextual_nodes_embedding_path")):
+                if self._model_kwargs.get(key) is not None:
+                    np.save(self._model_kwargs[key], e)
+        if return_dataframe:  # node2vec.py:104-109
+            node_names = graph.get_node_names() if hasattr(graph, "get_node_names") else None
+            node_embeddings = [pd.DataFrame(e, index=node_names) for e in node_embeddings]
+        return EmbeddingResult(embedding_method_name=self.model_name(),
+                               node_embeddings=node_embeddings)
+
+    # -- capability flags, the same non-redundant subset as node2vec.py:114-166 --
+    @classmethod
+    def requires_edge_weights(cls) -> bool:
+        return False
+
+    @classmethod
+    def requires_positive_edge_weights(cls) -> bool:
+        return True
+
+    @classmethod
+    def can_use_edge_weights(cls) -> bool:
+        """Returns whether the model can optionally use edge weights."""
+        return True
+
+    def is_using_edge_weights(self) -> bool:
+        """Returns whether the model is parametrized to use edge weights."""
+        return True
+
+    @classmethod
+    def can_use_node_types(cls) -> bool:
+        """Typed walks (change_node_type_weight) are not implemented by this engine."""
+        return False
+
+    @classmethod
+    def can_use_edge_types(cls) -> bool:
+        """Typed walks (change_edge_type_weight) are not implemented by this engine."""
+        return False
+
+    @classmethod
+    def is_stocastic(cls) -> bool:
+        """Returns whether the model is stocastic and has therefore a random state."""
+        return True
+
+
+def _node2vec_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
+                   number_of_negative_samples=10, walk_length=128, iterations=10, window_size=5,
+                   return_weight=0.25, explore_weight=4.0, change_node_type_weight=1.0,
+                   change_edge_type_weight=1.0, max_neighbours=100, learning_rate=0.01,
+                   learning_rate_decay=0.9, central_nodes_embedding_path=None,
+                   contextual_nodes_embedding_path=None, normalize_by_degree=False,
+                   stochastic_downsample_by_degree=False, normalize_learning_rate_by_degree=False,
+                   use_scale_free_distribution=True, random_state=42, dtype="f32", ring_bell=False,
+                   enable_cache=False, verbose=True, **b200_kwargs):
+    """Signature and defaults of node2vec_skipgram.py:9-35 (identical in node2vec_cbow.py),
+    plus the keyword-only B200 extras of ``_B200_DEFAULTS``."""
+    Node2VecB200.__init__(
+        self, embedding_size=embedding_size, epochs=epochs, clipping_value=clipping_value,
+        number_of_negative_samples=number_of_negative_samples, walk_length=walk_length,
+        iterations=iterations, window_size=window_size, return_weight=return_weight,
+        explore_weight=explore_weight, change_node_type_weight=change_node_type_weight,
+        change_edge_type_weight=change_edge_type_weight, max_neighbours=max_neighbours,
+        learning_rate=learning_rate, learning_rate_decay=learning_rate_decay,
+        central_nodes_embedding_path=central_nodes_embedding_path,
+        contextual_nodes_embedding_path=contextual_nodes_embedding_path,
+        normalize_by_degree=normalize_by_degree,
+        stochastic_downsample_by_degree=stochastic_downsample_by_degree,
+        normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
+        use_scale_free_distribution=use_scale_free_distribution, dtype=dtype,
+        random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+def _deepwalk_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
+                   number_of_negative_samples=10, walk_length=128, iterations=10, window_size=5,
+                   max_neighbours=100, learning_rate=0.01, learning_rate_decay=0.9,
+                   central_nodes_embedding_path=None, contextual_nodes_embedding_path=None,
+                   normalize_by_degree=False, stochastic_downsample_by_degree=False,
+                   normalize_learning_rate_by_degree=False, use_scale_free_distribution=True,
+                   random_state=42, dtype="f32", ring_bell=False, enable_cache=False, verbose=True,
+                   **b200_kwargs):
+    """Signature and defaults of deepwalk_skipgram.py:9-31 (identical in deepwalk_cbow.py):
+    no return / explore weights, i.e. p = q = 1, a first-order uniform walk."""
+    Node2VecB200.__init__(
+        self, embedding_size=embedding_size, epochs=epochs, clipping_value=clipping_value,
+        number_of_negative_samples=number_of_negative_samples, walk_length=walk_length,
+        iterations=iterations, window_size=window_size, max_neighbours=max_neighbours,
+        learning_rate=learning_rate, learning_rate_decay=learning_rate_decay,
+        central_nodes_embedding_path=central_nodes_embedding_path,
+        contextual_nodes_embedding_path=contextual_nodes_embedding_path,
+        normalize_by_degree=normalize_by_degree,
+        stochastic_downsample_by_degree=stochastic_downsample_by_degree,
+        normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
+        use_scale_free_distribution=use_scale_free_distribution, dtype=dtype,
+        random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+_NODE2VEC_HIDDEN = ("change_node_type_weight", "change_edge_type_weight", "alpha")
+_DEEPWALK_HIDDEN = ("return_weight", "explore_weight") + _NODE2VEC_HIDDEN
+
+
+class Node2VecSkipGramB200(Node2VecB200):
+    """Node2Vec SkipGram on B200 (counterpart of node2vec_skipgram.py:6-165)."""
+
+    __init__ = _node2vec_init
+
+    def parameters(self) -> Dict[str, Any]:
+        """Drops the same keys as node2vec_skipgram.py:148-161."""
+        return {k: v for k, v in super().parameters().items() if k not in _NODE2VEC_HIDDEN}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "Node2Vec SkipGram"
+
+
+class Node2VecCBOWB200(Node2VecB200):
+    """Node2Vec CBOW on B200 (counterpart of node2vec_cbow.py:6-165)."""
+
+    __init__ = _node2vec_init
+
+    def parameters(self) -> Dict[str, Any]:
+        return {k: v for k, v in super().parameters().items() if k not in _NODE2VEC_HIDDEN}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "Node2Vec CBOW"
+
+
+class DeepWalkSkipGramB200(Node2VecB200):
+    """DeepWalk SkipGram on B200 (counterpart of deepwalk_skipgram.py:6-139)."""
+
+    __init__ = _deepwalk_init
+
+    def parameters(self) -> Dict[str, Any]:
+        """Drops the same keys as deepwalk_skipgram.py:120-135."""
+        return {k: v for k, v in super().parameters().items() if k not in _DEEPWALK_HIDDEN}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "DeepWalk SkipGram"
+
+
+class DeepWalkCBOWB200(Node2VecB200):
+    """DeepWalk CBOW on B200 (counterpart of deepwalk_cbow.py:6-139)."""
+
+    __init__ = _deepwalk_init
+
+    def parameters(self) -> Dict[str, Any]:
+        return {k: v for k, v in super().parameters().items() if k not in _DEEPWALK_HIDDEN}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "DeepWalk CBOW"
+
+
+B200_EMBEDDERS = (Node2VecSkipGramB200, Node2VecCBOWB200, DeepWalkSkipGramB200, DeepWalkCBOWB200)
+for _model in B200_EMBEDDERS:  # abstract_model.py:721-749; Walklets are deliberately not registered
+    AbstractModel.register(_model)
+
+
+def embed_graph(graph, embedding_model, repository: Optional[str] = None,
+                version: Optional[str] = None, library_name: Optional[str] = "B200",
+                smoke_test: bool = False, return_dataframe: bool = True, **kwargs) -> EmbeddingResult:
+    """Same contract as /root/reference/embiggen/embedders/graph_embedding_pipeline.py:10-106
+    (model by name or instance, kwargs only with a name, smoke-test conversion, every failure
+    re-raised as ValueError), defaulting to this library."""
+    if isinstance(embedding_model, str):
+        embedding_model = AbstractEmbeddingModel.get_model_from_library(
+            model_name=embedding_model, task_name="Node Embedding", library_name=library_name)(**kwargs)
+    elif kwargs:
+        raise ValueError("Please be advised that even though you have provided yourself the "
+                         "embedding model, you have also provided the kwargs which would normally "
+                         "be forwarded to the creation of the embedding model. It is unclear what "
+                         "to do with these arguments.")
+    if not isinstance(embedding_model, AbstractEmbeddingModel):
+        raise ValueError("The provided object is not an embedding model, that is, it does not "
+                         "extend the class `AbstractEmbeddingModel`.")
+    if smoke_test:
+        try:
+            embedding_model = embedding_model.into_smoke_test()
+        except Exception as e:
+            raise ValueError(
+                "An exception was raised while trying to create a smoke test version of the model "
+                f"called {embedding_model.model_name()} from the library {library_name}. The body "
+                f"of the exception was: {e}.") from e
+    try:
+        return embedding_model.fit_transform(graph, repository=repository, version=version,
+                                             return_dataframe=return_dataframe)
+    except Exception as e:
+        name = graph.get_name() if hasattr(graph, "get_name") else type(graph).__name__
+        raise ValueError(
+            f"An exception was raised while trying to compute a node embedding on the graph {name} "
+            f"using the model called {embedding_model.model_name()} from the library "
+            f"{library_name}, specifically implemented in the class "
+            f"{embedding_model.__class__.__name__}. The body of the exception was: {e}") from e

@@ -1,0 +1,412 @@
+"""The embedder-side contract of the drop-in boundary.
+
+When ``embiggen`` itself is importable the four B200 embedders subclass its real
+``AbstractEmbeddingModel`` and return its real ``EmbeddingResult`` (so they register in
+``AbstractModel.MODELS_LIBRARY`` and work with ``embed_graph`` /
+``edge_prediction_evaluation`` unchanged).  Where it is not (this repository's CI, the GPU
+box) the compact restatements below supply the same surface, each method citing the
+reference code whose behaviour it keeps:
+
+* ``EmbeddingResult``           /root/reference/embiggen/utils/abstract_models/embedding_result.py:11-334
+* ``AbstractModel`` (registry)  /root/reference/embiggen/utils/abstract_models/abstract_model.py:27-760
+* ``AbstractEmbeddingModel``    /root/reference/embiggen/utils/abstract_models/abstract_embedding_model.py:12-259
+* ``normalize_kwargs``          /root/reference/embiggen/utils/normalize_kwargs.py:74-135
+
+Only what the Node2Vec / DeepWalk SkipGram / CBOW path touches is restated; the classifier
+half of ``AbstractModel`` is out of scope.
+"""
+import hashlib
+import json
+import warnings
+from typing import Any, Dict, List, Optional, Type, Union
+
+import numpy as np
+import pandas as pd
+
+try:  # the real thing, when the reference package and its dependencies are installed
+    from embiggen.utils.abstract_models import (  # type: ignore
+        AbstractEmbeddingModel, AbstractModel, EmbeddingResult, abstract_class)
+    HAVE_EMBIGGEN = True
+except Exception:  # ModuleNotFoundError for embiggen, ensmallen, dict_hash, ...
+    HAVE_EMBIGGEN = False
+
+Embedding = Union[np.ndarray, pd.DataFrame]
+
+# kwarg name -> accepted type names; the subset of the reference's normalization_schemas.json
+# this path uses, plus the B200-only extras (which the reference schema would reject,
+# normalize_kwargs.py:127-134, hence a private schema).
+KWARG_SCHEMA = {
+    "embedding_size": "int", "epochs": "int", "clipping_value": "float",
+    "number_of_negative_samples": "int", "walk_length": "int", "iterations": "int",
+    "window_size": "int", "return_weight": "float", "explore_weight": "float",
+    "change_node_type_weight": "float", "change_edge_type_weight": "float",
+    "max_neighbours": ["int", "None"], "learning_rate": ["float", "str"],
+    "learning_rate_decay": "float", "central_nodes_embedding_path": ["str", "None"],
+    "contextual_nodes_embedding_path": ["str", "None"], "normalize_by_degree": "bool",
+    "stochastic_downsample_by_degree": "bool", "normalize_learning_rate_by_degree": "bool",
+    "use_scale_free_distribution": "bool", "random_state": "int", "dtype": "str",
+    "verbose": "bool",
+    # B200 extras
+    "negative_sampling_exponent": "float", "scale_by_sqrt_dim": "bool", "deterministic": "bool",
+    "chunk_walks": "int", "sync_interval": "int", "device": ["int", "None"],
+}
+_TYPES = {"bool": bool, "int": int, "float": float, "str": str, "None": type(None)}
+
+
+def normalize_kwargs(model, kwargs: Dict[str, Any]) -> Dict[str, Any]:
+    """Coerce exotic scalar types (numpy bool_, float-typed ints from pandas) and reject
+    unknown names with NotImplementedError, like normalize_kwargs.py:74-135."""
+    unknown = [key for key in kwargs if key not in KWARG_SCHEMA]
+    if unknown:
+        raise NotImplementedError(
+            f"The following parameters are not supported: {unknown}. "
+            f"The model is {model.model_name()} from library {model.library_name()} "
+            f"for the task {model.task_name()}.")
+    for key, value in list(kwargs.items()):
+        names = KWARG_SCHEMA[key]
+        names = [names] if isinstance(names, str) else names
+        if isinstance(value, tuple(_TYPES[name] for name in names)) and not (
+                isinstance(value, bool) and "bool" not in names):
+            continue
+        for name in names:
+            if name == "None":
+                continue
+            try:
+                kwargs[key] = _TYPES[name](value)
+                break
+            except (TypeError, ValueError):
+                continue
+        else:
+            raise TypeError(
+                f"The parameter {key} has the value \"{value}\" with type {type(value)} "
+                f"but the expected type is {names}. The model is {model.model_name()} from "
+                f"library {model.library_name()} for the task {model.task_name()}.")
+    return kwargs
+
+
+if not HAVE_EMBIGGEN:
+
+    def abstract_class(klass):
+        """Marker only, as in abstract_model.py:11-13."""
+        return klass
+
+    class EmbeddingResult:
+        """Container of the embeddings a model produced (embedding_result.py:11-334)."""
+
+        _KINDS = (("node_embeddings", "node embedding"), ("edge_embeddings", "edge embedding"),
+                  ("node_type_embeddings", "node type embedding"),
+                  ("edge_type_embeddings", "edge type embedding"))
+
+        def __init__(self, embedding_method_name: str, node_embeddings=None, edge_embeddings=None,
+                     node_type_embeddings=None, edge_type_embeddings=None):
+            given = dict(node_embeddings=node_embeddings, edge_embeddings=edge_embeddings,
+                         node_type_embeddings=node_type_embeddings,
+                         edge_type_embeddings=edge_type_embeddings)
+            self._embedding_method_name = embedding_method_name
+            for attribute, label in self._KINDS:
+                embeddings = given[attribute]
+                if embeddings is not None and not isinstance(embeddings, list):
+                    embeddings = [embeddings]  # :41-51
+                for embedding in embeddings or []:
+                    self._validate(embedding, label)
+                setattr(self, "_" + attribute, embeddings)
+            if self.is_single_embedding():  # proxy the methods of the only embedding, :114-129
+                single = self.get_single_embedding()
+                for name in dir(single):
+                    if name.startswith("__") or hasattr(self, name):
+                        continue
+                    member = getattr(single, name, None)
+                    if callable(member):
+                        setattr(self, name, member)
+
+        def _validate(self, embedding, label):  # :59-106
+            name = self._embedding_method_name
+            if not isinstance(embedding, (np.ndarray, pd.DataFrame)):
+                raise ValueError(f"One of the provided {label} computed with the {name} method is "
+                                 f"neither a numpy array or a pandas DataFrame, but a "
+                                 f"`{type(embedding)}` object.")
+            if embedding.shape[0] == 0:
+                raise ValueError(f"One of the provided {label} computed with the {name} method "
+                                 "is empty.")
+            if embedding.shape[0] > 1_000_000:  # too large to scan, :77-79
+                return
+            values = embedding.to_numpy() if isinstance(embedding, pd.DataFrame) else embedding
+            if np.isnan(values).any():
+                raise ValueError(f"One of the provided {label} computed with the {name} method "
+                                 "contains NaN values.")
+            if np.isinf(values).any():
+                raise ValueError(f"One of the provided {label} computed with the {name} method "
+                                 f"contains {int(np.isinf(values).sum())} infinite values.")
+            if np.isclose(values, 0.0).all():
+                warnings.warn(f"One of the provided {label} computed with the {name} method "
+                              "contains exclusively zeros.")
+
+        def _lists(self):
+            return [getattr(self, "_" + attribute) for attribute, _ in self._KINDS]
+
+        def number_of_embeddings(self) -> int:
+            return sum(len(embeddings) for embeddings in self._lists() if embeddings is not None)
+
+        def is_single_embedding(self) -> bool:
+            return self.number_of_embeddings() == 1
+
+        def get_single_embedding(self) -> Embedding:
+            assert self.is_single_embedding()
+            return next(e[0] for e in self._lists() if e is not None)
+
+        def _all(self, attribute, label) -> List[Embedding]:
+            embeddings = getattr(self, attribute)
+            if embeddings is None:
+                raise ValueError(f"The {label} were requested but they were not computed by the "
+                                 f"{self._embedding_method_name} method.")
+            return embeddings
+
+        def _at(self, attribute, label, index) -> Embedding:
+            embeddings = self._all(attribute, label)
+            if index >= len(embeddings):
+                raise ValueError(f"The {label} computed with the {self._embedding_method_name} "
+                                 f"method are {len(embeddings)}, but you requested the embedding "
+                                 f"in position {index}.")
+            return embeddings[index]
+
+        def get_all_node_embedding(self):
+            return self._all("_node_embeddings", "node embedding")
+
+        def get_all_edge_embedding(self):
+            return self._all("_edge_embeddings", "edge embedding")
+
+        def get_all_node_type_embeddings(self):
+            return self._all("_node_type_embeddings", "node types embedding")
+
+        def get_all_edge_type_embeddings(self):
+            return self._all("_edge_type_embeddings", "edge types embedding")
+
+        def get_node_embedding_from_index(self, index: int):
+            return self._at("_node_embeddings", "node embedding", index)
+
+        def get_edge_embedding_from_index(self, index: int):
+            return self._at("_edge_embeddings", "edge embedding", index)
+
+        def get_node_type_embedding_from_index(self, index: int):
+            return self._at("_node_type_embeddings", "node type embedding", index)
+
+        def get_edge_type_embedding_from_index(self, index: int):
+            return self._at("_edge_type_embeddings", "edge type embedding", index)
+
+        @property
+        def embedding_method_name(self) -> str:
+            return self._embedding_method_name
+
+        def dump(self) -> Dict[str, Any]:  # :323-334
+            return dict(embedding_method_name=self._embedding_method_name,
+                        **{attribute: getattr(self, "_" + attribute) for attribute, _ in self._KINDS})
+
+        @staticmethod
+        def load(cached: Dict[str, Any]) -> "EmbeddingResult":
+            return EmbeddingResult(**cached)
+
+    @abstract_class
+    class AbstractModel:
+        """Registry + parameter plumbing of abstract_model.py, embedding half only."""
+
+        MODELS_LIBRARY: Dict[str, Dict[str, Dict[str, Type["AbstractModel"]]]] = {}
+
+        def __init__(self, random_state: Optional[int] = None):
+            if self.is_stocastic() and random_state is None:  # :41-48
+                raise ValueError(
+                    "The provided model is stocastic, yet no random state was provided. Please do "
+                    f"provide a random state to the model {self.model_name()} from library "
+                    f"{self.library_name()} and task {self.task_name()}.")
+            self._random_state = random_state
+
+        def parameters(self) -> Dict[str, Any]:
+            return {} if self._random_state is None else dict(random_state=self._random_state)
+
+        @classmethod
+        def smoke_test_parameters(cls) -> Dict[str, Any]:
+            raise NotImplementedError(f"`smoke_test_parameters` is not implemented in {cls.__name__}.")
+
+        def into_smoke_test(self):  # :152-154
+            return self.__class__(**{**self.parameters(), **self.smoke_test_parameters()})
+
+        def set_random_state(self, random_state: int):  # :582-589
+            if not self.is_stocastic():
+                raise ValueError("It does not make sense to set the random state of a "
+                                 "non-stocastic model.")
+            self._random_state = random_state
+
+        def consistent_hash(self) -> str:  # :555-564 (sha256 of parameters and names)
+            payload = dict(**self.parameters(), model_name=self.model_name(),
+                           library_name=self.library_name(), task_name=self.task_name())
+            return hashlib.sha256(json.dumps(payload, sort_keys=True, default=str).encode()).hexdigest()
+
+        @staticmethod
+        def is_available() -> bool:
+            return True
+
+        # requires_X defaults to False when the model says it cannot use X at all
+        # (abstract_model.py:156-171 and the node / edge type twins below it)
+        @classmethod
+        def requires_edge_weights(cls) -> bool:
+            if not cls.can_use_edge_weights():
+                return False
+            raise NotImplementedError(f"`requires_edge_weights` is not implemented in {cls.__name__}.")
+
+        @classmethod
+        def requires_node_types(cls) -> bool:
+            if not cls.can_use_node_types():
+                return False
+            raise NotImplementedError(f"`requires_node_types` is not implemented in {cls.__name__}.")
+
+        @classmethod
+        def requires_edge_types(cls) -> bool:
+            if not cls.can_use_edge_types():
+                return False
+            raise NotImplementedError(f"`requires_edge_types` is not implemented in {cls.__name__}.")
+
+        def is_using_node_types(self) -> bool:
+            return self.requires_node_types()
+
+        def is_using_edge_types(self) -> bool:
+            return self.requires_edge_types()
+
+        @staticmethod
+        def register(model_class):  # :721-749
+            by_model = AbstractModel.MODELS_LIBRARY.setdefault(model_class.task_name(), {})
+            by_library = by_model.setdefault(model_class.model_name(), {})
+            by_library.setdefault(model_class.library_name(), model_class)
+
+        @staticmethod
+        def get_task_data(model_name: str, task_name: str):
+            if not model_name:
+                raise ValueError("The provided model name is empty.")
+            if not task_name:
+                raise ValueError("The provided task name is empty.")
+            library = AbstractModel.MODELS_LIBRARY
+            if task_name not in library:
+                raise ValueError(f"The provided task name {task_name!r} is not in {sorted(library)}.")
+            if model_name not in library[task_name]:
+                raise ValueError(f"The provided model name {model_name!r} is not in "
+                                 f"{sorted(library[task_name])}.")
+            return library[task_name][model_name]
+
+        @classmethod
+        def get_model_from_library(cls, model_name: str, task_name: Optional[str] = None,
+                                   library_name: Optional[str] = None):  # :626-700
+            task_name = cls.task_name() if task_name is None else task_name
+            task_data = AbstractModel.get_task_data(model_name, task_name)
+            if library_name is None:
+                names = list(task_data)
+                if len(names) == 1:
+                    library_name = names[0]
+                elif "Ensmallen" in names:
+                    library_name = "Ensmallen"
+                else:
+                    raise ValueError(
+                        f"The requested model `{model_name}` is available for multiple libraries "
+                        f"({names}) and no specific library was requested.")
+            if library_name not in task_data:
+                raise ValueError(f"The provided library name {library_name!r} is not in "
+                                 f"{sorted(task_data)}.")
+            model_class = task_data[library_name]
+            if not model_class.is_available():
+                model_class()  # surfaces its helpful error, :692-696
+            return model_class
+
+        @staticmethod
+        def find_available_models(model_name: str, task_name: str):
+            return [model for model in AbstractModel.get_task_data(model_name, task_name).values()
+                    if model.is_available()]
+
+    @abstract_class
+    class AbstractEmbeddingModel(AbstractModel):
+        """fit_transform with the reference's graph validation (abstract_embedding_model.py)."""
+
+        def __init__(self, embedding_size: Optional[int] = None, enable_cache: bool = False,
+                     ring_bell: bool = False, random_state: Optional[int] = None):
+            super().__init__(random_state=random_state)
+            if embedding_size is not None and not isinstance(embedding_size, int) or embedding_size == 0:
+                raise ValueError("The embedding size, if provided, should be a strictly positive "
+                                 f"integer but {embedding_size} was provided.")  # :37-41
+            self._embedding_size = embedding_size
+            self._enable_cache = enable_cache  # accepted; result caching needs cache_decorator
+            self._ring_bell = None
+
+        def parameters(self) -> Dict[str, Any]:
+            extra = {} if self._embedding_size is None else dict(embedding_size=self._embedding_size)
+            return dict(**super().parameters(), **extra)
+
+        @classmethod
+        def task_name(cls) -> str:
+            return "Node Embedding"
+
+        @classmethod
+        def can_use_edge_type_features(cls) -> bool:
+            return False
+
+        @classmethod
+        def can_use_edge_features(cls) -> bool:
+            return False
+
+        def _validate_graph(self, graph) -> None:  # :114-180
+            name = graph.get_name()
+            if not graph.has_nodes():
+                raise ValueError(f"The provided graph {name} is empty.")
+            if self.requires_node_types() and not graph.has_node_types():
+                raise ValueError(f"The provided graph {name} does not have node types, but the "
+                                 f"{self.model_name()} requires node types.")
+            if self.requires_edge_types() and not graph.has_edge_types():
+                raise ValueError(f"The provided graph {name} does not have edge types, but the "
+                                 f"{self.model_name()} requires edge types.")
+            if self.requires_edge_weights() and not graph.has_edge_weights():
+                raise ValueError(f"The provided graph {name} does not have edge weights, but the "
+                                 f"{self.model_name()} requires edge weights.")
+            if (self.requires_positive_edge_weights() and graph.has_edge_weights()
+                    and graph.has_negative_edge_weights()):
+                raise ValueError(f"The provided graph {name} has negative edge weights, but the "
+                                 f"{self.model_name()} requires strictly positive edge weights.")
+            if self.is_topological():
+                if not graph.has_edges():
+                    raise ValueError(f"The provided graph {name} does not have edges.")
+                if graph.has_disconnected_nodes():
+                    warnings.warn(
+                        f"Please be advised that the {name} graph contains "
+                        f"{graph.get_number_of_disconnected_nodes()} disconnected nodes. Node "
+                        "embedding algorithms that only use topological information such as CBOW "
+                        "and SkipGram are not able to provide meaningful embeddings for these nodes.")
+
+        def fit_transform(self, graph, repository: Optional[str] = None,
+                          version: Optional[str] = None, return_dataframe: bool = True):  # :200-251
+            if isinstance(graph, str):
+                raise ValueError("Graph retrieval by name needs the `ensmallen` package; pass a "
+                                 "graph object (ensmallen.Graph, CSRGraph, (indptr, indices)).")
+            from .graph import as_graph
+            graph = as_graph(graph)
+            if return_dataframe and graph.get_number_of_nodes() > 100_000_000:
+                raise ValueError(
+                    "We cowardly refuse to execute this embedding with the added requirement to "
+                    f"also return the dataframe version of this graph. This graph has "
+                    f"{graph.get_number_of_nodes()}, and creating a Dataframe would most likely "
+                    "cause an OOM on your system.")
+            self._validate_graph(graph)
+            result = self._fit_transform(graph=graph, return_dataframe=return_dataframe)
+            if not isinstance(result, EmbeddingResult):
+                raise NotImplementedError(
+                    f"The embedding result produced by the {self.model_name()} method from the "
+                    f"library {self.library_name()} implemented in the class called "
+                    f"{self.__class__.__name__} does not return an Embeddingresult but returns "
+                    f"an object of type {type(result)}.")
+            return result
+
+
+def get_available_models_for_node_embedding() -> pd.DataFrame:
+    """One row per registered node-embedding model (reference: embiggen/utils/
+    abstract_models/abstract_model.py get_models_dataframe, as the reference tests iterate it,
+    tests/test_node_embedding_pipelines.py:19)."""
+    rows = []
+    for model_name, libraries in AbstractModel.MODELS_LIBRARY.get("Node Embedding", {}).items():
+        for library_name, model in libraries.items():
+            rows.append(dict(model_name=model_name, task_name="Node Embedding",
+                             library_name=library_name, available=model.is_available(),
+                             requires_edge_weights=model.requires_edge_weights()))
+    return pd.DataFrame(rows)

@@ -168,6 +168,14 @@ def as_csr(graph) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
     )
 
 
+def as_graph(graph):
+    """Anything ``as_csr`` accepts, as an object with the ``ensmallen.Graph`` accessors."""
+    if hasattr(graph, "get_number_of_nodes") and hasattr(graph, "has_edges"):
+        return graph
+    indptr, indices, weights = as_csr(graph)
+    return CSRGraph(indptr, indices, weights=weights)
+
+
 def csr_from_edges(src: np.ndarray, dst: np.ndarray, n: int, symmetrise: bool = True,
                    node_names=None, name: str = "graph") -> CSRGraph:
     """Sorted, de-duplicated, self-loop-free CSR from an edge list."""
