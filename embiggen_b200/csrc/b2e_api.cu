@@ -2,6 +2,7 @@
 // the chunked walk -> SGD pipeline on two streams, and the host-buffer entry points.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,6 +34,17 @@ static int fail(int status, const std::string &message) {
 
 extern "C" const char *b2e_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b2e_abi_version(void) { return B2E_ABI_VERSION; }
+
+extern "C" int b2e_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    int usable = 0;
+    for (int d = 0; d < count; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major >= 10) ++usable;
+    }
+    return usable;
+}
 
 // integer accept thresholds (DESIGN.md "second-order accept test")
 static void thresholds(float return_weight, float explore_weight, unsigned long long out[3]) {
@@ -85,7 +97,9 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (!h) return fail(B2E_ERR_INVALID, "out of host memory");
     h->cfg = c;
     h->sm_count = prop.multiProcessorCount;
-    h->row_stride = (c.embedding_size + 3u) / 4u * 4u;
+    h->row_stride = (c.embedding_size + 7u) / 8u * 8u;  // rows start on 32 B sectors
+    if (const char *env = getenv("B2E_PREFETCH")) h->prefetch = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
     for (int s = 0; s < 2; ++s) {
@@ -181,7 +195,7 @@ extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t
     REQUIRE_HANDLE(h);
     if (!indptr || (!indices && nnz)) return fail(B2E_ERR_INVALID, "null CSR pointer");
     if (n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
-    if (n >= 0xFFFFFFFFull) return fail(B2E_ERR_INVALID, "node ids must fit 32 bits");
+    if (n >= 0xFFFFFF00ull) return fail(B2E_ERR_INVALID, "node ids must be below 0xFFFFFF00");
     if (nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
     if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
         return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
@@ -227,8 +241,9 @@ extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t
     CUDA_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
 
     const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
-    uint64_t cap = c.chunk_walks ? c.chunk_walks : (1ull << 20);
-    cap = std::max<uint64_t>(1, std::min(cap, per_epoch));
+    // an explicit chunk_walks is honoured as given (parity tests feed host walks of that size)
+    const uint64_t cap = c.chunk_walks ? c.chunk_walks
+                                       : std::max<uint64_t>(1, std::min<uint64_t>(1ull << 20, per_epoch));
     h->chunk_cap = cap;
     for (int s = 0; s < 2; ++s)
         CUDA_TRY(cudaMalloc(&h->d_walks[s], cap * c.walk_length * sizeof(uint32_t)));
@@ -335,6 +350,8 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.use_alias = c.use_scale_free_distribution ? 1u : 0u;
     p.normalize_lr = c.normalize_learning_rate_by_degree ? 1u : 0u;
     p.scale_dot = c.scale_by_sqrt_dim ? 1u : 0u;
+    p.prefetch = h->prefetch;
+    p.variant = h->variant;
     p.alias = h->d_alias;
     p.indptr = h->d_indptr;
     p.t0 = h->d_t0;

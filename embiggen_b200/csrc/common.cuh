@@ -67,6 +67,8 @@ struct TrainParams {
     uint32_t row_stride;  // floats, multiple of 4
     float clip, lr, inv_scale;
     uint32_t use_alias, normalize_lr, scale_dot;
+    uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
+    uint32_t variant;   // tuning variant of the launch (0 = default)
     const uint2 *alias;  // {threshold, alias} per node
     const int64_t *indptr;
     float *t0, *t1;
@@ -78,6 +80,9 @@ cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedd
                                uint32_t row_stride, uint64_t seed, cudaStream_t stream);
 cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                          cudaStream_t stream);
+bool pipe_supported(const TrainParams &p, uint32_t model);
+cudaError_t launch_skipgram_pipe(const TrainParams &p, bool deterministic, int sm_count,
+                                 cudaStream_t stream);
 cudaError_t launch_pack_rows(const float *src, float *dst, uint64_t n, uint32_t embedding_size,
                              uint32_t row_stride, bool strip, cudaStream_t stream);
 
@@ -102,6 +107,8 @@ struct b2e_handle {
     b2e::DeviceCounters *d_counters = nullptr;
     unsigned long long thr[3] = {0, 0, 0};
     bool second_order = false;
+    uint32_t prefetch = 1;
+    uint32_t variant = 0;
     uint64_t launches = 0;
     std::vector<uint32_t> h_alias_thr, h_alias_idx;
 };

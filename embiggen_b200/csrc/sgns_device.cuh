@@ -1,0 +1,63 @@
+// Device helpers shared by the SGD kernels (sgns_kernels.cu: register-staged generic path,
+// sgns_pipe.cu: shared-memory pipelined path).  Normative floating point: DESIGN.md.
+#pragma once
+#include "common.cuh"
+
+namespace b2e {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float exp_det(float y) {
+    y = y > 80.0f ? 80.0f : y;
+    y = y < -80.0f ? -80.0f : y;
+    const float k = rintf(__fmul_rn(y, 1.44269504088896341f));
+    float r = __fmaf_rn(k, -0.693145751953125f, y);
+    r = __fmaf_rn(k, -1.42860682030941723212e-6f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    p = __fmaf_rn(p, __fmul_rn(r, r), r);
+    p = __fadd_rn(p, 1.0f);
+    return __fmul_rn(p, __int_as_float(((int)k + 127) << 23));
+}
+
+__device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre) {
+    if (!p.normalize_lr) return p.lr;
+    const uint32_t deg = (uint32_t)(__ldg(p.indptr + centre + 1) - __ldg(p.indptr + centre));
+    return __fdiv_rn(p.lr, (float)deg);
+}
+
+// ---- SkipGram: the draw sites of a walk are its (centre, context) pairs, in oracle order ----
+struct PairCursor {
+    uint32_t i, j;  // centre and context positions; start with i = 0xFFFFFFFF
+    uint32_t c, o;  // their tokens
+    uint32_t hi;    // last window position of centre i
+};
+
+// advance to the next pair of the walk; false when the walk is exhausted
+__device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uint32_t L, uint32_t W,
+                                          PairCursor &s) {
+    for (;;) {
+        if (s.i == 0xFFFFFFFFu || s.j >= s.hi) {
+            const uint32_t i = s.i + 1u;  // wraps 0xFFFFFFFF -> 0
+            if (i >= L) return false;
+            const uint32_t c = __ldg(walk + i);
+            if (c == PAD) return false;
+            s.i = i;
+            s.c = c;
+            s.hi = i + W < L - 1 ? i + W : L - 1;
+            s.j = i > W ? i - W : 0u;
+        } else {
+            ++s.j;
+        }
+        if (s.j == s.i) continue;
+        s.o = __ldg(walk + s.j);
+        if (s.o == PAD || s.o == s.c) continue;
+        return true;
+    }
+}
+
+}  // namespace b2e

@@ -2,43 +2,26 @@
 //
 // Replaces the training half of `ensmallen.models.SkipGram/CBOW.fit_transform`
 // (/root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:99; kwargs
-// .../node2vec_skipgram.py:37-119).  One warp per walk; a warp slides the window over its
-// walk, draws the negatives of a pair from the alias table (one lane per negative), gathers
-// the K+1 target rows of the contextual table with 128-bit loads issued back to back,
-// reduces the dot products with warp shuffles, and scatters the updated rows back
-// (Hogwild: plain vector stores, no locks).  The bound is HBM: 2 * 4D bytes per target row.
+// .../node2vec_skipgram.py:37-119).  One warp per walk, fetched dynamically.  The bound is
+// HBM: every (centre, context) pair gathers and scatters K+1 rows of the contextual table
+// (2 * 4D bytes each), K of them at random.  The kernel is therefore organised as a software
+// pipeline over the *draw sites* of a walk (a pair for SkipGram, a centre for CBOW):
+//
+//   site s+2 : Philox draw + alias-table gather issued (the ids depend on (seed, walk, site)
+//              only, never on the tables, so they can run arbitrarily far ahead);
+//   site s+1 : ids resolved, its K+1 target rows prefetched into L2 (CCTL.PF2, one line per
+//              lane) so the DRAM latency is paid while site s computes;
+//   site s   : rows gathered with 128-bit loads issued back to back (L2 hits), warp-shuffle
+//              dot products, sigmoid, axpy, rows scattered back with 128-bit stores
+//              (Hogwild: plain stores, no locks).
 //
 // Floating point follows the normative spec: explicit round-to-nearest
 // intrinsics, a fixed reduction order and a polynomial sigmoid, so a single-warp launch
-// (cfg.deterministic) reproduces the CPU oracle's tables bit for bit.
-#include "common.cuh"
+// (cfg.deterministic) reproduces the CPU oracle's tables bit for bit.  Prefetches never
+// change a value, so both launches run the same code.
+#include "sgns_device.cuh"
 
 namespace b2e {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ float exp_det(float y) {
-    y = y > 80.0f ? 80.0f : y;
-    y = y < -80.0f ? -80.0f : y;
-    const float k = rintf(__fmul_rn(y, 1.44269504088896341f));
-    float r = __fmaf_rn(k, -0.693145751953125f, y);
-    r = __fmaf_rn(k, -1.42860682030941723212e-6f, r);
-    float p = 1.9875691500e-4f;
-    p = __fmaf_rn(p, r, 1.3981999507e-3f);
-    p = __fmaf_rn(p, r, 8.3334519073e-3f);
-    p = __fmaf_rn(p, r, 4.1665795894e-2f);
-    p = __fmaf_rn(p, r, 1.6666665459e-1f);
-    p = __fmaf_rn(p, r, 5.0000001201e-1f);
-    p = __fmaf_rn(p, __fmul_rn(r, r), r);
-    p = __fadd_rn(p, 1.0f);
-    return __fmul_rn(p, __int_as_float(((int)k + 127) << 23));
-}
-
-__device__ __forceinline__ float sigmoid_det(float x) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_det(-x)));
-}
-
-__device__ __forceinline__ float softplus(float z) { return z > 15.0f ? z : log1pf(expf(z)); }
 
 template <int CH>
 __device__ __forceinline__ void load_row(const float *row, uint32_t chunks, uint32_t lane,
@@ -77,29 +60,81 @@ __device__ __forceinline__ float warp_dot(const float4 (&a)[CH], const float4 (&
     return p;
 }
 
-// lane k < K draws negative k of the site; returns the validity of that lane's draw
-__device__ __forceinline__ bool draw_negative(const TrainParams &p, uint32_t wid_lo,
-                                              uint32_t wid_hi, uint32_t site, uint32_t lane,
-                                              uint32_t centre, uint32_t context, uint32_t &neg) {
-    bool valid = false;
-    neg = PAD;
+template <int CH>
+__device__ __forceinline__ void add_rows(float4 (&a)[CH], const float4 (&b)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        a[ch].x = __fadd_rn(a[ch].x, b[ch].x);
+        a[ch].y = __fadd_rn(a[ch].y, b[ch].y);
+        a[ch].z = __fadd_rn(a[ch].z, b[ch].z);
+        a[ch].w = __fadd_rn(a[ch].w, b[ch].w);
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void zero_rows(float4 (&a)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) a[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- negative draws: issued one site early, resolved when the alias entry has arrived ----
+struct Draw {
+    uint32_t idx;  // uniform proposal of this lane (lane < K)
+    uint32_t ry;   // second random word, compared with the alias threshold
+    uint2 entry;   // {threshold, alias} gathered from the alias table (in flight)
+};
+
+__device__ __forceinline__ Draw draw_issue(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
+                                           uint32_t site, uint32_t lane) {
+    Draw d;
+    d.idx = PAD;
+    d.ry = 0;
+    d.entry = make_uint2(0xFFFFFFFFu, 0u);
     if (lane < p.negatives) {
         const uint4 r = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, site,
                                       (TAG_NEG << 24) | lane);
-        const uint32_t idx = __umulhi(r.x, p.n);
-        neg = idx;
-        if (p.use_alias) {
-            const uint2 e = __ldg(p.alias + idx);
-            neg = r.y < e.x ? idx : e.y;
+        d.idx = __umulhi(r.x, p.n);
+        d.ry = r.y;
+        if (p.use_alias) d.entry = __ldg(p.alias + d.idx);
+    }
+    return d;
+}
+
+// Returns the target mask of the site: bit 0 = positive, bit k+1 = negative k is valid.  A draw
+// equal to the centre, the context or an earlier draw of the same site is dropped.
+__device__ __forceinline__ uint32_t draw_resolve(const TrainParams &p, const Draw &d, uint32_t lane,
+                                                 uint32_t centre, uint32_t context, uint32_t &neg) {
+    neg = d.idx;
+    if (p.use_alias && lane < p.negatives) neg = d.ry < d.entry.x ? d.idx : d.entry.y;
+    const uint32_t same = __match_any_sync(FULL, neg);
+    const bool valid = lane < p.negatives && neg != centre && neg != context &&
+                       (same & ((1u << lane) - 1u)) == 0u;
+    return (__ballot_sync(FULL, valid) << 1) | 1u;
+}
+
+// One L2 prefetch per 128 B line of every row the next site will touch: slot 0 = row `first`
+// of T1, slots 1..K = the valid negatives (T1), slot K+1 = row `extra` of T0 (PAD: none).
+__device__ __forceinline__ void prefetch_site(const TrainParams &p, uint32_t lane, uint32_t first,
+                                              uint32_t neg, uint32_t vmask, uint32_t extra) {
+    if (p.prefetch == 0) return;
+    const uint32_t row_bytes = p.row_stride * 4u;
+    const uint32_t slots = p.negatives + 2u;
+    for (uint32_t first_t = 0; first_t < slots * 5u; first_t += 32u) {  // warp-uniform trip count
+        const uint32_t t = first_t + lane;
+        const uint32_t slot = t / 5u, line = t - slot * 5u;
+        const uint32_t id_neg = __shfl_sync(FULL, neg, (slot - 1u) & 31u);
+        const uint32_t id = slot == 0 ? first : (slot <= p.negatives ? id_neg : extra);
+        bool on = slot < slots;
+        if (on) on = slot <= p.negatives ? ((vmask >> slot) & 1u) : (extra != PAD);
+        if (on) {
+            const float *base = (slot <= p.negatives ? p.t1 : p.t0) + (uint64_t)id * p.row_stride;
+            const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 127u);
+            if (line * 128u < head + row_bytes) {
+                const char *addr = reinterpret_cast<const char *>(base) - head + line * 128u;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+            }
         }
-        valid = neg != centre && neg != context;
     }
-    // a draw equal to an earlier draw of the same site is dropped
-    for (uint32_t q = 0; q + 1 < p.negatives; ++q) {
-        const uint32_t other = __shfl_sync(FULL, neg, q);
-        if (lane > q && other == neg) valid = false;
-    }
-    return valid;
 }
 
 // Score h against slot 0 (= positive) and the valid negatives, in batches of NT rows whose
@@ -135,8 +170,11 @@ __device__ __forceinline__ void apply_targets(const TrainParams &p, uint32_t chu
         bool apply = false;
         if (my_on && !(fabsf(my_f) > p.clip)) {
             const bool is_positive = (b + lane) == 0;
-            g_mine = __fmul_rn(__fsub_rn(is_positive ? 1.0f : 0.0f, sigmoid_det(my_f)), lr);
-            loss_acc += softplus(is_positive ? -my_f : my_f);
+            const float e = exp_det(-my_f);
+            const float sigmoid = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+            g_mine = __fmul_rn(__fsub_rn(is_positive ? 1.0f : 0.0f, sigmoid), lr);
+            // -log sigmoid(f) = log(1 + e^-f);  -log sigmoid(-f) = log(1 + e^-f) + f
+            loss_acc += __logf(1.0f + e) + (is_positive ? 0.0f : my_f);
             apply = true;
         }
         const uint32_t amask = __ballot_sync(FULL, apply);
@@ -163,112 +201,176 @@ __device__ __forceinline__ void apply_targets(const TrainParams &p, uint32_t chu
     }
 }
 
-template <int CH>
-__device__ __forceinline__ void add_rows(float4 (&a)[CH], const float4 (&b)[CH]) {
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) {
-        a[ch].x = __fadd_rn(a[ch].x, b[ch].x);
-        a[ch].y = __fadd_rn(a[ch].y, b[ch].y);
-        a[ch].z = __fadd_rn(a[ch].z, b[ch].z);
-        a[ch].w = __fadd_rn(a[ch].w, b[ch].w);
+template <int CH, int NT>
+__device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32_t *walk, uint64_t wid,
+                                              uint32_t lane, float &loss_acc,
+                                              unsigned long long &n_pairs,
+                                              unsigned long long &n_targets) {
+    const uint32_t chunks = p.row_stride >> 2;
+    const uint32_t L = p.walk_length, W = p.window;
+    const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+
+    PairCursor scan;
+    scan.i = 0xFFFFFFFFu; scan.j = 0; scan.c = PAD; scan.o = PAD; scan.hi = 0;
+    bool ok_cur = next_pair(walk, L, W, scan);
+    if (!ok_cur) return;
+    PairCursor cur = scan;
+    uint32_t neg_cur;
+    uint32_t vmask_cur;
+    {
+        const Draw d = draw_issue(p, wid_lo, wid_hi, (cur.i << 16) | cur.j, lane);
+        vmask_cur = draw_resolve(p, d, lane, cur.c, cur.o, neg_cur);
+    }
+    bool ok_nxt = next_pair(walk, L, W, scan);
+    PairCursor nxt = scan;
+    Draw draw_nxt = draw_issue(p, wid_lo, wid_hi, (nxt.i << 16) | nxt.j, lane);
+
+    float4 h[CH], acc[CH];
+    uint32_t loaded = 0xFFFFFFFFu;  // position of the centre whose row is in h
+    float lr = p.lr;
+    while (ok_cur) {
+        // site s+1: ids are here by now; prefetch its rows into L2
+        uint32_t neg_nxt = PAD, vmask_nxt = 0;
+        if (ok_nxt) {
+            vmask_nxt = draw_resolve(p, draw_nxt, lane, nxt.c, nxt.o, neg_nxt);
+            prefetch_site(p, lane, nxt.o, neg_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
+        }
+        // site s+2: start its draw
+        const bool ok_far = ok_nxt && next_pair(walk, L, W, scan);
+        const PairCursor far = scan;
+        Draw draw_far = draw_nxt;
+        if (ok_far) draw_far = draw_issue(p, wid_lo, wid_hi, (far.i << 16) | far.j, lane);
+
+        // site s: train the pair
+        float *crow = p.t0 + (uint64_t)cur.c * p.row_stride;
+        if (loaded != cur.i) {
+            load_row<CH>(crow, chunks, lane, h);
+            lr = centre_lr(p, cur.c);
+            loaded = cur.i;
+        }
+        zero_rows<CH>(acc);
+        apply_targets<CH, NT>(p, chunks, lane, h, lr, cur.o, neg_cur, vmask_cur, acc, loss_acc,
+                              n_targets);
+        add_rows<CH>(h, acc);
+        ++n_pairs;
+        if (!ok_nxt || nxt.i != cur.i) store_row<CH>(crow, chunks, lane, h);
+
+        cur = nxt; neg_cur = neg_nxt; vmask_cur = vmask_nxt; ok_cur = ok_nxt;
+        nxt = far; draw_nxt = draw_far; ok_nxt = ok_far;
     }
 }
 
-template <int CH>
-__device__ __forceinline__ void zero_rows(float4 (&a)[CH]) {
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) a[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+// ---- CBOW: the draw sites of a walk are its centres ----
+// next centre position >= i with at least one valid context; returns L when exhausted
+__device__ __forceinline__ uint32_t next_centre(const uint32_t *__restrict__ walk, uint32_t L,
+                                                uint32_t W, uint32_t i, uint32_t &c) {
+    for (; i < L; ++i) {
+        c = __ldg(walk + i);
+        if (c == PAD) return L;
+        const uint32_t lo = i > W ? i - W : 0u;
+        const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+        for (uint32_t j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            const uint32_t o = __ldg(walk + j);
+            if (o != PAD && o != c) return i;
+        }
+    }
+    return L;
 }
 
-__device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre) {
-    if (!p.normalize_lr) return p.lr;
-    const uint32_t deg = (uint32_t)(__ldg(p.indptr + centre + 1) - __ldg(p.indptr + centre));
-    return __fdiv_rn(p.lr, (float)deg);
-}
-
-template <int MODEL, int CH, int NT>
-__global__ void __launch_bounds__(256) train_kernel(const TrainParams p) {
-    const uint32_t lane = threadIdx.x & 31u;
+template <int CH, int NT>
+__device__ __forceinline__ void cbow_walk(const TrainParams &p, const uint32_t *walk, uint64_t wid,
+                                          uint32_t lane, float &loss_acc, unsigned long long &n_pairs,
+                                          unsigned long long &n_targets) {
     const uint32_t chunks = p.row_stride >> 2;
     const uint32_t L = p.walk_length, W = p.window;
+    const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+
+    uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
+    uint32_t i_cur = next_centre(walk, L, W, 0, c_cur);
+    if (i_cur >= L) return;
+    uint32_t neg_cur, vmask_cur;
+    {
+        const Draw d = draw_issue(p, wid_lo, wid_hi, (i_cur << 16) | 0xFFFFu, lane);
+        vmask_cur = draw_resolve(p, d, lane, c_cur, c_cur, neg_cur);
+    }
+    uint32_t i_nxt = next_centre(walk, L, W, i_cur + 1, c_nxt);
+    Draw draw_nxt = draw_issue(p, wid_lo, wid_hi, (i_nxt << 16) | 0xFFFFu, lane);
+
+    while (i_cur < L) {
+        uint32_t neg_nxt = PAD, vmask_nxt = 0;
+        if (i_nxt < L) {
+            vmask_nxt = draw_resolve(p, draw_nxt, lane, c_nxt, c_nxt, neg_nxt);
+            // the context rows of the next centre are this centre's neighbours (hot) except the
+            // one entering the window
+            const uint32_t entering = i_nxt + W < L ? __ldg(walk + i_nxt + W) : PAD;
+            prefetch_site(p, lane, c_nxt, neg_nxt, vmask_nxt, entering);
+        }
+        const uint32_t i_far = i_nxt < L ? next_centre(walk, L, W, i_nxt + 1, c_far) : L;
+        Draw draw_far = draw_nxt;
+        if (i_far < L) draw_far = draw_issue(p, wid_lo, wid_hi, (i_far << 16) | 0xFFFFu, lane);
+
+        const uint32_t i = i_cur, c = c_cur;
+        const float lr = centre_lr(p, c);
+        const uint32_t lo = i > W ? i - W : 0u;
+        const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+        float4 h[CH], acc[CH], row[CH];
+        uint32_t m = 0;
+        for (uint32_t j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            const uint32_t o = __ldg(walk + j);
+            if (o == PAD || o == c) continue;
+            if (m == 0) {
+                load_row<CH>(p.t0 + (uint64_t)o * p.row_stride, chunks, lane, h);
+            } else {
+                load_row<CH>(p.t0 + (uint64_t)o * p.row_stride, chunks, lane, row);
+                add_rows<CH>(h, row);
+            }
+            ++m;
+        }
+        const float fm = (float)m;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+            h[ch].x = __fdiv_rn(h[ch].x, fm);
+            h[ch].y = __fdiv_rn(h[ch].y, fm);
+            h[ch].z = __fdiv_rn(h[ch].z, fm);
+            h[ch].w = __fdiv_rn(h[ch].w, fm);
+        }
+        zero_rows<CH>(acc);
+        apply_targets<CH, NT>(p, chunks, lane, h, lr, c, neg_cur, vmask_cur, acc, loss_acc,
+                              n_targets);
+        for (uint32_t j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            const uint32_t o = __ldg(walk + j);
+            if (o == PAD || o == c) continue;
+            float *orow = p.t0 + (uint64_t)o * p.row_stride;
+            load_row<CH>(orow, chunks, lane, row);
+            add_rows<CH>(row, acc);
+            store_row<CH>(orow, chunks, lane, row);
+        }
+        n_pairs += m;
+
+        i_cur = i_nxt; c_cur = c_nxt; neg_cur = neg_nxt; vmask_cur = vmask_nxt;
+        i_nxt = i_far; c_nxt = c_far; draw_nxt = draw_far;
+    }
+}
+
+template <int MODEL, int CH, int NT, int OCC>
+__global__ void __launch_bounds__(256, OCC) train_kernel(const TrainParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
     float loss_acc = 0.0f;
     unsigned long long n_pairs = 0, n_targets = 0;
-
     for (;;) {
         unsigned long long w = 0;
         if (lane == 0) w = atomicAdd(&p.counters->work_counter, 1ull);
         w = __shfl_sync(FULL, w, 0);
         if (w >= p.n_walks) break;
         const uint64_t wid = p.first_walk + w * p.walk_id_stride;
-        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
-        const uint32_t *walk = p.walks + w * (uint64_t)L;
-
-        for (uint32_t i = 0; i < L; ++i) {
-            const uint32_t c = __ldg(walk + i);
-            if (c == PAD) break;
-            const float lr = centre_lr(p, c);
-            const uint32_t lo = i > W ? i - W : 0u;
-            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
-            float4 h[CH], acc[CH];
-            if (MODEL == B2E_SKIPGRAM) {
-                float *crow = p.t0 + (uint64_t)c * p.row_stride;
-                load_row<CH>(crow, chunks, lane, h);
-                for (uint32_t j = lo; j <= hi; ++j) {
-                    if (j == i) continue;
-                    const uint32_t o = __ldg(walk + j);
-                    if (o == PAD || o == c) continue;
-                    uint32_t neg;
-                    const bool valid = draw_negative(p, wid_lo, wid_hi, (i << 16) | j, lane, c, o, neg);
-                    const uint32_t vmask = (__ballot_sync(FULL, valid) << 1) | 1u;
-                    zero_rows<CH>(acc);
-                    apply_targets<CH, NT>(p, chunks, lane, h, lr, o, neg, vmask, acc, loss_acc,
-                                          n_targets);
-                    add_rows<CH>(h, acc);
-                    ++n_pairs;
-                }
-                store_row<CH>(crow, chunks, lane, h);
-            } else {
-                uint32_t m = 0;
-                float4 row[CH];
-                for (uint32_t j = lo; j <= hi; ++j) {
-                    if (j == i) continue;
-                    const uint32_t o = __ldg(walk + j);
-                    if (o == PAD || o == c) continue;
-                    if (m == 0) {
-                        load_row<CH>(p.t0 + (uint64_t)o * p.row_stride, chunks, lane, h);
-                    } else {
-                        load_row<CH>(p.t0 + (uint64_t)o * p.row_stride, chunks, lane, row);
-                        add_rows<CH>(h, row);
-                    }
-                    ++m;
-                }
-                if (m == 0) continue;
-                const float fm = (float)m;
-#pragma unroll
-                for (int ch = 0; ch < CH; ++ch) {
-                    h[ch].x = __fdiv_rn(h[ch].x, fm);
-                    h[ch].y = __fdiv_rn(h[ch].y, fm);
-                    h[ch].z = __fdiv_rn(h[ch].z, fm);
-                    h[ch].w = __fdiv_rn(h[ch].w, fm);
-                }
-                uint32_t neg;
-                const bool valid = draw_negative(p, wid_lo, wid_hi, (i << 16) | 0xFFFFu, lane, c, c, neg);
-                const uint32_t vmask = (__ballot_sync(FULL, valid) << 1) | 1u;
-                zero_rows<CH>(acc);
-                apply_targets<CH, NT>(p, chunks, lane, h, lr, c, neg, vmask, acc, loss_acc,
-                                      n_targets);
-                for (uint32_t j = lo; j <= hi; ++j) {
-                    if (j == i) continue;
-                    const uint32_t o = __ldg(walk + j);
-                    if (o == PAD || o == c) continue;
-                    float *orow = p.t0 + (uint64_t)o * p.row_stride;
-                    load_row<CH>(orow, chunks, lane, row);
-                    add_rows<CH>(row, acc);
-                    store_row<CH>(orow, chunks, lane, row);
-                }
-                n_pairs += m;
-            }
-        }
+        const uint32_t *walk = p.walks + w * (uint64_t)p.walk_length;
+        if (MODEL == B2E_SKIPGRAM)
+            skipgram_walk<CH, NT>(p, walk, wid, lane, loss_acc, n_pairs, n_targets);
+        else
+            cbow_walk<CH, NT>(p, walk, wid, lane, loss_acc, n_pairs, n_targets);
     }
     double loss = (double)loss_acc;
 #pragma unroll
@@ -280,24 +382,25 @@ __global__ void __launch_bounds__(256) train_kernel(const TrainParams p) {
     }
 }
 
-template <int MODEL, int CH, int NT>
+template <int MODEL, int CH, int NT, int OCC>
 static cudaError_t launch_one(const TrainParams &p, bool deterministic, int sm_count,
                               cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     if (deterministic) {
-        train_kernel<MODEL, CH, NT><<<1, 32, 0, stream>>>(p);
+        train_kernel<MODEL, CH, NT, OCC><<<1, 32, 0, stream>>>(p);
         return cudaGetLastError();
     }
     const int block = 256;
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_kernel<MODEL, CH, NT>, block, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_kernel<MODEL, CH, NT, OCC>,
+                                                        block, 0);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
-    uint64_t grid = (uint64_t)sm_count * per_sm;
+    uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: every CTA resident, walks fetched
     const uint64_t needed = (p.n_walks + 7) / 8;
     if (grid > needed) grid = needed;
-    train_kernel<MODEL, CH, NT><<<(unsigned)grid, block, 0, stream>>>(p);
+    train_kernel<MODEL, CH, NT, OCC><<<(unsigned)grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -306,17 +409,28 @@ static cudaError_t launch_model(const TrainParams &p, bool deterministic, int sm
                                 cudaStream_t stream) {
     const uint32_t chunks = p.row_stride >> 2;
     if (chunks <= 32) {
-        if (p.negatives + 1 <= 6) return launch_one<MODEL, 1, 6>(p, deterministic, sm_count, stream);
-        return launch_one<MODEL, 1, 11>(p, deterministic, sm_count, stream);
+        // tuning variants (rows per load batch x resident CTAs per SM), B2E_VARIANT selects
+        switch (p.variant) {
+            case 1: return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, stream);
+            case 2: return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, stream);
+            case 3: return launch_one<MODEL, 1, 6, 4>(p, deterministic, sm_count, stream);
+            case 4: return launch_one<MODEL, 1, 4, 4>(p, deterministic, sm_count, stream);
+            default: break;
+        }
+        if (p.negatives + 1 <= 6) return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, stream);
+        return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, stream);
     }
-    if (chunks <= 64) return launch_one<MODEL, 2, 6>(p, deterministic, sm_count, stream);
-    if (chunks <= 128) return launch_one<MODEL, 4, 3>(p, deterministic, sm_count, stream);
+    if (chunks <= 64) return launch_one<MODEL, 2, 6, 2>(p, deterministic, sm_count, stream);
+    if (chunks <= 128) return launch_one<MODEL, 4, 3, 2>(p, deterministic, sm_count, stream);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                          cudaStream_t stream) {
     if (p.n_walks == 0) return cudaSuccess;
+    // production path: shared-memory pipelined kernel; B2E_VARIANT >= 1 keeps the register path
+    if (p.variant == 0 && pipe_supported(p, model))
+        return launch_skipgram_pipe(p, deterministic, sm_count, stream);
     if (model == B2E_SKIPGRAM) return launch_model<B2E_SKIPGRAM>(p, deterministic, sm_count, stream);
     return launch_model<B2E_CBOW>(p, deterministic, sm_count, stream);
 }

@@ -78,6 +78,8 @@ typedef struct b2e_handle b2e_handle;
 
 const char *b2e_last_error(void);
 int b2e_abi_version(void);
+/* number of visible devices this library can run on (compute capability >= 10.0); 0 if none */
+int b2e_device_count(void);
 
 int b2e_create(const b2e_config *config, b2e_handle **out);
 void b2e_destroy(b2e_handle *handle);

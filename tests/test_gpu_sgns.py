@@ -90,7 +90,7 @@ def test_deterministic_options(rmat_graph, model):
 
 
 @pytest.mark.parametrize("model,D", [("SkipGram", 100), ("CBOW", 128)])
-def test_hogwild_tracks_oracle(small_ppi, model, D):
+def test_hogwild_tracks_oracle(small_ppi, model, D):  # 2 iterations of 1064 start nodes
     """Production launch (all SMs, racy updates): same pair/target counts, loss within 2 %."""
     r = run_pair(small_ppi, model, D, 128, 4, 10, 0.25, 4.0, n_walks=2128, deterministic=False)
     assert r["counters"]["pairs"] == r["stats"]["pairs"]
