@@ -42,6 +42,9 @@ CONFIGS = {
     "small_n2v": dict(graph=("rmat", 17, 1_000_000, 100_000), model="SkipGram", embedding_size=100,
                       return_weight=2.0, explore_weight=0.5, iterations=1,
                       label="Node2Vec SkipGram p=0.5 q=2, R-MAT 100k nodes / 1M edges (REDUCED)"),
+    "small_cbow": dict(graph=("rmat", 17, 1_000_000, 100_000), model="CBOW", embedding_size=128,
+                       return_weight=0.5, explore_weight=2.0, iterations=1,
+                       label="Node2Vec CBOW p=2 q=0.5, R-MAT 100k nodes / 1M edges, dim=128 (REDUCED)"),
 }
 COMMON = dict(walk_length=128, window_size=4, number_of_negative_samples=10, learning_rate=0.01,
               learning_rate_decay=0.9, clipping_value=6.0)

@@ -40,6 +40,7 @@ class B2EConfig(ctypes.Structure):
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("deterministic", ctypes.c_uint32),
         ("chunk_walks", ctypes.c_uint32),
+        ("max_concurrent_walks", ctypes.c_uint32),
         ("device", ctypes.c_int32),
     ]
 

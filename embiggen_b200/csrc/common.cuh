@@ -64,7 +64,8 @@ struct TrainParams {
     uint32_t seed_lo, seed_hi;
     uint32_t n;
     uint32_t walk_length, window, negatives;
-    uint32_t row_stride;  // floats, multiple of 4
+    uint32_t row_stride;  // floats between rows in HBM: rows start on 128 B lines
+    uint32_t chunks;      // float4 chunks of a row that hold data: ceil(embedding_size / 4)
     float clip, lr, inv_scale;
     uint32_t use_alias, normalize_lr, scale_dot;
     uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
@@ -78,11 +79,12 @@ struct TrainParams {
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
                                uint32_t row_stride, uint64_t seed, cudaStream_t stream);
+// max_warps caps how many walks are trained concurrently (Hogwild staleness on small graphs)
 cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
-                         cudaStream_t stream);
+                         uint64_t max_warps, cudaStream_t stream);
 bool pipe_supported(const TrainParams &p, uint32_t model);
-cudaError_t launch_skipgram_pipe(const TrainParams &p, bool deterministic, int sm_count,
-                                 cudaStream_t stream);
+cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
+                              uint64_t max_warps, cudaStream_t stream);
 cudaError_t launch_pack_rows(const float *src, float *dst, uint64_t n, uint32_t embedding_size,
                              uint32_t row_stride, bool strip, cudaStream_t stream);
 

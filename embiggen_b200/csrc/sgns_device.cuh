@@ -37,14 +37,16 @@ struct PairCursor {
     uint32_t hi;    // last window position of centre i
 };
 
-// advance to the next pair of the walk; false when the walk is exhausted
+// advance to the next pair of the walk; false when the walk is exhausted.  STAGED: `walk` is a
+// shared-memory copy of the walk (plain loads) instead of global memory (read-only path).
+template <bool STAGED = false>
 __device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uint32_t L, uint32_t W,
                                           PairCursor &s) {
     for (;;) {
         if (s.i == 0xFFFFFFFFu || s.j >= s.hi) {
             const uint32_t i = s.i + 1u;  // wraps 0xFFFFFFFF -> 0
             if (i >= L) return false;
-            const uint32_t c = __ldg(walk + i);
+            const uint32_t c = STAGED ? walk[i] : __ldg(walk + i);
             if (c == PAD) return false;
             s.i = i;
             s.c = c;
@@ -54,10 +56,29 @@ __device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uin
             ++s.j;
         }
         if (s.j == s.i) continue;
-        s.o = __ldg(walk + s.j);
+        s.o = STAGED ? walk[s.j] : __ldg(walk + s.j);
         if (s.o == PAD || s.o == s.c) continue;
         return true;
     }
+}
+
+// ---- CBOW: the draw sites of a walk are its centres ----
+// next centre position >= i with at least one valid context; returns L when exhausted
+template <bool STAGED = false>
+__device__ __forceinline__ uint32_t next_centre(const uint32_t *__restrict__ walk, uint32_t L,
+                                                uint32_t W, uint32_t i, uint32_t &c) {
+    for (; i < L; ++i) {
+        c = STAGED ? walk[i] : __ldg(walk + i);
+        if (c == PAD) return L;
+        const uint32_t lo = i > W ? i - W : 0u;
+        const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+        for (uint32_t j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            const uint32_t o = STAGED ? walk[j] : __ldg(walk + j);
+            if (o != PAD && o != c) return i;
+        }
+    }
+    return L;
 }
 
 }  // namespace b2e

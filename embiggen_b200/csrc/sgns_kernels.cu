@@ -19,6 +19,8 @@
 // intrinsics, a fixed reduction order and a polynomial sigmoid, so a single-warp launch
 // (cfg.deterministic) reproduces the CPU oracle's tables bit for bit.  Prefetches never
 // change a value, so both launches run the same code.
+#include <algorithm>
+
 #include "sgns_device.cuh"
 
 namespace b2e {
@@ -117,7 +119,7 @@ __device__ __forceinline__ uint32_t draw_resolve(const TrainParams &p, const Dra
 __device__ __forceinline__ void prefetch_site(const TrainParams &p, uint32_t lane, uint32_t first,
                                               uint32_t neg, uint32_t vmask, uint32_t extra) {
     if (p.prefetch == 0) return;
-    const uint32_t row_bytes = p.row_stride * 4u;
+    const uint32_t row_bytes = p.chunks * 16u;
     const uint32_t slots = p.negatives + 2u;
     for (uint32_t first_t = 0; first_t < slots * 5u; first_t += 32u) {  // warp-uniform trip count
         const uint32_t t = first_t + lane;
@@ -206,7 +208,7 @@ __device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32
                                               uint32_t lane, float &loss_acc,
                                               unsigned long long &n_pairs,
                                               unsigned long long &n_targets) {
-    const uint32_t chunks = p.row_stride >> 2;
+    const uint32_t chunks = p.chunks;
     const uint32_t L = p.walk_length, W = p.window;
     const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
 
@@ -260,29 +262,11 @@ __device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32
     }
 }
 
-// ---- CBOW: the draw sites of a walk are its centres ----
-// next centre position >= i with at least one valid context; returns L when exhausted
-__device__ __forceinline__ uint32_t next_centre(const uint32_t *__restrict__ walk, uint32_t L,
-                                                uint32_t W, uint32_t i, uint32_t &c) {
-    for (; i < L; ++i) {
-        c = __ldg(walk + i);
-        if (c == PAD) return L;
-        const uint32_t lo = i > W ? i - W : 0u;
-        const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
-        for (uint32_t j = lo; j <= hi; ++j) {
-            if (j == i) continue;
-            const uint32_t o = __ldg(walk + j);
-            if (o != PAD && o != c) return i;
-        }
-    }
-    return L;
-}
-
 template <int CH, int NT>
 __device__ __forceinline__ void cbow_walk(const TrainParams &p, const uint32_t *walk, uint64_t wid,
                                           uint32_t lane, float &loss_acc, unsigned long long &n_pairs,
                                           unsigned long long &n_targets) {
-    const uint32_t chunks = p.row_stride >> 2;
+    const uint32_t chunks = p.chunks;
     const uint32_t L = p.walk_length, W = p.window;
     const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
 
@@ -384,7 +368,7 @@ __global__ void __launch_bounds__(256, OCC) train_kernel(const TrainParams p) {
 
 template <int MODEL, int CH, int NT, int OCC>
 static cudaError_t launch_one(const TrainParams &p, bool deterministic, int sm_count,
-                              cudaStream_t stream) {
+                              uint64_t max_warps, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     if (deterministic) {
@@ -398,41 +382,42 @@ static cudaError_t launch_one(const TrainParams &p, bool deterministic, int sm_c
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: every CTA resident, walks fetched
-    const uint64_t needed = (p.n_walks + 7) / 8;
+    const uint64_t needed = (std::min<uint64_t>(p.n_walks, max_warps) + 7) / 8;
     if (grid > needed) grid = needed;
+    if (grid < 1) grid = 1;
     train_kernel<MODEL, CH, NT, OCC><<<(unsigned)grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int MODEL>
 static cudaError_t launch_model(const TrainParams &p, bool deterministic, int sm_count,
-                                cudaStream_t stream) {
-    const uint32_t chunks = p.row_stride >> 2;
+                                uint64_t max_warps, cudaStream_t stream) {
+    const uint32_t chunks = p.chunks;
     if (chunks <= 32) {
         // tuning variants (rows per load batch x resident CTAs per SM), B2E_VARIANT selects
         switch (p.variant) {
-            case 1: return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, stream);
-            case 2: return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, stream);
-            case 3: return launch_one<MODEL, 1, 6, 4>(p, deterministic, sm_count, stream);
-            case 4: return launch_one<MODEL, 1, 4, 4>(p, deterministic, sm_count, stream);
+            case 1: return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, max_warps, stream);
+            case 2: return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, max_warps, stream);
+            case 3: return launch_one<MODEL, 1, 6, 4>(p, deterministic, sm_count, max_warps, stream);
+            case 4: return launch_one<MODEL, 1, 4, 4>(p, deterministic, sm_count, max_warps, stream);
             default: break;
         }
-        if (p.negatives + 1 <= 6) return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, stream);
-        return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, stream);
+        if (p.negatives + 1 <= 6) return launch_one<MODEL, 1, 6, 3>(p, deterministic, sm_count, max_warps, stream);
+        return launch_one<MODEL, 1, 11, 2>(p, deterministic, sm_count, max_warps, stream);
     }
-    if (chunks <= 64) return launch_one<MODEL, 2, 6, 2>(p, deterministic, sm_count, stream);
-    if (chunks <= 128) return launch_one<MODEL, 4, 3, 2>(p, deterministic, sm_count, stream);
+    if (chunks <= 64) return launch_one<MODEL, 2, 6, 2>(p, deterministic, sm_count, max_warps, stream);
+    if (chunks <= 128) return launch_one<MODEL, 4, 3, 2>(p, deterministic, sm_count, max_warps, stream);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
-                         cudaStream_t stream) {
+                         uint64_t max_warps, cudaStream_t stream) {
     if (p.n_walks == 0) return cudaSuccess;
     // production path: shared-memory pipelined kernel; B2E_VARIANT >= 1 keeps the register path
     if (p.variant == 0 && pipe_supported(p, model))
-        return launch_skipgram_pipe(p, deterministic, sm_count, stream);
-    if (model == B2E_SKIPGRAM) return launch_model<B2E_SKIPGRAM>(p, deterministic, sm_count, stream);
-    return launch_model<B2E_CBOW>(p, deterministic, sm_count, stream);
+        return launch_train_pipe(p, model, deterministic, sm_count, max_warps, stream);
+    if (model == B2E_SKIPGRAM) return launch_model<B2E_SKIPGRAM>(p, deterministic, sm_count, max_warps, stream);
+    return launch_model<B2E_CBOW>(p, deterministic, sm_count, max_warps, stream);
 }
 
 // ---- table initialisation: one thread per float4 chunk ----

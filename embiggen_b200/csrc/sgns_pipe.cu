@@ -16,12 +16,16 @@
 //                  train pair p out of stage p&1: dots (LDS.128 + transposed warp reduction),
 //                  sigmoid, axpy, rows scattered to global with 128-bit stores (Hogwild)
 //
-// A row of pair p+1 that pair p is about to update (repeated context, a negative equal to a
-// neighbour) would be copied stale; such pairs are detected (one MATCH over the two id sets)
-// and their copies are issued after pair p's stores instead.  Lane l copies, reads and stores
-// chunk l of every row, so no cross-lane shared-memory hazard exists and the deterministic
-// single-warp launch reproduces the CPU oracle bit for bit: the additions of the transposed
-// reduction are the same additions, in the same order, as the oracle's xor-butterfly.
+// The walk itself is staged in shared memory once (its tokens are re-read 2W+1 times each on
+// the critical path of the pair cursor).  A row of pair p+1 that pair p is about to update
+// (repeated context, a negative equal to a neighbour) would be copied stale; such pairs are
+// detected (one MATCH over the two id sets) and their copies are issued after pair p's stores
+// instead.  Lane l copies, reads and stores chunk l of every row, so no cross-lane
+// shared-memory hazard exists on the rows, and the deterministic single-warp launch
+// reproduces the CPU oracle bit for bit: the additions of the transposed reduction are the
+// same additions, in the same order, as the oracle's xor-butterfly.
+#include <algorithm>
+
 #include "sgns_device.cuh"
 
 namespace b2e {
@@ -42,9 +46,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ float4 lds128(const float *smem) {
     return *reinterpret_cast<const float4 *>(smem);
 }
-__device__ __forceinline__ void stg128(float *gmem, const float4 &v) {
-    *reinterpret_cast<float4 *>(gmem) = v;
-}
 
 // Sum 16 per-lane partials over the 32 lanes.  Level `off` pairs lane l with l^off exactly like
 // an xor-butterfly, but each lane keeps only half of the values it holds, so 16 shuffles do the
@@ -63,14 +64,30 @@ __device__ __forceinline__ float reduce16(float (&v)[16], uint32_t lane) {
     return __fadd_rn(v[0], __shfl_xor_sync(FULL, v[0], 1));
 }
 
-struct PipeSmem {  // per-warp carve-up of dynamic shared memory, two stages of each
-    float *rows_base;      // [2][slots + 1][row_stride]: target rows, then the centre row of T0
-    uint2 *alias_base;     // [2][32] alias entries of a draw in flight
-    uint32_t *ids_base;    // [2][PIPE_SLOTS] target id per slot (sentinel when the slot is off)
-    uint32_t stage_floats;
+// per-warp carve-up of dynamic shared memory; everything exists in two stages
+struct PipeSmem {
+    float *rows_base;    // [2][K + 2][row_stride]: target rows, then the centre row of T0
+    uint2 *alias_base;   // [2][32] alias entries of a draw in flight
+    uint32_t *ids_base;  // [2][PIPE_SLOTS] target id per slot (sentinel when the slot is off)
+    uint32_t *walk;      // [walk_length rounded up to 32] the warp's current walk
+    uint32_t stage_floats, pitch;  // floats per stage / per staged row
     __device__ __forceinline__ float *rows(uint32_t stage) const { return rows_base + stage * stage_floats; }
     __device__ __forceinline__ uint2 *alias(uint32_t a) const { return alias_base + a * 32u; }
     __device__ __forceinline__ uint32_t *ids(uint32_t stage) const { return ids_base + stage * PIPE_SLOTS; }
+};
+
+// `chunks` float4 per row are staged (dense pitch in shared memory, 128 B-aligned pitch in HBM)
+__host__ __device__ __forceinline__ uint32_t pipe_warp_bytes(uint32_t negatives, uint32_t chunks,
+                                                             uint32_t walk_length) {
+    return 2u * (negatives + 2u) * chunks * 16u + 2u * 32u * 8u + 2u * PIPE_SLOTS * 4u +
+           ((walk_length + 31u) & ~31u) * 4u;
+}
+
+// what a thread needs to address its 16 B chunk of any row
+struct LaneView {
+    const char *t0, *t1;  // table bases advanced by 16 * lane bytes
+    uint64_t row_bytes;
+    bool active;          // lane < chunks
 };
 
 // ids of the targets of a pair, one per lane: lane 0 = context, lane k+1 = negative k;
@@ -82,42 +99,121 @@ __device__ __forceinline__ uint32_t slot_ids(uint32_t lane, uint32_t context, ui
     return ((vmask >> lane) & 1u) ? id : (0xFFFFFF00u | lane);
 }
 
-__device__ __forceinline__ void issue_rows(const TrainParams &p, const PipeSmem &sm, uint32_t stage,
-                                           uint32_t lane, uint32_t chunks, uint32_t my_id,
+// KP1 = K + 1 when known at compile time (0: runtime, up to PIPE_SLOTS); ALL: every slot is on
+template <int KP1, bool ALL>
+__device__ __forceinline__ void issue_rows(const TrainParams &p, const PipeSmem &sm, const LaneView &v,
+                                           uint32_t stage, uint32_t lane, uint32_t my_id,
                                            uint32_t vmask, uint32_t centre_or_pad) {
     if (lane < PIPE_SLOTS) sm.ids(stage)[lane] = my_id;
     __syncwarp();  // ids are read back by every lane when the pair is trained
     float *dst = sm.rows(stage) + 4u * lane;
-    const uint32_t K = p.negatives;
+    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
+    constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
 #pragma unroll
-    for (int s = 0; s < PIPE_SLOTS; ++s) {
-        if (s <= (int)K && ((vmask >> s) & 1u)) {
+    for (int s = 0; s < S; ++s) {
+        if ((uint32_t)s < slots && (ALL || ((vmask >> s) & 1u))) {
             const uint32_t id = __shfl_sync(FULL, my_id, s);
-            if (lane < chunks)
-                cp_async16(dst + (uint32_t)s * p.row_stride,
-                           p.t1 + (uint64_t)id * p.row_stride + 4u * lane);
+            if (v.active) cp_async16(dst + (uint32_t)s * sm.pitch, v.t1 + id * v.row_bytes);
         }
     }
-    if (centre_or_pad != PAD && lane < chunks)
-        cp_async16(dst + (K + 1u) * p.row_stride,
-                   p.t0 + (uint64_t)centre_or_pad * p.row_stride + 4u * lane);
+    if (centre_or_pad != PAD && v.active)
+        cp_async16(dst + slots * sm.pitch, v.t0 + centre_or_pad * v.row_bytes);
 }
 
+// dots, sigmoid, axpy and scatter of the targets of one draw site out of stage `stage`;
+// returns this lane's chunk of sum g * row (rows as they were before the update)
+template <int KP1, bool ALL>
+__device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSmem &sm, const LaneView &v,
+                                             uint32_t stage, uint32_t lane, uint32_t vmask, float lr,
+                                             const float4 &h, float &loss_acc) {
+    const float *rows = sm.rows(stage) + 4u * lane;
+    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
+    constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
+    float part[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        float d = 0.0f;
+        if (s < S && (uint32_t)s < slots && (ALL || ((vmask >> s) & 1u))) {
+            if (v.active) {
+                const float4 r = lds128(rows + (uint32_t)s * sm.pitch);
+                d = __fmaf_rn(h.x, r.x, d);
+                d = __fmaf_rn(h.y, r.y, d);
+                d = __fmaf_rn(h.z, r.z, d);
+                d = __fmaf_rn(h.w, r.w, d);
+            }
+        }
+        part[s] = d;
+    }
+    float f = reduce16(part, lane);  // lane l: score of slot (l >> 1) & 15
+    if (p.scale_dot) f = __fmul_rn(f, p.inv_scale);
+    const uint32_t my_slot = (lane >> 1) & 15u;
+    const bool my_on = (vmask >> my_slot) & 1u;  // vmask has no bit above K
+    float g_mine = 0.0f;
+    bool apply = false;
+    if (my_on && !(fabsf(f) > p.clip)) {
+        const float e = exp_det(-f);
+        const float sigmoid = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+        g_mine = __fmul_rn(__fsub_rn(my_slot == 0 ? 1.0f : 0.0f, sigmoid), lr);
+        // -log sigmoid(f) = log(1 + e^-f);  -log sigmoid(-f) = log(1 + e^-f) + f
+        if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e) + (my_slot == 0 ? 0.0f : f);
+        apply = true;
+    }
+    const uint32_t amask = __ballot_sync(FULL, apply);  // bits 2s, 2s+1: slot s is applied
+    constexpr uint32_t all_bits = KP1 >= 16 ? FULL : ((1u << (2 * (KP1 ? KP1 : 1))) - 1u);
+    const bool all_applied = KP1 != 0 && ALL && amask == all_bits;
+    const uint32_t *ids = sm.ids(stage);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (all_applied || ((amask >> (2 * s)) & 1u)) {
+            const float g = __shfl_sync(FULL, g_mine, 2 * s);
+            const uint32_t id = ids[s];
+            if (v.active) {
+                float4 r = lds128(rows + (uint32_t)s * sm.pitch);
+                acc.x = __fmaf_rn(g, r.x, acc.x);
+                acc.y = __fmaf_rn(g, r.y, acc.y);
+                acc.z = __fmaf_rn(g, r.z, acc.z);
+                acc.w = __fmaf_rn(g, r.w, acc.w);
+                r.x = __fmaf_rn(g, h.x, r.x);
+                r.y = __fmaf_rn(g, h.y, r.y);
+                r.z = __fmaf_rn(g, h.z, r.z);
+                r.w = __fmaf_rn(g, h.w, r.w);
+                *reinterpret_cast<float4 *>(const_cast<char *>(v.t1) + id * v.row_bytes) = r;
+            }
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) {
+    a.x = __fadd_rn(a.x, b.x);
+    a.y = __fadd_rn(a.y, b.y);
+    a.z = __fadd_rn(a.z, b.z);
+    a.w = __fadd_rn(a.w, b.w);
+}
+
+template <int KP1>
 __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t chunks = p.row_stride >> 2;
-    const uint32_t K = p.negatives, L = p.walk_length, W = p.window;
-    const uint32_t stage_floats = (K + 2u) * p.row_stride;
-    const uint32_t warp_bytes = 2u * stage_floats * 4u + 2u * 32u * 8u + 2u * PIPE_SLOTS * 4u;
+    const uint32_t K = KP1 ? (uint32_t)(KP1 - 1) : p.negatives;
+    const uint32_t L = p.walk_length, W = p.window;
+    const uint32_t full_mask = (2u << K) - 1u;  // K + 1 ones
     PipeSmem sm;
     {
-        unsigned char *base = smem_raw + warp * warp_bytes;
-        sm.stage_floats = stage_floats;
+        unsigned char *base = smem_raw + warp * pipe_warp_bytes(K, p.chunks, L);
+        sm.pitch = p.chunks * 4u;
+        sm.stage_floats = (K + 2u) * sm.pitch;
         sm.rows_base = reinterpret_cast<float *>(base);
-        sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * stage_floats);
+        sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * sm.stage_floats);
         sm.ids_base = reinterpret_cast<uint32_t *>(sm.alias_base + 64);
+        sm.walk = sm.ids_base + 2 * PIPE_SLOTS;
     }
+    LaneView v;
+    v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
+    v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
+    v.row_bytes = (uint64_t)p.row_stride * 4u;
+    v.active = lane < p.chunks;
     float loss_acc = 0.0f;
     unsigned long long n_pairs = 0, n_targets = 0;
 
@@ -128,7 +224,13 @@ __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams
         if (w >= p.n_walks) break;
         const uint64_t wid = p.first_walk + w * p.walk_id_stride;
         const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
-        const uint32_t *walk = p.walks + w * (uint64_t)L;
+        {
+            const uint32_t *src = p.walks + w * (uint64_t)L;
+            __syncwarp();
+            for (uint32_t t = lane; t < L; t += 32u) sm.walk[t] = __ldg(src + t);
+            __syncwarp();
+        }
+        const uint32_t *walk = sm.walk;
 
         // draw of a site: proposal + second word stay in registers, the alias entry lands in
         // shared memory (slot `a`) through cp.async
@@ -155,23 +257,27 @@ __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams
                                (same & ((1u << lane) - 1u)) == 0u;
             return (__ballot_sync(FULL, valid) << 1) | 1u;
         };
+        auto issue = [&](uint32_t stage, uint32_t ids, uint32_t vmask, uint32_t centre_or_pad) {
+            if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, centre_or_pad);
+            else issue_rows<KP1, false>(p, sm, v, stage, lane, ids, vmask, centre_or_pad);
+        };
 
         PairCursor scan;
         scan.i = 0xFFFFFFFFu; scan.j = 0; scan.c = PAD; scan.o = PAD; scan.hi = 0;
-        bool ok_cur = next_pair(walk, L, W, scan);
+        bool ok_cur = next_pair<true>(walk, L, W, scan);
         if (!ok_cur) continue;
         PairCursor cur = scan;
         uint32_t stage = 0, slot_a = 0;
 
         // prologue: pair 0 synchronously, draw of pair 1 in flight
-        uint32_t idx_n, ry_n, neg_cur, vmask_cur, ids_cur;
+        uint32_t idx_n = PAD, ry_n = 0, neg_cur, vmask_cur, ids_cur;
         draw(cur, slot_a, idx_n, ry_n);
         cp_async_commit();
         cp_async_wait_all();
         vmask_cur = resolve(cur, slot_a, idx_n, ry_n, neg_cur);
         ids_cur = slot_ids(lane, cur.o, neg_cur, vmask_cur);
-        issue_rows(p, sm, stage, lane, chunks, ids_cur, vmask_cur, cur.c);
-        bool ok_nxt = next_pair(walk, L, W, scan);
+        issue(stage, ids_cur, vmask_cur, cur.c);
+        bool ok_nxt = next_pair<true>(walk, L, W, scan);
         PairCursor nxt = scan;
         slot_a ^= 1u;
         if (ok_nxt) draw(nxt, slot_a, idx_n, ry_n);
@@ -194,85 +300,33 @@ __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams
                 const uint32_t same = __match_any_sync(FULL, both);
                 deferred = __ballot_sync(FULL, lane < 16u && (same >> 16) != 0u) != 0u ||
                            (nxt.i != cur.i && nxt.c == cur.c);
-                if (!deferred)
-                    issue_rows(p, sm, stage ^ 1u, lane, chunks, ids_nxt, vmask_nxt,
-                               nxt.i != cur.i ? nxt.c : PAD);
+                if (!deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
             }
             // ---- pair p+2: start its draw ----
-            const bool ok_far = ok_nxt && next_pair(walk, L, W, scan);
+            const bool ok_far = ok_nxt && next_pair<true>(walk, L, W, scan);
             const PairCursor far = scan;
             uint32_t idx_f = PAD, ry_f = 0;
             if (ok_far) draw(far, slot_a ^ 1u, idx_f, ry_f);
             cp_async_commit();
 
             // ---- pair p: train out of shared memory ----
-            const float *rows = sm.rows(stage) + 4u * lane;
-            const bool active = lane < chunks;
             if (loaded != cur.i) {
-                h = active ? lds128(rows + (K + 1u) * p.row_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                h = v.active ? lds128(sm.rows(stage) + 4u * lane + (K + 1u) * sm.pitch)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
                 lr = centre_lr(p, cur.c);
                 loaded = cur.i;
             }
-            float part[16];
-#pragma unroll
-            for (int s = 0; s < PIPE_SLOTS; ++s) {
-                float d = 0.0f;
-                if (s <= (int)K && ((vmask_cur >> s) & 1u) && active) {
-                    const float4 r = lds128(rows + (uint32_t)s * p.row_stride);
-                    d = __fmaf_rn(h.x, r.x, d);
-                    d = __fmaf_rn(h.y, r.y, d);
-                    d = __fmaf_rn(h.z, r.z, d);
-                    d = __fmaf_rn(h.w, r.w, d);
-                }
-                part[s] = d;
-            }
-            float f = reduce16(part, lane);  // lane l: score of slot (l >> 1) & 15
-            if (p.scale_dot) f = __fmul_rn(f, p.inv_scale);
-            const uint32_t my_slot = (lane >> 1) & 15u;
-            const bool my_on = (vmask_cur >> my_slot) & 1u;  // vmask has no bit above K
-            float g_mine = 0.0f;
-            bool apply = false;
-            if (my_on && !(fabsf(f) > p.clip)) {
-                const float e = exp_det(-f);
-                const float sigmoid = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-                g_mine = __fmul_rn(__fsub_rn(my_slot == 0 ? 1.0f : 0.0f, sigmoid), lr);
-                // -log sigmoid(f) = log(1 + e^-f);  -log sigmoid(-f) = log(1 + e^-f) + f
-                if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e) + (my_slot == 0 ? 0.0f : f);
-                apply = true;
-            }
-            const uint32_t amask = __ballot_sync(FULL, apply);  // bit 2s: slot s is applied
+            const float4 acc = vmask_cur == full_mask
+                ? train_site<KP1, true>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc)
+                : train_site<KP1, false>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc);
+            add4(h, acc);
             n_targets += __popc(vmask_cur);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int s = 0; s < PIPE_SLOTS; ++s) {
-                if (s <= (int)K && ((amask >> (2 * s)) & 1u)) {
-                    const float g = __shfl_sync(FULL, g_mine, 2 * s);
-                    const uint32_t id = sm.ids(stage)[s];
-                    if (active) {
-                        float4 r = lds128(rows + (uint32_t)s * p.row_stride);
-                        acc.x = __fmaf_rn(g, r.x, acc.x);
-                        acc.y = __fmaf_rn(g, r.y, acc.y);
-                        acc.z = __fmaf_rn(g, r.z, acc.z);
-                        acc.w = __fmaf_rn(g, r.w, acc.w);
-                        r.x = __fmaf_rn(g, h.x, r.x);
-                        r.y = __fmaf_rn(g, h.y, r.y);
-                        r.z = __fmaf_rn(g, h.z, r.z);
-                        r.w = __fmaf_rn(g, h.w, r.w);
-                        stg128(p.t1 + (uint64_t)id * p.row_stride + 4u * lane, r);
-                    }
-                }
-            }
-            h.x = __fadd_rn(h.x, acc.x);
-            h.y = __fadd_rn(h.y, acc.y);
-            h.z = __fadd_rn(h.z, acc.z);
-            h.w = __fadd_rn(h.w, acc.w);
             ++n_pairs;
-            if ((!ok_nxt || nxt.i != cur.i) && active)
-                stg128(p.t0 + (uint64_t)cur.c * p.row_stride + 4u * lane, h);
+            if ((!ok_nxt || nxt.i != cur.i) && v.active)
+                *reinterpret_cast<float4 *>(const_cast<char *>(v.t0) + cur.c * v.row_bytes) = h;
 
             if (deferred) {  // its rows overlap the rows just stored: copy them now
-                issue_rows(p, sm, stage ^ 1u, lane, chunks, ids_nxt, vmask_nxt,
-                           nxt.i != cur.i ? nxt.c : PAD);
+                issue(stage ^ 1u, ids_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
                 cp_async_commit();
             }
             cur = nxt; neg_cur = neg_nxt; vmask_cur = vmask_nxt; ids_cur = ids_nxt; ok_cur = ok_nxt;
@@ -291,38 +345,270 @@ __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams
     }
 }
 
-bool pipe_supported(const TrainParams &p, uint32_t model) {
-    return model == B2E_SKIPGRAM && p.row_stride <= 128u && p.negatives + 1u <= PIPE_SLOTS;
+// ---- K5: CBOW.  A draw site is a centre: its K+1 target rows (T1) ride the same asynchronous
+// pipeline; the <= 2W context rows (T0) were written by this very warp one centre earlier, so
+// they are read synchronously (L2 hits) after the previous scatter, in batches whose loads are
+// issued back to back.  The row entering the window is prefetched into L2 one centre ahead.
+constexpr int CBOW_BATCH = 8;
+
+template <int KP1>
+__global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t K = KP1 ? (uint32_t)(KP1 - 1) : p.negatives;
+    const uint32_t L = p.walk_length, W = p.window;
+    const uint32_t full_mask = (2u << K) - 1u;
+    PipeSmem sm;
+    {
+        unsigned char *base = smem_raw + warp * pipe_warp_bytes(K, p.chunks, L);
+        sm.pitch = p.chunks * 4u;
+        sm.stage_floats = (K + 2u) * sm.pitch;
+        sm.rows_base = reinterpret_cast<float *>(base);
+        sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * sm.stage_floats);
+        sm.ids_base = reinterpret_cast<uint32_t *>(sm.alias_base + 64);
+        sm.walk = sm.ids_base + 2 * PIPE_SLOTS;
+    }
+    LaneView v;
+    v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
+    v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
+    v.row_bytes = (uint64_t)p.row_stride * 4u;
+    v.active = lane < p.chunks;
+    const uint32_t lower = (1u << lane) - 1u;
+    float loss_acc = 0.0f;
+    unsigned long long n_pairs = 0, n_targets = 0;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(&p.counters->work_counter, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= p.n_walks) break;
+        const uint64_t wid = p.first_walk + w * p.walk_id_stride;
+        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+        {
+            const uint32_t *src = p.walks + w * (uint64_t)L;
+            __syncwarp();
+            for (uint32_t t = lane; t < L; t += 32u) sm.walk[t] = __ldg(src + t);
+            __syncwarp();
+        }
+        const uint32_t *walk = sm.walk;
+
+        auto draw = [&](uint32_t i, uint32_t a, uint32_t &idx, uint32_t &ry) {
+            idx = PAD;
+            ry = 0;
+            if (lane < K) {
+                const uint4 r = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi,
+                                              (i << 16) | 0xFFFFu, (TAG_NEG << 24) | lane);
+                idx = __umulhi(r.x, p.n);
+                ry = r.y;
+                if (p.use_alias) cp_async8(sm.alias(a) + lane, p.alias + idx);
+            }
+        };
+        auto resolve = [&](uint32_t c, uint32_t a, uint32_t idx, uint32_t ry, uint32_t &neg) -> uint32_t {
+            neg = idx;
+            if (p.use_alias && lane < K) {
+                const uint2 e = sm.alias(a)[lane];
+                neg = ry < e.x ? idx : e.y;
+            }
+            const uint32_t same = __match_any_sync(FULL, neg);
+            const bool valid = lane < K && neg != c && (same & lower) == 0u;
+            return (__ballot_sync(FULL, valid) << 1) | 1u;
+        };
+        auto issue = [&](uint32_t stage, uint32_t ids, uint32_t vmask) {
+            if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, PAD);
+            else issue_rows<KP1, false>(p, sm, v, stage, lane, ids, vmask, PAD);
+        };
+
+        uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
+        uint32_t i_cur = next_centre<true>(walk, L, W, 0, c_cur);
+        if (i_cur >= L) continue;
+        uint32_t stage = 0, slot_a = 0;
+        uint32_t idx_n = PAD, ry_n = 0, neg_cur, vmask_cur, ids_cur;
+        draw(i_cur, slot_a, idx_n, ry_n);
+        cp_async_commit();
+        cp_async_wait_all();
+        vmask_cur = resolve(c_cur, slot_a, idx_n, ry_n, neg_cur);
+        ids_cur = slot_ids(lane, c_cur, neg_cur, vmask_cur);
+        issue(stage, ids_cur, vmask_cur);
+        uint32_t i_nxt = next_centre<true>(walk, L, W, i_cur + 1, c_nxt);
+        slot_a ^= 1u;
+        if (i_nxt < L) draw(i_nxt, slot_a, idx_n, ry_n);
+        cp_async_commit();
+
+        while (i_cur < L) {
+            cp_async_wait_all();
+            // ---- centre p+1: resolve ids, copy its target rows, prefetch the entering row ----
+            uint32_t neg_nxt = PAD, vmask_nxt = 0, ids_nxt = 0xFFFFFF00u | lane;
+            bool deferred = false;
+            if (i_nxt < L) {
+                vmask_nxt = resolve(c_nxt, slot_a, idx_n, ry_n, neg_nxt);
+                ids_nxt = slot_ids(lane, c_nxt, neg_nxt, vmask_nxt);
+                uint32_t moved = __shfl_sync(FULL, ids_nxt, lane & 15u);
+                if (moved >= 0xFFFFFF00u) moved |= 16u;
+                const uint32_t both = lane < 16u ? ids_cur : moved;
+                const uint32_t same = __match_any_sync(FULL, both);
+                deferred = __ballot_sync(FULL, lane < 16u && (same >> 16) != 0u) != 0u;
+                if (!deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt);
+                const uint32_t entering = i_nxt + W < L ? walk[i_nxt + W] : PAD;
+                if (entering != PAD && lane * 128u < p.chunks * 16u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                        reinterpret_cast<const char *>(p.t0) + entering * v.row_bytes + lane * 128u));
+            }
+            // ---- centre p+2: start its draw ----
+            const uint32_t i_far = i_nxt < L ? next_centre<true>(walk, L, W, i_nxt + 1, c_far) : L;
+            uint32_t idx_f = PAD, ry_f = 0;
+            if (i_far < L) draw(i_far, slot_a ^ 1u, idx_f, ry_f);
+            cp_async_commit();
+
+            // ---- centre p: hidden vector = mean of the context rows, in window order ----
+            const uint32_t i = i_cur, c = c_cur;
+            const float lr = centre_lr(p, c);
+            const uint32_t lo = i > W ? i - W : 0u;
+            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+            const uint32_t j = lo + lane;  // lane l looks at window slot l (2W + 1 <= 32)
+            const uint32_t tok = j <= hi ? walk[j] : PAD;
+            const bool ctx = j <= hi && j != i && tok != PAD && tok != c;
+            const uint32_t cmask = __ballot_sync(FULL, ctx);
+            const uint32_t m = __popc(cmask);
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                bool first = true;
+                uint32_t rem = cmask;
+                while (rem) {
+                    float4 r[CBOW_BATCH];
+                    uint32_t batch = 0;
+#pragma unroll
+                    for (int b = 0; b < CBOW_BATCH; ++b) {
+                        r[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rem) {
+                            const uint32_t q = __ffs(rem) - 1u;
+                            rem &= rem - 1u;
+                            const uint32_t t = __shfl_sync(FULL, tok, q);
+                            if (v.active) r[b] = __ldcg(reinterpret_cast<const float4 *>(v.t0 + t * v.row_bytes));
+                            batch |= 1u << b;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < CBOW_BATCH; ++b) {
+                        if ((batch >> b) & 1u) {
+                            if (first) h = r[b]; else add4(h, r[b]);
+                            first = false;
+                        }
+                    }
+                }
+            }
+            const float fm = (float)m;
+            h.x = __fdiv_rn(h.x, fm);
+            h.y = __fdiv_rn(h.y, fm);
+            h.z = __fdiv_rn(h.z, fm);
+            h.w = __fdiv_rn(h.w, fm);
+
+            const float4 acc = vmask_cur == full_mask
+                ? train_site<KP1, true>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc)
+                : train_site<KP1, false>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc);
+            n_targets += __popc(vmask_cur);
+            n_pairs += m;
+
+            // ---- scatter acc to every context position; a token that occurs k times in the
+            //      window receives k sequential additions, like the per-position oracle ----
+            {
+                const uint32_t key = ctx ? tok : (0xFFFFFF00u | lane);
+                const uint32_t same = __match_any_sync(FULL, key);
+                const uint32_t mult = __popc(same);
+                uint32_t rem = __ballot_sync(FULL, ctx && (same & lower) == 0u);
+                while (rem) {
+                    float4 r[CBOW_BATCH];
+                    uint32_t toks[CBOW_BATCH], mults[CBOW_BATCH];
+                    uint32_t batch = 0;
+#pragma unroll
+                    for (int b = 0; b < CBOW_BATCH; ++b) {
+                        r[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        toks[b] = 0;
+                        mults[b] = 0;
+                        if (rem) {
+                            const uint32_t q = __ffs(rem) - 1u;
+                            rem &= rem - 1u;
+                            toks[b] = __shfl_sync(FULL, tok, q);
+                            mults[b] = __shfl_sync(FULL, mult, q);
+                            if (v.active) r[b] = __ldcg(reinterpret_cast<const float4 *>(v.t0 + toks[b] * v.row_bytes));
+                            batch |= 1u << b;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < CBOW_BATCH; ++b) {
+                        if ((batch >> b) & 1u) {
+                            for (uint32_t t = 0; t < mults[b]; ++t) add4(r[b], acc);
+                            if (v.active)
+                                *reinterpret_cast<float4 *>(const_cast<char *>(v.t0) + toks[b] * v.row_bytes) = r[b];
+                        }
+                    }
+                }
+            }
+
+            if (deferred) {
+                issue(stage ^ 1u, ids_nxt, vmask_nxt);
+                cp_async_commit();
+            }
+            i_cur = i_nxt; c_cur = c_nxt; neg_cur = neg_nxt; vmask_cur = vmask_nxt; ids_cur = ids_nxt;
+            i_nxt = i_far; c_nxt = c_far; idx_n = idx_f; ry_n = ry_f;
+            stage ^= 1u;
+            slot_a ^= 1u;
+        }
+    }
+    double loss = (double)loss_acc;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(FULL, loss, off);
+    if (lane == 0) {
+        atomicAdd(&p.counters->pairs, n_pairs);
+        atomicAdd(&p.counters->targets, n_targets);
+        atomicAdd(&p.counters->loss_sum, loss);
+    }
 }
 
-cudaError_t launch_skipgram_pipe(const TrainParams &p, bool deterministic, int sm_count,
-                                 cudaStream_t stream) {
-    cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
-    if (err != cudaSuccess) return err;
-    const uint32_t stage_floats = (p.negatives + 2u) * p.row_stride;
-    const size_t warp_bytes = 2u * stage_floats * 4u + 2u * 32u * 8u + 2u * PIPE_SLOTS * 4u;
+bool pipe_supported(const TrainParams &p, uint32_t model) {
+    if (p.chunks > 32u || p.negatives + 1u > PIPE_SLOTS || p.walk_length > 1024u) return false;
+    return model == B2E_SKIPGRAM || 2u * p.window + 1u <= 32u;
+}
+
+template <typename Kernel>
+static cudaError_t launch_pipe(Kernel kernel, const TrainParams &p, bool deterministic, int sm_count,
+                               uint64_t max_warps, cudaStream_t stream) {
+    const size_t warp_bytes = pipe_warp_bytes(p.negatives, p.chunks, p.walk_length);
     const int warps = deterministic ? 1 : 4;
     const size_t smem = warp_bytes * warps;
-    static bool configured = false;
-    if (!configured) {
-        err = cudaFuncSetAttribute(skipgram_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024);
-        if (err != cudaSuccess) return err;
-        configured = true;
-    }
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return err;
     if (deterministic) {
-        skipgram_pipe_kernel<<<1, 32, smem, stream>>>(p);
+        kernel<<<1, 32, smem, stream>>>(p);
         return cudaGetLastError();
     }
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, skipgram_pipe_kernel, 128, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: every CTA resident, walks fetched
-    const uint64_t needed = (p.n_walks + warps - 1) / warps;
+    const uint64_t needed = (std::min<uint64_t>(p.n_walks, max_warps) + warps - 1) / warps;
     if (grid > needed) grid = needed;
-    skipgram_pipe_kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
+    if (grid < 1) grid = 1;
+    kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
+                              uint64_t max_warps, cudaStream_t stream) {
+    cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess) return err;
+    if (model == B2E_SKIPGRAM) {
+        switch (p.negatives + 1u) {
+            case 11: return launch_pipe(skipgram_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);
+            case 6: return launch_pipe(skipgram_pipe_kernel<6>, p, deterministic, sm_count, max_warps, stream);
+            default: return launch_pipe(skipgram_pipe_kernel<0>, p, deterministic, sm_count, max_warps, stream);
+        }
+    }
+    switch (p.negatives + 1u) {
+        case 11: return launch_pipe(cbow_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);
+        case 6: return launch_pipe(cbow_pipe_kernel<6>, p, deterministic, sm_count, max_warps, stream);
+        default: return launch_pipe(cbow_pipe_kernel<0>, p, deterministic, sm_count, max_warps, stream);
+    }
 }
 
 }  // namespace b2e

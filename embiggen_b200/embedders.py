@@ -34,7 +34,7 @@ from .graph import as_csr
 _DTYPES = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
 # engine options that are not part of the reference's signature (keyword-only, defaulted)
 _B200_DEFAULTS = dict(negative_sampling_exponent=0.75, scale_by_sqrt_dim=False, deterministic=False,
-                      chunk_walks=0, sync_interval=4, device=None)
+                      chunk_walks=0, max_concurrent_walks=0, sync_interval=4, device=None)
 
 
 @abstract_class
@@ -139,7 +139,8 @@ class Node2VecB200(B200Embedder):
             use_scale_free_distribution=k["use_scale_free_distribution"],
             normalize_learning_rate_by_degree=k["normalize_learning_rate_by_degree"],
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
-            chunk_walks=k["chunk_walks"], device=device)
+            chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
+            device=device)
 
     def _output_buffers(self, n: int):
         """float32 host buffers the engine writes; .npy memory maps when paths are given

@@ -48,7 +48,7 @@ KWARG_SCHEMA = {
     "verbose": "bool",
     # B200 extras
     "negative_sampling_exponent": "float", "scale_by_sqrt_dim": "bool", "deterministic": "bool",
-    "chunk_walks": "int", "sync_interval": "int", "device": ["int", "None"],
+    "chunk_walks": "int", "max_concurrent_walks": "int", "sync_interval": "int", "device": ["int", "None"],
 }
 _TYPES = {"bool": bool, "int": int, "float": float, "str": str, "None": type(None)}
 

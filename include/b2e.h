@@ -61,6 +61,7 @@ typedef struct {
     uint32_t scale_by_sqrt_dim;                 /* score = dot / sqrt(D) */
     uint32_t deterministic; /* 1: one warp trains walks in ascending id order (bit-exact) */
     uint32_t chunk_walks;   /* walks per walk->SGD chunk, 0 = automatic */
+    uint32_t max_concurrent_walks; /* walks trained concurrently (Hogwild), 0 = automatic */
     int32_t device;         /* CUDA device ordinal */
 } b2e_config;
 

@@ -95,20 +95,19 @@ int main(int argc, char **argv) {
     const uint32_t n_rows = argc > 1 ? (uint32_t)atoi(argv[1]) : 2000000u;  // 2M rows ~ T0+T1 of C2
     float *sink;
     CHECK(cudaMalloc(&sink, 4));
-    for (uint32_t stride : {100u, 104u, 128u}) {
+    struct Case { uint32_t stride, row; };
+    const Case cases[] = {{100u, 100u}, {104u, 100u}, {112u, 100u}, {128u, 100u}, {128u, 128u}};
+    for (const Case &c : cases) {
+        const uint32_t stride = c.stride, row = c.row;
         float *table;
         CHECK(cudaMalloc(&table, (size_t)n_rows * stride * 4));
         CHECK(cudaMemset(table, 0, (size_t)n_rows * stride * 4));
-        const uint32_t row = stride == 128u ? 128u : 100u;
-        printf("--- table %u rows x %u floats = %.0f MB\n", n_rows, stride, n_rows * (double)stride * 4 / 1e6);
-        for (int occ : {2, 4, 8}) {
-            run<1, false, false>("gather", table, n_rows, stride, row, occ, sink);
-            run<4, false, false>("gather", table, n_rows, stride, row, occ, sink);
+        printf("--- table %u rows x %u floats = %.0f MB, %u floats of each row touched\n", n_rows, stride,
+               n_rows * (double)stride * 4 / 1e6, row);
+        for (int occ : {2, 4}) {
             run<11, false, false>("gather", table, n_rows, stride, row, occ, sink);
-            run<1, true, false>("gather+scatter", table, n_rows, stride, row, occ, sink);
             run<4, true, false>("gather+scatter", table, n_rows, stride, row, occ, sink);
             run<11, true, false>("gather+scatter", table, n_rows, stride, row, occ, sink);
-            run<11, true, true>("gather+scatter+L2prefetch(next)", table, n_rows, stride, row, occ, sink);
         }
         CHECK(cudaFree(table));
     }

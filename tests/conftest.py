@@ -50,3 +50,30 @@ def tiny_graphs():
         np.array([0, 1, 2, 0]), np.array([1, 2, 3, 2]), 5, symmetrise=False,
         name="directed_dead_end")
     return graphs
+
+
+def heldout_sgns_loss(graph, central, contextual, window=4, negatives=5, n_walks=400, length=32,
+                      seed=987654321, return_weight=1.0, explore_weight=1.0):
+    """Mean SGNS objective of (central, contextual) tables on walks neither run trained on.
+
+    The same fixed sample of (centre, context, negatives) is scored for every embedding handed
+    in, which is how two training runs are compared (leg 3)."""
+    import oracle
+    walks, _ = oracle.walks(graph.indptr, graph.indices, seed, 10 ** 9, n_walks, length,
+                            return_weight, explore_weight)
+    rng = np.random.default_rng(seed)
+    n = graph.get_number_of_nodes()
+    total, count = 0.0, 0
+    c64, x64 = central.astype(np.float64), contextual.astype(np.float64)
+    for offset in range(1, window + 1):
+        a, b = walks[:, :-offset].ravel(), walks[:, offset:].ravel()
+        keep = (a != oracle.PAD_TOKEN) & (b != oracle.PAD_TOKEN) & (a != b)
+        a, b = a[keep].astype(np.int64), b[keep].astype(np.int64)
+        for centre, context in ((a, b), (b, a)):
+            positive = np.einsum("ij,ij->i", c64[centre], x64[context])
+            total += np.logaddexp(0.0, -positive).sum()
+            neg = rng.integers(0, n, size=(centre.shape[0], negatives))
+            scores = np.einsum("ij,ikj->ik", c64[centre], x64[neg])
+            total += np.logaddexp(0.0, scores).sum()
+            count += centre.shape[0]
+    return total / count
