@@ -29,6 +29,37 @@ def pairs_per_walk(walk_length: int, window_size: int) -> int:
     return 2 * w * walk_length - w * (w + 1)
 
 
+def shard_chunks(walks_per_epoch: int, chunk_capacity: int, world: int, rank: int, base: int = 0):
+    """Data-parallel schedule of one epoch: yields ``(first_walk_id, n_walks, stride)`` per step.
+
+    A step covers ``chunk_capacity * world`` consecutive walk ids; rank ``r`` takes the ids
+    congruent to ``r`` modulo ``world`` (strided, so R-MAT hubs spread over the ranks), i.e.
+    ``first_walk_id + k * stride`` for ``k < n_walks``.  Because walks are a pure function of
+    ``(seed, walk_id)`` the union over the ranks is exactly the single-GPU epoch.
+    """
+    step = chunk_capacity * world
+    done = 0
+    while done < walks_per_epoch:
+        count = min(step, walks_per_epoch - done)
+        mine = (count - rank + world - 1) // world if count > rank else 0
+        yield base + done + rank, mine, world
+        done += count
+
+
+def average_replicas(tables, process_group=None) -> None:
+    """In-place average of every rank's replica of the tables (the one exchange step of the
+    path).  NCCL reduces with AVG (no extra pass over HBM); gloo (CPU tests) sums then scales."""
+    import torch.distributed as dist
+    world = dist.get_world_size(process_group)
+    average = dist.get_backend(process_group) == "nccl"
+    for t in tables:
+        if average:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=process_group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group)
+            t.div_(world)
+
+
 class Engine:
     """One engine = one ``b2e_handle`` on one GPU."""
 
@@ -218,29 +249,22 @@ class Engine:
         tables = self.device_tables()
         self.init_tables(seed)  # identical on every rank (counter-based init)
         per_epoch = self.walks_per_epoch
-        chunk = self.chunk_capacity * world  # global walks per step, chunk_capacity per rank
         lr = np.float32(cfg.learning_rate)
         losses = []
 
         def average():
             self.sync()
-            for t in tables:
-                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=process_group)
+            average_replicas(tables, process_group)
             torch.cuda.synchronize(cfg.device)
 
         for epoch in range(cfg.epochs):
             self.reset_counters()
-            base = epoch * per_epoch
-            done, index = 0, 0
-            while done < per_epoch:
-                count = min(chunk, per_epoch - done)
-                mine = (count - rank + world - 1) // world if count > rank else 0
+            steps = list(shard_chunks(per_epoch, self.chunk_capacity, world, rank, epoch * per_epoch))
+            for index, (first, mine, stride) in enumerate(steps):
                 slot = index & 1
-                self.walk_chunk(seed, base + done + rank, mine, world, slot)
+                self.walk_chunk(seed, first, mine, stride, slot)
                 self.train_chunk(seed, slot, float(lr))
-                done += count
-                index += 1
-                if sync_interval and index % sync_interval == 0 and done < per_epoch:
+                if sync_interval and (index + 1) % sync_interval == 0 and index + 1 < len(steps):
                     average()
             average()
             c = self.counters()

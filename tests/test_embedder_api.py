@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's embedder API (CPU only; no kernel is launched).
+
+Modelled on the reference's own tests of this surface:
+/root/reference/tests/test_node_embedding_pipelines.py:83-105 (constructor round-trip),
+/root/reference/tests/test_normalize_kwargs.py:10-31 (kwargs coercion),
+/root/reference/tests/test_embedding_result.py:12-89 (container semantics),
+/root/reference/tests/test_embed_graph_pipeline.py:54-94 (argument validation of embed_graph),
+/root/reference/tests/test_abstract_model.py:123-137 (registry).
+"""
+import inspect
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from embiggen_b200 import embedders
+from embiggen_b200.embedders import (B200_EMBEDDERS, DeepWalkCBOWB200, DeepWalkSkipGramB200,
+                                     Node2VecCBOWB200, Node2VecSkipGramB200, embed_graph)
+from embiggen_b200.embedding_api import (AbstractEmbeddingModel, AbstractModel, EmbeddingResult,
+                                         get_available_models_for_node_embedding, normalize_kwargs)
+
+# defaults of node2vec_skipgram.py:9-35 (Node2Vec) and deepwalk_skipgram.py:9-31 (DeepWalk)
+REFERENCE_DEFAULTS = dict(
+    embedding_size=100, epochs=30, clipping_value=6.0, number_of_negative_samples=10,
+    walk_length=128, iterations=10, window_size=5, max_neighbours=100, learning_rate=0.01,
+    learning_rate_decay=0.9, central_nodes_embedding_path=None,
+    contextual_nodes_embedding_path=None, normalize_by_degree=False,
+    stochastic_downsample_by_degree=False, normalize_learning_rate_by_degree=False,
+    use_scale_free_distribution=True, random_state=42, dtype="f32", verbose=True)
+
+
+@pytest.mark.parametrize("model", B200_EMBEDDERS)
+def test_signature_matches_reference_defaults(model):
+    parameters = inspect.signature(model.__init__).parameters
+    for name, default in REFERENCE_DEFAULTS.items():
+        assert parameters[name].default == default, name
+    for name in ("ring_bell", "enable_cache"):
+        assert parameters[name].default is False
+    if "Node2Vec" in model.model_name():
+        assert parameters["return_weight"].default == 0.25
+        assert parameters["explore_weight"].default == 4.0
+        assert parameters["change_node_type_weight"].default == 1.0
+        assert parameters["change_edge_type_weight"].default == 1.0
+    else:
+        assert "return_weight" not in parameters and "explore_weight" not in parameters
+
+
+@pytest.mark.parametrize("model", B200_EMBEDDERS)
+def test_model_recreation_round_trip(model):
+    """M(**M().parameters()) must construct and report the same parameters."""
+    first = model()
+    parameters = first.parameters()
+    second = model(**parameters)
+    for key, value in second.parameters().items():
+        assert parameters[key] == value
+    hidden = {"change_node_type_weight", "change_edge_type_weight", "alpha"}
+    if "DeepWalk" in model.model_name():
+        hidden |= {"return_weight", "explore_weight"}
+    assert not hidden & set(parameters)
+    assert parameters["embedding_size"] == 100 and parameters["random_state"] == 42
+
+
+@pytest.mark.parametrize("model", B200_EMBEDDERS)
+def test_normalized_kwargs_construct(model):
+    m = model()
+    assert model(**normalize_kwargs(m, m.parameters())).parameters() == m.parameters()
+    smoke = normalize_kwargs(m, dict(m.smoke_test_parameters()))
+    assert model(**smoke).parameters()["walk_length"] == 4
+
+
+def test_kwarg_coercion_and_rejection():
+    m = Node2VecSkipGramB200(embedding_size=np.int64(16), epochs=3.0, use_scale_free_distribution=np.bool_(False),
+                             learning_rate=np.float32(0.5), return_weight=2)
+    p = m.parameters()
+    assert p["embedding_size"] == 16 and isinstance(p["embedding_size"], int)
+    assert p["epochs"] == 3 and isinstance(p["epochs"], int)
+    assert p["use_scale_free_distribution"] is False
+    assert isinstance(p["learning_rate"], float) and isinstance(p["return_weight"], float)
+    with pytest.raises(NotImplementedError):
+        Node2VecSkipGramB200(not_a_parameter=1)
+    with pytest.raises(TypeError):
+        Node2VecSkipGramB200(epochs="many")
+    with pytest.raises(ValueError):
+        Node2VecSkipGramB200(embedding_size=0)
+    with pytest.raises(ValueError):
+        Node2VecSkipGramB200(dtype="f8")
+    for unsupported in (dict(change_node_type_weight=2.0), dict(change_edge_type_weight=0.5),
+                        dict(normalize_by_degree=True), dict(stochastic_downsample_by_degree=True)):
+        with pytest.raises(NotImplementedError):
+            Node2VecSkipGramB200(**unsupported)
+
+
+@pytest.mark.parametrize("model", B200_EMBEDDERS)
+def test_smoke_test_conversion_and_random_state(model):
+    m = model(epochs=7, walk_length=64)
+    smoke = m.into_smoke_test()
+    assert type(smoke) is model
+    p = smoke.parameters()
+    assert (p["epochs"], p["embedding_size"], p["window_size"], p["walk_length"], p["max_neighbours"]) \
+        == (1, 5, 1, 4, 10)
+    m.set_random_state(1234)
+    assert m.parameters()["random_state"] == 1234
+    assert m.consistent_hash() != model(epochs=7, walk_length=64).consistent_hash()
+    assert model().consistent_hash() == model().consistent_hash()
+
+
+@pytest.mark.parametrize("model", B200_EMBEDDERS)
+def test_identity_and_capability_flags(model):
+    assert model.task_name() == "Node Embedding" and model.library_name() == "B200"
+    assert model.model_name() in ("Node2Vec SkipGram", "Node2Vec CBOW", "DeepWalk SkipGram", "DeepWalk CBOW")
+    assert model.is_stocastic() and model.is_topological()
+    assert not model.requires_nodes_sorted_by_decreasing_node_degree()
+    assert not model.requires_edge_weights() and model.requires_positive_edge_weights()
+    assert model.can_use_edge_weights() and model().is_using_edge_weights()
+    assert not model.requires_node_types() and not model.requires_edge_types()
+    assert not model.can_use_edge_type_features() and not model.can_use_edge_features()
+    assert isinstance(model.is_available(), bool)
+    # "implemented" is decided by inspect.getsource in the reference (abstract_model.py:16-23):
+    # no capability method of ours may contain that literal
+    for name in ("requires_edge_weights", "requires_positive_edge_weights", "can_use_edge_weights",
+                 "is_using_edge_weights", "can_use_node_types", "can_use_edge_types", "is_stocastic"):
+        assert "raise NotImplementedError" not in inspect.getsource(getattr(embedders.Node2VecB200, name))
+
+
+def test_registry():
+    frame = get_available_models_for_node_embedding()
+    ours = frame[frame.library_name == "B200"]
+    assert sorted(ours.model_name) == ["DeepWalk CBOW", "DeepWalk SkipGram", "Node2Vec CBOW", "Node2Vec SkipGram"]
+    assert not ours.requires_edge_weights.any()
+    # Walklets are deliberately not registered (reference registry counts, test_abstract_model.py:125-126)
+    assert not any("Walklets" in name for name in frame.model_name)
+    for model in B200_EMBEDDERS:
+        if model.is_available():
+            assert AbstractEmbeddingModel.get_model_from_library(
+                model.model_name(), task_name="Node Embedding", library_name="B200") is model
+    with pytest.raises(ValueError):
+        AbstractModel.get_task_data("No Such Model", "Node Embedding")
+    with pytest.raises(ValueError):
+        AbstractModel.get_task_data("", "Node Embedding")
+
+
+def test_embed_graph_argument_validation(small_ppi):
+    with pytest.raises(ValueError):  # kwargs together with a model instance
+        embed_graph(small_ppi, Node2VecSkipGramB200(), epochs=1)
+    with pytest.raises(ValueError):  # not an embedding model
+        embed_graph(small_ppi, object())
+    with pytest.raises(ValueError):  # unknown model name
+        embed_graph(small_ppi, "HOPE")
+    with pytest.raises((ValueError, TypeError)):
+        embed_graph(embedding_size=5)
+
+
+def test_fit_transform_validates_the_graph_before_touching_the_gpu():
+    from embiggen_b200.graph import CSRGraph
+    model = DeepWalkSkipGramB200()
+    no_edges = CSRGraph(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.uint32), name="no_edges")
+    with pytest.raises(ValueError, match="does not have edges"):
+        model.fit_transform(no_edges)
+    empty = CSRGraph(np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint32), name="empty")
+    with pytest.raises(ValueError, match="is empty"):
+        model.fit_transform(empty)
+    negative = CSRGraph(np.array([0, 1, 2]), np.array([1, 0]), weights=np.array([1.0, -1.0]), name="negative")
+    with pytest.raises(ValueError, match="negative edge weights"):
+        model.fit_transform(negative)
+    with pytest.raises(ValueError):
+        model.fit_transform("Cora")  # dataset retrieval needs ensmallen
+
+
+# ---- EmbeddingResult (test_embedding_result.py of the reference) ----
+def test_embedding_result_container():
+    a = np.arange(12, dtype=np.float32).reshape(4, 3)
+    b = pd.DataFrame(a + 1, index=list("wxyz"))
+    result = EmbeddingResult("Node2Vec SkipGram", node_embeddings=[a, b])
+    assert result.embedding_method_name == "Node2Vec SkipGram"
+    assert result.number_of_embeddings() == 2 and not result.is_single_embedding()
+    assert result.get_all_node_embedding()[0] is a
+    assert result.get_node_embedding_from_index(1) is b
+    with pytest.raises(ValueError):
+        result.get_node_embedding_from_index(2)
+    with pytest.raises(ValueError):
+        result.get_all_edge_embedding()
+    with pytest.raises(ValueError):
+        result.get_all_node_type_embeddings()
+    restored = EmbeddingResult.load(result.dump())
+    assert restored.get_all_node_embedding()[1].equals(b)
+    single = EmbeddingResult("X", node_embeddings=a)  # wrapped into a list
+    assert single.is_single_embedding() and single.get_single_embedding() is a
+    assert single.mean() == a.mean()  # proxies the methods of the only embedding
+
+
+def test_embedding_result_rejects_bad_embeddings():
+    with pytest.raises(ValueError):
+        EmbeddingResult("X", node_embeddings=[[1.0, 2.0]])
+    with pytest.raises(ValueError):
+        EmbeddingResult("X", node_embeddings=np.zeros((0, 3)))
+    with pytest.raises(ValueError):
+        EmbeddingResult("X", node_embeddings=np.array([[np.nan, 1.0]]))
+    with pytest.raises(ValueError):
+        EmbeddingResult("X", node_embeddings=pd.DataFrame([[np.inf, 1.0]]))
+    with pytest.warns(UserWarning):
+        EmbeddingResult("X", node_embeddings=np.zeros((2, 2)))
+
+
+def test_csr_hand_off_from_graph_accessors(small_ppi):
+    """as_csr pulls indptr / indices out of the ensmallen.Graph accessors the reference documents
+    (pecanpy_embedders/node2vec.py:144-148,161), by duck typing."""
+    from embiggen_b200.graph import as_csr, as_graph, validate_csr
+
+    class GraphLike:  # only the accessors, like a real ensmallen.Graph would offer
+        def get_number_of_nodes(self): return small_ppi.get_number_of_nodes()
+        def get_cumulative_node_degrees(self): return small_ppi.get_cumulative_node_degrees()
+        def get_directed_destination_node_ids(self): return small_ppi.indices
+        def has_edge_weights(self): return False
+
+    indptr, indices, weights = as_csr(GraphLike())
+    assert np.array_equal(indptr, small_ppi.indptr) and np.array_equal(indices, small_ppi.indices)
+    assert weights is None and indptr.dtype == np.int64 and indices.dtype == np.uint32
+    validate_csr(indptr, indices)
+    import scipy.sparse as sp
+    matrix = sp.csr_matrix((np.ones(len(indices)), indices, indptr), shape=(1064, 1064))
+    i2, x2, _ = as_csr(matrix)
+    assert np.array_equal(i2, indptr) and np.array_equal(x2, indices)
+    assert as_graph((indptr, indices)).get_number_of_nodes() == 1064
+    with pytest.raises(ValueError):
+        as_csr(42)
+    with pytest.raises(ValueError):
+        validate_csr(np.array([0, 2]), np.array([1, 0], dtype=np.uint32))  # unsorted row
