@@ -52,16 +52,24 @@ SEED = 42
 METRIC = "skipgram_context_pairs_per_s"
 
 
-def load_graph(spec):
-    """Synthetic graph of the named shape (generator seed 42), cached on local disk."""
+def load_graph(spec, device=None):
+    """Synthetic graph of the named shape (generator seed 42), cached on local disk.
+
+    With a GPU the graph is generated and its CSR built on the device (same graph as the numpy
+    generators, tests/test_gpu_graph_build.py); the CPU reference arm falls back to numpy."""
     from embiggen_b200.graph import CSRGraph, erdos_renyi, rmat
     tag = "_".join(str(x) for x in spec)
     path = os.path.join(os.environ.get("B2E_CACHE", "/tmp"), f"b2e_graph_{tag}.npz")
     if os.path.exists(path):
         data = np.load(path)
         return CSRGraph(data["indptr"], data["indices"], name=tag)
-    graph = erdos_renyi(spec[1], spec[2], seed=42) if spec[0] == "er" else \
-        rmat(spec[1], spec[2], n=spec[3], seed=42)
+    if device is not None:
+        from embiggen_b200.graph_gpu import erdos_renyi_gpu, rmat_gpu
+        graph = erdos_renyi_gpu(spec[1], spec[2], seed=42, device=device) if spec[0] == "er" else \
+            rmat_gpu(spec[1], spec[2], n=spec[3], seed=42, device=device)
+    else:
+        graph = erdos_renyi(spec[1], spec[2], seed=42) if spec[0] == "er" else \
+            rmat(spec[1], spec[2], n=spec[3], seed=42)
     try:
         tmp = path + f".{os.getpid()}.tmp.npz"
         np.savez(tmp, indptr=graph.indptr, indices=graph.indices)
@@ -69,6 +77,18 @@ def load_graph(spec):
     except OSError:
         pass
     return graph
+
+
+def measured_traffic(config_name, walks_per_launch):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture of the same
+    kernel and workload (profiles/traffic_<config>.json), scaled to this launch's walk count
+    (the kernel streams walks, its traffic is linear in them).  None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", f"traffic_{config_name}.json")
+    if not os.path.exists(path):
+        return None, None
+    record = json.load(open(path))
+    per_walk = (record["dram_bytes_read"] + record["dram_bytes_write"]) / record["walks_per_launch"]
+    return per_walk * walks_per_launch, record["source"]
 
 
 def measured_peak_gbs():
@@ -248,7 +268,7 @@ def run_ours(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    graph = load_graph(cfg["graph"])
+    graph = load_graph(cfg["graph"], device=local_rank)
     D = cfg["embedding_size"]
     L, w, K = COMMON["walk_length"], COMMON["window_size"], COMMON["number_of_negative_samples"]
     engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
@@ -353,6 +373,9 @@ def run_ours(args, cfg):
     walk_avg_ms = float(np.mean(walk_ms))
     walk_achieved = steps_per_launch * walk_bytes_per_step / (walk_avg_ms * 1e-3) / 1e9
 
+    kernel_name = ("skipgram_pipe_kernel" if cfg["model"] == "SkipGram" else "cbow_pipe_kernel") + \
+        f"<{K + 1}>"
+    traffic, traffic_source = measured_traffic(args.config, chunk)
     result = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -367,8 +390,9 @@ def run_ours(args, cfg):
                    if world > 1 else "single GPU"},
         "walk_steps_per_s": walk_steps_all / (elapsed_ms * 1e-3),
         "gpu_launches": int(launches_all),
-        "roofline": {"kernel": "train_kernel (SGD)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_source,
                      "peak_source": peak_source, "avg_launch_ms": sgd_avg_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes},
         "walk": {"kernel": "walk_kernel", "steps_per_s_alone": steps_per_launch / (walk_avg_ms * 1e-3),

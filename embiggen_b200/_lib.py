@@ -89,6 +89,10 @@ SIGNATURES = {
     "b2e_counters_read": (ctypes.c_int, [_H, _P(B2ECounters)]),
     "b2e_counters_reset": (ctypes.c_int, [_H]),
     "b2e_launch_count": (_U64, [_H]),
+    "b2e_csr_from_edges": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _P(_U64)]),
+    "b2e_synthetic_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _U64, _U32, _U64, _U64, _U64, _U64,
+                                         _U64, ctypes.c_void_p, ctypes.c_void_p, _U64, _P(_U64)]),
 }
 
 _lib = None

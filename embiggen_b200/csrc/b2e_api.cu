@@ -536,3 +536,53 @@ extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table
     if (c.model == B2E_CBOW) return b2e_export_tables(h, table1, table0);
     return b2e_export_tables(h, table0, table1);
 }
+
+// ---- graph ingest (csrc/graph_build.cu) ----
+static int select_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2E_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(B2E_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    return B2E_OK;
+}
+
+extern "C" int b2e_csr_from_edges(int device, const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                                  uint64_t n_nodes, int symmetrise, int64_t *indptr, uint32_t *indices,
+                                  uint64_t indices_capacity, uint64_t *nnz) {
+    if (!indptr || !nnz || (n_edges && (!src || !dst || !indices)))
+        return fail(B2E_ERR_INVALID, "null argument");
+    if (n_nodes == 0 || n_nodes >= 0xFFFFFF00ull)
+        return fail(B2E_ERR_INVALID, "the number of nodes must be in [1, 0xFFFFFF00)");
+    if (int rc = select_device(device)) return rc;
+    std::string error;
+    cudaError_t e = csr_from_edges(src, dst, n_edges, n_nodes, symmetrise, indptr, indices,
+                                   indices_capacity, nnz, error);
+    if (e == cudaErrorInvalidValue) return fail(B2E_ERR_INVALID, error);
+    if (e != cudaSuccess) return fail(B2E_ERR_CUDA, error);
+    return B2E_OK;
+}
+
+extern "C" int b2e_synthetic_csr(int device, int kind, uint64_t n_nodes, uint32_t scale, uint64_t n_edges,
+                                 uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc,
+                                 int64_t *indptr, uint32_t *indices, uint64_t indices_capacity,
+                                 uint64_t *nnz) {
+    if (!indptr || !indices || !nnz) return fail(B2E_ERR_INVALID, "null argument");
+    if (kind != 0 && kind != 1) return fail(B2E_ERR_INVALID, "kind must be 0 (Erdos-Renyi) or 1 (R-MAT)");
+    if (n_nodes < 2 || n_nodes >= 0xFFFFFF00ull)
+        return fail(B2E_ERR_INVALID, "the number of nodes must be in [2, 0xFFFFFF00)");
+    if (kind == 1 && (scale == 0 || scale > 32 || (scale < 32 && n_nodes > (1ull << scale))))
+        return fail(B2E_ERR_INVALID, "R-MAT needs 1 <= scale <= 32 and n_nodes <= 2^scale");
+    if ((double)n_edges > 0.5 * (double)n_nodes * (double)(n_nodes - 1) * 0.5)
+        return fail(B2E_ERR_INVALID, "Too many edges requested.");
+    if (indices_capacity < 2 * n_edges) return fail(B2E_ERR_INVALID, "indices_capacity must be >= 2 * n_edges");
+    if (int rc = select_device(device)) return rc;
+    std::string error;
+    cudaError_t e = synthetic_csr(kind, n_nodes, scale, n_edges, seed, t_a, t_ab, t_abc, indptr, indices,
+                                  indices_capacity, nnz, error);
+    if (e == cudaErrorInvalidValue) return fail(B2E_ERR_INVALID, error);
+    if (e != cudaSuccess) return fail(B2E_ERR_CUDA, error);
+    return B2E_OK;
+}

@@ -88,6 +88,14 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
 cudaError_t launch_pack_rows(const float *src, float *dst, uint64_t n, uint32_t embedding_size,
                              uint32_t row_stride, bool strip, cudaStream_t stream);
 
+cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint64_t n,
+                           int symmetrise, int64_t *indptr, uint32_t *indices, uint64_t capacity,
+                           uint64_t *nnz_out, std::string &error);
+cudaError_t synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t m, uint64_t seed,
+                          unsigned long long t_a, unsigned long long t_ab, unsigned long long t_abc,
+                          int64_t *indptr, uint32_t *indices, uint64_t capacity, uint64_t *nnz_out,
+                          std::string &error);
+
 }  // namespace b2e
 
 struct b2e_handle {

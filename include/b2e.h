@@ -143,6 +143,30 @@ int b2e_counters_reset(b2e_handle *handle);
 /* number of kernels this handle has launched since creation */
 uint64_t b2e_launch_count(const b2e_handle *handle);
 
+/* ---- graph ingest on the GPU (no handle needed) ---- */
+
+/*
+ * Sorted, de-duplicated, self-loop-free CSR from a host edge list: the layout an
+ * ensmallen.Graph hands over (.../pecanpy_embedders/node2vec.py:139-163), built without
+ * Ensmallen (the reference's only in-tree idiom is the GraphBuilder loop of
+ * .../utils/networkx_utils.py:79-113).  indptr receives n_nodes + 1 entries, indices at most
+ * indices_capacity entries (2 * n_edges always suffices when symmetrise != 0).
+ */
+int b2e_csr_from_edges(int device, const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                       uint64_t n_nodes, int symmetrise, int64_t *indptr, uint32_t *indices,
+                       uint64_t indices_capacity, uint64_t *nnz);
+
+/*
+ * Seeded synthetic graphs of the BASELINE.json shapes: the first n_edges distinct undirected
+ * edges, in draw order, of the Philox stream (seed, draw index).  kind 0 = Erdos-Renyi G(n, m);
+ * kind 1 = R-MAT over 2^scale ids with ids >= n_nodes rejected, quadrant thresholds
+ * t_a = floor(a 2^32), t_ab = floor((a + b) 2^32), t_abc = floor((a + b + c) 2^32).
+ * indices_capacity must be at least 2 * n_edges.
+ */
+int b2e_synthetic_csr(int device, int kind, uint64_t n_nodes, uint32_t scale, uint64_t n_edges,
+                      uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, int64_t *indptr,
+                      uint32_t *indices, uint64_t indices_capacity, uint64_t *nnz);
+
 #ifdef __cplusplus
 }
 #endif
