@@ -1,0 +1,107 @@
+"""Downstream leg of the parity contract (north_star, SURVEY.md 8c leg 4): edge-prediction AUROC
+of the GPU embedding against the embedding of the CPU oracle trained on the same graph with the
+same kwargs.  The reference runs this comparison with `edge_prediction_evaluation`
+(/root/reference/embiggen/edge_prediction/edge_prediction_evaluation.py:12-200: connected
+Monte-Carlo holdout, embedder fitted on the training graph, sklearn-style classifier on
+Hadamard edge features, `binary_auroc`); without the `ensmallen` wheel the same protocol is
+restated here with numpy + scikit-learn and the oracle stands where Ensmallen would.
+
+Tolerance (stated, as the contract asks): |AUROC_gpu - AUROC_oracle| <= 0.005 on the mean over
+three holdouts (the 0.005 of north_star), and <= 0.015 on any single holdout.
+"""
+import numpy as np
+import pytest
+from sklearn.linear_model import LogisticRegression
+from sklearn.metrics import roc_auc_score
+
+import oracle
+from embiggen_b200.graph import csr_from_edges
+
+KW = dict(embedding_size=32, walk_length=32, window_size=4, iterations=8, epochs=4,
+          number_of_negative_samples=5, learning_rate=0.05, learning_rate_decay=0.9)
+
+
+def block_model(seed, n=1500, blocks=15, inside=0.06, outside=0.0008):
+    """Planted-partition graph: dense blocks, sparse background; returns the edge list."""
+    rng = np.random.default_rng(seed)
+    label = np.arange(n) % blocks
+    upper = np.triu(rng.random((n, n)) < np.where(label[:, None] == label[None, :], inside, outside), 1)
+    src, dst = np.nonzero(upper)
+    return src, dst, n
+
+
+def holdout(src, dst, n, seed, train_fraction=0.8):
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(len(src))
+    cut = int(train_fraction * len(src))
+    train, test = order[:cut], order[cut:]
+    existing = set(zip(src.tolist(), dst.tolist()))
+
+    def negatives(count):
+        out = []
+        while len(out) < count:
+            a, b = rng.integers(0, n, 2)
+            if a != b and (min(a, b), max(a, b)) not in existing:
+                out.append((a, b))
+        return np.array(out)
+
+    return (src[train], dst[train]), (src[test], dst[test]), negatives(len(train)), negatives(len(test))
+
+
+def auroc(embedding, train_pos, test_pos, train_neg, test_neg):
+    """Hadamard edge features + logistic regression, AUROC on the held-out edges."""
+    def features(a, b):
+        return embedding[a] * embedding[b]
+    x_train = np.vstack([features(*train_pos), features(train_neg[:, 0], train_neg[:, 1])])
+    y_train = np.r_[np.ones(len(train_pos[0])), np.zeros(len(train_neg))]
+    x_test = np.vstack([features(*test_pos), features(test_neg[:, 0], test_neg[:, 1])])
+    y_test = np.r_[np.ones(len(test_pos[0])), np.zeros(len(test_neg))]
+    scale = np.abs(x_train).max() + 1e-12
+    model = LogisticRegression(max_iter=500, C=10.0).fit(x_train / scale, y_train)
+    return roc_auc_score(y_test, model.decision_function(x_test / scale))
+
+
+def oracle_embedding(model, graph, seed, rw, ew, threads):
+    oracle.set_threads(threads)
+    try:
+        t0, t1, _ = oracle.fit(model, graph.indptr, graph.indices, seed, KW["embedding_size"], KW["epochs"],
+                               KW["iterations"], KW["walk_length"], KW["window_size"],
+                               KW["number_of_negative_samples"], KW["learning_rate"],
+                               KW["learning_rate_decay"], return_weight=rw, explore_weight=ew)
+    finally:
+        oracle.set_threads(1)
+    D = KW["embedding_size"]
+    return np.hstack([t0[:, :D], t1[:, :D]])  # classifiers hstack both tables (node_transformer.py:108-116)
+
+
+def test_oracle_embedding_predicts_held_out_edges():
+    """CPU only: the normative algorithm learns the planted structure (sanity of the spec)."""
+    src, dst, n = block_model(0)
+    train_pos, test_pos, train_neg, test_neg = holdout(src, dst, n, 0)
+    graph = csr_from_edges(train_pos[0], train_pos[1], n)
+    embedding = oracle_embedding("SkipGram", graph, 42, 1.0, 1.0, threads=8)
+    assert auroc(embedding, train_pos, test_pos, train_neg, test_neg) > 0.80
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,rw,ew", [("SkipGram", 1.0, 1.0), ("SkipGram", 0.25, 4.0), ("CBOW", 2.0, 0.5)])
+def test_gpu_auroc_matches_oracle_auroc(model, rw, ew):
+    from embiggen_b200.engine import Engine
+    deltas = []
+    for trial in range(3):
+        src, dst, n = block_model(trial)
+        train_pos, test_pos, train_neg, test_neg = holdout(src, dst, n, trial)
+        graph = csr_from_edges(train_pos[0], train_pos[1], n)
+        reference = oracle_embedding(model, graph, 42 + trial, rw, ew, threads=8)
+        with Engine(model, return_weight=rw, explore_weight=ew, **KW) as engine:
+            engine.load_csr(graph.indptr, graph.indices)
+            central, contextual, losses = engine.fit(42 + trial)
+        assert losses[-1] < losses[0]
+        ours = np.hstack([central, contextual])
+        a_ref = auroc(reference, train_pos, test_pos, train_neg, test_neg)
+        a_gpu = auroc(ours, train_pos, test_pos, train_neg, test_neg)
+        print(f"{model} rw={rw} ew={ew} holdout {trial}: AUROC oracle {a_ref:.4f}  gpu {a_gpu:.4f}")
+        assert a_gpu > 0.80
+        assert abs(a_gpu - a_ref) <= 0.015
+        deltas.append(a_gpu - a_ref)
+    assert abs(np.mean(deltas)) <= 0.005
