@@ -71,6 +71,8 @@ SIGNATURES = {
     "b2e_create": (ctypes.c_int, [_P(B2EConfig), _P(_H)]),
     "b2e_destroy": (None, [_H]),
     "b2e_load_csr": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64]),
+    "b2e_load_csr_weighted": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _U64,
+                                             _U64]),
     "b2e_number_of_sources": (_U64, [_H]),
     "b2e_row_stride": (_U64, [_H]),
     "b2e_fit": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

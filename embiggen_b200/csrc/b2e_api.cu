@@ -126,6 +126,7 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
 static void free_graph(b2e_handle *h) {
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
+    cudaFree(h->d_cdf); h->d_cdf = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
     cudaFree(h->d_alias); h->d_alias = nullptr;
     cudaFree(h->d_t0); h->d_t0 = nullptr;
@@ -192,8 +193,33 @@ static bool build_alias(const int64_t *indptr, uint64_t n, double alpha, std::ve
     return true;
 }
 
+// per-edge sampling table of a weighted graph; normative construction: oracle/walks.c
+static bool build_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, std::vector<uint32_t> &cdf) {
+    for (uint64_t v = 0; v < n; ++v) {
+        const int64_t begin = indptr[v], end = indptr[v + 1];
+        double total = 0.0;
+        for (int64_t e = begin; e < end; ++e) {
+            if (!(weights[e] >= 0.0f)) return false;
+            total += (double)weights[e];
+        }
+        double running = 0.0;
+        for (int64_t e = begin; e < end; ++e) {
+            running += (double)weights[e];
+            const double t = total > 0.0 ? floor(running / total * 4294967296.0) : 4294967295.0;
+            cdf[e] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        }
+        if (end > begin) cdf[end - 1] = 0xFFFFFFFFu;
+    }
+    return true;
+}
+
 extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
                             uint64_t n, uint64_t nnz) {
+    return b2e_load_csr_weighted(h, indptr, indices, nullptr, n, nnz);
+}
+
+extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
+                                     const float *weights, uint64_t n, uint64_t nnz) {
     REQUIRE_HANDLE(h);
     if (!indptr || (!indices && nnz)) return fail(B2E_ERR_INVALID, "null CSR pointer");
     if (n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
@@ -222,6 +248,13 @@ extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t
         if (indptr[v + 1] > indptr[v]) sources.push_back((uint32_t)v);
     }
     h->n_src = sources.size();
+    if (weights) {
+        std::vector<uint32_t> cdf(nnz);
+        if (!build_edge_cdf(indptr, weights, n, cdf))
+            return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
+        CUDA_TRY(cudaMalloc(&h->d_cdf, nnz * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(h->d_cdf, cdf.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
                              cudaMemcpyHostToDevice, h->walk_stream));
@@ -295,6 +328,7 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     WalkParams p;
     p.indptr = h->d_indptr;
     p.indices = h->d_indices;
+    p.cdf = h->d_cdf;
     p.sources = h->d_sources;
     p.n_src = h->n_src;
     p.seed_lo = (uint32_t)seed;

@@ -48,6 +48,7 @@ struct DeviceCounters {
 struct WalkParams {
     const int64_t *indptr;
     const uint32_t *indices;
+    const uint32_t *cdf;  // per-edge sampling table of a weighted graph, or nullptr
     const uint32_t *sources;
     uint64_t n_src;
     uint32_t seed_lo, seed_hi;
@@ -105,6 +106,7 @@ struct b2e_handle {
     uint32_t row_stride = 0;
     int64_t *d_indptr = nullptr;
     uint32_t *d_indices = nullptr;
+    uint32_t *d_cdf = nullptr;
     uint32_t *d_sources = nullptr;
     uint2 *d_alias = nullptr;
     float *d_t0 = nullptr, *d_t1 = nullptr;

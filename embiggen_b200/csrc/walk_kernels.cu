@@ -24,7 +24,22 @@ __device__ __forceinline__ bool row_contains(const uint32_t *__restrict__ row, u
     return lo < len && __ldg(row + lo) == key;
 }
 
-template <bool SECOND, bool VEC>
+// index of a proposal inside a row: uniform, or proportional to the edge weights through the
+// per-edge table built at load time (first entry whose cdf exceeds the random word)
+template <bool WEIGHTED>
+__device__ __forceinline__ uint32_t propose(const uint32_t *__restrict__ cdf, int64_t off, uint32_t deg,
+                                            uint32_t r) {
+    if (!WEIGHTED) return __umulhi(r, deg);
+    const uint32_t *row = cdf + off;
+    uint32_t lo = 0, hi = deg;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(row + mid) > r) hi = mid; else lo = mid + 1;
+    }
+    return lo < deg ? lo : deg - 1;
+}
+
+template <bool SECOND, bool VEC, bool WEIGHTED>
 __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
@@ -62,7 +77,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                                                     TAG_WALK1 << 24);
                             const uint32_t r = (s & 3u) == 0 ? rnd.x : (s & 3u) == 1 ? rnd.y
                                              : (s & 3u) == 2 ? rnd.z : rnd.w;
-                            next = __ldg(p.indices + off + __umulhi(r, deg));
+                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r));
                         } else {
                             const uint32_t *prow = p.indices + prev_off;
                             uint32_t trial = 0;
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                                                         (TAG_WALK2 << 24) | (trial >> 1));
                                 const uint32_t r0 = (trial & 1u) ? rnd.z : rnd.x;
                                 const unsigned long long r1 = (trial & 1u) ? rnd.w : rnd.y;
-                                next = __ldg(p.indices + off + __umulhi(r0, deg));
+                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r0));
                                 ++n_trials;
                                 bool accept;
                                 if (next == prev) {
@@ -130,13 +145,16 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     const unsigned block = 256;
     const unsigned grid = (unsigned)((p.n_walks + block - 1) / block);
     const bool vec = (p.walk_length % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16u) == 0;
+    const bool weighted = p.cdf != nullptr;
+#define B2E_LAUNCH_WALK(S, V, W) walk_kernel<S, V, W><<<grid, block, 0, stream>>>(p)
     if (second_order) {
-        if (vec) walk_kernel<true, true><<<grid, block, 0, stream>>>(p);
-        else walk_kernel<true, false><<<grid, block, 0, stream>>>(p);
+        if (vec) { if (weighted) B2E_LAUNCH_WALK(true, true, true); else B2E_LAUNCH_WALK(true, true, false); }
+        else { if (weighted) B2E_LAUNCH_WALK(true, false, true); else B2E_LAUNCH_WALK(true, false, false); }
     } else {
-        if (vec) walk_kernel<false, true><<<grid, block, 0, stream>>>(p);
-        else walk_kernel<false, false><<<grid, block, 0, stream>>>(p);
+        if (vec) { if (weighted) B2E_LAUNCH_WALK(false, true, true); else B2E_LAUNCH_WALK(false, true, false); }
+        else { if (weighted) B2E_LAUNCH_WALK(false, false, true); else B2E_LAUNCH_WALK(false, false, false); }
     }
+#undef B2E_LAUNCH_WALK
     return cudaGetLastError();
 }
 

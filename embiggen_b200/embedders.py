@@ -19,7 +19,6 @@ registry keeps preferring "Ensmallen" (abstract_model.py:670-675), so registrati
 non-breaking.
 """
 import os
-import warnings
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -157,9 +156,6 @@ class Node2VecB200(B200Embedder):
 
     def _fit_transform(self, graph, return_dataframe: bool = True) -> EmbeddingResult:
         indptr, indices, weights = as_csr(graph)
-        if weights is not None:
-            warnings.warn("The B200 engine currently walks the graph topology only: edge weights "
-                          "are ignored.")
         # max_neighbours (approximated walks for hubs) is accepted for compatibility: the walk
         # kernel always samples the exact transition distribution.
         device = self._model_kwargs["device"]
@@ -178,7 +174,7 @@ class Node2VecB200(B200Embedder):
         seed = int(self._random_state) & 0xFFFFFFFFFFFFFFFF
         central, contextual = self._output_buffers(n)
         with Engine(**self._engine_kwargs(device)) as engine:
-            engine.load_csr(indptr, indices)
+            engine.load_csr(indptr, indices, weights)  # weighted graphs walk by weight
             if world > 1:
                 c, x, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"])
                 central[:], contextual[:] = c, x

@@ -115,13 +115,21 @@ class Engine:
         self.close()
 
     # ---- K1 ----
-    def load_csr(self, indptr: np.ndarray, indices: np.ndarray) -> None:
+    def load_csr(self, indptr: np.ndarray, indices: np.ndarray,
+                 weights: Optional[np.ndarray] = None) -> None:
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.uint32)
         if indptr.ndim != 1 or indptr.shape[0] < 2:
             raise ValueError("The provided graph is empty.")
         n, nnz = indptr.shape[0] - 1, indices.shape[0]
-        check(self._lib.b2e_load_csr(self._handle, indptr.ctypes.data, indices.ctypes.data, n, nnz))
+        pointer = None
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float32)
+            if weights.shape != indices.shape:
+                raise ValueError("weights must have one entry per directed edge.")
+            pointer = weights.ctypes.data
+        check(self._lib.b2e_load_csr_weighted(self._handle, indptr.ctypes.data, indices.ctypes.data,
+                                              pointer, n, nnz))
         self.n = n
 
     @property

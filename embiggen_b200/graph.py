@@ -177,20 +177,26 @@ def as_graph(graph):
 
 
 def csr_from_edges(src: np.ndarray, dst: np.ndarray, n: int, symmetrise: bool = True,
-                   node_names=None, name: str = "graph") -> CSRGraph:
-    """Sorted, de-duplicated, self-loop-free CSR from an edge list."""
+                   node_names=None, name: str = "graph", weights=None) -> CSRGraph:
+    """Sorted, de-duplicated, self-loop-free CSR from an edge list (a duplicated edge keeps the
+    weight of its first occurrence)."""
     src = np.asarray(src, dtype=np.int64)
     dst = np.asarray(dst, dtype=np.int64)
     keep = src != dst
     src, dst = src[keep], dst[keep]
+    if weights is not None:
+        weights = np.asarray(weights, dtype=np.float32)[keep]
     if symmetrise:
         src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
-    keys = np.unique(src * np.int64(n) + dst)
+        if weights is not None:
+            weights = np.concatenate([weights, weights])
+    keys, first = np.unique(src * np.int64(n) + dst, return_index=True)
     rows = keys // np.int64(n)
     indices = (keys - rows * np.int64(n)).astype(np.uint32)
     indptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=n), out=indptr[1:])
-    return CSRGraph(indptr, indices, node_names=node_names, name=name, directed=not symmetrise)
+    return CSRGraph(indptr, indices, node_names=node_names, name=name, directed=not symmetrise,
+                    weights=None if weights is None else weights[first])
 
 
 def erdos_renyi(n: int, m: int, seed: int = 42) -> CSRGraph:
@@ -251,24 +257,28 @@ def rmat(scale: int, m: int, n: Optional[int] = None, seed: int = 42,
 
 
 def read_edge_list(path: str, source_column: int = 0, destination_column: int = 1,
-                   header: bool = True, separator: str = "\t", name: Optional[str] = None
-                   ) -> CSRGraph:
-    """Undirected, unweighted graph from a TSV edge list (e.g. tests/data/small_ppi.tsv).
+                   header: bool = True, separator: str = "\t", name: Optional[str] = None,
+                   weight_column: Optional[int] = None) -> CSRGraph:
+    """Undirected graph from a TSV edge list (e.g. tests/data/small_ppi.tsv), weighted when a
+    weight column is named.
 
     Node ids are assigned by sorted node name, as GRAPE does for an unsorted vocabulary.
     """
-    sources, destinations = [], []
+    sources, destinations, weights = [], [], []
     with open(path) as handle:
         if header:
             next(handle)
         for line in handle:
             fields = line.rstrip("\n").split(separator)
-            if len(fields) <= max(source_column, destination_column):
+            if len(fields) <= max(source_column, destination_column, weight_column or 0):
                 continue
             sources.append(fields[source_column])
             destinations.append(fields[destination_column])
+            if weight_column is not None:
+                weights.append(float(fields[weight_column]))
     names = sorted(set(sources) | set(destinations))
     ids = {node: i for i, node in enumerate(names)}
     src = np.fromiter((ids[s] for s in sources), dtype=np.int64, count=len(sources))
     dst = np.fromiter((ids[d] for d in destinations), dtype=np.int64, count=len(destinations))
-    return csr_from_edges(src, dst, len(names), node_names=names, name=name or path)
+    return csr_from_edges(src, dst, len(names), node_names=names, name=name or path,
+                          weights=weights if weight_column is not None else None)

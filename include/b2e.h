@@ -94,6 +94,15 @@ void b2e_destroy(b2e_handle *handle);
 int b2e_load_csr(b2e_handle *handle, const int64_t *indptr, const uint32_t *indices,
                  uint64_t n, uint64_t nnz);
 
+/*
+ * Same with edge weights (get_directed_edge_weights(), .../pecanpy_embedders/node2vec.py:147):
+ * nnz non-negative float32 aligned with indices; proposals are drawn proportionally to them
+ * (the reference's classes are `is_using_edge_weights`, .../ensmallen_embedders/node2vec.py:119-129).
+ * weights == NULL is b2e_load_csr.
+ */
+int b2e_load_csr_weighted(b2e_handle *handle, const int64_t *indptr, const uint32_t *indices,
+                          const float *weights, uint64_t n, uint64_t nnz);
+
 uint64_t b2e_number_of_sources(const b2e_handle *handle);
 uint64_t b2e_row_stride(const b2e_handle *handle); /* floats per table row on the device */
 

@@ -82,6 +82,11 @@ def lib():
         l.orc_walks.restype = ctypes.c_int
         l.orc_walks.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32), u64, u64, u64, u64, u64,
                                 u32, f32, f32, P(u32), P(WalkCounters)]
+        l.orc_edge_cdf.restype = ctypes.c_int
+        l.orc_edge_cdf.argtypes = [P(ctypes.c_int64), P(f32), u64, P(u32)]
+        l.orc_walks_weighted.restype = ctypes.c_int
+        l.orc_walks_weighted.argtypes = [P(ctypes.c_int64), P(u32), P(u32), u64, P(u32), u64, u64, u64,
+                                         u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
         l.orc_alias_build.restype = ctypes.c_int
         l.orc_alias_build.argtypes = [P(ctypes.c_int64), u64, ctypes.c_double, P(u32), P(u32)]
         l.orc_set_threads.restype = None
@@ -134,20 +139,34 @@ def thresholds(return_weight: float, explore_weight: float) -> np.ndarray:
     return out
 
 
+def edge_cdf(indptr, weights) -> np.ndarray:
+    """Per-edge sampling table of a weighted graph (normative construction in walks.c)."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    cdf = np.empty(weights.shape[0], dtype=np.uint32)
+    rc = lib().orc_edge_cdf(_ptr(indptr, ctypes.c_int64), _ptr(weights, ctypes.c_float),
+                            indptr.shape[0] - 1, _ptr(cdf, ctypes.c_uint32))
+    if rc != 0:
+        raise ValueError(f"orc_edge_cdf failed with status {rc}")
+    return cdf
+
+
 def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length: int,
           return_weight: float = 1.0, explore_weight: float = 1.0, walk_id_stride: int = 1,
-          srcs: Optional[np.ndarray] = None) -> Tuple[np.ndarray, dict]:
+          srcs: Optional[np.ndarray] = None, weights=None) -> Tuple[np.ndarray, dict]:
     indptr, indices = _csr(indptr, indices)
+    cdf = None if weights is None else edge_cdf(indptr, weights)
     n = indptr.shape[0] - 1
     if srcs is None:
         srcs = sources(indptr)
     srcs = np.ascontiguousarray(srcs, dtype=np.uint32)
     out = np.empty((n_walks, walk_length), dtype=np.uint32)
     counters = WalkCounters()
-    rc = lib().orc_walks(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32), n,
-                         _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
-                         walk_id_stride, walk_length, return_weight, explore_weight,
-                         _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
+    rc = lib().orc_walks_weighted(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                                  _ptr(cdf, ctypes.c_uint32), n, _ptr(srcs, ctypes.c_uint32),
+                                  srcs.shape[0], seed, first_walk, n_walks, walk_id_stride,
+                                  walk_length, return_weight, explore_weight,
+                                  _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
     if rc != 0:
         raise ValueError(f"orc_walks failed with status {rc}")
     return out, counters.as_dict()

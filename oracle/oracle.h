@@ -58,6 +58,16 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
               uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
               float explore_weight, uint32_t *out, orc_walk_counters *counters);
 
+/* per-edge sampling table of a weighted graph (see walks.c); cdf has nnz entries */
+int orc_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *cdf);
+
+/* orc_walks with proposals proportional to the edge weights (cdf from orc_edge_cdf; NULL: uniform) */
+int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+                       const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                       uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                       float return_weight, float explore_weight, uint32_t *out,
+                       orc_walk_counters *counters);
+
 /* Vose alias table over deg^alpha; thr/alias have n entries. */
 int orc_alias_build(const int64_t *indptr, uint64_t n, double alpha, uint32_t *thr,
                     uint32_t *alias);

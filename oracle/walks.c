@@ -69,10 +69,59 @@ static uint64_t probe_sectors(uint64_t len) {
     return levels > 3 ? levels - 2 : 1;
 }
 
+/*
+ * Edge weights ("next" row f-2; the reference's classes advertise them:
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:119-129).  Normative
+ * construction of the per-row sampling table: running = left-to-right double sum of the row's
+ * weights; cdf[i] = min(2^32 - 1, floor(running_i / total * 2^32)), last entry 2^32 - 1.  A
+ * proposal with random word r picks the first entry whose cdf exceeds r (the last one if none),
+ * i.e. edge i with probability w_i / total up to 2^-32; second order keeps the p/q accept test
+ * (KnightKing: proposal proportional to the static weight, acceptance by the dynamic bias).
+ */
+int orc_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *cdf) {
+    if (!indptr || !weights || !cdf) return -1;
+    for (uint64_t v = 0; v < n; ++v) {
+        const int64_t begin = indptr[v], end = indptr[v + 1];
+        double total = 0.0;
+        for (int64_t e = begin; e < end; ++e) {
+            if (!(weights[e] >= 0.0f)) return -2; /* negative or NaN */
+            total += (double)weights[e];
+        }
+        double running = 0.0;
+        for (int64_t e = begin; e < end; ++e) {
+            running += (double)weights[e];
+            double t = total > 0.0 ? floor(running / total * 4294967296.0) : 4294967295.0;
+            cdf[e] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        }
+        if (end > begin) cdf[end - 1] = 0xFFFFFFFFu;
+    }
+    return 0;
+}
+
+/* index of the proposal inside a row: uniform (cdf == NULL) or weighted */
+static uint32_t propose(const uint32_t *cdf_row, uint32_t deg, uint32_t r) {
+    if (!cdf_row) return orc_mulhi(r, deg);
+    uint32_t lo = 0, hi = deg;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cdf_row[mid] > r) hi = mid; else lo = mid + 1;
+    }
+    return lo < deg ? lo : deg - 1;
+}
+
 int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const uint32_t *sources,
               uint64_t n_src, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
               uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
               float explore_weight, uint32_t *out, orc_walk_counters *counters) {
+    return orc_walks_weighted(indptr, indices, NULL, n, sources, n_src, seed, first_walk, n_walks,
+                              walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+}
+
+int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+                       const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                       uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                       float return_weight, float explore_weight, uint32_t *out,
+                       orc_walk_counters *counters) {
     if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
     (void)n;
     const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
@@ -105,7 +154,7 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
                 const uint32_t s = t - 1;
                 orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, s >> 2, ORC_TAG_WALK1 << 24,
                                   rnd);
-                next = indices[off + orc_mulhi(rnd[s & 3], (uint32_t)deg)];
+                next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, rnd[s & 3])];
                 ++c.first_order;
             } else {
                 const int64_t poff = indptr[prev];
@@ -116,7 +165,7 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
                         orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
                                           (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
                     const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
-                    next = indices[off + orc_mulhi(r0, (uint32_t)deg)];
+                    next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, r0)];
                     ++c.trials;
                     int cls;
                     if (next == prev) {

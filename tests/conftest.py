@@ -25,6 +25,15 @@ def small_ppi():
 
 
 @pytest.fixture(scope="session")
+def small_ppi_weighted():
+    """The same graph with the fixture's native edge weights (700 .. 999)."""
+    from embiggen_b200.graph import CSRGraph
+    data = np.load(os.path.join(GOLDEN, "small_ppi_csr.npz"))
+    return CSRGraph(data["indptr"], data["indices"], node_names=list(data["node_names"]),
+                    weights=data["weights"], name="small_ppi_weighted")
+
+
+@pytest.fixture(scope="session")
 def er_graph():
     from embiggen_b200.graph import erdos_renyi
     return erdos_renyi(2000, 12000, seed=7)

@@ -15,10 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from embiggen_b200.graph import read_edge_list  # noqa: E402
 
-graph = read_edge_list("/root/reference/tests/data/small_ppi.tsv", name="small_ppi")
+graph = read_edge_list("/root/reference/tests/data/small_ppi.tsv", name="small_ppi", weight_column=2)
 assert graph.get_number_of_nodes() == 1064 and graph.indices.shape[0] == 6000
 np.savez_compressed(
     os.path.join(ROOT, "tests", "golden", "small_ppi_csr.npz"),
     indptr=graph.indptr, indices=graph.indices, node_names=np.array(graph.get_node_names()),
+    weights=graph.weights,  # the fixture's native edge weights (the parity configs ignore them)
 )
 print("wrote small_ppi_csr.npz", graph.get_number_of_nodes(), graph.indices.shape[0])

@@ -93,3 +93,42 @@ def test_full_size_properties():
     # the oracle agrees on a bounded sample of the same walks
     expected, _ = oracle.walks(graph.indptr, graph.indices, 42, n_src - 1000, 2000, 128)
     assert np.array_equal(walks[:2000], expected)
+
+
+# ---- edge weights (C ABI b2e_load_csr_weighted) ----
+def gpu_weighted_walks(graph, weights, seed, first, count, length, rw, ew):
+    with Engine("SkipGram", walk_length=length, return_weight=rw, explore_weight=ew,
+                iterations=1) as engine:
+        engine.load_csr(graph.indptr, graph.indices, weights)
+        return engine.walks(seed, first, count), engine.counters()
+
+
+@pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
+def test_weighted_walks_bit_exact(small_ppi_weighted, er_graph, rw, ew):
+    g = small_ppi_weighted
+    expected, oc = oracle.walks(g.indptr, g.indices, 42, 3, 2500, 64, rw, ew, weights=g.weights)
+    got, gc = gpu_weighted_walks(g, g.weights, 42, 3, 2500, 64, rw, ew)
+    assert np.array_equal(got, expected)
+    assert (gc["walk_steps"], gc["walk_trials"], gc["walk_searches"]) == (oc["steps"], oc["trials"], oc["searches"])
+    # random weights over six orders of magnitude, some exactly zero
+    rng = np.random.default_rng(1)
+    weights = np.exp(rng.uniform(-7, 7, er_graph.indices.shape[0])).astype(np.float32)
+    weights[rng.random(weights.shape[0]) < 0.05] = 0.0
+    expected, _ = oracle.walks(er_graph.indptr, er_graph.indices, 9, 0, 3000, 40, rw, ew, weights=weights)
+    got, _ = gpu_weighted_walks(er_graph, weights, 9, 0, 3000, 40, rw, ew)
+    assert np.array_equal(got, expected)
+
+
+def test_weighted_embedder_runs_and_rejects_negative_weights(small_ppi_weighted):
+    from embiggen_b200.embedders import Node2VecSkipGramB200
+    from embiggen_b200.graph import CSRGraph
+    model = Node2VecSkipGramB200(embedding_size=8, epochs=1, walk_length=8, iterations=1, verbose=False)
+    tables = model.fit_transform(small_ppi_weighted, return_dataframe=False).get_all_node_embedding()
+    assert np.isfinite(tables[0]).all()
+    g = small_ppi_weighted
+    with Engine("SkipGram") as engine:
+        with pytest.raises(ValueError):
+            engine.load_csr(g.indptr, g.indices, -g.weights)
+    negative = CSRGraph(g.indptr, g.indices, weights=-g.weights, name="negative")
+    with pytest.raises(ValueError, match="negative edge weights"):
+        model.fit_transform(negative)

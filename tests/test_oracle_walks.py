@@ -163,3 +163,78 @@ def test_edge_case_graphs(name):
         if name == "star":
             hub_positions = walks[walks[:, 0] == 0][:, ::2]
             assert (hub_positions == 0).all()
+
+
+# ---- edge weights: proposals proportional to the weights, p/q bias on top (KnightKing) ----
+def weighted_test_graph():
+    graph = dense_test_graph()
+    rng = np.random.default_rng(4)
+    n = graph.get_number_of_nodes()
+    rows = np.repeat(np.arange(n), np.diff(graph.indptr))
+    # symmetric weights spanning three orders of magnitude, one zero-weight edge (never taken)
+    table = np.exp(rng.uniform(-3, 3, size=(n, n)))
+    table = np.minimum(table, table.T)
+    weights = table[rows, graph.indices].astype(np.float32)
+    weights[(rows == 0) & (graph.indices == 11)] = 0.0
+    weights[(rows == 11) & (graph.indices == 0)] = 0.0
+    return graph, weights
+
+
+def test_edge_cdf_is_the_quantised_cumulative_distribution():
+    graph, weights = weighted_test_graph()
+    cdf = oracle.edge_cdf(graph.indptr, weights)
+    for v in range(graph.get_number_of_nodes()):
+        lo, hi = graph.indptr[v], graph.indptr[v + 1]
+        row = weights[lo:hi].astype(np.float64)
+        expected = np.minimum(np.floor(np.cumsum(row) / row.sum() * 2.0 ** 32), 2.0 ** 32 - 1)
+        assert cdf[hi - 1] == 0xFFFFFFFF
+        assert np.array_equal(cdf[lo:hi - 1], expected[:-1].astype(np.uint32))
+    with pytest.raises(ValueError):
+        oracle.edge_cdf(graph.indptr, -weights)
+
+
+def test_weighted_first_order_follows_the_weights():
+    graph, weights = weighted_test_graph()
+    walks, _ = oracle.walks(graph.indptr, graph.indices, 8, 0, 240_000, 2, weights=weights)
+    for v in (0, 4, 2, 7):
+        lo, hi = graph.indptr[v], graph.indptr[v + 1]
+        nxt = walks[walks[:, 0] == v, 1]
+        counts = np.array([(nxt == x).sum() for x in graph.indices[lo:hi]])
+        pmf = weights[lo:hi].astype(np.float64) / weights[lo:hi].sum()
+        assert counts[pmf == 0].sum() == 0
+        keep = pmf * len(nxt) >= 5
+        assert keep.sum() >= 2
+        expected = pmf[keep] * len(nxt)
+        assert stats.chisquare(counts[keep], expected * counts[keep].sum() / expected.sum()).pvalue > 1e-3
+
+
+@pytest.mark.parametrize("rw,ew", [(0.25, 4.0), (2.0, 0.5)])
+def test_weighted_second_order_matches_analytic_pmf(rw, ew):
+    graph, weights = weighted_test_graph()
+    walks, _ = oracle.walks(graph.indptr, graph.indices, 77, 0, 480_000, 3, rw, ew, weights=weights)
+    checked = 0
+    for prev, cur in [(4, 0), (0, 4), (1, 2), (5, 6), (2, 7)]:
+        sel = walks[(walks[:, 0] == prev) & (walks[:, 1] == cur), 2]
+        lo, hi = graph.indptr[cur], graph.indptr[cur + 1]
+        nv, bias = analytic_pmf(graph, prev, cur, rw, ew)  # pure p/q bias ...
+        pmf = bias * weights[lo:hi]                         # ... times the static weight
+        pmf = pmf / pmf.sum()
+        counts = np.array([(sel == x).sum() for x in nv])
+        keep = pmf * len(sel) >= 5
+        if len(sel) < 500 or keep.sum() < 2:
+            continue
+        expected = pmf[keep] * len(sel)
+        assert stats.chisquare(counts[keep], expected * counts[keep].sum() / expected.sum()).pvalue > 1e-3
+        checked += 1
+    assert checked >= 3
+
+
+def test_unit_weights_reproduce_nothing_else_than_valid_walks(small_ppi_weighted):
+    g = small_ppi_weighted
+    walks, counters = oracle.walks(g.indptr, g.indices, 5, 0, 2000, 24, 0.25, 4.0, weights=g.weights)
+    n = g.get_number_of_nodes()
+    edge_keys = np.repeat(np.arange(n, dtype=np.int64), np.diff(g.indptr)) * n + g.indices
+    keys = walks[:, :-1].astype(np.int64).ravel() * n + walks[:, 1:].astype(np.int64).ravel()
+    assert np.isin(keys, edge_keys).all() and counters["steps"] == 2000 * 23
+    unweighted, _ = oracle.walks(g.indptr, g.indices, 5, 0, 2000, 24, 0.25, 4.0)
+    assert not np.array_equal(walks, unweighted)
