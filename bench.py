@@ -403,32 +403,47 @@ def run_ours(args, cfg):
         "mean_pair_loss": counters["loss_sum"] / max(counters["pairs"], 1),
     }
 
-    if rank == 0:
-        # ---- e2e: the host-buffer C-ABI call (CSR H2D + init + K steps + tables D2H) ----
-        if world == 1 and not args.no_e2e:
-            del engine
-            torch.cuda.synchronize(device)
-            e2e_engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=args.steps,
-                                return_weight=cfg["return_weight"],
-                                explore_weight=cfg["explore_weight"],
-                                chunk_walks=args.chunk_walks, device=local_rank, **COMMON)
-            n = graph.get_number_of_nodes()
-            out0 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
-            out1 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
-            begin = time.perf_counter()
-            e2e_engine.load_csr(graph.indptr, graph.indices)
+    # ---- e2e: the reference-facing call with HOST buffers in and out, on every rank: CSR H2D +
+    # init + K steps per GPU (+ the all-reduces) + tables D2H; max over ranks ----
+    if not args.no_e2e:
+        del engine, tables
+        torch.cuda.synchronize(device)
+        e2e_engine = Engine(cfg["model"], embedding_size=D, epochs=1,
+                            iterations=args.steps * world, return_weight=cfg["return_weight"],
+                            explore_weight=cfg["explore_weight"], chunk_walks=args.chunk_walks,
+                            device=local_rank, **COMMON)
+        n = graph.get_number_of_nodes()
+        out0 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
+        out1 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
+        if world > 1:
+            dist.barrier()
+        begin = time.perf_counter()
+        e2e_engine.load_csr(graph.indptr, graph.indices)
+        if world > 1:
+            t0, t1, _ = e2e_engine.fit_distributed(SEED, args.sync_interval)
+            out0[:], out1[:] = t0, t1
+        else:
             e2e_engine.fit(SEED, out0, out1)
-            e2e_engine.sync()
-            e2e_s = time.perf_counter() - begin
-            e2e_pairs = e2e_engine.counters()["pairs"]
-            h2d = graph.indptr.nbytes + graph.indices.nbytes + 12 * n  # + sources, alias table
-            result["e2e"] = {"value": e2e_pairs / e2e_s, "unit": "pairs/s",
-                             "h2d_bytes_per_step": h2d / args.steps,
-                             "d2h_bytes_per_step": (out0.nbytes + out1.nbytes) / args.steps,
-                             "seconds": e2e_s,
-                             "call": "b2e_load_csr + b2e_fit (host buffers in/out, "
-                                     f"iterations={args.steps}, epochs=1)"}
-            e2e_engine.close()
+        e2e_engine.sync()
+        e2e_s = time.perf_counter() - begin
+        stats = torch.tensor([e2e_s, float(e2e_engine.counters()["pairs"])], dtype=torch.float64,
+                             device=device)
+        if world > 1:
+            slowest = stats[:1].clone()
+            dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
+            dist.all_reduce(stats[1:], op=dist.ReduceOp.SUM)
+            stats[0] = slowest[0]
+        e2e_s, e2e_pairs = float(stats[0]), float(stats[1])
+        h2d = graph.indptr.nbytes + graph.indices.nbytes + 12 * n  # + sources, alias table
+        result["e2e"] = {"value": e2e_pairs / e2e_s, "unit": "pairs/s",
+                         "h2d_bytes_per_step": h2d / args.steps,
+                         "d2h_bytes_per_step": (out0.nbytes + out1.nbytes) / args.steps,
+                         "seconds": e2e_s,
+                         "call": ("b2e_load_csr + b2e_fit" if world == 1 else
+                                  "Engine.load_csr + Engine.fit_distributed on every rank") +
+                                 f" (host buffers in/out, {args.steps} steps per GPU, epochs=1)"}
+        e2e_engine.close()
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(graph, cfg, budget_s=args.cpu_budget)
         print(json.dumps(result), flush=True)

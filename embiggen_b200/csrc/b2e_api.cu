@@ -102,6 +102,7 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     h->row_stride = (c.embedding_size + 31u) / 32u * 32u;
     if (const char *env = getenv("B2E_PREFETCH")) h->prefetch = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_WALK_SM")) h->walk_state_machine = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
     for (int s = 0; s < 2; ++s) {
@@ -272,6 +273,21 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `packed` dies here
     }
 
+    // Is the graph undirected (every edge mirrored)?  Then the second-order walk kernel may
+    // check adjacency in the shorter of the two rows.  Verified here, never assumed.
+    h->undirected = false;
+    if (h->second_order && !getenv("B2E_ASSUME_DIRECTED")) {
+        int *d_flag = nullptr, flag = 1;
+        CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(d_flag, &flag, sizeof(int), cudaMemcpyHostToDevice, h->walk_stream));
+        CUDA_TRY(launch_symmetry_check(h->d_indptr, h->d_indices, n, nnz, d_flag, h->walk_stream));
+        CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+        cudaFree(d_flag);
+        h->undirected = flag != 0;
+        ++h->launches;
+    }
+
     CUDA_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
 
@@ -342,6 +358,9 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     p.thr_explore = h->thr[2];
     p.out = d_out;
     p.counters = h->d_counters;
+    p.undirected = h->undirected ? 1u : 0u;
+    p.state_machine = h->walk_state_machine;
+    p.sm_count = h->sm_count;
     CUDA_TRY(launch_walks(p, h->second_order, stream));
     if (n_walks) ++h->launches;
     return B2E_OK;

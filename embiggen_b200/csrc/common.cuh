@@ -57,6 +57,9 @@ struct WalkParams {
     unsigned long long thr_return, thr_common, thr_explore;
     uint32_t *out;
     DeviceCounters *counters;
+    uint32_t undirected;     // every edge has its mirror (verified at load): allows the short-row check
+    uint32_t state_machine;  // second-order walks as a per-lane state machine (0: plain kernel)
+    int sm_count;
 };
 
 struct TrainParams {
@@ -78,6 +81,8 @@ struct TrainParams {
 };
 
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
+cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                  uint64_t nnz, int *d_flag, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
                                uint32_t row_stride, uint64_t seed, cudaStream_t stream);
 // max_warps caps how many walks are trained concurrently (Hogwild staleness on small graphs)
@@ -119,6 +124,8 @@ struct b2e_handle {
     b2e::DeviceCounters *d_counters = nullptr;
     unsigned long long thr[3] = {0, 0, 0};
     bool second_order = false;
+    bool undirected = false;
+    uint32_t walk_state_machine = 0;  // B2E_WALK_SM=1 selects walk_sm_kernel
     uint32_t prefetch = 1;
     uint32_t variant = 0;
     uint64_t launches = 0;

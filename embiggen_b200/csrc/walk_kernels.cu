@@ -10,6 +10,8 @@
 //
 // Tokens are buffered four at a time in registers and written with one 16 B store: two
 // consecutive stores fill a 32 B sector while the line is still resident in L2.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b2e {
@@ -140,12 +142,279 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
     }
 }
 
+
+// ---- second-order walks as a per-lane state machine ----
+//
+// In the plain kernel a warp advances at the pace of its slowest lane: every step waits for
+// the lane with the most rejected trials, every trial for the lane with the longest adjacency
+// search.  Here every lane carries its own walk through the states below and performs exactly
+// ONE dependent gather per loop iteration, so no lane ever idles on a neighbour's retry and the
+// loads of all 32 lanes are issued by the same instruction (maximum memory-level parallelism).
+// Finished lanes fetch the next walk (grid-stride), so warps stay full until the chunk ends.
+//
+//   SRC   : start node of the walk                      (sources[wid mod n_src])
+//   ROW   : row bounds of the current node              (indptr[cur], indptr[cur + 1])
+//   TRIAL : one proposal                                (indices[off + idx]) -> accept / reject /
+//           needs an adjacency check
+//   XROW  : (undirected graphs) row bounds of the proposal, to search the shorter of
+//           N(prev) and N(x): x in N(prev) <=> prev in N(x); reused if x is accepted
+//   SEARCH: one bisection step of the adjacency check
+//
+// Decisions are the oracle's (same Philox words, same integer thresholds), only their schedule
+// differs, so the walks stay bit-identical.
+enum WalkState : uint32_t { W_SRC = 0, W_ROW = 1, W_TRIAL = 2, W_XROW = 3, W_SEARCH = 4, W_DONE = 5 };
+
+template <bool UNDIRECTED, bool VEC>
+__global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
+    const uint64_t threads = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = p.walk_length;
+    const unsigned long long thr_lo = min(p.thr_common, p.thr_explore);
+    const unsigned long long thr_hi = max(p.thr_common, p.thr_explore);
+    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
+
+    uint32_t state = i < p.n_walks ? W_SRC : W_DONE;
+    uint64_t wid = 0;
+    uint32_t t = 0, cur = PAD, prev = PAD, deg = 0, pdeg = 0, trial = 0;
+    int64_t off = 0, poff = 0;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    uint32_t x = PAD;                  // proposal under examination
+    unsigned long long r1 = 0;         // its accept word
+    int64_t xoff = 0;                  // its row, when XROW fetched it
+    uint32_t xdeg = 0;
+    bool have_xrow = false;
+    int64_t sbase = 0;                 // bisection: row base, bounds, key
+    uint32_t slo = 0, shi = 0, skey = 0;
+    uint32_t tok[4] = {PAD, PAD, PAD, PAD};
+    uint32_t *out = nullptr;
+
+    // append one token to the walk; groups of four leave as one 16-byte store
+    auto emit = [&](uint32_t token) {
+        const uint32_t slot = t & 3u;  // explicit selects keep the group in registers
+        if (slot == 0) tok[0] = token; else if (slot == 1) tok[1] = token;
+        else if (slot == 2) tok[2] = token; else tok[3] = token;
+        ++t;
+        const uint32_t filled = t & 3u;
+        if (filled == 0) {
+            if (VEC) {
+                *reinterpret_cast<uint4 *>(out + t - 4u) = make_uint4(tok[0], tok[1], tok[2], tok[3]);
+            } else {
+                out[t - 4u] = tok[0]; out[t - 3u] = tok[1]; out[t - 2u] = tok[2]; out[t - 1u] = tok[3];
+            }
+        } else if (t == L) {
+            out[t - filled] = tok[0];
+            if (filled > 1) out[t - filled + 1u] = tok[1];
+            if (filled > 2) out[t - filled + 2u] = tok[2];
+        }
+    };
+
+    while (__any_sync(0xffffffffu, state != W_DONE)) {
+        // ---- phase A: the address of this iteration's gather ----
+        const void *addr = p.sources;
+        bool wide = false;  // two 8-byte entries of indptr vs one 4-byte token
+        switch (state) {
+            case W_SRC:
+                wid = p.first_walk + i * p.walk_id_stride;
+                out = p.out + i * (uint64_t)L;
+                addr = p.sources + (wid % p.n_src);
+                break;
+            case W_ROW:
+                addr = p.indptr + cur;
+                wide = true;
+                break;
+            case W_XROW:
+                addr = p.indptr + x;
+                wide = true;
+                break;
+            case W_TRIAL: {
+                const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+                uint32_t r0;
+                if (t == 1) {
+                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, 0u, TAG_WALK1 << 24);
+                    r0 = rnd.x;
+                } else {
+                    if ((trial & 1u) == 0)
+                        rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                            (TAG_WALK2 << 24) | (trial >> 1));
+                    r0 = (trial & 1u) ? rnd.z : rnd.x;
+                    r1 = (trial & 1u) ? rnd.w : rnd.y;
+                    ++n_trials;
+                }
+                addr = p.indices + off + __umulhi(r0, deg);
+                break;
+            }
+            case W_SEARCH:
+                addr = p.indices + sbase + (slo + ((shi - slo) >> 1));
+                break;
+            default:
+                break;
+        }
+        // ---- phase B: one gather per lane, issued by the whole warp at once ----
+        uint32_t word = 0;
+        long long first = 0, second = 0;
+        if (state != W_DONE) {
+            if (wide) {
+                first = __ldg(reinterpret_cast<const long long *>(addr));
+                second = __ldg(reinterpret_cast<const long long *>(addr) + 1);
+            } else {
+                word = __ldg(reinterpret_cast<const uint32_t *>(addr));
+            }
+        }
+        // ---- phase C: consume it ----
+        bool accept = false, reject = false, new_row = false;
+        switch (state) {
+            case W_SRC:
+                cur = word;
+                prev = PAD;
+                t = 0;
+                emit(cur);
+                have_xrow = false;
+                state = L > 1 ? W_ROW : W_DONE;
+                break;
+            case W_ROW:
+                off = first;
+                deg = (uint32_t)(second - first);
+                new_row = true;
+                break;
+            case W_TRIAL:
+                x = word;
+                if (t == 1) {
+                    accept = true;
+                } else if (x == prev) {
+                    if (r1 < p.thr_return) accept = true; else reject = true;
+                } else if (r1 < thr_lo) {
+                    accept = true;
+                } else if (r1 >= thr_hi) {
+                    reject = true;
+                } else {
+                    ++n_searches;
+                    if (UNDIRECTED) {
+                        state = W_XROW;
+                    } else {
+                        sbase = poff; slo = 0; shi = pdeg; skey = x;
+                        state = W_SEARCH;
+                    }
+                }
+                break;
+            case W_XROW:
+                xoff = first;
+                xdeg = (uint32_t)(second - first);
+                have_xrow = true;
+                // x in N(prev) <=> prev in N(x) on an undirected graph: bisect the shorter row
+                if (xdeg < pdeg) { sbase = xoff; slo = 0; shi = xdeg; skey = prev; }
+                else { sbase = poff; slo = 0; shi = pdeg; skey = x; }
+                state = W_SEARCH;
+                break;
+            case W_SEARCH: {
+                const uint32_t mid = slo + ((shi - slo) >> 1);
+                bool decided = false, common = false;
+                if (word == skey) { decided = true; common = true; }
+                else if (word < skey) slo = mid + 1;
+                else shi = mid;
+                if (!decided && slo >= shi) decided = true;
+                if (decided) {
+                    if (r1 < (common ? p.thr_common : p.thr_explore)) accept = true; else reject = true;
+                }
+                break;
+            }
+            default:
+                break;
+        }
+        if (reject) {
+            ++trial;
+            have_xrow = false;
+            if (trial >= MAX_TRIALS) accept = true; else state = W_TRIAL;
+        }
+        if (accept) {
+            ++n_steps;
+            prev = cur; poff = off; pdeg = deg;
+            cur = x;
+            emit(x);
+            if (t >= L) {
+                state = W_DONE;
+            } else if (have_xrow) {
+                off = xoff; deg = xdeg;
+                new_row = true;
+            } else {
+                state = W_ROW;
+            }
+            have_xrow = false;
+        }
+        if (new_row) {  // the row of the current node is known: walk on, or pad after a dead end
+            trial = 0;
+            state = W_TRIAL;
+            if (deg == 0) {
+                while (t < L) emit(PAD);
+                state = W_DONE;
+            }
+        }
+        if (state == W_DONE && i < p.n_walks) {  // this lane's walk is complete: fetch the next one
+            i += threads;
+            if (i < p.n_walks) state = W_SRC; else i = p.n_walks;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        n_steps += __shfl_xor_sync(0xffffffffu, n_steps, o);
+        n_trials += __shfl_xor_sync(0xffffffffu, n_trials, o);
+        n_searches += __shfl_xor_sync(0xffffffffu, n_searches, o);
+    }
+    if ((threadIdx.x & 31) == 0 && p.counters) {
+        atomicAdd(&p.counters->walk_steps, n_steps);
+        atomicAdd(&p.counters->walk_trials, n_trials);
+        atomicAdd(&p.counters->walk_searches, n_searches);
+    }
+}
+
+// One thread per directed edge (u, v): is u in the row of v?  Clears *symmetric otherwise.
+__global__ void __launch_bounds__(256) symmetry_kernel(const int64_t *__restrict__ indptr,
+                                                       const uint32_t *__restrict__ indices, uint64_t n,
+                                                       uint64_t nnz, int *symmetric) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz || *symmetric == 0) return;
+    uint64_t lo = 0, hi = n;  // row of edge e: last u with indptr[u] <= e
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo + 1) >> 1);
+        if ((uint64_t)__ldg(indptr + mid) <= e) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t u = (uint32_t)lo, v = __ldg(indices + e);
+    const int64_t begin = __ldg(indptr + v);
+    const uint32_t len = (uint32_t)(__ldg(indptr + v + 1) - begin);
+    if (!row_contains(indices + begin, len, u)) *symmetric = 0;
+}
+
+cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                  uint64_t nnz, int *d_flag, cudaStream_t stream) {
+    if (nnz == 0) return cudaSuccess;
+    symmetry_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(indptr, indices, n, nnz, d_flag);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream) {
     if (p.n_walks == 0) return cudaSuccess;
     const unsigned block = 256;
     const unsigned grid = (unsigned)((p.n_walks + block - 1) / block);
     const bool vec = (p.walk_length % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16u) == 0;
     const bool weighted = p.cdf != nullptr;
+    if (second_order && !weighted && p.state_machine) {
+        // persistent grid: lanes fetch walks grid-stride, so size it to the machine, not the chunk
+        int per_sm = 0;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, p.undirected ? (vec ? walk_sm_kernel<true, true> : walk_sm_kernel<true, false>)
+                                  : (vec ? walk_sm_kernel<false, true> : walk_sm_kernel<false, false>),
+            (int)block, 0);
+        if (err != cudaSuccess) return err;
+        unsigned resident = (unsigned)std::max(1, per_sm) * (unsigned)p.sm_count;
+        const unsigned sm_grid = std::min(grid, resident);
+        if (p.undirected) {
+            if (vec) walk_sm_kernel<true, true><<<sm_grid, block, 0, stream>>>(p);
+            else walk_sm_kernel<true, false><<<sm_grid, block, 0, stream>>>(p);
+        } else {
+            if (vec) walk_sm_kernel<false, true><<<sm_grid, block, 0, stream>>>(p);
+            else walk_sm_kernel<false, false><<<sm_grid, block, 0, stream>>>(p);
+        }
+        return cudaGetLastError();
+    }
 #define B2E_LAUNCH_WALK(S, V, W) walk_kernel<S, V, W><<<grid, block, 0, stream>>>(p)
     if (second_order) {
         if (vec) { if (weighted) B2E_LAUNCH_WALK(true, true, true); else B2E_LAUNCH_WALK(true, true, false); }

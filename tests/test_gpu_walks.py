@@ -132,3 +132,24 @@ def test_weighted_embedder_runs_and_rejects_negative_weights(small_ppi_weighted)
     negative = CSRGraph(g.indptr, g.indices, weights=-g.weights, name="negative")
     with pytest.raises(ValueError, match="negative edge weights"):
         model.fit_transform(negative)
+
+
+def test_state_machine_walk_kernel_bit_exact(monkeypatch, small_ppi, rmat_graph):
+    """walk_sm_kernel (B2E_WALK_SM=1: one gather per lane per iteration, adjacency check in the
+    shorter row on undirected graphs) makes the oracle's decisions on another schedule."""
+    from conftest import tiny_graphs
+    monkeypatch.setenv("B2E_WALK_SM", "1")
+    graphs = [small_ppi, rmat_graph, tiny_graphs()["directed_dead_end"], tiny_graphs()["star"]]
+    for graph in graphs:
+        for rw, ew in [(0.25, 4.0), (2.0, 0.5), (7.5, 1.0)]:
+            for length in (2, 5, 64, 130):
+                count = 3 * int((np.diff(graph.indptr) > 0).sum()) + 5
+                expected, oc = oracle.walks(graph.indptr, graph.indices, 42, 9, count, length, rw, ew)
+                got, gc = gpu_walks(graph, 42, 9, count, length, rw, ew)
+                assert np.array_equal(got, expected)
+                assert (gc["walk_steps"], gc["walk_trials"], gc["walk_searches"]) == \
+                    (oc["steps"], oc["trials"], oc["searches"])
+    monkeypatch.setenv("B2E_ASSUME_DIRECTED", "1")  # without the short-row check
+    expected, _ = oracle.walks(rmat_graph.indptr, rmat_graph.indices, 1, 0, 5000, 64, 2.0, 0.5)
+    got, _ = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
+    assert np.array_equal(got, expected)
