@@ -49,6 +49,7 @@ CONFIGS = {
 COMMON = dict(walk_length=128, window_size=4, number_of_negative_samples=10, learning_rate=0.01,
               learning_rate_decay=0.9, clipping_value=6.0)
 SEED = 42
+GATHER_CEILING = 40.6e9  # measured random 4-byte gathers/s of a B200 over a 1.6 GB array
 METRIC = "skipgram_context_pairs_per_s"
 
 
@@ -372,6 +373,13 @@ def run_ours(args, cfg):
     walk_bytes_per_step = 36 + 32 * max(trials, 1.0)  # + probe sectors (needs the oracle's count)
     walk_avg_ms = float(np.mean(walk_ms))
     walk_achieved = steps_per_launch * walk_bytes_per_step / (walk_avg_ms * 1e-3) / 1e9
+    # A walk is a chain of dependent random gathers; when the CSR does not fit L2 the memory
+    # system serves at most GATHER_CEILING random 4-byte gathers per second
+    # (scripts/microbench_gather.cu, profiles/r01_microbench_random_gathers.txt).  Every step
+    # needs at least its row bounds, its proposals and one probe per adjacency search.
+    searches = walk_counters["walk_searches"] / max(walk_counters["walk_steps"], 1)
+    gathers_per_step = 1.0 + max(trials, 1.0) + searches
+    walk_gathers = steps_per_launch * gathers_per_step / (walk_avg_ms * 1e-3)
 
     kernel_name = ("skipgram_pipe_kernel" if cfg["model"] == "SkipGram" else "cbow_pipe_kernel") + \
         f"<{K + 1}>"
@@ -398,7 +406,11 @@ def run_ours(args, cfg):
         "walk": {"kernel": "walk_kernel", "steps_per_s_alone": steps_per_launch / (walk_avg_ms * 1e-3),
                  "avg_launch_ms": walk_avg_ms, "trials_per_step": trials,
                  "bytes_per_step": walk_bytes_per_step, "achieved_gbs": walk_achieved,
-                 "frac": walk_achieved / peak},
+                 "frac": walk_achieved / peak,
+                 "gathers_per_step_lower_bound": gathers_per_step,
+                 "gathers_per_s_lower_bound": walk_gathers,
+                 "gather_ceiling_per_s": GATHER_CEILING,
+                 "gather_frac_lower_bound": walk_gathers / GATHER_CEILING},
         "clocks": clocks,
         "mean_pair_loss": counters["loss_sum"] / max(counters["pairs"], 1),
     }

@@ -107,3 +107,88 @@ def test_gpu_auroc_matches_oracle_auroc(model, rw, ew):
         assert abs(a_gpu - a_ref) <= 0.015
         deltas.append(a_gpu - a_ref)
     assert np.mean(deltas) >= -0.005
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["SkipGram", "CBOW"])
+def test_loss_curve_tracks_the_oracle(model):
+    """Loss-curve leg (north_star, SURVEY.md 8c leg 3): the per-epoch mean pair loss of the GPU
+    run (thousands of concurrent walks) against the 8-thread Hogwild oracle on the same graph,
+    kwargs and seed.  Stated tolerance: 5 % per epoch after the first, 10 % on the first
+    (where the staleness of concurrent updates is largest)."""
+    from embiggen_b200.engine import Engine
+    src, dst, n = block_model(7)
+    graph = csr_from_edges(src, dst, n)
+    kw = dict(KW, epochs=6)
+    oracle.set_threads(8)
+    try:
+        _, _, expected = oracle.fit(model, graph.indptr, graph.indices, 5, kw["embedding_size"], kw["epochs"],
+                                    kw["iterations"], kw["walk_length"], kw["window_size"],
+                                    kw["number_of_negative_samples"], kw["learning_rate"],
+                                    kw["learning_rate_decay"], return_weight=0.5, explore_weight=2.0)
+    finally:
+        oracle.set_threads(1)
+    with Engine(model, return_weight=0.5, explore_weight=2.0, **kw) as engine:
+        engine.load_csr(graph.indptr, graph.indices)
+        _, _, got = engine.fit(5)
+    print(model, "oracle", np.round(expected, 4), "gpu", np.round(got, 4))
+    assert all(b < a for a, b in zip(got[:-1], got[1:]))  # monotone decrease
+    for epoch, (a, b) in enumerate(zip(expected, got)):
+        assert abs(b - a) <= (0.10 if epoch == 0 else 0.05) * a, (epoch, a, b)
+
+
+@pytest.mark.gpu
+def test_replica_averaging_keeps_the_quality():
+    """The data-parallel exchange step on one GPU: two replicas (two handles) train the two
+    shards of every step and are averaged at the driver's sync points, exactly like two ranks;
+    the averaged embedding must predict held-out edges as well as the single-replica one
+    (tolerance 0.01 AUROC on one holdout)."""
+    import torch
+    from embiggen_b200.engine import Engine, shard_chunks
+    src, dst, n = block_model(3)
+    train_pos, test_pos, train_neg, test_neg = holdout(src, dst, n, 3)
+    graph = csr_from_edges(train_pos[0], train_pos[1], n)
+    seed, world, sync_interval = 17, 2, 2
+    with Engine("SkipGram", **KW) as single:
+        single.load_csr(graph.indptr, graph.indices)
+        c, x, _ = single.fit(seed)
+    baseline = auroc(np.hstack([c, x]), train_pos, test_pos, train_neg, test_neg)
+
+    replicas = [Engine("SkipGram", chunk_walks=512, **KW) for _ in range(world)]
+    try:
+        for engine in replicas:
+            engine.load_csr(graph.indptr, graph.indices)
+            engine.init_tables(seed)
+        tables = [engine.device_tables() for engine in replicas]
+
+        def average():
+            for engine in replicas:
+                engine.sync()
+            for k in range(2):
+                mean = (tables[0][k] + tables[1][k]) / 2
+                for rank in range(world):
+                    tables[rank][k].copy_(mean)
+            torch.cuda.synchronize()
+
+        per_epoch = replicas[0].walks_per_epoch
+        lr = np.float32(KW["learning_rate"])
+        for epoch in range(KW["epochs"]):
+            plans = [list(shard_chunks(per_epoch, 512, world, rank, epoch * per_epoch)) for rank in range(world)]
+            for index in range(len(plans[0])):
+                for rank, engine in enumerate(replicas):
+                    first, count, stride = plans[rank][index]
+                    engine.walk_chunk(seed, first, count, stride, index & 1)
+                    engine.train_chunk(seed, index & 1, float(lr))
+                if (index + 1) % sync_interval == 0:
+                    average()
+            average()
+            lr = np.float32(lr * np.float32(KW["learning_rate_decay"]))
+        a0, a1 = replicas[0].export_tables()
+        b0, _ = replicas[1].export_tables()
+        assert np.array_equal(a0, b0)  # replicas agree after the exchange
+    finally:
+        for engine in replicas:
+            engine.close()
+    averaged = auroc(np.hstack([a0, a1]), train_pos, test_pos, train_neg, test_neg)
+    print(f"AUROC single replica {baseline:.4f}  two averaged replicas {averaged:.4f}")
+    assert averaged >= baseline - 0.01
