@@ -414,9 +414,10 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.t1 = h->d_t1;
     p.counters = h->d_counters;
     // Hogwild staleness: on a small graph thousands of concurrent walks would all train against
-    // nearly the same stale rows; keep about one walk in flight per 32 nodes unless told otherwise
+    // nearly the same stale rows; keep about one walk in flight per 64 nodes unless told otherwise
+    // (graphs above ~200 k nodes are not affected: fewer than 3 000 warps are resident anyway)
     const uint64_t max_warps = c.max_concurrent_walks ? c.max_concurrent_walks
-                                                       : std::max<uint64_t>(8, h->n / 32);
+                                                       : std::max<uint64_t>(8, h->n / 64);
     CUDA_TRY(launch_train(p, c.model, c.deterministic != 0, h->sm_count, max_warps, h->train_stream));
     if (p.n_walks) ++h->launches;
     return B2E_OK;
