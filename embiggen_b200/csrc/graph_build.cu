@@ -147,22 +147,30 @@ static cudaError_t sort_keys(DeviceBuffer &temp, const unsigned long long *keys_
     return cudaSuccess;
 }
 
-// directed keys (any order, INVALID_KEY allowed) -> CSR in host buffers
+// directed keys (any order) -> CSR in host buffers.  `scratch` is the alternate buffer of the
+// radix sort (no third copy).  With `dedup` the keys may repeat and contain INVALID_KEY.
 static cudaError_t keys_to_csr(DeviceBuffer &temp, unsigned long long *keys, unsigned long long *scratch,
-                               uint64_t count, uint64_t n, int64_t *indptr, uint32_t *indices,
+                               uint64_t count, uint64_t n, bool dedup, int64_t *indptr, uint32_t *indices,
                                uint64_t capacity, uint64_t *nnz_out, std::string &error) {
-    GB_TRY(sort_keys(temp, keys, scratch, count, error));
-    DeviceBuffer selected;
-    GB_TRY(selected.reserve(sizeof(unsigned long long)));
+    cub::DoubleBuffer<unsigned long long> buffers(keys, scratch);
     size_t bytes = 0;
-    GB_TRY(cub::DeviceSelect::Unique(nullptr, bytes, scratch, keys, selected.as<unsigned long long>(), count));
+    GB_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bytes, buffers, count));
     GB_TRY(temp.reserve(bytes));
-    GB_TRY(cub::DeviceSelect::Unique(temp.ptr, bytes, scratch, keys, selected.as<unsigned long long>(), count));
-    unsigned long long unique = 0, last = 0;
-    GB_TRY(cudaMemcpy(&unique, selected.ptr, sizeof(unique), cudaMemcpyDeviceToHost));
-    if (unique) GB_TRY(cudaMemcpy(&last, keys + unique - 1, sizeof(last), cudaMemcpyDeviceToHost));
-    uint64_t nnz = unique;
-    if (unique && last == INVALID_KEY) --nnz;
+    GB_TRY(cub::DeviceRadixSort::SortKeys(temp.ptr, bytes, buffers, count));
+    unsigned long long *sorted = buffers.Current(), *other = buffers.Alternate();
+    uint64_t nnz = count;
+    if (dedup) {
+        DeviceBuffer selected;
+        GB_TRY(selected.reserve(sizeof(unsigned long long)));
+        GB_TRY(cub::DeviceSelect::Unique(nullptr, bytes, sorted, other, selected.as<unsigned long long>(), count));
+        GB_TRY(temp.reserve(bytes));
+        GB_TRY(cub::DeviceSelect::Unique(temp.ptr, bytes, sorted, other, selected.as<unsigned long long>(), count));
+        unsigned long long unique = 0, last = 0;
+        GB_TRY(cudaMemcpy(&unique, selected.ptr, sizeof(unique), cudaMemcpyDeviceToHost));
+        if (unique) GB_TRY(cudaMemcpy(&last, other + unique - 1, sizeof(last), cudaMemcpyDeviceToHost));
+        nnz = unique - ((unique && last == INVALID_KEY) ? 1 : 0);
+        sorted = other;
+    }
     *nnz_out = nnz;
     if (nnz > capacity) {
         error = "indices buffer too small for the de-duplicated graph";
@@ -172,7 +180,7 @@ static cudaError_t keys_to_csr(DeviceBuffer &temp, unsigned long long *keys, uns
     GB_TRY(d_indices.reserve(std::max<uint64_t>(nnz, 1) * sizeof(uint32_t)));
     GB_TRY(d_indptr.reserve((n + 1) * sizeof(long long)));
     csr_from_keys_kernel<<<blocks_for(std::max<uint64_t>(nnz, n + 1)), 256>>>(
-        keys, nnz, n, d_indices.as<uint32_t>(), d_indptr.as<long long>());
+        sorted, nnz, n, d_indices.as<uint32_t>(), d_indptr.as<long long>());
     GB_TRY(cudaGetLastError());
     GB_TRY(cudaMemcpy(indptr, d_indptr.ptr, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
     if (nnz) GB_TRY(cudaMemcpy(indices, d_indices.ptr, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -205,72 +213,125 @@ cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_
         return cudaErrorInvalidValue;
     }
     return keys_to_csr(temp, keys.as<unsigned long long>(), scratch.as<unsigned long long>(), count, n,
-                       indptr, indices, capacity, nnz_out, error);
+                       true, indptr, indices, capacity, nnz_out, error);
 }
 
+// flags[j] = 1 when keys[j] is a real key that the sorted pool does not hold yet
+__global__ void __launch_bounds__(256) new_key_flags_kernel(const unsigned long long *keys, uint64_t count,
+                                                            const unsigned long long *pool, uint64_t have,
+                                                            unsigned char *flags) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const unsigned long long key = keys[k];
+    uint64_t lo = 0, hi = have;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (pool[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    flags[k] = key != INVALID_KEY && !(lo < have && pool[lo] == key);
+}
+
+template <typename T>
+static cudaError_t select_flagged(DeviceBuffer &temp, const T *in, const unsigned char *flags, T *out,
+                                  unsigned long long *d_count, uint64_t count, std::string &error) {
+    size_t bytes = 0;
+    GB_TRY(cub::DeviceSelect::Flagged(nullptr, bytes, in, flags, out, d_count, count));
+    GB_TRY(temp.reserve(bytes));
+    GB_TRY(cub::DeviceSelect::Flagged(temp.ptr, bytes, in, flags, out, d_count, count));
+    return cudaSuccess;
+}
+
+// The first m distinct undirected edges of the Philox stream, in draw order.  Candidates are
+// drawn in batches; a batch is sorted, de-duplicated (earliest draw wins), filtered against the
+// sorted pool of edges already kept, and merged into it.  Every pool edge was first drawn before
+// any edge of a later batch, so only the last batch can overshoot m, and only its new edges
+// need their draw index to be cut back to "the m earliest".  Memory: two pool buffers of m keys
+// plus a few batch-sized arrays, which is what makes the 2-billion-edge shape fit one GPU.
 cudaError_t synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t m, uint64_t seed,
                           unsigned long long t_a, unsigned long long t_ab, unsigned long long t_abc,
                           int64_t *indptr, uint32_t *indices, uint64_t capacity, uint64_t *nnz_out,
                           std::string &error) {
     typedef unsigned long long u64;
-    // pool of distinct (key, first draw index) so far, kept sorted by key
-    DeviceBuffer pool_keys, pool_ids, in_keys, in_ids, out_keys, out_ids, temp, selected;
-    GB_TRY(selected.reserve(sizeof(u64)));
+    const uint64_t batch_max = 1ull << 29;
+    DeviceBuffer pool[2], keys_in, ids_in, keys_sorted, ids_sorted, keys_unique, ids_unique, keys_new,
+        ids_new, flags, temp, d_count;
+    GB_TRY(d_count.reserve(sizeof(u64)));
+    GB_TRY(pool[0].reserve(std::max<uint64_t>(m, 1) * sizeof(u64)));
+    GB_TRY(pool[1].reserve(std::max<uint64_t>(m, 1) * sizeof(u64)));
+    int cur = 0;
     uint64_t have = 0, drawn = 0;
     for (int round = 0; have < m; ++round) {
-        if (round > 200) {
+        if (round > 400) {
             error = "could not draw enough distinct edges (graph too dense for its shape?)";
             return cudaErrorInvalidValue;
         }
-        const uint64_t want = (uint64_t)((double)(m - have) * 1.3) + 1024;
-        const uint64_t total = have + want;
-        GB_TRY(in_keys.reserve(total * sizeof(u64)));
-        GB_TRY(in_ids.reserve(total * sizeof(u64)));
-        GB_TRY(out_keys.reserve(total * sizeof(u64)));
-        GB_TRY(out_ids.reserve(total * sizeof(u64)));
-        if (have) {
-            GB_TRY(cudaMemcpy(in_keys.ptr, pool_keys.ptr, have * sizeof(u64), cudaMemcpyDeviceToDevice));
-            GB_TRY(cudaMemcpy(in_ids.ptr, pool_ids.ptr, have * sizeof(u64), cudaMemcpyDeviceToDevice));
-        }
+        const uint64_t want = std::min<uint64_t>(batch_max, (uint64_t)((double)(m - have) * 1.3) + 1024);
+        for (DeviceBuffer *buffer : {&keys_in, &ids_in, &keys_sorted, &ids_sorted, &keys_unique, &ids_unique,
+                                     &keys_new, &ids_new})
+            GB_TRY(buffer->reserve(want * sizeof(u64)));
+        GB_TRY(flags.reserve(want));
         draw_edges_kernel<<<blocks_for(want), 256>>>(kind, n, scale, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                     t_a, t_ab, t_abc, drawn, want,
-                                                     in_keys.as<u64>() + have, in_ids.as<u64>() + have);
+                                                     t_a, t_ab, t_abc, drawn, want, keys_in.as<u64>(),
+                                                     ids_in.as<u64>());
         GB_TRY(cudaGetLastError());
         drawn += want;
         // stable sort by key: equal keys stay in ascending draw order, so "first" = earliest draw
-        GB_TRY(sort_pairs(temp, in_keys.as<u64>(), out_keys.as<u64>(), in_ids.as<u64>(), out_ids.as<u64>(),
-                          total, error));
-        GB_TRY(pool_keys.reserve(total * sizeof(u64)));
-        GB_TRY(pool_ids.reserve(total * sizeof(u64)));
+        GB_TRY(sort_pairs(temp, keys_in.as<u64>(), keys_sorted.as<u64>(), ids_in.as<u64>(),
+                          ids_sorted.as<u64>(), want, error));
         size_t bytes = 0;
-        GB_TRY(cub::DeviceSelect::UniqueByKey(nullptr, bytes, out_keys.as<u64>(), out_ids.as<u64>(),
-                                              pool_keys.as<u64>(), pool_ids.as<u64>(),
-                                              selected.as<u64>(), total));
+        GB_TRY(cub::DeviceSelect::UniqueByKey(nullptr, bytes, keys_sorted.as<u64>(), ids_sorted.as<u64>(),
+                                              keys_unique.as<u64>(), ids_unique.as<u64>(), d_count.as<u64>(),
+                                              want));
         GB_TRY(temp.reserve(bytes));
-        GB_TRY(cub::DeviceSelect::UniqueByKey(temp.ptr, bytes, out_keys.as<u64>(), out_ids.as<u64>(),
-                                              pool_keys.as<u64>(), pool_ids.as<u64>(),
-                                              selected.as<u64>(), total));
-        u64 unique = 0, last = 0;
-        GB_TRY(cudaMemcpy(&unique, selected.ptr, sizeof(unique), cudaMemcpyDeviceToHost));
-        if (unique) GB_TRY(cudaMemcpy(&last, pool_keys.as<u64>() + unique - 1, sizeof(last), cudaMemcpyDeviceToHost));
-        have = unique - ((unique && last == INVALID_KEY) ? 1 : 0);
+        GB_TRY(cub::DeviceSelect::UniqueByKey(temp.ptr, bytes, keys_sorted.as<u64>(), ids_sorted.as<u64>(),
+                                              keys_unique.as<u64>(), ids_unique.as<u64>(), d_count.as<u64>(),
+                                              want));
+        u64 unique = 0;
+        GB_TRY(cudaMemcpy(&unique, d_count.ptr, sizeof(unique), cudaMemcpyDeviceToHost));
+        if (unique == 0) continue;
+        new_key_flags_kernel<<<blocks_for(unique), 256>>>(keys_unique.as<u64>(), unique, pool[cur].as<u64>(),
+                                                          have, flags.as<unsigned char>());
+        GB_TRY(cudaGetLastError());
+        GB_TRY(select_flagged(temp, keys_unique.as<u64>(), flags.as<unsigned char>(), keys_new.as<u64>(),
+                              d_count.as<u64>(), unique, error));
+        GB_TRY(select_flagged(temp, ids_unique.as<u64>(), flags.as<unsigned char>(), ids_new.as<u64>(),
+                              d_count.as<u64>(), unique, error));
+        u64 fresh = 0;
+        GB_TRY(cudaMemcpy(&fresh, d_count.ptr, sizeof(fresh), cudaMemcpyDeviceToHost));
+        if (fresh == 0) continue;
+        if (have + fresh > m) {  // the last batch overshoots: keep its m - have earliest draws
+            const uint64_t keep = m - have;
+            GB_TRY(sort_pairs(temp, ids_new.as<u64>(), ids_sorted.as<u64>(), keys_new.as<u64>(),
+                              keys_sorted.as<u64>(), fresh, error));
+            GB_TRY(sort_keys(temp, keys_sorted.as<u64>(), keys_new.as<u64>(), keep, error));
+            fresh = keep;
+        }
+        GB_TRY(cub::DeviceMerge::MergeKeys(nullptr, bytes, pool[cur].as<u64>(), (int64_t)have,
+                                           keys_new.as<u64>(), (int64_t)fresh, pool[cur ^ 1].as<u64>()));
+        GB_TRY(temp.reserve(bytes));
+        GB_TRY(cub::DeviceMerge::MergeKeys(temp.ptr, bytes, pool[cur].as<u64>(), (int64_t)have,
+                                           keys_new.as<u64>(), (int64_t)fresh, pool[cur ^ 1].as<u64>()));
+        cur ^= 1;
+        have += fresh;
     }
-    if (have > m) {  // keep the m earliest draws: sort by draw index, truncate
-        GB_TRY(sort_pairs(temp, pool_ids.as<u64>(), out_ids.as<u64>(), pool_keys.as<u64>(), out_keys.as<u64>(),
-                          have, error));
-        GB_TRY(cudaMemcpy(pool_keys.ptr, out_keys.ptr, m * sizeof(u64), cudaMemcpyDeviceToDevice));
-        have = m;
+    for (DeviceBuffer *buffer : {&keys_in, &ids_in, &keys_sorted, &ids_sorted, &keys_unique, &ids_unique,
+                                 &keys_new, &ids_new, &flags, &pool[cur ^ 1]}) {
+        cudaFree(buffer->ptr);
+        buffer->ptr = nullptr;
+        buffer->bytes = 0;
     }
     // both directions, sorted -> CSR
-    GB_TRY(in_keys.reserve(2 * have * sizeof(u64)));
-    GB_TRY(out_keys.reserve(2 * have * sizeof(u64)));
-    mirror_keys_kernel<<<blocks_for(have), 256>>>(pool_keys.as<u64>(), have, in_keys.as<u64>());
+    DeviceBuffer directed, alternate;
+    GB_TRY(directed.reserve(2 * have * sizeof(u64)));
+    mirror_keys_kernel<<<blocks_for(have), 256>>>(pool[cur].as<u64>(), have, directed.as<u64>());
     GB_TRY(cudaGetLastError());
-    cudaFree(pool_ids.ptr); pool_ids.ptr = nullptr; pool_ids.bytes = 0;
-    cudaFree(in_ids.ptr); in_ids.ptr = nullptr; in_ids.bytes = 0;
-    cudaFree(out_ids.ptr); out_ids.ptr = nullptr; out_ids.bytes = 0;
-    return keys_to_csr(temp, in_keys.as<u64>(), out_keys.as<u64>(), 2 * have, n, indptr, indices, capacity,
-                       nnz_out, error);
+    GB_TRY(cudaDeviceSynchronize());
+    cudaFree(pool[cur].ptr);
+    pool[cur].ptr = nullptr;
+    pool[cur].bytes = 0;
+    GB_TRY(alternate.reserve(2 * have * sizeof(u64)));
+    return keys_to_csr(temp, directed.as<u64>(), alternate.as<u64>(), 2 * have, n, false, indptr, indices,
+                       capacity, nnz_out, error);
 }
 
 }  // namespace b2e
