@@ -56,31 +56,47 @@ GATHER_CEILING = 40.6e9  # measured random 4-byte gathers/s of a B200 over a 1.6
 METRIC = "skipgram_context_pairs_per_s"
 
 
-def load_graph(spec, device=None):
-    """Synthetic graph of the named shape (generator seed 42), cached on local disk.
+def load_graph(spec, device=None, world=1, local_rank=0, barrier=None):
+    """Synthetic graph of the named shape (generator seed 42), cached as raw .npy files (tmpfs
+    when available) and memory-mapped, so that the ranks of one node share one copy.
 
     With a GPU the graph is generated and its CSR built on the device (same graph as the numpy
-    generators, tests/test_gpu_graph_build.py); the CPU reference arm falls back to numpy."""
+    generators, tests/test_gpu_graph_build.py); the CPU reference arm falls back to numpy.
+    With several ranks only local rank 0 generates; the others wait at `barrier` and map it."""
     from embiggen_b200.graph import CSRGraph, erdos_renyi, rmat
     tag = "_".join(str(x) for x in spec)
-    path = os.path.join(os.environ.get("B2E_CACHE", "/tmp"), f"b2e_graph_{tag}.npz")
-    if os.path.exists(path):
-        data = np.load(path)
-        return CSRGraph(data["indptr"], data["indices"], name=tag)
-    if device is not None:
-        from embiggen_b200.graph_gpu import erdos_renyi_gpu, rmat_gpu
-        graph = erdos_renyi_gpu(spec[1], spec[2], seed=42, device=device) if spec[0] == "er" else \
-            rmat_gpu(spec[1], spec[2], n=spec[3], seed=42, device=device)
-    else:
-        graph = erdos_renyi(spec[1], spec[2], seed=42) if spec[0] == "er" else \
-            rmat(spec[1], spec[2], n=spec[3], seed=42)
-    if graph.indices.shape[0] <= 1_000_000_000:  # the 2-billion-edge shape is not worth a 17 GB file
-        try:
-            tmp = path + f".{os.getpid()}.tmp.npz"
-            np.savez(tmp, indptr=graph.indptr, indices=graph.indices)
-            os.replace(tmp, path)
-        except OSError:
-            pass
+    default_cache = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    base = os.path.join(os.environ.get("B2E_CACHE", default_cache), f"b2e_graph_{tag}")
+    paths = (base + ".indptr.npy", base + ".indices.npy")
+
+    def cached():
+        if all(os.path.exists(p) for p in paths):
+            return CSRGraph(np.load(paths[0], mmap_mode="r"), np.load(paths[1], mmap_mode="r"), name=tag)
+        return None
+
+    graph = cached()
+    if graph is None and local_rank == 0:
+        if device is not None:
+            from embiggen_b200.graph_gpu import erdos_renyi_gpu, rmat_gpu
+            graph = erdos_renyi_gpu(spec[1], spec[2], seed=42, device=device) if spec[0] == "er" else \
+                rmat_gpu(spec[1], spec[2], n=spec[3], seed=42, device=device)
+        else:
+            graph = erdos_renyi(spec[1], spec[2], seed=42) if spec[0] == "er" else \
+                rmat(spec[1], spec[2], n=spec[3], seed=42)
+        if world > 1 or graph.indices.shape[0] <= 1_000_000_000:  # one rank alone keeps 2 B edges in RAM
+            try:
+                for path, array in zip(paths, (graph.indptr, graph.indices)):
+                    tmp = path + f".{os.getpid()}.tmp.npy"
+                    np.save(tmp, array)
+                    os.replace(tmp, path)
+            except OSError:
+                pass
+    if barrier is not None:
+        barrier()
+    if graph is None:
+        graph = cached()
+    if graph is None:
+        raise RuntimeError("the graph cache written by local rank 0 is not visible on this rank")
     return graph
 
 
@@ -273,7 +289,8 @@ def run_ours(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    graph = load_graph(cfg["graph"], device=local_rank)
+    graph = load_graph(cfg["graph"], device=local_rank, world=world, local_rank=local_rank,
+                       barrier=dist.barrier if world > 1 else None)
     D = cfg["embedding_size"]
     L, w, K = COMMON["walk_length"], COMMON["window_size"], COMMON["number_of_negative_samples"]
     engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
