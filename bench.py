@@ -287,6 +287,8 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     graph = load_graph(cfg["graph"], device=local_rank, world=world, local_rank=local_rank,
