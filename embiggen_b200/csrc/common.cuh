@@ -91,8 +91,6 @@ cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministi
 bool pipe_supported(const TrainParams &p, uint32_t model);
 cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                               uint64_t max_warps, cudaStream_t stream);
-cudaError_t launch_pack_rows(const float *src, float *dst, uint64_t n, uint32_t embedding_size,
-                             uint32_t row_stride, bool strip, cudaStream_t stream);
 
 cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint64_t n,
                            int symmetrise, int64_t *indptr, uint32_t *indices, uint64_t capacity,

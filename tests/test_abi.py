@@ -52,3 +52,14 @@ def test_no_cpu_fallback_without_device():
     from embiggen_b200.engine import Engine
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         Engine("SkipGram")
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under embiggen_b200/ may import, load or link it."""
+    package = os.path.join(ROOT, "embiggen_b200")
+    for folder, _, files in os.walk(package):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(folder, name)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), name
+                assert "liboracle" not in text and "oracle.h" not in text, name
