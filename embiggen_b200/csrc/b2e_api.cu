@@ -115,7 +115,8 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (cudaStreamCreateWithFlags(&h->walk_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->train_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&h->d_counters, sizeof(DeviceCounters)) != cudaSuccess ||
-        cudaMemset(h->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) {
+        cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->train_stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->train_stream) != cudaSuccess) {
         b2e_destroy(h);
         return fail(B2E_ERR_CUDA, "stream / counter allocation failed");
     }
@@ -254,7 +255,9 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         if (!build_edge_cdf(indptr, weights, n, cdf))
             return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
         CUDA_TRY(cudaMalloc(&h->d_cdf, nnz * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpy(h->d_cdf, cdf.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cdf, cdf.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                 h->walk_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `cdf` dies here
     }
     CUDA_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
@@ -442,8 +445,8 @@ extern "C" int b2e_train_host_walks(b2e_handle *h, uint64_t seed, const uint32_t
     if (n_walks > h->chunk_cap) return fail(B2E_ERR_INVALID, "n_walks exceeds the chunk capacity");
     CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
     CUDA_TRY(cudaStreamSynchronize(h->train_stream));
-    CUDA_TRY(cudaMemcpy(h->d_walks[0], walks, n_walks * h->cfg.walk_length * sizeof(uint32_t),
-                        cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(h->d_walks[0], walks, n_walks * h->cfg.walk_length * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, h->train_stream));  // ordered before the kernel
     h->slot_first[0] = first_walk;
     h->slot_count[0] = n_walks;
     h->slot_stride[0] = walk_id_stride;
@@ -497,8 +500,11 @@ extern "C" int b2e_export_tables(b2e_handle *h, float *table0, float *table1) {
     if (int rc = b2e_sync(h)) return rc;
     const size_t width = h->cfg.embedding_size * sizeof(float);
     const size_t pitch = h->row_stride * sizeof(float);
-    CUDA_TRY(cudaMemcpy2D(table0, width, h->d_t0, pitch, width, h->n, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy2D(table1, width, h->d_t1, pitch, width, h->n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy2DAsync(table0, width, h->d_t0, pitch, width, h->n, cudaMemcpyDeviceToHost,
+                               h->train_stream));
+    CUDA_TRY(cudaMemcpy2DAsync(table1, width, h->d_t1, pitch, width, h->n, cudaMemcpyDeviceToHost,
+                               h->train_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
     return B2E_OK;
 }
 
@@ -509,10 +515,16 @@ extern "C" int b2e_import_tables(b2e_handle *h, const float *table0, const float
     if (int rc = b2e_sync(h)) return rc;
     const size_t width = h->cfg.embedding_size * sizeof(float);
     const size_t pitch = h->row_stride * sizeof(float);
-    CUDA_TRY(cudaMemset(h->d_t0, 0, h->n * pitch));
-    CUDA_TRY(cudaMemset(h->d_t1, 0, h->n * pitch));
-    CUDA_TRY(cudaMemcpy2D(h->d_t0, pitch, table0, width, width, h->n, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy2D(h->d_t1, pitch, table1, width, width, h->n, cudaMemcpyHostToDevice));
+    // the handle's streams are non-blocking: work on the legacy default stream is not ordered
+    // with them, so everything here runs on the train stream and is waited for
+    CUDA_TRY(cudaMemsetAsync(h->d_t0, 0, h->n * pitch, h->train_stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_t1, 0, h->n * pitch, h->train_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_t0, pitch, table0, width, width, h->n, cudaMemcpyHostToDevice,
+                               h->train_stream));
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_t1, pitch, table1, width, width, h->n, cudaMemcpyHostToDevice,
+                               h->train_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
     return B2E_OK;
 }
 
@@ -529,7 +541,8 @@ extern "C" int b2e_counters_read(b2e_handle *h, b2e_counters *out) {
     if (!out) return fail(B2E_ERR_INVALID, "null argument");
     if (int rc = b2e_sync(h)) return rc;
     DeviceCounters c;
-    CUDA_TRY(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->train_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
     out->walk_steps = c.walk_steps;
     out->walk_trials = c.walk_trials;
     out->walk_searches = c.walk_searches;
@@ -542,7 +555,10 @@ extern "C" int b2e_counters_read(b2e_handle *h, b2e_counters *out) {
 extern "C" int b2e_counters_reset(b2e_handle *h) {
     REQUIRE_HANDLE(h);
     if (int rc = b2e_sync(h)) return rc;
-    CUDA_TRY(cudaMemset(h->d_counters, 0, sizeof(DeviceCounters)));
+    // not cudaMemset: the legacy default stream is not ordered with the non-blocking streams of
+    // the handle, and a late memset would also clear the work counter of a running SGD kernel
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->train_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
     return B2E_OK;
 }
 
