@@ -87,7 +87,8 @@ __host__ __device__ __forceinline__ uint32_t pipe_warp_bytes(uint32_t negatives,
 struct LaneView {
     const char *t0, *t1;  // table bases advanced by 16 * lane bytes
     uint64_t row_bytes;
-    bool active;          // lane < chunks
+    uint32_t smem_chunk;  // 4 * min(lane, chunks - 1): lanes past the row re-read its last chunk
+    bool active;          // lane < chunks; only active lanes copy and store
 };
 
 // ids of the targets of a pair, one per lane: lane 0 = context, lane k+1 = negative k;
@@ -126,7 +127,9 @@ template <int KP1, bool ALL>
 __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSmem &sm, const LaneView &v,
                                              uint32_t stage, uint32_t lane, uint32_t vmask, float lr,
                                              const float4 &h, float &loss_acc) {
-    const float *rows = sm.rows(stage) + 4u * lane;
+    // Lanes past the end of the row read its last chunk instead of branching; their h is zero,
+    // so they add nothing to a score; their stores are predicated off and their acc is dropped.
+    const float *rows = sm.rows(stage) + v.smem_chunk;
     const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
     constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
     float part[16];
@@ -134,13 +137,11 @@ __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSme
     for (int s = 0; s < 16; ++s) {
         float d = 0.0f;
         if (s < S && (uint32_t)s < slots && (ALL || ((vmask >> s) & 1u))) {
-            if (v.active) {
-                const float4 r = lds128(rows + (uint32_t)s * sm.pitch);
-                d = __fmaf_rn(h.x, r.x, d);
-                d = __fmaf_rn(h.y, r.y, d);
-                d = __fmaf_rn(h.z, r.z, d);
-                d = __fmaf_rn(h.w, r.w, d);
-            }
+            const float4 r = lds128(rows + (uint32_t)s * sm.pitch);
+            d = __fmaf_rn(h.x, r.x, d);
+            d = __fmaf_rn(h.y, r.y, d);
+            d = __fmaf_rn(h.z, r.z, d);
+            d = __fmaf_rn(h.w, r.w, d);
         }
         part[s] = d;
     }
@@ -168,20 +169,19 @@ __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSme
         if (all_applied || ((amask >> (2 * s)) & 1u)) {
             const float g = __shfl_sync(FULL, g_mine, 2 * s);
             const uint32_t id = ids[s];
-            if (v.active) {
-                float4 r = lds128(rows + (uint32_t)s * sm.pitch);
-                acc.x = __fmaf_rn(g, r.x, acc.x);
-                acc.y = __fmaf_rn(g, r.y, acc.y);
-                acc.z = __fmaf_rn(g, r.z, acc.z);
-                acc.w = __fmaf_rn(g, r.w, acc.w);
-                r.x = __fmaf_rn(g, h.x, r.x);
-                r.y = __fmaf_rn(g, h.y, r.y);
-                r.z = __fmaf_rn(g, h.z, r.z);
-                r.w = __fmaf_rn(g, h.w, r.w);
-                *reinterpret_cast<float4 *>(const_cast<char *>(v.t1) + id * v.row_bytes) = r;
-            }
+            float4 r = lds128(rows + (uint32_t)s * sm.pitch);
+            acc.x = __fmaf_rn(g, r.x, acc.x);
+            acc.y = __fmaf_rn(g, r.y, acc.y);
+            acc.z = __fmaf_rn(g, r.z, acc.z);
+            acc.w = __fmaf_rn(g, r.w, acc.w);
+            r.x = __fmaf_rn(g, h.x, r.x);
+            r.y = __fmaf_rn(g, h.y, r.y);
+            r.z = __fmaf_rn(g, h.z, r.z);
+            r.w = __fmaf_rn(g, h.w, r.w);
+            if (v.active) *reinterpret_cast<float4 *>(const_cast<char *>(v.t1) + id * v.row_bytes) = r;
         }
     }
+    if (!v.active) acc = make_float4(0.f, 0.f, 0.f, 0.f);
     return acc;
 }
 
@@ -193,7 +193,7 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
 }
 
 template <int KP1>
-__global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams p) {
+__global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t K = KP1 ? (uint32_t)(KP1 - 1) : p.negatives;
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(128, 5) skipgram_pipe_kernel(const TrainParams
     v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
     v.row_bytes = (uint64_t)p.row_stride * 4u;
     v.active = lane < p.chunks;
+    v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
     float loss_acc = 0.0f;
     unsigned long long n_pairs = 0, n_targets = 0;
 
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
     v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
     v.row_bytes = (uint64_t)p.row_stride * 4u;
     v.active = lane < p.chunks;
+    v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
     const uint32_t lower = (1u << lane) - 1u;
     float loss_acc = 0.0f;
     unsigned long long n_pairs = 0, n_targets = 0;
