@@ -416,11 +416,14 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.t0 = h->d_t0;
     p.t1 = h->d_t1;
     p.counters = h->d_counters;
-    // Hogwild staleness: on a small graph thousands of concurrent walks would all train against
-    // nearly the same stale rows; keep about one walk in flight per 64 nodes unless told otherwise
-    // (graphs above ~200 k nodes are not affected: fewer than 3 000 warps are resident anyway)
+    // Hogwild staleness: on a tiny graph thousands of concurrent walks would all train against
+    // nearly the same stale rows, which slows the first epochs down (the final quality is not
+    // affected: scripts/exp_concurrency.py).  Unless told otherwise keep about one walk in flight
+    // per 16 nodes for SkipGram and per 64 nodes for CBOW, whose averaged context rows make it
+    // lag more; graphs above ~50 k (200 k) nodes are not limited: < 3 000 warps are resident.
+    const uint64_t per_walk_nodes = c.model == B2E_CBOW ? 64 : 16;
     const uint64_t max_warps = c.max_concurrent_walks ? c.max_concurrent_walks
-                                                       : std::max<uint64_t>(8, h->n / 64);
+                                                       : std::max<uint64_t>(16, h->n / per_walk_nodes);
     CUDA_TRY(launch_train(p, c.model, c.deterministic != 0, h->sm_count, max_warps, h->train_stream));
     if (p.n_walks) ++h->launches;
     return B2E_OK;

@@ -8,7 +8,7 @@ restated here with numpy + scikit-learn and the oracle stands where Ensmallen wo
 
 Tolerance (stated, as the contract asks): over three holdouts the mean AUROC of the GPU embedding
 may not fall more than 0.005 below the oracle's (the 0.005 of north_star, read as "not worse
-than"; on these 1 500-node graphs the GPU run is usually a few thousandths *better* than the
+than"; the GPU run is usually a few thousandths *better* than the
 8-thread Hogwild oracle), and no single holdout may differ by more than 0.015 either way.
 """
 import numpy as np
@@ -19,17 +19,27 @@ from sklearn.metrics import roc_auc_score
 import oracle
 from embiggen_b200.graph import csr_from_edges
 
-KW = dict(embedding_size=32, walk_length=32, window_size=4, iterations=8, epochs=4,
+KW = dict(embedding_size=32, walk_length=32, window_size=4, iterations=3, epochs=4,
           number_of_negative_samples=5, learning_rate=0.05, learning_rate_decay=0.9)
 
 
-def block_model(seed, n=1500, blocks=15, inside=0.06, outside=0.0008):
-    """Planted-partition graph: dense blocks, sparse background; returns the edge list."""
+def block_model(seed, n=6000, block=100, degree_in=10, degree_out=2):
+    """Planted-partition graph: blocks of `block` nodes with about `degree_in` neighbours inside
+    and `degree_out` anywhere; returns the (deduplicated, upper-triangular) edge list."""
     rng = np.random.default_rng(seed)
-    label = np.arange(n) % blocks
-    upper = np.triu(rng.random((n, n)) < np.where(label[:, None] == label[None, :], inside, outside), 1)
-    src, dst = np.nonzero(upper)
-    return src, dst, n
+    src, dst = [], []
+    for b in range(n // block):
+        m = block * degree_in // 2
+        src.append(rng.integers(0, block, m) + b * block)
+        dst.append(rng.integers(0, block, m) + b * block)
+    m = n * degree_out // 2
+    src.append(rng.integers(0, n, m))
+    dst.append(rng.integers(0, n, m))
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    keep = src != dst
+    lo, hi = np.minimum(src[keep], dst[keep]), np.maximum(src[keep], dst[keep])
+    keys = np.unique(lo * n + hi)
+    return keys // n, keys % n, n
 
 
 def holdout(src, dst, n, seed, train_fraction=0.8):
@@ -37,15 +47,12 @@ def holdout(src, dst, n, seed, train_fraction=0.8):
     order = rng.permutation(len(src))
     cut = int(train_fraction * len(src))
     train, test = order[:cut], order[cut:]
-    existing = set(zip(src.tolist(), dst.tolist()))
+    existing = src * n + dst
 
     def negatives(count):
-        out = []
-        while len(out) < count:
-            a, b = rng.integers(0, n, 2)
-            if a != b and (min(a, b), max(a, b)) not in existing:
-                out.append((a, b))
-        return np.array(out)
+        a, b = rng.integers(0, n, 2 * count), rng.integers(0, n, 2 * count)
+        ok = (a != b) & ~np.isin(np.minimum(a, b) * n + np.maximum(a, b), existing)
+        return np.stack([a[ok][:count], b[ok][:count]], axis=1)
 
     return (src[train], dst[train]), (src[test], dst[test]), negatives(len(train)), negatives(len(test))
 
@@ -82,7 +89,7 @@ def test_oracle_embedding_predicts_held_out_edges():
     train_pos, test_pos, train_neg, test_neg = holdout(src, dst, n, 0)
     graph = csr_from_edges(train_pos[0], train_pos[1], n)
     embedding = oracle_embedding("SkipGram", graph, 42, 1.0, 1.0, threads=8)
-    assert auroc(embedding, train_pos, test_pos, train_neg, test_neg) > 0.80
+    assert auroc(embedding, train_pos, test_pos, train_neg, test_neg) > 0.85
 
 
 @pytest.mark.gpu
@@ -103,7 +110,7 @@ def test_gpu_auroc_matches_oracle_auroc(model, rw, ew):
         a_ref = auroc(reference, train_pos, test_pos, train_neg, test_neg)
         a_gpu = auroc(ours, train_pos, test_pos, train_neg, test_neg)
         print(f"{model} rw={rw} ew={ew} holdout {trial}: AUROC oracle {a_ref:.4f}  gpu {a_gpu:.4f}")
-        assert a_gpu > (0.80 if model == "SkipGram" else 0.70)
+        assert a_gpu > 0.85
         assert abs(a_gpu - a_ref) <= 0.015
         deltas.append(a_gpu - a_ref)
     assert np.mean(deltas) >= -0.005
@@ -114,8 +121,9 @@ def test_gpu_auroc_matches_oracle_auroc(model, rw, ew):
 def test_loss_curve_tracks_the_oracle(model):
     """Loss-curve leg (north_star, SURVEY.md 8c leg 3): the per-epoch mean pair loss of the GPU
     run (thousands of concurrent walks) against the 8-thread Hogwild oracle on the same graph,
-    kwargs and seed.  Stated tolerance: 5 % per epoch after the first, 10 % on the first
-    (where the staleness of concurrent updates is largest)."""
+    kwargs and seed.  Stated tolerance: 5 % per epoch from the third on, 20 % on the first two
+    (where the staleness of concurrent updates is largest; the number of walks in flight is
+    capped on small graphs for exactly this reason, see b2e_config.max_concurrent_walks)."""
     from embiggen_b200.engine import Engine
     src, dst, n = block_model(7)
     graph = csr_from_edges(src, dst, n)
@@ -134,7 +142,7 @@ def test_loss_curve_tracks_the_oracle(model):
     print(model, "oracle", np.round(expected, 4), "gpu", np.round(got, 4))
     assert got[-1] < got[1] < got[0]
     for epoch, (a, b) in enumerate(zip(expected, got)):
-        assert abs(b - a) <= (0.10 if epoch == 0 else 0.05) * a, (epoch, a, b)
+        assert abs(b - a) <= (0.20 if epoch < 2 else 0.05) * a, (epoch, a, b)
 
 
 @pytest.mark.gpu
@@ -154,7 +162,7 @@ def test_replica_averaging_keeps_the_quality():
         c, x, _ = single.fit(seed)
     baseline = auroc(np.hstack([c, x]), train_pos, test_pos, train_neg, test_neg)
 
-    replicas = [Engine("SkipGram", chunk_walks=512, **KW) for _ in range(world)]
+    replicas = [Engine("SkipGram", chunk_walks=2048, **KW) for _ in range(world)]
     try:
         for engine in replicas:
             engine.load_csr(graph.indptr, graph.indices)
@@ -173,7 +181,7 @@ def test_replica_averaging_keeps_the_quality():
         per_epoch = replicas[0].walks_per_epoch
         lr = np.float32(KW["learning_rate"])
         for epoch in range(KW["epochs"]):
-            plans = [list(shard_chunks(per_epoch, 512, world, rank, epoch * per_epoch)) for rank in range(world)]
+            plans = [list(shard_chunks(per_epoch, 2048, world, rank, epoch * per_epoch)) for rank in range(world)]
             for index in range(len(plans[0])):
                 for rank, engine in enumerate(replicas):
                     first, count, stride = plans[rank][index]
