@@ -151,3 +151,30 @@ def test_error_paths(small_ppi):
             engine.load_csr(np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint32))
         with pytest.raises(ValueError):
             engine.load_csr(np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.uint32))
+
+
+def test_baseline_config_c1(small_ppi):
+    """BASELINE.json configs[0]: Node2Vec SkipGram on the reference's tests/data graph, dim=100,
+    walk_length=128, window=4, 1 epoch, the reference's default p/q and iterations, through the
+    embedder class; the 8-thread Hogwild oracle stands where the Ensmallen CPU run would."""
+    from embiggen_b200.embedders import Node2VecSkipGramB200
+    kw = dict(embedding_size=100, walk_length=128, window_size=4, epochs=1, iterations=10,
+              number_of_negative_samples=10, learning_rate=0.01, learning_rate_decay=0.9)
+    oracle.set_threads(8)
+    try:
+        o0, o1, expected = oracle.fit("SkipGram", small_ppi.indptr, small_ppi.indices, 42, negatives=10,
+                                      return_weight=0.25, explore_weight=4.0,
+                                      **{k: v for k, v in kw.items() if k != "number_of_negative_samples"})
+    finally:
+        oracle.set_threads(1)
+    model = Node2VecSkipGramB200(return_weight=0.25, explore_weight=4.0, random_state=42, verbose=False, **kw)
+    result = model.fit_transform(small_ppi, return_dataframe=False)
+    central, contextual = result.get_all_node_embedding()
+    assert central.shape == (1064, 100) and contextual.shape == (1064, 100)
+    got = model.get_losses()
+    print("C1 mean pair loss: oracle", expected, "gpu", got)
+    assert abs(got[0] - expected[0]) <= 0.10 * expected[0]
+    quality_oracle = heldout_sgns_loss(small_ppi, o0[:, :100], o1[:, :100], return_weight=0.25, explore_weight=4.0)
+    quality_gpu = heldout_sgns_loss(small_ppi, central, contextual, return_weight=0.25, explore_weight=4.0)
+    print("C1 held-out objective: oracle", quality_oracle, "gpu", quality_gpu)
+    assert abs(quality_gpu - quality_oracle) <= 0.10 * quality_oracle
