@@ -37,6 +37,7 @@ class B2EConfig(ctypes.Structure):
         ("negative_sampling_exponent", ctypes.c_float),
         ("use_scale_free_distribution", ctypes.c_uint32),
         ("normalize_learning_rate_by_degree", ctypes.c_uint32),
+        ("normalize_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("deterministic", ctypes.c_uint32),
         ("chunk_walks", ctypes.c_uint32),

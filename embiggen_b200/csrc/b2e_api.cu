@@ -129,6 +129,7 @@ static void free_graph(b2e_handle *h) {
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
     cudaFree(h->d_cdf); h->d_cdf = nullptr;
+    cudaFree(h->d_mindeg); h->d_mindeg = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
     cudaFree(h->d_alias); h->d_alias = nullptr;
     cudaFree(h->d_t0); h->d_t0 = nullptr;
@@ -276,6 +277,12 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `packed` dies here
     }
 
+    if (c.normalize_by_degree) {
+        CUDA_TRY(cudaMalloc(&h->d_mindeg, n * sizeof(uint32_t)));
+        CUDA_TRY(launch_min_neighbour_degree(h->d_indptr, h->d_indices, n, h->d_mindeg, h->walk_stream));
+        ++h->launches;
+    }
+
     // Is the graph undirected (every edge mirrored)?  Then the second-order walk kernel may
     // check adjacency in the shorter of the two rows.  Verified here, never assumed.
     h->undirected = false;
@@ -348,6 +355,7 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     p.indptr = h->d_indptr;
     p.indices = h->d_indices;
     p.cdf = h->d_cdf;
+    p.mindeg = h->d_mindeg;
     p.sources = h->d_sources;
     p.n_src = h->n_src;
     p.seed_lo = (uint32_t)seed;

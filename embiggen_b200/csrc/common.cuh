@@ -49,6 +49,7 @@ struct WalkParams {
     const int64_t *indptr;
     const uint32_t *indices;
     const uint32_t *cdf;  // per-edge sampling table of a weighted graph, or nullptr
+    const uint32_t *mindeg;  // smallest neighbour degree per node (normalize_by_degree), or nullptr
     const uint32_t *sources;
     uint64_t n_src;
     uint32_t seed_lo, seed_hi;
@@ -81,6 +82,8 @@ struct TrainParams {
 };
 
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
+cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                        uint32_t *out, cudaStream_t stream);
 cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                   uint64_t nnz, int *d_flag, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
@@ -110,6 +113,7 @@ struct b2e_handle {
     int64_t *d_indptr = nullptr;
     uint32_t *d_indices = nullptr;
     uint32_t *d_cdf = nullptr;
+    uint32_t *d_mindeg = nullptr;
     uint32_t *d_sources = nullptr;
     uint2 *d_alias = nullptr;
     float *d_t0 = nullptr, *d_t1 = nullptr;

@@ -366,6 +366,128 @@ __global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
     }
 }
 
+
+// ---- normalize_by_degree: transition weight divided by the degree of the destination ----
+// (.../node2vec_skipgram.py:94-96).  Every transition, the first one included, is a trial loop:
+// propose x, accept iff r1 * deg(x) < thr[class] * mindeg[cur], where mindeg[cur] is the smallest
+// neighbour degree of the current node (the bound rejection sampling needs for 1 / deg(x)).  All
+// products fit 64 bits (thr <= 2^32, degrees < 2^32), so the decisions are the oracle's.
+__global__ void __launch_bounds__(256) min_neighbour_degree_kernel(const int64_t *__restrict__ indptr,
+                                                                   const uint32_t *__restrict__ indices,
+                                                                   uint64_t n, uint32_t *__restrict__ out) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    uint32_t best = 0xFFFFFFFFu;
+    for (int64_t e = __ldg(indptr + v), end = __ldg(indptr + v + 1); e < end; ++e) {
+        const uint32_t x = __ldg(indices + e);
+        const uint32_t d = (uint32_t)(__ldg(indptr + x + 1) - __ldg(indptr + x));
+        best = min(best, max(d, 1u));  // a dead end weighs like a leaf
+    }
+    out[v] = best;
+}
+
+cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                        uint32_t *out, cudaStream_t stream) {
+    min_neighbour_degree_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(indptr, indices, n, out);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ unsigned long long scaled_threshold(unsigned long long thr, uint32_t bound) {
+    return thr >= 4294967296ull ? ((unsigned long long)bound << 32) : thr * bound;
+}
+
+template <bool VEC, bool WEIGHTED>
+__global__ void __launch_bounds__(256) walk_norm_kernel(const WalkParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
+    if (i < p.n_walks) {
+        const uint64_t wid = p.first_walk + i * p.walk_id_stride;
+        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+        uint32_t *out = p.out + i * (uint64_t)p.walk_length;
+        const unsigned long long thr_lo = min(p.thr_common, p.thr_explore);
+        const unsigned long long thr_hi = max(p.thr_common, p.thr_explore);
+        uint32_t cur = __ldg(p.sources + (wid % p.n_src));
+        int64_t prev_off = 0;
+        uint32_t prev = PAD, prev_deg = 0;
+        bool alive = true;
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        uint32_t tok[4];
+        const uint32_t L = p.walk_length;
+        for (uint32_t base = 0; base < L; base += 4) {
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t t = base + u;
+                if (t == 0) { tok[0] = cur; continue; }
+                if (t >= L) { tok[u] = PAD; continue; }
+                uint32_t next = PAD;
+                if (alive) {
+                    const int64_t off = __ldg(p.indptr + cur);
+                    const uint32_t deg = (uint32_t)(__ldg(p.indptr + cur + 1) - off);
+                    if (deg == 0) {
+                        alive = false;
+                    } else {
+                        const uint32_t bound = __ldg(p.mindeg + cur);
+                        uint32_t trial = 0;
+                        for (;;) {
+                            if ((trial & 1u) == 0)
+                                rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                    (TAG_WALK2 << 24) | (trial >> 1));
+                            const uint32_t r0 = (trial & 1u) ? rnd.z : rnd.x;
+                            const unsigned long long r1 = (trial & 1u) ? rnd.w : rnd.y;
+                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r0));
+                            ++n_trials;
+                            const uint32_t next_deg = max(
+                                (uint32_t)(__ldg(p.indptr + next + 1) - __ldg(p.indptr + next)), 1u);
+                            const unsigned long long lhs = r1 * next_deg;
+                            bool accept;
+                            if (t == 1) {
+                                accept = lhs < scaled_threshold(4294967296ull, bound);
+                            } else if (next == prev) {
+                                accept = lhs < scaled_threshold(p.thr_return, bound);
+                            } else if (lhs < scaled_threshold(thr_lo, bound)) {
+                                accept = true;
+                            } else if (lhs >= scaled_threshold(thr_hi, bound)) {
+                                accept = false;
+                            } else {
+                                ++n_searches;
+                                const bool common = row_contains(p.indices + prev_off, prev_deg, next);
+                                accept = lhs < scaled_threshold(common ? p.thr_common : p.thr_explore, bound);
+                            }
+                            if (accept) break;
+                            ++trial;
+                            if (trial >= MAX_TRIALS) break;
+                        }
+                        ++n_steps;
+                        prev = cur;
+                        prev_off = off;
+                        prev_deg = deg;
+                        cur = next;
+                    }
+                }
+                tok[u] = next;
+            }
+            if (VEC) {
+                *reinterpret_cast<uint4 *>(out + base) = make_uint4(tok[0], tok[1], tok[2], tok[3]);
+            } else {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u)
+                    if (base + u < L) out[base + u] = tok[u];
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        n_steps += __shfl_xor_sync(0xffffffffu, n_steps, off);
+        n_trials += __shfl_xor_sync(0xffffffffu, n_trials, off);
+        n_searches += __shfl_xor_sync(0xffffffffu, n_searches, off);
+    }
+    if ((threadIdx.x & 31) == 0 && p.counters) {
+        atomicAdd(&p.counters->walk_steps, n_steps);
+        atomicAdd(&p.counters->walk_trials, n_trials);
+        atomicAdd(&p.counters->walk_searches, n_searches);
+    }
+}
+
 // One thread per directed edge (u, v): is u in the row of v?  Clears *symmetric otherwise.
 __global__ void __launch_bounds__(256) symmetry_kernel(const int64_t *__restrict__ indptr,
                                                        const uint32_t *__restrict__ indices, uint64_t n,
@@ -396,6 +518,13 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     const unsigned grid = (unsigned)((p.n_walks + block - 1) / block);
     const bool vec = (p.walk_length % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16u) == 0;
     const bool weighted = p.cdf != nullptr;
+    if (p.mindeg) {  // normalize_by_degree: one trial loop for every transition
+        if (vec) { if (weighted) walk_norm_kernel<true, true><<<grid, block, 0, stream>>>(p);
+                   else walk_norm_kernel<true, false><<<grid, block, 0, stream>>>(p); }
+        else { if (weighted) walk_norm_kernel<false, true><<<grid, block, 0, stream>>>(p);
+               else walk_norm_kernel<false, false><<<grid, block, 0, stream>>>(p); }
+        return cudaGetLastError();
+    }
     if (second_order && !weighted && p.state_machine) {
         // persistent grid: lanes fetch walks grid-stride, so size it to the machine, not the chunk
         int per_sm = 0;

@@ -87,6 +87,11 @@ def lib():
         l.orc_walks_weighted.restype = ctypes.c_int
         l.orc_walks_weighted.argtypes = [P(ctypes.c_int64), P(u32), P(u32), u64, P(u32), u64, u64, u64,
                                          u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
+        l.orc_min_neighbour_degree.restype = ctypes.c_int
+        l.orc_min_neighbour_degree.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32)]
+        l.orc_walks_full.restype = ctypes.c_int
+        l.orc_walks_full.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), u64, P(u32), u64, u64, u64,
+                                     u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
         l.orc_alias_build.restype = ctypes.c_int
         l.orc_alias_build.argtypes = [P(ctypes.c_int64), u64, ctypes.c_double, P(u32), P(u32)]
         l.orc_set_threads.restype = None
@@ -151,22 +156,34 @@ def edge_cdf(indptr, weights) -> np.ndarray:
     return cdf
 
 
+def min_neighbour_degree(indptr, indices) -> np.ndarray:
+    indptr, indices = _csr(indptr, indices)
+    out = np.empty(indptr.shape[0] - 1, dtype=np.uint32)
+    rc = lib().orc_min_neighbour_degree(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                                        indptr.shape[0] - 1, _ptr(out, ctypes.c_uint32))
+    if rc != 0:
+        raise ValueError(f"orc_min_neighbour_degree failed with status {rc}")
+    return out
+
+
 def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length: int,
           return_weight: float = 1.0, explore_weight: float = 1.0, walk_id_stride: int = 1,
-          srcs: Optional[np.ndarray] = None, weights=None) -> Tuple[np.ndarray, dict]:
+          srcs: Optional[np.ndarray] = None, weights=None,
+          normalize_by_degree: bool = False) -> Tuple[np.ndarray, dict]:
     indptr, indices = _csr(indptr, indices)
     cdf = None if weights is None else edge_cdf(indptr, weights)
+    mindeg = min_neighbour_degree(indptr, indices) if normalize_by_degree else None
     n = indptr.shape[0] - 1
     if srcs is None:
         srcs = sources(indptr)
     srcs = np.ascontiguousarray(srcs, dtype=np.uint32)
     out = np.empty((n_walks, walk_length), dtype=np.uint32)
     counters = WalkCounters()
-    rc = lib().orc_walks_weighted(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
-                                  _ptr(cdf, ctypes.c_uint32), n, _ptr(srcs, ctypes.c_uint32),
-                                  srcs.shape[0], seed, first_walk, n_walks, walk_id_stride,
-                                  walk_length, return_weight, explore_weight,
-                                  _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
+    rc = lib().orc_walks_full(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                              _ptr(cdf, ctypes.c_uint32), _ptr(mindeg, ctypes.c_uint32), n,
+                              _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
+                              walk_id_stride, walk_length, return_weight, explore_weight,
+                              _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
     if rc != 0:
         raise ValueError(f"orc_walks failed with status {rc}")
     return out, counters.as_dict()

@@ -68,6 +68,16 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
                        float return_weight, float explore_weight, uint32_t *out,
                        orc_walk_counters *counters);
 
+/* smallest degree among the neighbours of every node (0xFFFFFFFF for a node without any) */
+int orc_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n, uint32_t *out);
+
+/* orc_walks_weighted plus normalize_by_degree (mindeg from orc_min_neighbour_degree; NULL: off) */
+int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                   const uint32_t *mindeg, uint64_t n, const uint32_t *sources, uint64_t n_src,
+                   uint64_t seed, uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                   uint32_t walk_length, float return_weight, float explore_weight, uint32_t *out,
+                   orc_walk_counters *counters);
+
 /* Vose alias table over deg^alpha; thr/alias have n entries. */
 int orc_alias_build(const int64_t *indptr, uint64_t n, double alpha, uint32_t *thr,
                     uint32_t *alias);

@@ -122,7 +122,117 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
                        orc_walk_counters *counters) {
+    return orc_walks_full(indptr, indices, cdf, NULL, n, sources, n_src, seed, first_walk, n_walks,
+                          walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+}
+
+/*
+ * `normalize_by_degree` ("Whether to normalize the random walk by the node degree of the
+ * destination node degrees", .../node2vec_skipgram.py:94-96): the transition weight of v -> x is
+ * divided by deg(x).  Rejection sampling needs a bound of 1 / deg(x) over N(v): the smallest
+ * neighbour degree mindeg[v], one value per node computed at load.
+ */
+int orc_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n, uint32_t *out) {
+    if (!indptr || !indices || !out) return -1;
+    for (uint64_t v = 0; v < n; ++v) {
+        uint32_t best = 0xFFFFFFFFu;
+        for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+            const uint32_t x = indices[e];
+            uint64_t d = (uint64_t)(indptr[x + 1] - indptr[x]);
+            if (d == 0) d = 1; /* a dead end weighs like a leaf: 1 / max(deg, 1) */
+            if (d < best) best = (uint32_t)d;
+        }
+        out[v] = best;
+    }
+    return 0;
+}
+
+/*
+ * With mindeg != NULL every transition, the first one included, is a trial loop on the
+ * second-order stream: propose x, accept iff r1 * deg(x) < thr[class] * mindeg[cur] (exact
+ * integer arithmetic; the first transition has no previous node and uses thr = 2^32).
+ */
+static int walks_normalized(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                            const uint32_t *mindeg, const uint32_t *sources, uint64_t n_src, uint64_t seed,
+                            uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                            uint32_t walk_length, float return_weight, float explore_weight,
+                            uint32_t *out, orc_walk_counters *counters) {
+    const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+    uint64_t thr[3];
+    orc_thresholds(return_weight, explore_weight, thr);
+    const uint64_t thr_lo = thr[1] < thr[2] ? thr[1] : thr[2];
+    const uint64_t thr_hi = thr[1] < thr[2] ? thr[2] : thr[1];
+    uint64_t n_steps = 0, n_trials = 0, n_searches = 0, n_probe = 0, n_capped = 0;
+    const int threads = orc_get_threads();
+#pragma omp parallel for num_threads(threads) if (threads > 1) schedule(dynamic, 256) \
+    reduction(+ : n_steps, n_trials, n_searches, n_probe, n_capped)
+    for (uint64_t i = 0; i < n_walks; ++i) {
+        const uint64_t wid = first_walk + i * walk_id_stride;
+        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+        uint32_t *walk = out + i * (uint64_t)walk_length;
+        uint32_t cur = sources[wid % n_src], prev = ORC_PAD_TOKEN;
+        walk[0] = cur;
+        uint32_t rnd[4] = {0, 0, 0, 0};
+        uint32_t t = 1;
+        for (; t < walk_length; ++t) {
+            const int64_t off = indptr[cur];
+            const uint64_t deg = (uint64_t)(indptr[cur + 1] - off);
+            if (deg == 0) break;
+            const unsigned __int128 bound = mindeg[cur];
+            uint32_t next, trial = 0;
+            for (;;) {
+                if ((trial & 1u) == 0)
+                    orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
+                                      (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
+                const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
+                next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, r0)];
+                ++n_trials;
+                uint64_t next_deg = (uint64_t)(indptr[next + 1] - indptr[next]);
+                if (next_deg == 0) next_deg = 1;
+                const unsigned __int128 lhs = (unsigned __int128)r1 * next_deg;
+                uint64_t limit = 4294967296ull;  /* first transition: no bias */
+                if (t > 1) {
+                    int cls;
+                    if (next == prev) {
+                        cls = 0;
+                    } else {
+                        const int64_t poff = indptr[prev];
+                        const uint64_t pdeg = (uint64_t)(indptr[prev + 1] - poff);
+                        cls = row_contains(indices + poff, pdeg, next) ? 1 : 2;
+                        if (lhs >= thr_lo * bound && lhs < thr_hi * bound) {
+                            ++n_searches;
+                            n_probe += probe_sectors(pdeg);
+                        }
+                    }
+                    limit = thr[cls];
+                }
+                if (lhs < limit * bound) break;
+                ++trial;
+                if (trial >= ORC_MAX_TRIALS) { ++n_capped; break; }
+            }
+            ++n_steps;
+            walk[t] = next;
+            prev = cur;
+            cur = next;
+        }
+        for (; t < walk_length; ++t) walk[t] = ORC_PAD_TOKEN;
+    }
+    if (counters) {
+        counters->steps = n_steps; counters->trials = n_trials; counters->first_order = 0;
+        counters->searches = n_searches; counters->probe_sectors = n_probe; counters->capped = n_capped;
+    }
+    return 0;
+}
+
+int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                   const uint32_t *mindeg, uint64_t n, const uint32_t *sources, uint64_t n_src,
+                   uint64_t seed, uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                   uint32_t walk_length, float return_weight, float explore_weight, uint32_t *out,
+                   orc_walk_counters *counters) {
     if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
+    if (mindeg)
+        return walks_normalized(indptr, indices, cdf, mindeg, sources, n_src, seed, first_walk, n_walks,
+                                walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
     (void)n;
     const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
     const int second_order = !(return_weight == 1.0f && explore_weight == 1.0f);

@@ -85,7 +85,7 @@ def test_kwarg_coercion_and_rejection():
     with pytest.raises(ValueError):
         Node2VecSkipGramB200(dtype="f8")
     for unsupported in (dict(change_node_type_weight=2.0), dict(change_edge_type_weight=0.5),
-                        dict(normalize_by_degree=True), dict(stochastic_downsample_by_degree=True)):
+                        dict(stochastic_downsample_by_degree=True)):
         with pytest.raises(NotImplementedError):
             Node2VecSkipGramB200(**unsupported)
 

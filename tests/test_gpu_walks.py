@@ -153,3 +153,32 @@ def test_state_machine_walk_kernel_bit_exact(monkeypatch, small_ppi, rmat_graph)
     expected, _ = oracle.walks(rmat_graph.indptr, rmat_graph.indices, 1, 0, 5000, 64, 2.0, 0.5)
     got, _ = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
     assert np.array_equal(got, expected)
+
+
+# ---- normalize_by_degree (b2e_config.normalize_by_degree; walk_norm_kernel) ----
+@pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
+def test_normalize_by_degree_walks_bit_exact(small_ppi_weighted, rmat_graph, rw, ew):
+    from conftest import tiny_graphs
+    cases = [(rmat_graph, None, 64), (small_ppi_weighted, small_ppi_weighted.weights, 33),
+             (small_ppi_weighted, None, 130), (tiny_graphs()["directed_dead_end"], None, 9),
+             (tiny_graphs()["star"], None, 8)]
+    for graph, weights, length in cases:
+        count = 2 * int((np.diff(graph.indptr) > 0).sum()) + 3
+        expected, oc = oracle.walks(graph.indptr, graph.indices, 42, 5, count, length, rw, ew,
+                                    weights=weights, normalize_by_degree=True)
+        with Engine("SkipGram", walk_length=length, return_weight=rw, explore_weight=ew,
+                    iterations=1, normalize_by_degree=True) as engine:
+            engine.load_csr(graph.indptr, graph.indices, weights)
+            got, gc = engine.walks(42, 5, count), engine.counters()
+        assert np.array_equal(got, expected)
+        assert (gc["walk_steps"], gc["walk_trials"], gc["walk_searches"]) == \
+            (oc["steps"], oc["trials"], oc["searches"])
+        assert oc["capped"] == 0
+
+
+def test_normalize_by_degree_embedder_runs(small_ppi):
+    from embiggen_b200.embedders import Node2VecCBOWB200
+    model = Node2VecCBOWB200(embedding_size=8, epochs=1, walk_length=8, iterations=1,
+                             normalize_by_degree=True, verbose=False)
+    tables = model.fit_transform(small_ppi, return_dataframe=False).get_all_node_embedding()
+    assert all(np.isfinite(t).all() for t in tables)

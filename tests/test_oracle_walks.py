@@ -238,3 +238,69 @@ def test_unit_weights_reproduce_nothing_else_than_valid_walks(small_ppi_weighted
     assert np.isin(keys, edge_keys).all() and counters["steps"] == 2000 * 23
     unweighted, _ = oracle.walks(g.indptr, g.indices, 5, 0, 2000, 24, 0.25, 4.0)
     assert not np.array_equal(walks, unweighted)
+
+
+# ---- normalize_by_degree: transition weight / deg(destination) (node2vec_skipgram.py:94-96) ----
+def test_min_neighbour_degree():
+    graph = dense_test_graph()
+    degrees = np.diff(graph.indptr)
+    expected = np.array([degrees[neighbours(graph, v)].min() for v in range(12)], dtype=np.uint32)
+    assert np.array_equal(oracle.min_neighbour_degree(graph.indptr, graph.indices), expected)
+    dead = tiny_graphs()["directed_dead_end"]
+    got = oracle.min_neighbour_degree(dead.indptr, dead.indices)
+    deg = np.maximum(np.diff(dead.indptr), 1)
+    for v in range(dead.get_number_of_nodes()):
+        nv = neighbours(dead, v)
+        assert got[v] == (deg[nv].min() if len(nv) else 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_normalize_by_degree_matches_analytic_pmf(rw, ew, weighted):
+    """First transition ~ w(v,x) / deg(x); later ones ~ bias(prev,x) * w(v,x) / deg(x)."""
+    graph, weights = weighted_test_graph()
+    if not weighted:
+        weights = None
+    degrees = np.diff(graph.indptr).astype(np.float64)
+    walks, counters = oracle.walks(graph.indptr, graph.indices, 31, 0, 480_000, 3, rw, ew,
+                                   weights=weights, normalize_by_degree=True)
+    assert counters["capped"] == 0 and counters["first_order"] == 0
+    for v in (0, 4, 2):
+        lo, hi = graph.indptr[v], graph.indptr[v + 1]
+        nxt = walks[walks[:, 0] == v, 1]
+        pmf = (1.0 if weights is None else weights[lo:hi].astype(np.float64)) / degrees[graph.indices[lo:hi]]
+        pmf = pmf / pmf.sum()
+        counts = np.array([(nxt == x).sum() for x in graph.indices[lo:hi]])
+        keep = pmf * len(nxt) >= 5
+        expected = pmf[keep] * len(nxt)
+        assert stats.chisquare(counts[keep], expected * counts[keep].sum() / expected.sum()).pvalue > 1e-3
+    checked = 0
+    for prev, cur in [(4, 0), (0, 4), (1, 2), (5, 6), (2, 7)]:
+        sel = walks[(walks[:, 0] == prev) & (walks[:, 1] == cur), 2]
+        lo, hi = graph.indptr[cur], graph.indptr[cur + 1]
+        nv, bias = analytic_pmf(graph, prev, cur, rw, ew)
+        pmf = bias * (1.0 if weights is None else weights[lo:hi]) / degrees[nv]
+        pmf = pmf / pmf.sum()
+        counts = np.array([(sel == x).sum() for x in nv])
+        keep = pmf * len(sel) >= 5
+        if len(sel) < 500 or keep.sum() < 2:
+            continue
+        expected = pmf[keep] * len(sel)
+        assert stats.chisquare(counts[keep], expected * counts[keep].sum() / expected.sum()).pvalue > 1e-3
+        checked += 1
+    assert checked >= 3
+
+
+@pytest.mark.parametrize("name", sorted(tiny_graphs()))
+def test_normalize_by_degree_edge_case_graphs(name):
+    graph = tiny_graphs()[name]
+    if (np.diff(graph.indptr) > 0).sum() == 0:
+        return
+    walks, counters = oracle.walks(graph.indptr, graph.indices, 3, 0, 200, 9, 0.25, 4.0,
+                                   normalize_by_degree=True)
+    n = graph.get_number_of_nodes()
+    edge_keys = np.repeat(np.arange(n, dtype=np.int64), np.diff(graph.indptr)) * n + graph.indices
+    a, b = walks[:, :-1].ravel(), walks[:, 1:].ravel()
+    live = b != 0xFFFFFFFF
+    assert np.isin(a[live].astype(np.int64) * n + b[live], edge_keys).all()
+    assert counters["capped"] == 0
