@@ -38,6 +38,7 @@ class B2EConfig(ctypes.Structure):
         ("use_scale_free_distribution", ctypes.c_uint32),
         ("normalize_learning_rate_by_degree", ctypes.c_uint32),
         ("normalize_by_degree", ctypes.c_uint32),
+        ("stochastic_downsample_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("deterministic", ctypes.c_uint32),
         ("chunk_walks", ctypes.c_uint32),

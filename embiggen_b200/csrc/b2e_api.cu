@@ -246,11 +246,14 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
 
     std::vector<uint32_t> sources;
     sources.reserve(n);
+    uint64_t max_degree = 0;
     for (uint64_t v = 0; v < n; ++v) {
         if (indptr[v + 1] < indptr[v]) return fail(B2E_ERR_INVALID, "indptr must be non-decreasing");
         if (indptr[v + 1] > indptr[v]) sources.push_back((uint32_t)v);
+        max_degree = std::max<uint64_t>(max_degree, (uint64_t)(indptr[v + 1] - indptr[v]));
     }
     h->n_src = sources.size();
+    h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
     if (weights) {
         std::vector<uint32_t> cdf(nnz);
         if (!build_edge_cdf(indptr, weights, n, cdf))
@@ -416,6 +419,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.inv_scale = 1.0f / sqrtf((float)c.embedding_size);
     p.use_alias = c.use_scale_free_distribution ? 1u : 0u;
     p.normalize_lr = c.normalize_learning_rate_by_degree ? 1u : 0u;
+    p.downsample = c.stochastic_downsample_by_degree ? h->max_degree + 1u : 0u;
     p.scale_dot = c.scale_by_sqrt_dim ? 1u : 0u;
     p.prefetch = h->prefetch;
     p.variant = h->variant;

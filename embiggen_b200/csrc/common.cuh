@@ -16,6 +16,7 @@ constexpr uint32_t TAG_WALK2 = 2u;  // second-order trials, 2 per block
 constexpr uint32_t TAG_NEG = 3u;    // negative draws
 constexpr uint32_t TAG_INIT0 = 4u;  // table 0 initialisation
 constexpr uint32_t TAG_INIT1 = 5u;  // table 1 initialisation
+constexpr uint32_t TAG_SKIP = 6u;   // stochastic_downsample_by_degree, one draw per centre
 constexpr uint32_t MAX_TRIALS = 1u << 20;
 constexpr uint32_t PAD = B2E_PAD_TOKEN;
 
@@ -73,6 +74,7 @@ struct TrainParams {
     uint32_t chunks;      // float4 chunks of a row that hold data: ceil(embedding_size / 4)
     float clip, lr, inv_scale;
     uint32_t use_alias, normalize_lr, scale_dot;
+    uint32_t downsample;  // stochastic_downsample_by_degree: max degree + 1, 0 = off
     uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
     uint32_t variant;   // tuning variant of the launch (0 = default)
     const uint2 *alias;  // {threshold, alias} per node
@@ -114,6 +116,7 @@ struct b2e_handle {
     uint32_t *d_indices = nullptr;
     uint32_t *d_cdf = nullptr;
     uint32_t *d_mindeg = nullptr;
+    uint32_t max_degree = 0;
     uint32_t *d_sources = nullptr;
     uint2 *d_alias = nullptr;
     float *d_t0 = nullptr, *d_t1 = nullptr;

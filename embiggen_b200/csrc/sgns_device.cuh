@@ -30,6 +30,16 @@ __device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre
     return __fdiv_rn(p.lr, (float)deg);
 }
 
+// stochastic_downsample_by_degree: the centre at position i is skipped with probability
+// deg(c) / (max degree + 1); one Philox block per centre, the same on every lane.
+__device__ __forceinline__ bool skip_centre(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
+                                            uint32_t i, uint32_t c) {
+    if (!p.downsample) return false;
+    const uint4 r = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, i, TAG_SKIP << 24);
+    const uint32_t deg = (uint32_t)(__ldg(p.indptr + c + 1) - __ldg(p.indptr + c));
+    return __umulhi(r.x, p.downsample) < deg;
+}
+
 // ---- SkipGram: the draw sites of a walk are its (centre, context) pairs, in oracle order ----
 struct PairCursor {
     uint32_t i, j;  // centre and context positions; start with i = 0xFFFFFFFF
@@ -38,9 +48,12 @@ struct PairCursor {
 };
 
 // advance to the next pair of the walk; false when the walk is exhausted.  STAGED: `walk` is a
-// shared-memory copy of the walk (plain loads) instead of global memory (read-only path).
+// shared-memory copy of the walk (plain loads) instead of global memory (read-only path).  The
+// pipelined kernels (STAGED) are never launched with stochastic_downsample_by_degree (it is
+// routed to the generic kernel), so the skip test exists only in the non-staged instantiation.
 template <bool STAGED = false>
-__device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uint32_t L, uint32_t W,
+__device__ __forceinline__ bool next_pair(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
+                                          const uint32_t *__restrict__ walk, uint32_t L, uint32_t W,
                                           PairCursor &s) {
     for (;;) {
         if (s.i == 0xFFFFFFFFu || s.j >= s.hi) {
@@ -49,6 +62,7 @@ __device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uin
             const uint32_t c = STAGED ? walk[i] : __ldg(walk + i);
             if (c == PAD) return false;
             s.i = i;
+            if (!STAGED && skip_centre(p, wid_lo, wid_hi, i, c)) { s.j = s.hi = 0; continue; }
             s.c = c;
             s.hi = i + W < L - 1 ? i + W : L - 1;
             s.j = i > W ? i - W : 0u;
@@ -65,11 +79,13 @@ __device__ __forceinline__ bool next_pair(const uint32_t *__restrict__ walk, uin
 // ---- CBOW: the draw sites of a walk are its centres ----
 // next centre position >= i with at least one valid context; returns L when exhausted
 template <bool STAGED = false>
-__device__ __forceinline__ uint32_t next_centre(const uint32_t *__restrict__ walk, uint32_t L,
+__device__ __forceinline__ uint32_t next_centre(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
+                                                const uint32_t *__restrict__ walk, uint32_t L,
                                                 uint32_t W, uint32_t i, uint32_t &c) {
     for (; i < L; ++i) {
         c = STAGED ? walk[i] : __ldg(walk + i);
         if (c == PAD) return L;
+        if (!STAGED && skip_centre(p, wid_lo, wid_hi, i, c)) continue;
         const uint32_t lo = i > W ? i - W : 0u;
         const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
         for (uint32_t j = lo; j <= hi; ++j) {

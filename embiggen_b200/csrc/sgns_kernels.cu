@@ -214,7 +214,7 @@ __device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32
 
     PairCursor scan;
     scan.i = 0xFFFFFFFFu; scan.j = 0; scan.c = PAD; scan.o = PAD; scan.hi = 0;
-    bool ok_cur = next_pair(walk, L, W, scan);
+    bool ok_cur = next_pair(p, wid_lo, wid_hi, walk, L, W, scan);
     if (!ok_cur) return;
     PairCursor cur = scan;
     uint32_t neg_cur;
@@ -223,7 +223,7 @@ __device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32
         const Draw d = draw_issue(p, wid_lo, wid_hi, (cur.i << 16) | cur.j, lane);
         vmask_cur = draw_resolve(p, d, lane, cur.c, cur.o, neg_cur);
     }
-    bool ok_nxt = next_pair(walk, L, W, scan);
+    bool ok_nxt = next_pair(p, wid_lo, wid_hi, walk, L, W, scan);
     PairCursor nxt = scan;
     Draw draw_nxt = draw_issue(p, wid_lo, wid_hi, (nxt.i << 16) | nxt.j, lane);
 
@@ -238,7 +238,7 @@ __device__ __forceinline__ void skipgram_walk(const TrainParams &p, const uint32
             prefetch_site(p, lane, nxt.o, neg_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
         }
         // site s+2: start its draw
-        const bool ok_far = ok_nxt && next_pair(walk, L, W, scan);
+        const bool ok_far = ok_nxt && next_pair(p, wid_lo, wid_hi, walk, L, W, scan);
         const PairCursor far = scan;
         Draw draw_far = draw_nxt;
         if (ok_far) draw_far = draw_issue(p, wid_lo, wid_hi, (far.i << 16) | far.j, lane);
@@ -271,14 +271,14 @@ __device__ __forceinline__ void cbow_walk(const TrainParams &p, const uint32_t *
     const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
 
     uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
-    uint32_t i_cur = next_centre(walk, L, W, 0, c_cur);
+    uint32_t i_cur = next_centre(p, wid_lo, wid_hi, walk, L, W, 0, c_cur);
     if (i_cur >= L) return;
     uint32_t neg_cur, vmask_cur;
     {
         const Draw d = draw_issue(p, wid_lo, wid_hi, (i_cur << 16) | 0xFFFFu, lane);
         vmask_cur = draw_resolve(p, d, lane, c_cur, c_cur, neg_cur);
     }
-    uint32_t i_nxt = next_centre(walk, L, W, i_cur + 1, c_nxt);
+    uint32_t i_nxt = next_centre(p, wid_lo, wid_hi, walk, L, W, i_cur + 1, c_nxt);
     Draw draw_nxt = draw_issue(p, wid_lo, wid_hi, (i_nxt << 16) | 0xFFFFu, lane);
 
     while (i_cur < L) {
@@ -290,7 +290,7 @@ __device__ __forceinline__ void cbow_walk(const TrainParams &p, const uint32_t *
             const uint32_t entering = i_nxt + W < L ? __ldg(walk + i_nxt + W) : PAD;
             prefetch_site(p, lane, c_nxt, neg_nxt, vmask_nxt, entering);
         }
-        const uint32_t i_far = i_nxt < L ? next_centre(walk, L, W, i_nxt + 1, c_far) : L;
+        const uint32_t i_far = i_nxt < L ? next_centre(p, wid_lo, wid_hi, walk, L, W, i_nxt + 1, c_far) : L;
         Draw draw_far = draw_nxt;
         if (i_far < L) draw_far = draw_issue(p, wid_lo, wid_hi, (i_far << 16) | 0xFFFFu, lane);
 

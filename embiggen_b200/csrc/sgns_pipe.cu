@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
 
         PairCursor scan;
         scan.i = 0xFFFFFFFFu; scan.j = 0; scan.c = PAD; scan.o = PAD; scan.hi = 0;
-        bool ok_cur = next_pair<true>(walk, L, W, scan);
+        bool ok_cur = next_pair<true>(p, wid_lo, wid_hi, walk, L, W, scan);
         if (!ok_cur) continue;
         PairCursor cur = scan;
         uint32_t stage = 0, slot_a = 0;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
         vmask_cur = resolve(cur, slot_a, idx_n, ry_n, neg_cur);
         ids_cur = slot_ids(lane, cur.o, neg_cur, vmask_cur);
         issue(stage, ids_cur, vmask_cur, cur.c);
-        bool ok_nxt = next_pair<true>(walk, L, W, scan);
+        bool ok_nxt = next_pair<true>(p, wid_lo, wid_hi, walk, L, W, scan);
         PairCursor nxt = scan;
         slot_a ^= 1u;
         if (ok_nxt) draw(nxt, slot_a, idx_n, ry_n);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
                 if (!deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
             }
             // ---- pair p+2: start its draw ----
-            const bool ok_far = ok_nxt && next_pair<true>(walk, L, W, scan);
+            const bool ok_far = ok_nxt && next_pair<true>(p, wid_lo, wid_hi, walk, L, W, scan);
             const PairCursor far = scan;
             uint32_t idx_f = PAD, ry_f = 0;
             if (ok_far) draw(far, slot_a ^ 1u, idx_f, ry_f);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
         };
 
         uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
-        uint32_t i_cur = next_centre<true>(walk, L, W, 0, c_cur);
+        uint32_t i_cur = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, 0, c_cur);
         if (i_cur >= L) continue;
         uint32_t stage = 0, slot_a = 0;
         uint32_t idx_n = PAD, ry_n = 0, neg_cur, vmask_cur, ids_cur;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
         vmask_cur = resolve(c_cur, slot_a, idx_n, ry_n, neg_cur);
         ids_cur = slot_ids(lane, c_cur, neg_cur, vmask_cur);
         issue(stage, ids_cur, vmask_cur);
-        uint32_t i_nxt = next_centre<true>(walk, L, W, i_cur + 1, c_nxt);
+        uint32_t i_nxt = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_cur + 1, c_nxt);
         slot_a ^= 1u;
         if (i_nxt < L) draw(i_nxt, slot_a, idx_n, ry_n);
         cp_async_commit();
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
                         reinterpret_cast<const char *>(p.t0) + entering * v.row_bytes + lane * 128u));
             }
             // ---- centre p+2: start its draw ----
-            const uint32_t i_far = i_nxt < L ? next_centre<true>(walk, L, W, i_nxt + 1, c_far) : L;
+            const uint32_t i_far = i_nxt < L ? next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_nxt + 1, c_far) : L;
             uint32_t idx_f = PAD, ry_f = 0;
             if (i_far < L) draw(i_far, slot_a ^ 1u, idx_f, ry_f);
             cp_async_commit();
@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
 
 bool pipe_supported(const TrainParams &p, uint32_t model) {
     if (p.chunks > 32u || p.negatives + 1u > PIPE_SLOTS || p.walk_length > 1024u) return false;
+    if (p.downsample) return false;  // the centre skip test lives in the generic kernel only
     return model == B2E_SKIPGRAM || 2u * p.window + 1u <= 32u;
 }
 

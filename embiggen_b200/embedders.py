@@ -103,9 +103,6 @@ class Node2VecB200(B200Embedder):
             if kwargs.get(name, 1.0) != 1.0:
                 raise NotImplementedError(
                     f"{name} != 1.0 (typed walks) is not implemented by the B200 engine.")
-        if kwargs.get("stochastic_downsample_by_degree", False):
-            raise NotImplementedError(
-                "stochastic_downsample_by_degree=True is not implemented by the B200 engine.")
         if kwargs.get("dtype", "f32") not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}, got {kwargs.get('dtype')!r}.")
         if isinstance(kwargs.get("learning_rate"), str):
@@ -138,6 +135,7 @@ class Node2VecB200(B200Embedder):
             use_scale_free_distribution=k["use_scale_free_distribution"],
             normalize_learning_rate_by_degree=k["normalize_learning_rate_by_degree"],
             normalize_by_degree=k["normalize_by_degree"],
+            stochastic_downsample_by_degree=bool(k["stochastic_downsample_by_degree"]),
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
             device=device)

@@ -72,6 +72,7 @@ class Engine:
                  use_scale_free_distribution: bool = True,
                  normalize_learning_rate_by_degree: bool = False,
                  normalize_by_degree: bool = False,
+                 stochastic_downsample_by_degree: bool = False,
                  scale_by_sqrt_dim: bool = False, deterministic: bool = False,
                  chunk_walks: int = 0, max_concurrent_walks: int = 0, device: int = 0):
         self._lib = _lib.load()
@@ -91,6 +92,7 @@ class Engine:
             use_scale_free_distribution=int(bool(use_scale_free_distribution)),
             normalize_learning_rate_by_degree=int(bool(normalize_learning_rate_by_degree)),
             normalize_by_degree=int(bool(normalize_by_degree)),
+            stochastic_downsample_by_degree=int(bool(stochastic_downsample_by_degree)),
             scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), deterministic=int(bool(deterministic)),
             chunk_walks=chunk_walks, max_concurrent_walks=max_concurrent_walks, device=device,
         )

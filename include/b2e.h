@@ -59,6 +59,7 @@ typedef struct {
     uint32_t use_scale_free_distribution;       /* 0 => uniform negatives */
     uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre) */
     uint32_t normalize_by_degree;               /* walk transition weight / deg(destination) */
+    uint32_t stochastic_downsample_by_degree;   /* skip a centre with probability deg / (max deg + 1) */
     uint32_t scale_by_sqrt_dim;                 /* score = dot / sqrt(D) */
     uint32_t deterministic; /* 1: one warp trains walks in ascending id order (bit-exact) */
     uint32_t chunk_walks;   /* walks per walk->SGD chunk, 0 = automatic */

@@ -46,6 +46,7 @@ class SgnsCfg(ctypes.Structure):
         ("use_alias", ctypes.c_uint32),
         ("normalize_learning_rate_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
+        ("downsample_bound", ctypes.c_uint32),
     ]
 
 
@@ -227,7 +228,7 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
           clipping_value: float = 6.0, first_walk: int = 0, walk_id_stride: int = 1,
           thr: Optional[np.ndarray] = None, alias: Optional[np.ndarray] = None,
           indptr: Optional[np.ndarray] = None, normalize_learning_rate_by_degree: bool = False,
-          scale_by_sqrt_dim: bool = False) -> dict:
+          scale_by_sqrt_dim: bool = False, stochastic_downsample_by_degree: bool = False) -> dict:
     """Train in place over row-major walks; returns loss_sum / pairs / targets."""
     walk_array = np.ascontiguousarray(walk_array, dtype=np.uint32)
     assert t0.dtype == np.float32 and t1.dtype == np.float32
@@ -247,6 +248,8 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
     )
     if indptr is not None:
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    if stochastic_downsample_by_degree:
+        cfg.downsample_bound = int(np.diff(indptr).max()) + 1
     loss = ctypes.c_double(0.0)
     pairs = ctypes.c_uint64(0)
     targets = ctypes.c_uint64(0)
@@ -264,7 +267,8 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
         walk_length: int, window_size: int, negatives: int, learning_rate: float,
         learning_rate_decay: float, return_weight: float = 1.0, explore_weight: float = 1.0,
         clipping_value: float = 6.0, alpha: float = 0.75, use_scale_free_distribution: bool = True,
-        normalize_learning_rate_by_degree: bool = False, chunk_walks: int = 1 << 16):
+        normalize_learning_rate_by_degree: bool = False, chunk_walks: int = 1 << 16,
+        stochastic_downsample_by_degree: bool = False, normalize_by_degree: bool = False):
     """Whole path: walks + SGD for ``epochs`` epochs in ascending walk-id order.
 
     Returns (t0, t1, epoch_mean_loss) with padded row stride.
@@ -286,10 +290,11 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
             count = min(chunk_walks, walks_per_epoch - done)
             first = epoch * walks_per_epoch + done
             w, _ = walks(indptr, indices, seed, first, count, walk_length, return_weight,
-                         explore_weight, srcs=srcs)
+                         explore_weight, srcs=srcs, normalize_by_degree=normalize_by_degree)
             r = train(model, w, t0, t1, seed, n, embedding_size, window_size, negatives, float(lr),
                       clipping_value, first_walk=first, thr=thr, alias=alias, indptr=indptr,
-                      normalize_learning_rate_by_degree=normalize_learning_rate_by_degree)
+                      normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
+                      stochastic_downsample_by_degree=stochastic_downsample_by_degree)
             loss_sum += r["loss_sum"]
             pairs += r["pairs"]
             done += count

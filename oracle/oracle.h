@@ -94,6 +94,7 @@ typedef struct {
     uint32_t use_alias;                         /* 0 => uniform negatives                   */
     uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre)                         */
     uint32_t scale_by_sqrt_dim;                 /* dot / sqrt(D)  (P)   */
+    uint32_t downsample_bound; /* stochastic_downsample_by_degree: max degree + 1, 0 => off */
 } orc_sgns_cfg;
 
 /*

@@ -17,6 +17,7 @@
 #define ORC_TAG_NEG 3u   /* negative draws                                   */
 #define ORC_TAG_INIT0 4u /* table 0 initialisation                           */
 #define ORC_TAG_INIT1 5u /* table 1 initialisation                           */
+#define ORC_TAG_SKIP 6u  /* stochastic_downsample_by_degree, one per centre     */
 
 static inline void orc_philox4x32_10(uint32_t seed_lo, uint32_t seed_hi, uint32_t c0, uint32_t c1,
                                      uint32_t c2, uint32_t c3, uint32_t out[4]) {

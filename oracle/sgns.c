@@ -173,6 +173,15 @@ static void train_one_walk(const orc_sgns_cfg *cfg, const uint32_t *walk, uint64
     for (uint32_t i = 0; i < L; ++i) {
         const uint32_t c = walk[i];
         if (c == ORC_PAD_TOKEN) break;
+        /* stochastic_downsample_by_degree (.../node2vec_skipgram.py:97-98): the centre is skipped
+         * with probability deg(c) / (max degree + 1); it still serves as context of its neighbours */
+        if (cfg->downsample_bound) {
+            uint32_t rnd[4];
+            orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)wid,
+                              (uint32_t)(wid >> 32), i, ORC_TAG_SKIP << 24, rnd);
+            if (orc_mulhi(rnd[0], cfg->downsample_bound) < (uint64_t)(indptr[c + 1] - indptr[c]))
+                continue;
+        }
         float lr = cfg->learning_rate;
         if (cfg->normalize_learning_rate_by_degree)
             lr = lr / (float)(uint64_t)(indptr[c + 1] - indptr[c]);
@@ -234,7 +243,7 @@ int orc_train(const orc_sgns_cfg *cfg, const uint32_t *walks, uint64_t n_walks,
         (cfg->row_stride & 3) || cfg->row_stride < cfg->embedding_size || n > 0xFFFFFFFFull)
         return -1;
     if (cfg->use_alias && (!thr || !alias)) return -1;
-    if (cfg->normalize_learning_rate_by_degree && !indptr) return -1;
+    if ((cfg->normalize_learning_rate_by_degree || cfg->downsample_bound) && !indptr) return -1;
     train_acc total = {0.0, 0, 0};
     int failed = 0;
 #pragma omp parallel num_threads(g_threads) if (g_threads > 1)

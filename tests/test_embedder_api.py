@@ -84,8 +84,7 @@ def test_kwarg_coercion_and_rejection():
         Node2VecSkipGramB200(embedding_size=0)
     with pytest.raises(ValueError):
         Node2VecSkipGramB200(dtype="f8")
-    for unsupported in (dict(change_node_type_weight=2.0), dict(change_edge_type_weight=0.5),
-                        dict(stochastic_downsample_by_degree=True)):
+    for unsupported in (dict(change_node_type_weight=2.0), dict(change_edge_type_weight=0.5)):
         with pytest.raises(NotImplementedError):
             Node2VecSkipGramB200(**unsupported)
 

@@ -16,7 +16,7 @@ SEED = 42
 
 
 def run_pair(graph, model, D, L, w, K, rw, ew, n_walks, lr=0.05, deterministic=True,
-             use_alias=True, normalize=False, clip=6.0, alpha=0.75, scale=False):
+             use_alias=True, normalize=False, clip=6.0, alpha=0.75, scale=False, downsample=False):
     n = graph.get_number_of_nodes()
     walks, _ = oracle.walks(graph.indptr, graph.indices, SEED, 0, n_walks, L, rw, ew)
     t0, t1 = oracle.init_tables(n, D, SEED)
@@ -25,12 +25,13 @@ def run_pair(graph, model, D, L, w, K, rw, ew, n_walks, lr=0.05, deterministic=T
         thr, alias = oracle.alias_build(graph.indptr, alpha)
     stats = oracle.train(model, walks, t0, t1, SEED, n, D, w, K, lr, clip, thr=thr, alias=alias,
                          indptr=graph.indptr, normalize_learning_rate_by_degree=normalize,
-                         scale_by_sqrt_dim=scale)
+                         scale_by_sqrt_dim=scale, stochastic_downsample_by_degree=downsample)
     with Engine(model, embedding_size=D, walk_length=L, window_size=w, iterations=1,
                 number_of_negative_samples=K, return_weight=rw, explore_weight=ew,
                 clipping_value=clip, use_scale_free_distribution=use_alias,
                 negative_sampling_exponent=alpha, normalize_learning_rate_by_degree=normalize,
                 scale_by_sqrt_dim=scale, deterministic=deterministic,
+                stochastic_downsample_by_degree=downsample,
                 chunk_walks=n_walks) as engine:
         engine.load_csr(graph.indptr, graph.indices)
         engine.init_tables(SEED)
@@ -83,11 +84,27 @@ def test_deterministic_tables_bit_exact(small_ppi, model, D, K, w):
 def test_deterministic_options(rmat_graph, model):
     """uniform negatives, lr / degree, dot / sqrt(D), tight clipping: still bit exact."""
     for kwargs in (dict(use_alias=False), dict(normalize=True, lr=0.5), dict(scale=True),
-                   dict(clip=0.01, lr=0.5), dict(alpha=1.0)):
+                   dict(clip=0.01, lr=0.5), dict(alpha=1.0), dict(downsample=True)):
         r = run_pair(rmat_graph, model, 100, 24, 3, 7, 2.0, 0.5, n_walks=200, **kwargs)
         assert np.array_equal(r["g0"], r["o0"]), kwargs
         assert np.array_equal(r["g1"], r["o1"]), kwargs
         assert r["counters"]["targets"] == r["stats"]["targets"]
+
+
+@pytest.mark.parametrize("model,D,K", [("SkipGram", 100, 10), ("CBOW", 128, 10), ("SkipGram", 200, 5),
+                                       ("CBOW", 300, 20)])
+def test_stochastic_downsample_by_degree(small_ppi, model, D, K):
+    """Pipelined and generic kernels: bit exact in the single-warp launch, the same pairs and
+    targets as the oracle in the production launch, and fewer pairs than without the option."""
+    r = run_pair(small_ppi, model, D, 32, 4, K, 0.25, 4.0, n_walks=300, downsample=True)
+    assert np.array_equal(r["g0"], r["o0"]) and np.array_equal(r["g1"], r["o1"])
+    assert r["counters"]["pairs"] == r["stats"]["pairs"]
+    full = run_pair(small_ppi, model, D, 32, 4, K, 0.25, 4.0, n_walks=300, deterministic=False)
+    hog = run_pair(small_ppi, model, D, 32, 4, K, 0.25, 4.0, n_walks=300, deterministic=False,
+                   downsample=True)
+    assert (hog["counters"]["pairs"], hog["counters"]["targets"]) == \
+        (hog["stats"]["pairs"], hog["stats"]["targets"])
+    assert hog["counters"]["pairs"] < full["counters"]["pairs"]
 
 
 @pytest.mark.parametrize("model,D", [("SkipGram", 100), ("CBOW", 128)])

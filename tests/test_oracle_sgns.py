@@ -89,7 +89,8 @@ def apply_targets(h, t1, targets, valid, lr, clip, scale, stats_out):
 
 
 def reference_train(model, walks, t0, t1, seed, n, D, w, K, lr, clip=6.0, first_walk=0, thr=None,
-                    alias=None, indptr=None, normalize=False, scale_by_sqrt_dim=False):
+                    alias=None, indptr=None, normalize=False, scale_by_sqrt_dim=False, downsample=False):
+    bound = int(np.diff(indptr).max()) + 1 if downsample else 0
     t0, t1 = t0.astype(np.float64), t1.astype(np.float64)
     out = {"pairs": 0, "targets": 0, "loss": 0.0}
     scale = 1.0 / np.sqrt(D) if scale_by_sqrt_dim else 1.0
@@ -100,6 +101,9 @@ def reference_train(model, walks, t0, t1, seed, n, D, w, K, lr, clip=6.0, first_
             c = int(walk[i])
             if c == PAD:
                 break
+            if bound and (oracle.philox(seed, wid & 0xFFFFFFFF, wid >> 32, i, 6 << 24)[0] * bound) >> 32 \
+                    < int(indptr[c + 1] - indptr[c]):
+                continue  # stochastic_downsample_by_degree
             step = lr / float(indptr[c + 1] - indptr[c]) if normalize else lr
             window = [j for j in range(max(0, i - w), min(L - 1, i + w) + 1)
                       if j != i and int(walk[j]) != PAD and int(walk[j]) != c]
@@ -132,6 +136,8 @@ CASES = [
     ("SkipGram", 20, 6, 3, dict(scale_by_sqrt_dim=True, lr=0.2)),
     ("SkipGram", 8, 10, 4, dict(clip=0.02, lr=0.5)),
     ("CBOW", 8, 0, 2, dict()),
+    ("SkipGram", 9, 4, 3, dict(downsample=True)),
+    ("CBOW", 9, 4, 3, dict(downsample=True)),
 ]
 
 
@@ -151,11 +157,13 @@ def test_c_oracle_matches_numpy_restatement(small_ppi, model, D, K, w, options):
     t1 *= 30.0
     e0, e1, expected = reference_train(
         model, walks, t0[:, :D], t1[:, :D], seed, n, D, w, K, lr, clip, first, thr, alias,
-        small_ppi.indptr, options.get("normalize", False), options.get("scale_by_sqrt_dim", False))
+        small_ppi.indptr, options.get("normalize", False), options.get("scale_by_sqrt_dim", False),
+        options.get("downsample", False))
     got = oracle.train(model, walks, t0, t1, seed, n, D, w, K, lr, clip, first_walk=first, thr=thr,
                        alias=alias, indptr=small_ppi.indptr,
                        normalize_learning_rate_by_degree=options.get("normalize", False),
-                       scale_by_sqrt_dim=options.get("scale_by_sqrt_dim", False))
+                       scale_by_sqrt_dim=options.get("scale_by_sqrt_dim", False),
+                       stochastic_downsample_by_degree=options.get("downsample", False))
     assert got["pairs"] == expected["pairs"] and got["targets"] == expected["targets"]
     assert got["pairs"] > 0
     assert np.isclose(got["loss_sum"], expected["loss"], rtol=1e-5)
@@ -208,3 +216,29 @@ def test_training_lowers_the_objective(small_ppi):
     o0, o1, losses = oracle.fit("SkipGram", small_ppi.indptr, small_ppi.indices, 42, 16, 3, 1, 24, 3,
                                 5, 0.05, 0.9, return_weight=0.25, explore_weight=4.0)
     assert losses[0] > losses[-1] and np.isfinite(o0).all() and np.isfinite(o1).all()
+
+
+def test_stochastic_downsample_skips_centres_in_proportion_to_degree():
+    """A star: the hub (degree 40 = max) is skipped with probability 40/41, a leaf with 1/41.
+    With window 1 and no negatives every surviving centre contributes exactly its context
+    count, so the pair count measures the skip rate (node2vec_skipgram.py:97-98)."""
+    from conftest import tiny_graphs
+    star = tiny_graphs()["star"]
+    n = star.get_number_of_nodes()
+    deg = np.diff(star.indptr)
+    hub = int(deg.argmax())
+    bound = int(deg.max()) + 1
+    walks, _ = oracle.walks(star.indptr, star.indices, 3, 0, 4000, 16)
+    t0, t1 = oracle.init_tables(n, 4, 3)
+    full = oracle.train("SkipGram", walks, t0.copy(), t1.copy(), 3, n, 4, 1, 0, 0.01, indptr=star.indptr)
+    kept = oracle.train("SkipGram", walks, t0, t1, 3, n, 4, 1, 0, 0.01, indptr=star.indptr,
+                        stochastic_downsample_by_degree=True)
+    # expected surviving pairs: sum over centres of contexts * (1 - deg/bound)
+    L = walks.shape[1]
+    contexts = np.full(walks.shape, 2); contexts[:, 0] = 1; contexts[:, -1] = 1
+    keep_p = 1.0 - deg[walks] / bound
+    expected = (contexts * keep_p).sum()
+    assert full["pairs"] == contexts.sum()
+    sd = np.sqrt((contexts ** 2 * keep_p * (1 - keep_p)).sum())
+    assert abs(kept["pairs"] - expected) < 5 * sd
+    assert kept["pairs"] < 0.7 * full["pairs"] and (walks == hub).mean() > 0.4
