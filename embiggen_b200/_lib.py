@@ -35,6 +35,8 @@ class B2EConfig(ctypes.Structure):
         ("learning_rate", ctypes.c_float),
         ("learning_rate_decay", ctypes.c_float),
         ("negative_sampling_exponent", ctypes.c_float),
+        ("change_node_type_weight", ctypes.c_float),
+        ("change_edge_type_weight", ctypes.c_float),
         ("use_scale_free_distribution", ctypes.c_uint32),
         ("normalize_learning_rate_by_degree", ctypes.c_uint32),
         ("normalize_by_degree", ctypes.c_uint32),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "b2e_load_csr": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64]),
     "b2e_load_csr_weighted": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _U64,
                                              _U64]),
+    "b2e_load_types": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_number_of_sources": (_U64, [_H]),
     "b2e_row_stride": (_U64, [_H]),
     "b2e_fit": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

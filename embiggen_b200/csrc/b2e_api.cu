@@ -46,6 +46,16 @@ extern "C" int b2e_device_count(void) {
     return usable;
 }
 
+// accept thresholds of the typed-walk tests, [same type, changed type] (oracle/walks.c)
+static void type_thresholds(float change_weight, unsigned long long q[2]) {
+    const double w = (double)change_weight, m = w > 1.0 ? w : 1.0;
+    const double ratio[2] = {1.0 / m, w / m};
+    for (int i = 0; i < 2; ++i) {
+        const double t = std::floor(ratio[i] * 4294967296.0);
+        q[i] = t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t;
+    }
+}
+
 // integer accept thresholds (DESIGN.md "second-order accept test")
 static void thresholds(float return_weight, float explore_weight, unsigned long long out[3]) {
     const double w[3] = {(double)return_weight, 1.0, (double)explore_weight};
@@ -77,6 +87,8 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (c.iterations == 0) return fail(B2E_ERR_INVALID, "iterations must be positive");
     if (!(c.return_weight > 0.0f) || !(c.explore_weight > 0.0f))
         return fail(B2E_ERR_INVALID, "return_weight and explore_weight must be strictly positive");
+    if (!(c.change_node_type_weight > 0.0f) || !(c.change_edge_type_weight > 0.0f))
+        return fail(B2E_ERR_INVALID, "change_node_type_weight and change_edge_type_weight must be strictly positive");
     if (!(c.clipping_value > 0.0f)) return fail(B2E_ERR_INVALID, "clipping_value must be positive");
     if (!(c.negative_sampling_exponent >= 0.0f))
         return fail(B2E_ERR_INVALID, "negative_sampling_exponent must be non-negative");
@@ -130,6 +142,8 @@ static void free_graph(b2e_handle *h) {
     cudaFree(h->d_indices); h->d_indices = nullptr;
     cudaFree(h->d_cdf); h->d_cdf = nullptr;
     cudaFree(h->d_mindeg); h->d_mindeg = nullptr;
+    cudaFree(h->d_node_types); h->d_node_types = nullptr;
+    cudaFree(h->d_edge_types); h->d_edge_types = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
     cudaFree(h->d_alias); h->d_alias = nullptr;
     cudaFree(h->d_t0); h->d_t0 = nullptr;
@@ -214,6 +228,26 @@ static bool build_edge_cdf(const int64_t *indptr, const float *weights, uint64_t
         if (end > begin) cdf[end - 1] = 0xFFFFFFFFu;
     }
     return true;
+}
+
+extern "C" int b2e_load_types(b2e_handle *h, const uint32_t *node_types, const uint32_t *edge_types) {
+    REQUIRE_HANDLE(h);
+    if (!h->d_indptr) return fail(B2E_ERR_STATE, "b2e_load_csr must be called first");
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    cudaFree(h->d_node_types); h->d_node_types = nullptr;
+    cudaFree(h->d_edge_types); h->d_edge_types = nullptr;
+    if (node_types && h->n) {
+        CUDA_TRY(cudaMalloc(&h->d_node_types, h->n * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_node_types, node_types, h->n * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, h->walk_stream));
+    }
+    if (edge_types && h->nnz) {
+        CUDA_TRY(cudaMalloc(&h->d_edge_types, h->nnz * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_edge_types, edge_types, h->nnz * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, h->walk_stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // the caller's buffers may go away
+    return B2E_OK;
 }
 
 extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
@@ -359,6 +393,10 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     p.indices = h->d_indices;
     p.cdf = h->d_cdf;
     p.mindeg = h->d_mindeg;
+    p.node_types = h->d_node_types;
+    p.edge_types = h->d_edge_types;
+    type_thresholds(h->d_node_types ? h->cfg.change_node_type_weight : 1.0f, p.q_node);
+    type_thresholds(h->d_edge_types ? h->cfg.change_edge_type_weight : 1.0f, p.q_edge);
     p.sources = h->d_sources;
     p.n_src = h->n_src;
     p.seed_lo = (uint32_t)seed;

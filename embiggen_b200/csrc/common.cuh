@@ -16,6 +16,7 @@ constexpr uint32_t TAG_WALK2 = 2u;  // second-order trials, 2 per block
 constexpr uint32_t TAG_NEG = 3u;    // negative draws
 constexpr uint32_t TAG_INIT0 = 4u;  // table 0 initialisation
 constexpr uint32_t TAG_INIT1 = 5u;  // table 1 initialisation
+constexpr uint32_t TAG_WALK3 = 7u;  // general walks (normalize_by_degree, typed): 1 trial per block
 constexpr uint32_t TAG_SKIP = 6u;   // stochastic_downsample_by_degree, one draw per centre
 constexpr uint32_t MAX_TRIALS = 1u << 20;
 constexpr uint32_t PAD = B2E_PAD_TOKEN;
@@ -51,6 +52,8 @@ struct WalkParams {
     const uint32_t *indices;
     const uint32_t *cdf;  // per-edge sampling table of a weighted graph, or nullptr
     const uint32_t *mindeg;  // smallest neighbour degree per node (normalize_by_degree), or nullptr
+    const uint32_t *node_types, *edge_types;  // [n] / [nnz] type ids of typed walks, or nullptr
+    unsigned long long q_node[2], q_edge[2];  // accept thresholds [same type, changed type]
     const uint32_t *sources;
     uint64_t n_src;
     uint32_t seed_lo, seed_hi;
@@ -116,6 +119,7 @@ struct b2e_handle {
     uint32_t *d_indices = nullptr;
     uint32_t *d_cdf = nullptr;
     uint32_t *d_mindeg = nullptr;
+    uint32_t *d_node_types = nullptr, *d_edge_types = nullptr;
     uint32_t max_degree = 0;
     uint32_t *d_sources = nullptr;
     uint2 *d_alias = nullptr;

@@ -368,10 +368,10 @@ __global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
 
 
 // ---- normalize_by_degree: transition weight divided by the degree of the destination ----
-// (.../node2vec_skipgram.py:94-96).  Every transition, the first one included, is a trial loop:
-// propose x, accept iff r1 * deg(x) < thr[class] * mindeg[cur], where mindeg[cur] is the smallest
-// neighbour degree of the current node (the bound rejection sampling needs for 1 / deg(x)).  All
-// products fit 64 bits (thr <= 2^32, degrees < 2^32), so the decisions are the oracle's.
+// (.../node2vec_skipgram.py:94-96): accept iff r1 * deg(x) < thr[class] * mindeg[cur], where
+// mindeg[cur] is the smallest neighbour degree of the current node (the bound rejection sampling
+// needs for 1 / deg(x)).  All products fit 64 bits (thr <= 2^32, degrees < 2^32), so the
+// decisions are the oracle's.
 __global__ void __launch_bounds__(256) min_neighbour_degree_kernel(const int64_t *__restrict__ indptr,
                                                                    const uint32_t *__restrict__ indices,
                                                                    uint64_t n, uint32_t *__restrict__ out) {
@@ -396,8 +396,12 @@ __device__ __forceinline__ unsigned long long scaled_threshold(unsigned long lon
     return thr >= 4294967296ull ? ((unsigned long long)bound << 32) : thr * bound;
 }
 
+// General walks (normalize_by_degree and / or typed walks): every transition is a trial loop with
+// ONE Philox block per trial (tag 7): x proposal, z node-type test, w edge-type test, y p/q test
+// with the degree normalisation folded in.  Independent words => the acceptance probability is
+// the product of the three ratios.  Cheap tests first; see oracle/walks.c:walks_general.
 template <bool VEC, bool WEIGHTED>
-__global__ void __launch_bounds__(256) walk_norm_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
     if (i < p.n_walks) {
@@ -406,11 +410,12 @@ __global__ void __launch_bounds__(256) walk_norm_kernel(const WalkParams p) {
         uint32_t *out = p.out + i * (uint64_t)p.walk_length;
         const unsigned long long thr_lo = min(p.thr_common, p.thr_explore);
         const unsigned long long thr_hi = max(p.thr_common, p.thr_explore);
+        const bool use_nt = p.node_types != nullptr && p.q_node[0] != p.q_node[1];
+        const bool use_et = p.edge_types != nullptr && p.q_edge[0] != p.q_edge[1];
         uint32_t cur = __ldg(p.sources + (wid % p.n_src));
         int64_t prev_off = 0;
-        uint32_t prev = PAD, prev_deg = 0;
+        uint32_t prev = PAD, prev_deg = 0, prev_etype = 0;
         bool alive = true;
-        uint4 rnd = make_uint4(0, 0, 0, 0);
         uint32_t tok[4];
         const uint32_t L = p.walk_length;
         for (uint32_t base = 0; base < L; base += 4) {
@@ -426,38 +431,46 @@ __global__ void __launch_bounds__(256) walk_norm_kernel(const WalkParams p) {
                     if (deg == 0) {
                         alive = false;
                     } else {
-                        const uint32_t bound = __ldg(p.mindeg + cur);
+                        const uint32_t bound = p.mindeg ? __ldg(p.mindeg + cur) : 1u;
+                        const uint32_t cur_type = use_nt ? __ldg(p.node_types + cur) : 0u;
                         uint32_t trial = 0;
+                        int64_t e = off;
                         for (;;) {
-                            if ((trial & 1u) == 0)
-                                rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
-                                                    (TAG_WALK2 << 24) | (trial >> 1));
-                            const uint32_t r0 = (trial & 1u) ? rnd.z : rnd.x;
-                            const unsigned long long r1 = (trial & 1u) ? rnd.w : rnd.y;
-                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r0));
+                            const uint4 rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                            (TAG_WALK3 << 24) | trial);
+                            e = off + propose<WEIGHTED>(p.cdf, off, deg, rnd.x);
+                            next = __ldg(p.indices + e);
                             ++n_trials;
-                            const uint32_t next_deg = max(
-                                (uint32_t)(__ldg(p.indptr + next + 1) - __ldg(p.indptr + next)), 1u);
-                            const unsigned long long lhs = r1 * next_deg;
-                            bool accept;
-                            if (t == 1) {
-                                accept = lhs < scaled_threshold(4294967296ull, bound);
-                            } else if (next == prev) {
-                                accept = lhs < scaled_threshold(p.thr_return, bound);
-                            } else if (lhs < scaled_threshold(thr_lo, bound)) {
-                                accept = true;
-                            } else if (lhs >= scaled_threshold(thr_hi, bound)) {
-                                accept = false;
-                            } else {
-                                ++n_searches;
-                                const bool common = row_contains(p.indices + prev_off, prev_deg, next);
-                                accept = lhs < scaled_threshold(common ? p.thr_common : p.thr_explore, bound);
+                            bool accept = true;
+                            if (use_nt)
+                                accept = rnd.z < p.q_node[__ldg(p.node_types + next) != cur_type ? 1 : 0];
+                            if (accept && use_et && t > 1)
+                                accept = rnd.w < p.q_edge[__ldg(p.edge_types + e) != prev_etype ? 1 : 0];
+                            if (accept) {
+                                uint32_t next_deg = 1u;
+                                if (p.mindeg)
+                                    next_deg = max((uint32_t)(__ldg(p.indptr + next + 1) - __ldg(p.indptr + next)), 1u);
+                                const unsigned long long lhs = (unsigned long long)rnd.y * next_deg;
+                                if (t == 1) {
+                                    accept = lhs < scaled_threshold(4294967296ull, bound);
+                                } else if (next == prev) {
+                                    accept = lhs < scaled_threshold(p.thr_return, bound);
+                                } else if (lhs < scaled_threshold(thr_lo, bound)) {
+                                    accept = true;
+                                } else if (lhs >= scaled_threshold(thr_hi, bound)) {
+                                    accept = false;
+                                } else {
+                                    ++n_searches;
+                                    const bool common = row_contains(p.indices + prev_off, prev_deg, next);
+                                    accept = lhs < scaled_threshold(common ? p.thr_common : p.thr_explore, bound);
+                                }
                             }
                             if (accept) break;
                             ++trial;
                             if (trial >= MAX_TRIALS) break;
                         }
                         ++n_steps;
+                        if (p.edge_types) prev_etype = __ldg(p.edge_types + e);
                         prev = cur;
                         prev_off = off;
                         prev_deg = deg;
@@ -518,11 +531,13 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     const unsigned grid = (unsigned)((p.n_walks + block - 1) / block);
     const bool vec = (p.walk_length % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16u) == 0;
     const bool weighted = p.cdf != nullptr;
-    if (p.mindeg) {  // normalize_by_degree: one trial loop for every transition
-        if (vec) { if (weighted) walk_norm_kernel<true, true><<<grid, block, 0, stream>>>(p);
-                   else walk_norm_kernel<true, false><<<grid, block, 0, stream>>>(p); }
-        else { if (weighted) walk_norm_kernel<false, true><<<grid, block, 0, stream>>>(p);
-               else walk_norm_kernel<false, false><<<grid, block, 0, stream>>>(p); }
+    const bool typed = (p.node_types && p.q_node[0] != p.q_node[1]) ||
+                       (p.edge_types && p.q_edge[0] != p.q_edge[1]);
+    if (p.mindeg || typed) {  // normalize_by_degree / typed walks: one trial loop per transition
+        if (vec) { if (weighted) walk_general_kernel<true, true><<<grid, block, 0, stream>>>(p);
+                   else walk_general_kernel<true, false><<<grid, block, 0, stream>>>(p); }
+        else { if (weighted) walk_general_kernel<false, true><<<grid, block, 0, stream>>>(p);
+               else walk_general_kernel<false, false><<<grid, block, 0, stream>>>(p); }
         return cudaGetLastError();
     }
     if (second_order && !weighted && p.state_machine) {

@@ -28,7 +28,7 @@ from . import _lib
 from .embedding_api import (AbstractEmbeddingModel, AbstractModel, EmbeddingResult, abstract_class,
                             normalize_kwargs)
 from .engine import Engine
-from .graph import as_csr
+from .graph import as_csr, as_types
 
 _DTYPES = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
 # engine options that are not part of the reference's signature (keyword-only, defaulted)
@@ -100,9 +100,8 @@ class Node2VecB200(B200Embedder):
     @staticmethod
     def _check_supported(kwargs: Dict[str, Any]) -> None:
         for name in ("change_node_type_weight", "change_edge_type_weight"):
-            if kwargs.get(name, 1.0) != 1.0:
-                raise NotImplementedError(
-                    f"{name} != 1.0 (typed walks) is not implemented by the B200 engine.")
+            if not kwargs.get(name, 1.0) > 0.0:
+                raise ValueError(f"{name} must be strictly positive, got {kwargs.get(name)!r}.")
         if kwargs.get("dtype", "f32") not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}, got {kwargs.get('dtype')!r}.")
         if isinstance(kwargs.get("learning_rate"), str):
@@ -135,6 +134,8 @@ class Node2VecB200(B200Embedder):
             use_scale_free_distribution=k["use_scale_free_distribution"],
             normalize_learning_rate_by_degree=k["normalize_learning_rate_by_degree"],
             normalize_by_degree=k["normalize_by_degree"],
+            change_node_type_weight=k.get("change_node_type_weight", 1.0),
+            change_edge_type_weight=k.get("change_edge_type_weight", 1.0),
             stochastic_downsample_by_degree=bool(k["stochastic_downsample_by_degree"]),
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
@@ -174,6 +175,10 @@ class Node2VecB200(B200Embedder):
         central, contextual = self._output_buffers(n)
         with Engine(**self._engine_kwargs(device)) as engine:
             engine.load_csr(indptr, indices, weights)  # weighted graphs walk by weight
+            if self.is_using_node_types() or self.is_using_edge_types():
+                node_types, edge_types = as_types(graph)  # a graph without types walks untyped
+                engine.load_types(node_types if self.is_using_node_types() else None,
+                                  edge_types if self.is_using_edge_types() else None)
             if world > 1:
                 c, x, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"])
                 central[:], contextual[:] = c, x
@@ -217,12 +222,28 @@ class Node2VecB200(B200Embedder):
 
     @classmethod
     def can_use_node_types(cls) -> bool:
-        """Typed walks (change_node_type_weight) are not implemented by this engine."""
-        return False
+        """Returns whether the model can optionally use node types."""
+        return True
+
+    def is_using_node_types(self) -> bool:
+        """Returns whether the model is parametrized to use node types."""
+        return self._model_kwargs.get("change_node_type_weight", 1.0) != 1.0
 
     @classmethod
     def can_use_edge_types(cls) -> bool:
-        """Typed walks (change_edge_type_weight) are not implemented by this engine."""
+        """Returns whether the model can optionally use edge types."""
+        return True
+
+    def is_using_edge_types(self) -> bool:
+        """Returns whether the model is parametrized to use edge types."""
+        return self._model_kwargs.get("change_edge_type_weight", 1.0) != 1.0
+
+    @classmethod
+    def requires_node_types(cls) -> bool:
+        return False
+
+    @classmethod
+    def requires_edge_types(cls) -> bool:
         return False
 
     @classmethod

@@ -72,6 +72,7 @@ class Engine:
                  use_scale_free_distribution: bool = True,
                  normalize_learning_rate_by_degree: bool = False,
                  normalize_by_degree: bool = False,
+                 change_node_type_weight: float = 1.0, change_edge_type_weight: float = 1.0,
                  stochastic_downsample_by_degree: bool = False,
                  scale_by_sqrt_dim: bool = False, deterministic: bool = False,
                  chunk_walks: int = 0, max_concurrent_walks: int = 0, device: int = 0):
@@ -92,6 +93,8 @@ class Engine:
             use_scale_free_distribution=int(bool(use_scale_free_distribution)),
             normalize_learning_rate_by_degree=int(bool(normalize_learning_rate_by_degree)),
             normalize_by_degree=int(bool(normalize_by_degree)),
+            change_node_type_weight=change_node_type_weight,
+            change_edge_type_weight=change_edge_type_weight,
             stochastic_downsample_by_degree=int(bool(stochastic_downsample_by_degree)),
             scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), deterministic=int(bool(deterministic)),
             chunk_walks=chunk_walks, max_concurrent_walks=max_concurrent_walks, device=device,
@@ -135,6 +138,23 @@ class Engine:
         check(self._lib.b2e_load_csr_weighted(self._handle, indptr.ctypes.data, indices.ctypes.data,
                                               pointer, n, nnz))
         self.n = n
+        self.nnz = nnz
+
+    def load_types(self, node_types: Optional[np.ndarray] = None,
+                   edge_types: Optional[np.ndarray] = None) -> None:
+        """Type ids of typed walks (``change_node_type_weight`` / ``change_edge_type_weight``):
+        one uint32 per node / per directed edge in CSR order."""
+        if node_types is not None:
+            node_types = np.ascontiguousarray(node_types, dtype=np.uint32)
+            if node_types.shape != (self.n,):
+                raise ValueError("node_types must have one entry per node.")
+        if edge_types is not None:
+            edge_types = np.ascontiguousarray(edge_types, dtype=np.uint32)
+            if edge_types.shape != (self.nnz,):
+                raise ValueError("edge_types must have one entry per directed edge.")
+        check(self._lib.b2e_load_types(self._handle,
+                                       None if node_types is None else node_types.ctypes.data,
+                                       None if edge_types is None else edge_types.ctypes.data))
 
     @property
     def number_of_sources(self) -> int:

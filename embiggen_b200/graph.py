@@ -49,7 +49,8 @@ class CSRGraph:
     """Minimal stand-in for ``ensmallen.Graph`` exposing the accessors this path calls."""
 
     def __init__(self, indptr, indices, node_names: Optional[Sequence[str]] = None,
-                 weights=None, name: str = "graph", directed: bool = False):
+                 weights=None, name: str = "graph", directed: bool = False,
+                 node_types=None, edge_types=None):
         self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         self.indices = np.ascontiguousarray(indices, dtype=np.uint32)
         if self.indptr.ndim != 1 or self.indptr.shape[0] < 1:
@@ -57,6 +58,12 @@ class CSRGraph:
         if self.indptr[0] != 0 or self.indptr[-1] != self.indices.shape[0]:
             raise ValueError("indptr must start at 0 and end at len(indices).")
         self.weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        self.node_types = None if node_types is None else np.ascontiguousarray(node_types, dtype=np.uint32)
+        self.edge_types = None if edge_types is None else np.ascontiguousarray(edge_types, dtype=np.uint32)
+        if self.node_types is not None and self.node_types.shape != (self.indptr.shape[0] - 1,):
+            raise ValueError("node_types must have one entry per node.")
+        if self.edge_types is not None and self.edge_types.shape != self.indices.shape:
+            raise ValueError("edge_types must have one entry per directed edge.")
         self._node_names = None if node_names is None else list(node_names)
         self._name = name
         self._directed = directed
@@ -103,13 +110,26 @@ class CSRGraph:
         return self.weights is not None and bool((self.weights < 0).any())
 
     def has_node_types(self) -> bool:
-        return False
+        return self.node_types is not None
 
     def has_edge_types(self) -> bool:
-        return False
+        return self.edge_types is not None
 
     def get_number_of_node_types(self) -> int:
-        return 0
+        return 0 if self.node_types is None else int(np.unique(self.node_types).shape[0])
+
+    def get_number_of_edge_types(self) -> int:
+        return 0 if self.edge_types is None else int(np.unique(self.edge_types).shape[0])
+
+    def get_single_label_node_type_ids(self) -> np.ndarray:
+        if self.node_types is None:
+            raise ValueError("The graph has no node types.")
+        return self.node_types
+
+    def get_directed_edge_type_ids(self) -> np.ndarray:
+        if self.edge_types is None:
+            raise ValueError("The graph has no edge types.")
+        return self.edge_types
 
     def is_directed(self) -> bool:
         return self._directed
@@ -166,6 +186,18 @@ def as_csr(graph) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
         f"Cannot extract a CSR from an object of type {type(graph)}: expected an "
         "ensmallen.Graph, a CSRGraph, a (indptr, indices) pair or a scipy sparse matrix."
     )
+
+
+def as_types(graph) -> Tuple[Optional[np.ndarray], Optional[np.ndarray]]:
+    """(node type id per node, edge type id per directed edge in CSR order), each None when the
+    graph has none; read through the accessors the reference uses on an ``ensmallen.Graph``
+    (``get_single_label_node_type_ids``, ``get_directed_edge_type_ids``)."""
+    node_types = edge_types = None
+    if hasattr(graph, "has_node_types") and graph.has_node_types():
+        node_types = np.ascontiguousarray(graph.get_single_label_node_type_ids(), dtype=np.uint32)
+    if hasattr(graph, "has_edge_types") and graph.has_edge_types():
+        edge_types = np.ascontiguousarray(graph.get_directed_edge_type_ids(), dtype=np.uint32)
+    return node_types, edge_types
 
 
 def as_graph(graph):

@@ -56,6 +56,8 @@ typedef struct {
     float learning_rate;
     float learning_rate_decay;
     float negative_sampling_exponent;           /* alias table over deg^alpha; north_star: 0.75 */
+    float change_node_type_weight; /* walk weight x this when the node type changes (b2e_load_types) */
+    float change_edge_type_weight; /* ... when the edge type changes; 1 = untyped walks */
     uint32_t use_scale_free_distribution;       /* 0 => uniform negatives */
     uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre) */
     uint32_t normalize_by_degree;               /* walk transition weight / deg(destination) */
@@ -104,6 +106,16 @@ int b2e_load_csr(b2e_handle *handle, const int64_t *indptr, const uint32_t *indi
  */
 int b2e_load_csr_weighted(b2e_handle *handle, const int64_t *indptr, const uint32_t *indices,
                           const float *weights, uint64_t n, uint64_t nnz);
+
+/*
+ * Typed walks: the type ids behind `change_node_type_weight` / `change_edge_type_weight`
+ * (.../node2vec_skipgram.py:72-77; the reference reads them from the graph:
+ * `graph.get_single_label_node_type_ids()`, `graph.get_directed_edge_type_ids()`).  node_types
+ * has n entries, edge_types nnz entries in CSR order; either may be NULL.  Call after
+ * b2e_load_csr* (which drops the types of the previous graph); a change weight whose types were
+ * never loaded has no effect (the graph walks untyped).
+ */
+int b2e_load_types(b2e_handle *handle, const uint32_t *node_types, const uint32_t *edge_types);
 
 uint64_t b2e_number_of_sources(const b2e_handle *handle);
 uint64_t b2e_row_stride(const b2e_handle *handle); /* floats per table row on the device */

@@ -93,6 +93,10 @@ def lib():
         l.orc_walks_full.restype = ctypes.c_int
         l.orc_walks_full.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), u64, P(u32), u64, u64, u64,
                                      u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
+        l.orc_walks_typed.restype = ctypes.c_int
+        l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), P(u32), f32, f32,
+                                      u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, P(u32),
+                                      P(WalkCounters)]
         l.orc_alias_build.restype = ctypes.c_int
         l.orc_alias_build.argtypes = [P(ctypes.c_int64), u64, ctypes.c_double, P(u32), P(u32)]
         l.orc_set_threads.restype = None
@@ -170,7 +174,9 @@ def min_neighbour_degree(indptr, indices) -> np.ndarray:
 def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length: int,
           return_weight: float = 1.0, explore_weight: float = 1.0, walk_id_stride: int = 1,
           srcs: Optional[np.ndarray] = None, weights=None,
-          normalize_by_degree: bool = False) -> Tuple[np.ndarray, dict]:
+          normalize_by_degree: bool = False, node_types=None, edge_types=None,
+          change_node_type_weight: float = 1.0,
+          change_edge_type_weight: float = 1.0) -> Tuple[np.ndarray, dict]:
     indptr, indices = _csr(indptr, indices)
     cdf = None if weights is None else edge_cdf(indptr, weights)
     mindeg = min_neighbour_degree(indptr, indices) if normalize_by_degree else None
@@ -180,11 +186,19 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
     srcs = np.ascontiguousarray(srcs, dtype=np.uint32)
     out = np.empty((n_walks, walk_length), dtype=np.uint32)
     counters = WalkCounters()
-    rc = lib().orc_walks_full(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
-                              _ptr(cdf, ctypes.c_uint32), _ptr(mindeg, ctypes.c_uint32), n,
-                              _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
-                              walk_id_stride, walk_length, return_weight, explore_weight,
-                              _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
+    if node_types is not None:
+        node_types = np.ascontiguousarray(node_types, dtype=np.uint32)
+        assert node_types.shape[0] == n
+    if edge_types is not None:
+        edge_types = np.ascontiguousarray(edge_types, dtype=np.uint32)
+        assert edge_types.shape[0] == indices.shape[0]
+    rc = lib().orc_walks_typed(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                               _ptr(cdf, ctypes.c_uint32), _ptr(mindeg, ctypes.c_uint32),
+                               _ptr(node_types, ctypes.c_uint32), _ptr(edge_types, ctypes.c_uint32),
+                               change_node_type_weight, change_edge_type_weight, n,
+                               _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
+                               walk_id_stride, walk_length, return_weight, explore_weight,
+                               _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
     if rc != 0:
         raise ValueError(f"orc_walks failed with status {rc}")
     return out, counters.as_dict()

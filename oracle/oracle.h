@@ -78,6 +78,17 @@ int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_
                    uint32_t walk_length, float return_weight, float explore_weight, uint32_t *out,
                    orc_walk_counters *counters);
 
+/* orc_walks_full plus typed walks: node_types[n] / edge_types[nnz] (NULL: untyped) and the
+ * weights multiplied in when the node type / the edge type changes */
+void orc_type_thresholds(float change_weight, uint64_t q[2]);
+int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                    const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                    float change_node_type_weight, float change_edge_type_weight, uint64_t n,
+                    const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                    uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                    float return_weight, float explore_weight, uint32_t *out,
+                    orc_walk_counters *counters);
+
 /* Vose alias table over deg^alpha; thr/alias have n entries. */
 int orc_alias_build(const int64_t *indptr, uint64_t n, double alpha, uint32_t *thr,
                     uint32_t *alias);

@@ -148,18 +148,45 @@ int orc_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uin
 }
 
 /*
- * With mindeg != NULL every transition, the first one included, is a trial loop on the
- * second-order stream: propose x, accept iff r1 * deg(x) < thr[class] * mindeg[cur] (exact
- * integer arithmetic; the first transition has no previous node and uses thr = 2^32).
+ * General walks: normalize_by_degree and / or typed walks ("next" row f-2,
+ * .../node2vec_skipgram.py:72-77, 94-96).  Every transition, the first one included, is a trial
+ * loop on its own Philox stream (tag 7, ONE block per trial: c2 = t - 1, c3 = trial):
+ *   word 0  proposal (uniform, or proportional to the edge weight);
+ *   word 2  node-type test: the weight of v -> x is multiplied by change_node_type_weight when
+ *           type(x) != type(v); accept iff r2 < q_node[changed];
+ *   word 3  edge-type test (from the second transition on): multiplied by
+ *           change_edge_type_weight when type(v -> x) != type(prev -> v); accept iff r3 < q_edge[changed];
+ *   word 1  p/q test, with normalize_by_degree folded in: accept iff
+ *           r1 * max(deg(x), 1) < thr[class] * mindeg[v]   (thr = 2^32 for the first transition).
+ * q[changed] = floor(w / max(1, w) * 2^32), q[same] = floor(1 / max(1, w) * 2^32).  The three
+ * tests use independent words, so the acceptance probability is the product of the three
+ * ratios and the walk follows  weight * bias_pq * type factors / deg(x)  exactly (up to 2^-32).
+ * Integer arithmetic only; the cheap tests come first and the adjacency search is counted only
+ * when it is reached and undecided.
  */
-static int walks_normalized(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                            const uint32_t *mindeg, const uint32_t *sources, uint64_t n_src, uint64_t seed,
-                            uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
-                            uint32_t walk_length, float return_weight, float explore_weight,
-                            uint32_t *out, orc_walk_counters *counters) {
+void orc_type_thresholds(float change_weight, uint64_t q[2]) {
+    const double w = (double)change_weight, m = w > 1.0 ? w : 1.0;
+    const double ratio[2] = {1.0 / m, w / m}; /* [same, changed] */
+    for (int i = 0; i < 2; ++i) {
+        double t = floor(ratio[i] * 4294967296.0);
+        q[i] = t >= 4294967296.0 ? 4294967296ull : (uint64_t)t;
+    }
+}
+
+static int walks_general(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                         const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                         float change_node_type_weight, float change_edge_type_weight,
+                         const uint32_t *sources, uint64_t n_src, uint64_t seed,
+                         uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
+                         uint32_t walk_length, float return_weight, float explore_weight,
+                         uint32_t *out, orc_walk_counters *counters) {
     const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
-    uint64_t thr[3];
+    uint64_t thr[3], qn[2], qe[2];
     orc_thresholds(return_weight, explore_weight, thr);
+    orc_type_thresholds(node_types ? change_node_type_weight : 1.0f, qn);
+    orc_type_thresholds(edge_types ? change_edge_type_weight : 1.0f, qe);
+    const int use_nt = node_types && qn[0] != qn[1];
+    const int use_et = edge_types && qe[0] != qe[1];
     const uint64_t thr_lo = thr[1] < thr[2] ? thr[1] : thr[2];
     const uint64_t thr_hi = thr[1] < thr[2] ? thr[2] : thr[1];
     uint64_t n_steps = 0, n_trials = 0, n_searches = 0, n_probe = 0, n_capped = 0;
@@ -170,48 +197,59 @@ static int walks_normalized(const int64_t *indptr, const uint32_t *indices, cons
         const uint64_t wid = first_walk + i * walk_id_stride;
         const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
         uint32_t *walk = out + i * (uint64_t)walk_length;
-        uint32_t cur = sources[wid % n_src], prev = ORC_PAD_TOKEN;
+        uint32_t cur = sources[wid % n_src], prev = ORC_PAD_TOKEN, prev_etype = 0;
         walk[0] = cur;
-        uint32_t rnd[4] = {0, 0, 0, 0};
         uint32_t t = 1;
         for (; t < walk_length; ++t) {
             const int64_t off = indptr[cur];
             const uint64_t deg = (uint64_t)(indptr[cur + 1] - off);
             if (deg == 0) break;
-            const unsigned __int128 bound = mindeg[cur];
+            const unsigned __int128 bound = mindeg ? mindeg[cur] : 1u;
             uint32_t next, trial = 0;
+            int64_t e;
             for (;;) {
-                if ((trial & 1u) == 0)
-                    orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
-                                      (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
-                const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
-                next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, r0)];
+                uint32_t rnd[4];
+                orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
+                                  (ORC_TAG_WALK3 << 24) | trial, rnd);
+                e = off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, rnd[0]);
+                next = indices[e];
                 ++n_trials;
-                uint64_t next_deg = (uint64_t)(indptr[next + 1] - indptr[next]);
-                if (next_deg == 0) next_deg = 1;
-                const unsigned __int128 lhs = (unsigned __int128)r1 * next_deg;
-                uint64_t limit = 4294967296ull;  /* first transition: no bias */
-                if (t > 1) {
-                    int cls;
-                    if (next == prev) {
-                        cls = 0;
-                    } else {
-                        const int64_t poff = indptr[prev];
-                        const uint64_t pdeg = (uint64_t)(indptr[prev + 1] - poff);
-                        cls = row_contains(indices + poff, pdeg, next) ? 1 : 2;
-                        if (lhs >= thr_lo * bound && lhs < thr_hi * bound) {
-                            ++n_searches;
-                            n_probe += probe_sectors(pdeg);
-                        }
+                int accept = 1;
+                if (use_nt && (uint64_t)rnd[2] >= qn[node_types[next] != node_types[cur]]) accept = 0;
+                if (accept && use_et && t > 1 && (uint64_t)rnd[3] >= qe[edge_types[e] != prev_etype])
+                    accept = 0;
+                if (accept) {
+                    uint64_t next_deg = 1;
+                    if (mindeg) {
+                        next_deg = (uint64_t)(indptr[next + 1] - indptr[next]);
+                        if (next_deg == 0) next_deg = 1;
                     }
-                    limit = thr[cls];
+                    const unsigned __int128 lhs = (unsigned __int128)rnd[1] * next_deg;
+                    uint64_t limit = 4294967296ull; /* first transition: no p/q bias */
+                    if (t > 1) {
+                        int cls;
+                        if (next == prev) {
+                            cls = 0;
+                        } else {
+                            const int64_t poff = indptr[prev];
+                            const uint64_t pdeg = (uint64_t)(indptr[prev + 1] - poff);
+                            cls = row_contains(indices + poff, pdeg, next) ? 1 : 2;
+                            if (lhs >= thr_lo * bound && lhs < thr_hi * bound) {
+                                ++n_searches;
+                                n_probe += probe_sectors(pdeg);
+                            }
+                        }
+                        limit = thr[cls];
+                    }
+                    accept = lhs < limit * bound;
                 }
-                if (lhs < limit * bound) break;
+                if (accept) break;
                 ++trial;
                 if (trial >= ORC_MAX_TRIALS) { ++n_capped; break; }
             }
             ++n_steps;
             walk[t] = next;
+            if (edge_types) prev_etype = edge_types[e];
             prev = cur;
             cur = next;
         }
@@ -224,6 +262,24 @@ static int walks_normalized(const int64_t *indptr, const uint32_t *indices, cons
     return 0;
 }
 
+int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+                    const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                    float change_node_type_weight, float change_edge_type_weight, uint64_t n,
+                    const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                    uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                    float return_weight, float explore_weight, uint32_t *out,
+                    orc_walk_counters *counters) {
+    if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
+    const int typed = (node_types && change_node_type_weight != 1.0f) ||
+                      (edge_types && change_edge_type_weight != 1.0f);
+    if (!mindeg && !typed)
+        return orc_walks_full(indptr, indices, cdf, NULL, n, sources, n_src, seed, first_walk, n_walks,
+                              walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+    return walks_general(indptr, indices, cdf, mindeg, node_types, edge_types, change_node_type_weight,
+                         change_edge_type_weight, sources, n_src, seed, first_walk, n_walks,
+                         walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+}
+
 int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
                    const uint32_t *mindeg, uint64_t n, const uint32_t *sources, uint64_t n_src,
                    uint64_t seed, uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
@@ -231,8 +287,9 @@ int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_
                    orc_walk_counters *counters) {
     if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
     if (mindeg)
-        return walks_normalized(indptr, indices, cdf, mindeg, sources, n_src, seed, first_walk, n_walks,
-                                walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+        return walks_general(indptr, indices, cdf, mindeg, NULL, NULL, 1.0f, 1.0f, sources, n_src, seed,
+                             first_walk, n_walks, walk_id_stride, walk_length, return_weight,
+                             explore_weight, out, counters);
     (void)n;
     const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
     const int second_order = !(return_weight == 1.0f && explore_weight == 1.0f);

@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header_layout():
-    # 23 four-byte fields, no padding
-    assert ctypes.sizeof(_lib.B2EConfig) == 92
+    # 25 four-byte fields, no padding
+    assert ctypes.sizeof(_lib.B2EConfig) == 100
     assert ctypes.sizeof(_lib.B2ECounters) == 48
 
 

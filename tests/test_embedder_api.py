@@ -84,9 +84,13 @@ def test_kwarg_coercion_and_rejection():
         Node2VecSkipGramB200(embedding_size=0)
     with pytest.raises(ValueError):
         Node2VecSkipGramB200(dtype="f8")
-    for unsupported in (dict(change_node_type_weight=2.0), dict(change_edge_type_weight=0.5)):
-        with pytest.raises(NotImplementedError):
-            Node2VecSkipGramB200(**unsupported)
+    typed = Node2VecSkipGramB200(change_node_type_weight=2.0, change_edge_type_weight=0.5)
+    assert typed.is_using_node_types() and typed.is_using_edge_types()
+    assert not Node2VecSkipGramB200().is_using_node_types() and not Node2VecSkipGramB200().is_using_edge_types()
+    assert Node2VecSkipGramB200.can_use_node_types() and Node2VecSkipGramB200.can_use_edge_types()
+    for invalid in (dict(change_node_type_weight=0.0), dict(change_edge_type_weight=-1.0)):
+        with pytest.raises(ValueError):
+            Node2VecSkipGramB200(**invalid)
 
 
 @pytest.mark.parametrize("model", B200_EMBEDDERS)

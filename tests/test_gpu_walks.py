@@ -182,3 +182,73 @@ def test_normalize_by_degree_embedder_runs(small_ppi):
                              normalize_by_degree=True, verbose=False)
     tables = model.fit_transform(small_ppi, return_dataframe=False).get_all_node_embedding()
     assert all(np.isfinite(t).all() for t in tables)
+
+
+# ---- typed walks (b2e_load_types, change_node_type_weight / change_edge_type_weight) ----
+def _types_for(graph, seed):
+    rng = np.random.default_rng(seed)
+    n = graph.get_number_of_nodes()
+    node_types = rng.integers(0, 4, n).astype(np.uint32)
+    rows = np.repeat(np.arange(n), np.diff(graph.indptr))
+    lo, hi = np.minimum(rows, graph.indices), np.maximum(rows, graph.indices)
+    edge_types = ((lo * 2654435761 + hi * 40503) % 3).astype(np.uint32)  # one type per undirected edge
+    return node_types, edge_types
+
+
+@pytest.mark.parametrize("rw,ew,cn,ce", [(1.0, 1.0, 3.0, 1.0), (1.0, 1.0, 1.0, 0.25),
+                                         (0.25, 4.0, 0.2, 5.0), (2.0, 0.5, 4.0, 0.5)])
+def test_typed_walks_bit_exact(small_ppi_weighted, rmat_graph, rw, ew, cn, ce):
+    from conftest import tiny_graphs
+    cases = [(rmat_graph, None, 64, False), (small_ppi_weighted, small_ppi_weighted.weights, 33, False),
+             (small_ppi_weighted, None, 130, True), (tiny_graphs()["directed_dead_end"], None, 9, False),
+             (tiny_graphs()["star"], None, 8, True)]
+    for graph, weights, length, normalize in cases:
+        node_types, edge_types = _types_for(graph, 3)
+        count = 2 * int((np.diff(graph.indptr) > 0).sum()) + 3
+        expected, oc = oracle.walks(graph.indptr, graph.indices, 42, 5, count, length, rw, ew,
+                                    weights=weights, normalize_by_degree=normalize,
+                                    node_types=node_types, edge_types=edge_types,
+                                    change_node_type_weight=cn, change_edge_type_weight=ce)
+        with Engine("SkipGram", walk_length=length, return_weight=rw, explore_weight=ew,
+                    iterations=1, normalize_by_degree=normalize, change_node_type_weight=cn,
+                    change_edge_type_weight=ce) as engine:
+            engine.load_csr(graph.indptr, graph.indices, weights)
+            engine.load_types(node_types, edge_types)
+            got, gc = engine.walks(42, 5, count), engine.counters()
+        assert np.array_equal(got, expected)
+        assert (gc["walk_steps"], gc["walk_trials"], gc["walk_searches"]) == \
+            (oc["steps"], oc["trials"], oc["searches"])
+        assert oc["capped"] == 0
+
+
+def test_typed_walks_without_types_or_with_unit_weights_are_plain(small_ppi):
+    node_types, edge_types = _types_for(small_ppi, 1)
+    plain = gpu_walks(small_ppi, 7, 0, 2000, 40, 0.25, 4.0)[0]
+    with Engine("SkipGram", walk_length=40, return_weight=0.25, explore_weight=4.0, iterations=1,
+                change_node_type_weight=3.0) as engine:
+        engine.load_csr(small_ppi.indptr, small_ppi.indices)  # no types loaded: untyped walks
+        assert np.array_equal(engine.walks(7, 0, 2000), plain)
+        engine.load_types(node_types, None)
+        assert not np.array_equal(engine.walks(7, 0, 2000), plain)
+        engine.load_csr(small_ppi.indptr, small_ppi.indices)  # a new graph drops the types
+        assert np.array_equal(engine.walks(7, 0, 2000), plain)
+    with Engine("SkipGram", walk_length=40, return_weight=0.25, explore_weight=4.0, iterations=1) as engine:
+        engine.load_csr(small_ppi.indptr, small_ppi.indices)
+        engine.load_types(node_types, edge_types)  # unit change weights: plain kernel
+        assert np.array_equal(engine.walks(7, 0, 2000), plain)
+        with pytest.raises(ValueError):
+            engine.load_types(node_types[:-1], None)
+
+
+def test_typed_embedder(small_ppi):
+    from embiggen_b200.embedders import Node2VecSkipGramB200
+    from embiggen_b200.graph import CSRGraph
+    node_types, edge_types = _types_for(small_ppi, 2)
+    typed = CSRGraph(small_ppi.indptr, small_ppi.indices, node_types=node_types, edge_types=edge_types)
+    kw = dict(embedding_size=8, epochs=1, walk_length=16, iterations=1, verbose=False, deterministic=True)
+    model = Node2VecSkipGramB200(change_node_type_weight=0.05, change_edge_type_weight=2.0, **kw)
+    assert model.is_using_node_types() and model.is_using_edge_types()
+    a = model.fit_transform(typed, return_dataframe=False).get_all_node_embedding()[0]
+    b = Node2VecSkipGramB200(**kw).fit_transform(typed, return_dataframe=False).get_all_node_embedding()[0]
+    c = model.fit_transform(small_ppi, return_dataframe=False).get_all_node_embedding()[0]  # untyped graph
+    assert np.isfinite(a).all() and not np.array_equal(a, b) and np.array_equal(b, c)

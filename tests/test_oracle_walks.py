@@ -304,3 +304,80 @@ def test_normalize_by_degree_edge_case_graphs(name):
     live = b != 0xFFFFFFFF
     assert np.isin(a[live].astype(np.int64) * n + b[live], edge_keys).all()
     assert counters["capped"] == 0
+
+
+# ---- typed walks: change_node_type_weight / change_edge_type_weight (node2vec_skipgram.py:72-77) ----
+def typed_test_graph():
+    graph, weights = weighted_test_graph()
+    rng = np.random.default_rng(9)
+    n = graph.get_number_of_nodes()
+    node_types = rng.integers(0, 3, n).astype(np.uint32)
+    rows = np.repeat(np.arange(n), np.diff(graph.indptr))
+    table = rng.integers(0, 3, (n, n))
+    table = np.triu(table) + np.triu(table, 1).T           # an undirected edge has one type
+    edge_types = table[rows, graph.indices].astype(np.uint32)
+    return graph, weights, node_types, edge_types
+
+
+def typed_pmf(graph, weights, node_types, edge_types, prev, cur, rw, ew, cn, ce, normalize):
+    lo, hi = graph.indptr[cur], graph.indptr[cur + 1]
+    nv = graph.indices[lo:hi]
+    w = np.ones(len(nv)) if weights is None else weights[lo:hi].astype(np.float64)
+    if prev is not None:
+        _, bias = analytic_pmf(graph, prev, cur, rw, ew)
+        plo = graph.indptr[prev]
+        back = plo + int(np.searchsorted(neighbours(graph, prev), cur))
+        w = w * bias * np.where(edge_types[lo:hi] != edge_types[back], ce, 1.0)
+    w = w * np.where(node_types[nv] != node_types[cur], cn, 1.0)
+    if normalize:
+        w = w / np.diff(graph.indptr)[nv]
+    return nv, w / w.sum()
+
+
+@pytest.mark.parametrize("rw,ew,cn,ce,weighted,normalize", [
+    (1.0, 1.0, 3.0, 1.0, False, False), (1.0, 1.0, 1.0, 0.25, False, False),
+    (0.25, 4.0, 0.2, 5.0, False, False), (2.0, 0.5, 4.0, 0.5, True, False),
+    (0.5, 2.0, 0.5, 2.0, True, True)])
+def test_typed_walks_match_analytic_pmf(rw, ew, cn, ce, weighted, normalize):
+    graph, weights, node_types, edge_types = typed_test_graph()
+    if not weighted:
+        weights = None
+    walks, counters = oracle.walks(graph.indptr, graph.indices, 5, 0, 480_000, 3, rw, ew, weights=weights,
+                                   normalize_by_degree=normalize, node_types=node_types,
+                                   edge_types=edge_types, change_node_type_weight=cn,
+                                   change_edge_type_weight=ce)
+    assert counters["capped"] == 0
+
+    def check(sel, pmf, nv):
+        counts = np.array([(sel == x).sum() for x in nv])
+        keep = pmf * len(sel) >= 5
+        if len(sel) < 500 or keep.sum() < 2:
+            return 0
+        expected = pmf[keep] * len(sel)
+        assert stats.chisquare(counts[keep], expected * counts[keep].sum() / expected.sum()).pvalue > 1e-3
+        return 1
+
+    checked = 0
+    for v in (0, 4, 2):
+        nv, pmf = typed_pmf(graph, weights, node_types, edge_types, None, v, rw, ew, cn, ce, normalize)
+        checked += check(walks[walks[:, 0] == v, 1], pmf, nv)
+    for prev, cur in [(4, 0), (0, 4), (1, 2), (5, 6), (2, 7)]:
+        nv, pmf = typed_pmf(graph, weights, node_types, edge_types, prev, cur, rw, ew, cn, ce, normalize)
+        checked += check(walks[(walks[:, 0] == prev) & (walks[:, 1] == cur), 2], pmf, nv)
+    assert checked >= 6
+
+
+def test_unit_type_weights_leave_the_walks_unchanged(small_ppi):
+    n = small_ppi.get_number_of_nodes()
+    node_types = (np.arange(n) % 4).astype(np.uint32)
+    edge_types = (np.arange(small_ppi.indices.shape[0]) % 3).astype(np.uint32)
+    plain, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 1, 0, 500, 20, 0.25, 4.0)
+    typed, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 1, 0, 500, 20, 0.25, 4.0,
+                            node_types=node_types, edge_types=edge_types)
+    assert np.array_equal(plain, typed)
+    changed, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 1, 0, 500, 20, 0.25, 4.0,
+                              node_types=node_types, change_node_type_weight=0.1)
+    assert not np.array_equal(plain, changed)
+    # a very small change weight keeps the walk inside the type of its start node when it can
+    stay = (node_types[changed[:, 1:]] == node_types[changed[:, :-1]]).mean()
+    assert stay > (node_types[plain[:, 1:]] == node_types[plain[:, :-1]]).mean() + 0.2
