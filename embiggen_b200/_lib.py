@@ -42,6 +42,7 @@ class B2EConfig(ctypes.Structure):
         ("normalize_by_degree", ctypes.c_uint32),
         ("stochastic_downsample_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
+        ("walklet_scale", ctypes.c_uint32),
         ("deterministic", ctypes.c_uint32),
         ("chunk_walks", ctypes.c_uint32),
         ("max_concurrent_walks", ctypes.c_uint32),

@@ -56,6 +56,11 @@ static void type_thresholds(float change_weight, unsigned long long q[2]) {
     }
 }
 
+static bool walklet(const b2e_config &c) { return c.walklet_scale >= 2; }
+static uint32_t sub_walk_length(const b2e_config &c) {
+    return walklet(c) ? (c.walk_length + c.walklet_scale - 1) / c.walklet_scale : c.walk_length;
+}
+
 // integer accept thresholds (DESIGN.md "second-order accept test")
 static void thresholds(float return_weight, float explore_weight, unsigned long long out[3]) {
     const double w[3] = {(double)return_weight, 1.0, (double)explore_weight};
@@ -80,6 +85,8 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
         return fail(B2E_ERR_INVALID, "embedding_size must be in [1, 512]");
     if (c.walk_length < 2 || c.walk_length > 65535)
         return fail(B2E_ERR_INVALID, "walk_length must be in [2, 65535]");
+    if (c.walklet_scale >= c.walk_length)
+        return fail(B2E_ERR_INVALID, "walklet_scale must be smaller than walk_length");
     if (c.window_size == 0 || c.window_size > 64)
         return fail(B2E_ERR_INVALID, "window_size must be in [1, 64]");
     if (c.number_of_negative_samples > 31)
@@ -149,6 +156,7 @@ static void free_graph(b2e_handle *h) {
     cudaFree(h->d_t0); h->d_t0 = nullptr;
     cudaFree(h->d_t1); h->d_t1 = nullptr;
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_walks[s]); h->d_walks[s] = nullptr; }
+    cudaFree(h->d_walk_raw); h->d_walk_raw = nullptr;
 }
 
 extern "C" void b2e_destroy(b2e_handle *h) {
@@ -343,8 +351,11 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     const uint64_t cap = c.chunk_walks ? c.chunk_walks
                                        : std::max<uint64_t>(1, std::min<uint64_t>(1ull << 20, per_epoch));
     h->chunk_cap = cap;
+    // Walklets: a slot holds the k sub-walks of every walk, k * ceil(L / k) >= L tokens per walk
+    const uint64_t slot_tokens = walklet(c) ? (uint64_t)c.walklet_scale * sub_walk_length(c) : c.walk_length;
     for (int s = 0; s < 2; ++s)
-        CUDA_TRY(cudaMalloc(&h->d_walks[s], cap * c.walk_length * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&h->d_walks[s], cap * slot_tokens * sizeof(uint32_t)));
+    if (walklet(c)) CUDA_TRY(cudaMalloc(&h->d_walk_raw, cap * c.walk_length * sizeof(uint32_t)));
     CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
     return B2E_OK;
 }
@@ -428,8 +439,14 @@ extern "C" int b2e_walk_chunk(b2e_handle *h, uint64_t seed, uint64_t first_walk,
     if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
     // the slot may still be read by the SGD kernel of two chunks ago
     CUDA_TRY(cudaStreamWaitEvent(h->walk_stream, h->train_done[slot], 0));
-    if (int rc = walk_into(h, seed, first_walk, n_walks, walk_id_stride, h->d_walks[slot], h->walk_stream))
+    uint32_t *target = walklet(h->cfg) ? h->d_walk_raw : h->d_walks[slot];
+    if (int rc = walk_into(h, seed, first_walk, n_walks, walk_id_stride, target, h->walk_stream))
         return rc;
+    if (walklet(h->cfg)) {
+        CUDA_TRY(launch_walklet_split(h->d_walk_raw, n_walks, h->cfg.walk_length, h->cfg.walklet_scale,
+                                      h->d_walks[slot], h->walk_stream));
+        if (n_walks) ++h->launches;
+    }
     CUDA_TRY(cudaEventRecord(h->walk_done[slot], h->walk_stream));
     h->slot_first[slot] = first_walk;
     h->slot_count[slot] = n_walks;
@@ -447,7 +464,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.seed_lo = (uint32_t)seed;
     p.seed_hi = (uint32_t)(seed >> 32);
     p.n = (uint32_t)h->n;
-    p.walk_length = c.walk_length;
+    p.walk_length = sub_walk_length(c);
     p.window = c.window_size;
     p.negatives = c.number_of_negative_samples;
     p.row_stride = h->row_stride;
@@ -474,8 +491,15 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     const uint64_t per_walk_nodes = c.model == B2E_CBOW ? 64 : 16;
     const uint64_t max_warps = c.max_concurrent_walks ? c.max_concurrent_walks
                                                        : std::max<uint64_t>(16, h->n / per_walk_nodes);
-    CUDA_TRY(launch_train(p, c.model, c.deterministic != 0, h->sm_count, max_warps, h->train_stream));
-    if (p.n_walks) ++h->launches;
+    // Walklets: one launch per residue r; sub-walk r of walk g draws its negatives as walk
+    // g + r * 2^48 (walk ids stay far below 2^48), the slot is laid out [r][walk][token]
+    const uint32_t passes = walklet(c) ? c.walklet_scale : 1u;
+    for (uint32_t r = 0; r < passes; ++r) {
+        p.walks = h->d_walks[slot] + (uint64_t)r * p.n_walks * p.walk_length;
+        p.first_walk = h->slot_first[slot] + ((uint64_t)r << 48);
+        CUDA_TRY(launch_train(p, c.model, c.deterministic != 0, h->sm_count, max_warps, h->train_stream));
+        if (p.n_walks) ++h->launches;
+    }
     return B2E_OK;
 }
 
@@ -498,8 +522,12 @@ extern "C" int b2e_train_host_walks(b2e_handle *h, uint64_t seed, const uint32_t
     if (n_walks > h->chunk_cap) return fail(B2E_ERR_INVALID, "n_walks exceeds the chunk capacity");
     CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
     CUDA_TRY(cudaStreamSynchronize(h->train_stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_walks[0], walks, n_walks * h->cfg.walk_length * sizeof(uint32_t),
+    uint32_t *target = walklet(h->cfg) ? h->d_walk_raw : h->d_walks[0];
+    CUDA_TRY(cudaMemcpyAsync(target, walks, n_walks * h->cfg.walk_length * sizeof(uint32_t),
                              cudaMemcpyHostToDevice, h->train_stream));  // ordered before the kernel
+    if (walklet(h->cfg))
+        CUDA_TRY(launch_walklet_split(h->d_walk_raw, n_walks, h->cfg.walk_length, h->cfg.walklet_scale,
+                                      h->d_walks[0], h->train_stream));
     h->slot_first[0] = first_walk;
     h->slot_count[0] = n_walks;
     h->slot_stride[0] = walk_id_stride;

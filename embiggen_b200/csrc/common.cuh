@@ -87,6 +87,8 @@ struct TrainParams {
 };
 
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
+cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,
+                                 uint32_t *out, cudaStream_t stream);
 cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                         uint32_t *out, cudaStream_t stream);
 cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
@@ -120,6 +122,7 @@ struct b2e_handle {
     uint32_t *d_cdf = nullptr;
     uint32_t *d_mindeg = nullptr;
     uint32_t *d_node_types = nullptr, *d_edge_types = nullptr;
+    uint32_t *d_walk_raw = nullptr;  // Walklets: the chunk as walked, before it is split by stride
     uint32_t max_degree = 0;
     uint32_t *d_sources = nullptr;
     uint2 *d_alias = nullptr;

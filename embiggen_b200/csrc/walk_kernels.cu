@@ -501,6 +501,34 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
     }
 }
 
+// Walklets (.../walklets.py:7-149): scale k keeps the pairs exactly k hops apart, i.e. adjacent
+// tokens of the k sub-walks made of every k-th token.  out[r][w][m] = raw[w][r + m k] (PAD past
+// the end), sub-walk length ceil(L / k); the SGD kernels then run unchanged on the sub-walks.
+__global__ void __launch_bounds__(256) walklet_split_kernel(const uint32_t *__restrict__ raw, uint64_t n_walks,
+                                                            uint32_t L, uint32_t k, uint32_t Ls,
+                                                            uint32_t *__restrict__ out) {
+    const uint64_t total = n_walks * k * Ls;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = (uint32_t)(idx % Ls);
+        const uint64_t rest = idx / Ls;
+        const uint64_t w = rest % n_walks;
+        const uint32_t r = (uint32_t)(rest / n_walks);
+        const uint32_t t = r + m * k;
+        out[idx] = t < L ? __ldg(raw + w * L + t) : PAD;
+    }
+}
+
+cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,
+                                 uint32_t *out, cudaStream_t stream) {
+    const uint32_t Ls = (walk_length + scale - 1) / scale;
+    const uint64_t total = n_walks * scale * Ls;
+    if (total == 0) return cudaSuccess;
+    const uint64_t grid = std::min<uint64_t>((total + 255) / 256, 148ull * 16);
+    walklet_split_kernel<<<(unsigned)grid, 256, 0, stream>>>(raw, n_walks, walk_length, scale, Ls, out);
+    return cudaGetLastError();
+}
+
 // One thread per directed edge (u, v): is u in the row of v?  Clears *symmetric otherwise.
 __global__ void __launch_bounds__(256) symmetry_kernel(const int64_t *__restrict__ indptr,
                                                        const uint32_t *__restrict__ indices, uint64_t n,

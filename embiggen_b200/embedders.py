@@ -122,10 +122,12 @@ class Node2VecB200(B200Embedder):
     # -- what stands where the reference calls self._model.fit_transform(graph), node2vec.py:99 --
     def _engine_kwargs(self, device: int) -> Dict[str, Any]:
         k = self._model_kwargs
+        # Walklets (WalkletsB200): scale k trains window 1 on the sub-walks of every k-th token
+        scale = getattr(self, "_walklet_scale", 0)
         return dict(
             model=self.MODELS[self.model_name()], embedding_size=self._embedding_size,
             epochs=k["epochs"], walk_length=k["walk_length"], iterations=k["iterations"],
-            window_size=k["window_size"],
+            window_size=1 if scale else k["window_size"],
             number_of_negative_samples=k["number_of_negative_samples"],
             clipping_value=k["clipping_value"], return_weight=k.get("return_weight", 1.0),
             explore_weight=k.get("explore_weight", 1.0), learning_rate=k["learning_rate"],
@@ -138,6 +140,7 @@ class Node2VecB200(B200Embedder):
             change_edge_type_weight=k.get("change_edge_type_weight", 1.0),
             stochastic_downsample_by_degree=bool(k["stochastic_downsample_by_degree"]),
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
+            walklet_scale=scale,
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
             device=device)
 
@@ -361,6 +364,84 @@ class DeepWalkCBOWB200(Node2VecB200):
     @classmethod
     def model_name(cls) -> str:
         return "DeepWalk CBOW"
+
+
+def _walklets_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
+                   number_of_negative_samples=10, walk_length=128, iterations=10, window_size=4,
+                   return_weight=1.0, explore_weight=1.0, max_neighbours=100, learning_rate=0.01,
+                   learning_rate_decay=0.9, central_nodes_embedding_path=None,
+                   contextual_nodes_embedding_path=None, normalize_by_degree=False,
+                   stochastic_downsample_by_degree=False, normalize_learning_rate_by_degree=False,
+                   use_scale_free_distribution=True, random_state=42, dtype="f32", ring_bell=False,
+                   enable_cache=False, verbose=True, **b200_kwargs):
+    """Signature and defaults of walklets_skipgram.py:9-33 (identical in walklets_cbow.py).  Like
+    walklets.py:112-113 the per-scale embedding size is ``embedding_size // window_size``."""
+    if central_nodes_embedding_path is not None or contextual_nodes_embedding_path is not None:
+        raise NotImplementedError("Walklets return one embedding per scale; embedding paths are not supported.")
+    Node2VecB200.__init__(
+        self, embedding_size=embedding_size // window_size, epochs=epochs,
+        clipping_value=clipping_value, number_of_negative_samples=number_of_negative_samples,
+        walk_length=walk_length, iterations=iterations, window_size=window_size,
+        return_weight=return_weight, explore_weight=explore_weight, max_neighbours=max_neighbours,
+        learning_rate=learning_rate, learning_rate_decay=learning_rate_decay,
+        normalize_by_degree=normalize_by_degree,
+        stochastic_downsample_by_degree=stochastic_downsample_by_degree,
+        normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
+        use_scale_free_distribution=use_scale_free_distribution, dtype=dtype,
+        random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+@abstract_class
+class WalkletsB200(Node2VecB200):
+    """Counterpart of ``WalkletsEnsmallen`` (walklets.py:7-149): one SkipGram / CBOW embedding of
+    ``embedding_size // window_size`` dimensions per scale k = 1 .. window_size, scale k trained
+    on the pairs exactly k hops apart (the sub-walks of every k-th token, window 1).
+
+    ``fit_transform`` returns 2 * window_size embeddings, the [central, contextual] pair of scale
+    1 first, then of scale 2, ...  Not registered, like the reference's registry expects
+    (tests/test_abstract_model.py:125-126)."""
+
+    MODELS = {"Walklets SkipGram": "SkipGram", "Walklets CBOW": "CBOW"}
+    __init__ = _walklets_init
+
+    def parameters(self) -> Dict[str, Any]:
+        """walklets.py:137-141: the public embedding size is the per-scale size x window_size."""
+        parameters = {k: v for k, v in super().parameters().items()
+                      if k not in _NODE2VEC_HIDDEN + ("central_nodes_embedding_path",
+                                                      "contextual_nodes_embedding_path")}
+        parameters["embedding_size"] = parameters["embedding_size"] * parameters["window_size"]
+        return parameters
+
+    def _fit_transform(self, graph, return_dataframe: bool = True) -> EmbeddingResult:
+        window_size = self._model_kwargs["window_size"]
+        node_embeddings, losses = [], []
+        try:
+            for scale in range(1, window_size + 1):
+                self._walklet_scale = scale
+                result = super()._fit_transform(graph, return_dataframe=return_dataframe)
+                node_embeddings.extend(result.get_all_node_embedding())
+                losses.append(self._last_losses)
+        finally:
+            self._walklet_scale = 0
+        self._last_losses = [float(np.mean(epoch)) for epoch in zip(*losses)]
+        return EmbeddingResult(embedding_method_name=self.model_name(), node_embeddings=node_embeddings)
+
+
+class WalkletsSkipGramB200(WalkletsB200):
+    """Walklets SkipGram on B200 (counterpart of walklets_skipgram.py)."""
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "Walklets SkipGram"
+
+
+class WalkletsCBOWB200(WalkletsB200):
+    """Walklets CBOW on B200 (counterpart of walklets_cbow.py)."""
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "Walklets CBOW"
 
 
 B200_EMBEDDERS = (Node2VecSkipGramB200, Node2VecCBOWB200, DeepWalkSkipGramB200, DeepWalkCBOWB200)

@@ -74,7 +74,7 @@ class Engine:
                  normalize_by_degree: bool = False,
                  change_node_type_weight: float = 1.0, change_edge_type_weight: float = 1.0,
                  stochastic_downsample_by_degree: bool = False,
-                 scale_by_sqrt_dim: bool = False, deterministic: bool = False,
+                 scale_by_sqrt_dim: bool = False, walklet_scale: int = 0, deterministic: bool = False,
                  chunk_walks: int = 0, max_concurrent_walks: int = 0, device: int = 0):
         self._lib = _lib.load()
         self._handle = ctypes.c_void_p()
@@ -96,7 +96,8 @@ class Engine:
             change_node_type_weight=change_node_type_weight,
             change_edge_type_weight=change_edge_type_weight,
             stochastic_downsample_by_degree=int(bool(stochastic_downsample_by_degree)),
-            scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), deterministic=int(bool(deterministic)),
+            scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), walklet_scale=int(walklet_scale),
+            deterministic=int(bool(deterministic)),
             chunk_walks=chunk_walks, max_concurrent_walks=max_concurrent_walks, device=device,
         )
         check(self._lib.b2e_create(ctypes.byref(self.config), ctypes.byref(self._handle)))

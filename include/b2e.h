@@ -63,6 +63,8 @@ typedef struct {
     uint32_t normalize_by_degree;               /* walk transition weight / deg(destination) */
     uint32_t stochastic_downsample_by_degree;   /* skip a centre with probability deg / (max deg + 1) */
     uint32_t scale_by_sqrt_dim;                 /* score = dot / sqrt(D) */
+    uint32_t walklet_scale; /* k >= 2: Walklets (.../walklets.py), train on the k sub-walks made of
+                               every k-th token, so that `window_size` counts in hops of k */
     uint32_t deterministic; /* 1: one warp trains walks in ascending id order (bit-exact) */
     uint32_t chunk_walks;   /* walks per walk->SGD chunk, 0 = automatic */
     uint32_t max_concurrent_walks; /* walks trained concurrently (Hogwild), 0 = automatic */

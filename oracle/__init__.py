@@ -277,12 +277,43 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
     return {"loss_sum": loss.value, "pairs": pairs.value, "targets": targets.value}
 
 
+def walklet_split(walk_array: np.ndarray, scale: int) -> np.ndarray:
+    """Walklets (/root/reference/embiggen/embedders/ensmallen_embedders/walklets.py:7-149): the
+    ``scale`` sub-walks made of every ``scale``-th token, as [scale][n_walks][ceil(L / scale)],
+    padded with the PAD token.  Adjacent tokens of a sub-walk are exactly ``scale`` hops apart."""
+    n_walks, L = walk_array.shape
+    Ls = (L + scale - 1) // scale
+    out = np.full((scale, n_walks, Ls), PAD_TOKEN, dtype=np.uint32)
+    for r in range(scale):
+        part = walk_array[:, r::scale]
+        out[r, :, :part.shape[1]] = part
+    return out
+
+
+def train_walklets(model: str, walk_array: np.ndarray, scale: int, t0, t1, seed: int, n: int,
+                   embedding_size: int, window_size: int, negatives: int, learning_rate: float,
+                   first_walk: int = 0, **kwargs) -> dict:
+    """``train`` over the sub-walks of scale ``scale``; sub-walk r of walk g draws its negatives
+    as walk g + r * 2^48."""
+    if scale < 2:
+        return train(model, walk_array, t0, t1, seed, n, embedding_size, window_size, negatives,
+                     learning_rate, first_walk=first_walk, **kwargs)
+    total = {"loss_sum": 0.0, "pairs": 0, "targets": 0}
+    for r, sub in enumerate(walklet_split(walk_array, scale)):
+        stats = train(model, np.ascontiguousarray(sub), t0, t1, seed, n, embedding_size, window_size,
+                      negatives, learning_rate, first_walk=first_walk + (r << 48), **kwargs)
+        for key in total:
+            total[key] += stats[key]
+    return total
+
+
 def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int, iterations: int,
         walk_length: int, window_size: int, negatives: int, learning_rate: float,
         learning_rate_decay: float, return_weight: float = 1.0, explore_weight: float = 1.0,
         clipping_value: float = 6.0, alpha: float = 0.75, use_scale_free_distribution: bool = True,
         normalize_learning_rate_by_degree: bool = False, chunk_walks: int = 1 << 16,
-        stochastic_downsample_by_degree: bool = False, normalize_by_degree: bool = False):
+        stochastic_downsample_by_degree: bool = False, normalize_by_degree: bool = False,
+        walklet_scale: int = 0):
     """Whole path: walks + SGD for ``epochs`` epochs in ascending walk-id order.
 
     Returns (t0, t1, epoch_mean_loss) with padded row stride.
@@ -305,8 +336,9 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
             first = epoch * walks_per_epoch + done
             w, _ = walks(indptr, indices, seed, first, count, walk_length, return_weight,
                          explore_weight, srcs=srcs, normalize_by_degree=normalize_by_degree)
-            r = train(model, w, t0, t1, seed, n, embedding_size, window_size, negatives, float(lr),
-                      clipping_value, first_walk=first, thr=thr, alias=alias, indptr=indptr,
+            r = train_walklets(model, w, walklet_scale, t0, t1, seed, n, embedding_size, window_size,
+                      negatives, float(lr), clipping_value=clipping_value,
+                      first_walk=first, thr=thr, alias=alias, indptr=indptr,
                       normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
                       stochastic_downsample_by_degree=stochastic_downsample_by_degree)
             loss_sum += r["loss_sum"]

@@ -228,3 +228,24 @@ def test_csr_hand_off_from_graph_accessors(small_ppi):
         as_csr(42)
     with pytest.raises(ValueError):
         validate_csr(np.array([0, 2]), np.array([1, 0], dtype=np.uint32))  # unsorted row
+
+
+def test_walklets_classes_mirror_the_reference_surface():
+    """walklets.py:7-149: per-scale size = embedding_size // window_size, parameters() reports
+    the public size, the classes are not in the registry (test_abstract_model.py:125-126)."""
+    from embiggen_b200.embedders import WalkletsSkipGramB200, WalkletsCBOWB200
+    for cls, name in ((WalkletsSkipGramB200, "Walklets SkipGram"), (WalkletsCBOWB200, "Walklets CBOW")):
+        model = cls(embedding_size=100, window_size=4)
+        assert model.model_name() == name and model.library_name() == "B200"
+        p = model.parameters()
+        assert p["embedding_size"] == 100 and p["window_size"] == 4
+        assert (p["return_weight"], p["explore_weight"], p["epochs"]) == (1.0, 1.0, 30)
+        again = cls(**p)
+        assert again.parameters() == p
+        assert model._embedding_size == 25
+        smoke = model.into_smoke_test()
+        assert type(smoke) is cls
+    frame = get_available_models_for_node_embedding()
+    assert not any("Walklets" in name for name in frame.model_name)
+    with pytest.raises(NotImplementedError):
+        WalkletsSkipGramB200(central_nodes_embedding_path="x.npy")

@@ -195,3 +195,47 @@ def test_baseline_config_c1(small_ppi):
     quality_gpu = heldout_sgns_loss(small_ppi, central, contextual, return_weight=0.25, explore_weight=4.0)
     print("C1 held-out objective: oracle", quality_oracle, "gpu", quality_gpu)
     assert abs(quality_gpu - quality_oracle) <= 0.10 * quality_oracle
+
+
+# ---- Walklets (b2e_config.walklet_scale; walklet_split_kernel) ----
+@pytest.mark.parametrize("model,k,L", [("SkipGram", 2, 32), ("SkipGram", 3, 31), ("CBOW", 2, 33), ("CBOW", 5, 32)])
+def test_walklets_deterministic_bit_exact(small_ppi, model, k, L):
+    n, D, K, n_walks, lr = small_ppi.get_number_of_nodes(), 25, 5, 200, 0.05
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, SEED, 0, n_walks, L, 0.25, 4.0)
+    t0, t1 = oracle.init_tables(n, D, SEED)
+    thr, alias = oracle.alias_build(small_ppi.indptr, 0.75)
+    stats = oracle.train_walklets(model, walks, k, t0, t1, SEED, n, D, 1, K, lr, thr=thr, alias=alias)
+    for deterministic in (True, False):
+        with Engine(model, embedding_size=D, walk_length=L, window_size=1, iterations=1,
+                    number_of_negative_samples=K, return_weight=0.25, explore_weight=4.0,
+                    walklet_scale=k, deterministic=deterministic, chunk_walks=n_walks) as engine:
+            engine.load_csr(small_ppi.indptr, small_ppi.indices)
+            assert np.array_equal(engine.walks(SEED, 0, n_walks), walks)  # the export stays raw
+            engine.init_tables(SEED)
+            engine.reset_counters()
+            engine.walk_chunk(SEED, 0, n_walks, 1, 0)
+            engine.train_chunk(SEED, 0, lr)
+            g0, g1 = engine.export_tables()
+            counters = engine.counters()
+            assert (counters["pairs"], counters["targets"]) == (stats["pairs"], stats["targets"])
+            if deterministic:
+                assert np.array_equal(g0, t0[:, :D]) and np.array_equal(g1, t1[:, :D])
+                # host walks take the same route
+                engine.init_tables(SEED)
+                engine.train_host_walks(SEED, walks, lr)
+                h0, h1 = engine.export_tables()
+                assert np.array_equal(h0, g0) and np.array_equal(h1, g1)
+
+
+def test_walklets_embedder(small_ppi):
+    from embiggen_b200.embedders import WalkletsSkipGramB200, WalkletsCBOWB200
+    for cls in (WalkletsSkipGramB200, WalkletsCBOWB200):
+        model = cls(embedding_size=24, window_size=3, epochs=2, walk_length=32, iterations=2, verbose=False)
+        result = model.fit_transform(small_ppi, return_dataframe=False)
+        tables = result.get_all_node_embedding()
+        assert len(tables) == 6 and all(t.shape == (1064, 8) and np.isfinite(t).all() for t in tables)
+        assert not np.array_equal(tables[0], tables[2])  # scales differ
+        losses = model.get_losses()
+        assert len(losses) == 2 and losses[1] < losses[0]
+        frames = model.fit_transform(small_ppi).get_all_node_embedding()
+        assert list(frames[0].index) == small_ppi.get_node_names()

@@ -242,3 +242,34 @@ def test_stochastic_downsample_skips_centres_in_proportion_to_degree():
     sd = np.sqrt((contexts ** 2 * keep_p * (1 - keep_p)).sum())
     assert abs(kept["pairs"] - expected) < 5 * sd
     assert kept["pairs"] < 0.7 * full["pairs"] and (walks == hub).mean() > 0.4
+
+
+# ---- Walklets (walklets.py:7-149): scale k = pairs exactly k hops apart ----
+def test_walklet_split_keeps_exactly_the_pairs_k_hops_apart(er_graph):
+    L = 23
+    walks, _ = oracle.walks(er_graph.indptr, er_graph.indices, 4, 0, 50, L)
+    walks[7, 15:] = oracle.PAD_TOKEN  # a walk that ended early
+    for k in (1, 2, 3, 5, 22):
+        sub = oracle.walklet_split(walks, k)
+        assert sub.shape == (k, 50, (L + k - 1) // k)
+        pairs = set()
+        for r in range(k):
+            for w in range(50):
+                row = sub[r, w]
+                for m in range(len(row) - 1):
+                    if row[m] != oracle.PAD_TOKEN and row[m + 1] != oracle.PAD_TOKEN:
+                        pairs.add((w, r + m * k, r + (m + 1) * k))
+        expected = {(w, i, i + k) for w in range(50) for i in range(L - k)
+                    if walks[w, i] != oracle.PAD_TOKEN and walks[w, i + k] != oracle.PAD_TOKEN}
+        assert pairs == expected
+
+
+def test_walklet_training_counts_the_pairs_of_its_scale(small_ppi):
+    n, D, L = small_ppi.get_number_of_nodes(), 8, 20
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 9, 0, 64, L, 0.25, 4.0)
+    for k in (2, 3):
+        t0, t1 = oracle.init_tables(n, D, 9)
+        stats = oracle.train_walklets("SkipGram", walks, k, t0, t1, 9, n, D, 1, 0, 0.05)
+        # every ordered pair (i, i +- k) with two different tokens
+        a, b = walks[:, :-k], walks[:, k:]
+        assert stats["pairs"] == 2 * int((a != b).sum())
