@@ -15,7 +15,7 @@ B2E_ERR_INVALID = -1
 B2E_ERR_CUDA = -2
 B2E_ERR_STATE = -3
 
-MODEL_IDS = {"skipgram": 0, "cbow": 1}
+MODEL_IDS = {"skipgram": 0, "cbow": 1, "glove": 2}
 
 
 class B2EConfig(ctypes.Structure):
@@ -35,6 +35,7 @@ class B2EConfig(ctypes.Structure):
         ("learning_rate", ctypes.c_float),
         ("learning_rate_decay", ctypes.c_float),
         ("negative_sampling_exponent", ctypes.c_float),
+        ("glove_alpha", ctypes.c_float),
         ("change_node_type_weight", ctypes.c_float),
         ("change_edge_type_weight", ctypes.c_float),
         ("use_scale_free_distribution", ctypes.c_uint32),
@@ -79,6 +80,9 @@ SIGNATURES = {
     "b2e_load_csr_weighted": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _U64,
                                              _U64]),
     "b2e_load_types": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "b2e_cooccurrence": (ctypes.c_int, [_H, _U64, _U64, _U64, _U64, ctypes.c_int, _P(_U64)]),
+    "b2e_cooccurrence_export": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b2e_glove_train": (ctypes.c_int, [_H, _F32]),
     "b2e_number_of_sources": (_U64, [_H]),
     "b2e_row_stride": (_U64, [_H]),
     "b2e_fit": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

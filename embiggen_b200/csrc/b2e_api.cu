@@ -80,7 +80,11 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (config->struct_size != sizeof(b2e_config))
         return fail(B2E_ERR_INVALID, "b2e_config.struct_size does not match this library (ABI mismatch)");
     const b2e_config &c = *config;
-    if (c.model > B2E_CBOW) return fail(B2E_ERR_INVALID, "model must be 0 (SkipGram) or 1 (CBOW)");
+    if (c.model > B2E_GLOVE) return fail(B2E_ERR_INVALID, "model must be 0 (SkipGram), 1 (CBOW) or 2 (GloVe)");
+    if (c.model == B2E_GLOVE && (c.walklet_scale >= 2 || c.stochastic_downsample_by_degree))
+        return fail(B2E_ERR_INVALID, "GloVe supports neither walklet_scale nor stochastic_downsample_by_degree");
+    if (c.model == B2E_GLOVE && !(c.glove_alpha >= 0.0f))
+        return fail(B2E_ERR_INVALID, "glove_alpha must be non-negative");
     if (c.embedding_size == 0 || c.embedding_size > 512)
         return fail(B2E_ERR_INVALID, "embedding_size must be in [1, 512]");
     if (c.walk_length < 2 || c.walk_length > 65535)
@@ -157,6 +161,7 @@ static void free_graph(b2e_handle *h) {
     cudaFree(h->d_t1); h->d_t1 = nullptr;
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_walks[s]); h->d_walks[s] = nullptr; }
     cudaFree(h->d_walk_raw); h->d_walk_raw = nullptr;
+    b2e::glove_free(h->glove);
 }
 
 extern "C" void b2e_destroy(b2e_handle *h) {
@@ -456,6 +461,8 @@ extern "C" int b2e_walk_chunk(b2e_handle *h, uint64_t seed, uint64_t first_walk,
 
 static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learning_rate) {
     const b2e_config &c = h->cfg;
+    if (c.model == B2E_GLOVE)
+        return fail(B2E_ERR_STATE, "a GloVe handle trains with b2e_cooccurrence + b2e_glove_train");
     TrainParams p;
     p.walks = h->d_walks[slot];
     p.first_walk = h->slot_first[slot];
@@ -643,6 +650,84 @@ extern "C" int b2e_counters_reset(b2e_handle *h) {
     return B2E_OK;
 }
 
+// ---- GloVe: co-occurrence of the walks, then one SGD pass over the triples ----
+extern "C" int b2e_cooccurrence(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                                uint64_t walk_id_stride, int accumulate, uint64_t *n_triples) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (walk_id_stride == 0) return fail(B2E_ERR_INVALID, "walk_id_stride must be positive");
+    if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
+    if (int rc = b2e_sync(h)) return rc;
+    const b2e_config &c = h->cfg;
+    if (!accumulate) { h->glove.n_triples = 0; h->glove.finalised = false; }
+    const uint64_t step = std::min<uint64_t>(h->chunk_cap, b2e::glove_chunk_walks(c.walk_length, c.window_size));
+    for (uint64_t done = 0; done < n_walks; done += step) {
+        const uint64_t count = std::min(step, n_walks - done);
+        if (h->glove.n_triples + 2ull * count * c.walk_length * c.window_size >= (1ull << 31))
+            return fail(B2E_ERR_INVALID, "more than 2^31 co-occurrence entries in flight: lower walk_length, "
+                                         "window_size or iterations");
+        if (int rc = walk_into(h, seed, first_walk + done * walk_id_stride, count, walk_id_stride,
+                               h->d_walks[0], h->walk_stream))
+            return rc;
+        CUDA_TRY(b2e::glove_accumulate(h->glove, h->d_walks[0], count, c.walk_length, c.window_size,
+                                       h->walk_stream));
+        h->launches += 2;
+    }
+    CUDA_TRY(b2e::glove_finalise(h->glove, h->n, h->walk_stream));
+    ++h->launches;
+    if (n_triples) *n_triples = h->glove.n_triples;
+    return B2E_OK;
+}
+
+extern "C" int b2e_cooccurrence_export(b2e_handle *h, uint32_t *centre, uint32_t *context, uint32_t *count) {
+    REQUIRE_HANDLE(h);
+    if (!centre || !context || !count) return fail(B2E_ERR_INVALID, "null output buffer");
+    if (int rc = b2e_sync(h)) return rc;
+    const uint64_t m = h->glove.n_triples;
+    std::vector<unsigned long long> keys(m);
+    CUDA_TRY(cudaMemcpyAsync(keys.data(), h->glove.d_keys, m * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, h->walk_stream));
+    CUDA_TRY(cudaMemcpyAsync(count, h->glove.d_counts, m * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             h->walk_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    for (uint64_t i = 0; i < m; ++i) {
+        centre[i] = (uint32_t)(keys[i] >> 32);
+        context[i] = (uint32_t)keys[i];
+    }
+    return B2E_OK;
+}
+
+extern "C" int b2e_glove_train(b2e_handle *h, float learning_rate) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (h->cfg.model != B2E_GLOVE) return fail(B2E_ERR_STATE, "the handle was not created for GloVe");
+    if (!h->glove.finalised) return fail(B2E_ERR_STATE, "b2e_cooccurrence must be called first");
+    const b2e_config &c = h->cfg;
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    CUDA_TRY(b2e::glove_train(h->glove, h->n, h->row_stride, c.embedding_size, c.glove_alpha, c.clipping_value,
+                              learning_rate, h->d_t0, h->d_t1, h->d_counters, c.deterministic != 0,
+                              h->sm_count, h->train_stream));
+    if (h->glove.n_triples) ++h->launches;
+    return B2E_OK;
+}
+
+static int fit_glove(b2e_handle *h, uint64_t seed, float *table0, float *table1, float *epoch_loss) {
+    const b2e_config &c = h->cfg;
+    if (int rc = b2e_init_tables(h, seed)) return rc;
+    const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
+    float lr = c.learning_rate;
+    for (uint32_t epoch = 0; epoch < c.epochs; ++epoch) {
+        if (int rc = b2e_counters_reset(h)) return rc;
+        if (int rc = b2e_cooccurrence(h, seed, (uint64_t)epoch * per_epoch, per_epoch, 1, 0, nullptr)) return rc;
+        if (int rc = b2e_glove_train(h, lr)) return rc;
+        b2e_counters counters;
+        if (int rc = b2e_counters_read(h, &counters)) return rc;
+        if (epoch_loss) epoch_loss[epoch] = counters.pairs ? (float)(counters.loss_sum / (double)counters.pairs) : 0.0f;
+        lr = lr * c.learning_rate_decay;
+    }
+    return b2e_export_tables(h, table0, table1);
+}
+
 // The whole path: init, then per epoch walk chunk k+1 on the walk stream while the SGD
 // kernel consumes chunk k on the train stream (two walk buffers, event-ordered).
 extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table1, float *epoch_loss) {
@@ -651,6 +736,7 @@ extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table
     if (!table0 || !table1) return fail(B2E_ERR_INVALID, "null output buffer");
     if (h->n_src == 0) return fail(B2E_ERR_INVALID, "the graph has no node with outgoing edges");
     const b2e_config &c = h->cfg;
+    if (c.model == B2E_GLOVE) return fit_glove(h, seed, table0, table1, epoch_loss);
     if (int rc = b2e_init_tables(h, seed)) return rc;
     const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
     float lr = c.learning_rate;

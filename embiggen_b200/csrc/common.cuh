@@ -87,6 +87,29 @@ struct TrainParams {
 };
 
 cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t stream);
+// GloVe (glove.cu): the co-occurrence triples of an epoch, sorted by (centre << 32 | context)
+struct GloveState {
+    unsigned long long *d_keys = nullptr;
+    uint32_t *d_counts = nullptr;
+    uint64_t *d_rowptr = nullptr;
+    uint64_t n_triples = 0;
+    uint32_t max_count = 1;
+    bool finalised = false;
+    size_t keys_bytes = 0, counts_bytes = 0, rowptr_bytes = 0;
+    unsigned long long *d_scratch_keys = nullptr, *d_merge_keys = nullptr;
+    uint32_t *d_merge_counts = nullptr;
+    void *d_temp = nullptr, *d_scalar = nullptr;
+    size_t scratch_keys_bytes = 0, merge_keys_bytes = 0, merge_counts_bytes = 0, temp_bytes = 0, scalar_bytes = 0;
+};
+uint64_t glove_chunk_walks(uint32_t walk_length, uint32_t window);
+cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_walks, uint32_t walk_length,
+                             uint32_t window, cudaStream_t stream);
+cudaError_t glove_finalise(GloveState &g, uint64_t n, cudaStream_t stream);
+cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, uint32_t embedding_size,
+                        float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
+                        bool deterministic, int sm_count, cudaStream_t stream);
+void glove_free(GloveState &g);
+
 cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,
                                  uint32_t *out, cudaStream_t stream);
 cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
@@ -122,6 +145,7 @@ struct b2e_handle {
     uint32_t *d_cdf = nullptr;
     uint32_t *d_mindeg = nullptr;
     uint32_t *d_node_types = nullptr, *d_edge_types = nullptr;
+    b2e::GloveState glove;
     uint32_t *d_walk_raw = nullptr;  // Walklets: the chunk as walked, before it is split by stride
     uint32_t max_degree = 0;
     uint32_t *d_sources = nullptr;

@@ -1,0 +1,322 @@
+// GloVe on random-walk co-occurrences for sm_100a.
+//
+// Counterpart of what `ensmallen.models.GloVe.fit_transform` does behind
+// `Node2VecGloVeEnsmallen` / `DeepWalkGloVeEnsmallen`
+// (/root/reference/embiggen/embedders/ensmallen_embedders/node2vec_glove.py:5-140,
+// deepwalk_glove.py): per epoch one walk per node, the co-occurrence counts of the walks'
+// windows, one pass of weighted least squares over the non-zero counts (Pennington et al. 2014,
+// eq. 8, no bias terms; normative statement: oracle/glove.c).
+//
+//   1. cooc_keys_kernel      every (position, offset <= window) of a walk chunk emits the two
+//                            ordered keys (centre << 32 | context), or an all-ones key
+//   2. CUB radix sort + run-length encode -> (key, count) of the chunk; chunks are merged by
+//      sort-by-key + reduce-by-key (library calls: this is bookkeeping around the hot kernel)
+//   3. cooc_rowptr_kernel    CSR offsets of the sorted keys by centre (one bisection per node)
+//   4. glove_train_kernel    one warp per centre: the centre row stays in registers while its
+//                            context rows (all distinct) are gathered NT at a time with 128-bit
+//                            loads, scored with the warp-shaped dot of the SGD kernels, updated
+//                            and scattered back (Hogwild across warps).  HBM-bound: 2 * 4D
+//                            bytes per triple.  A single-warp launch reproduces oracle/glove.c
+//                            bit for bit (explicit round-to-nearest intrinsics, log / exp from
+//                            IEEE single operations only).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "sgns_device.cuh"
+
+namespace b2e {
+
+constexpr unsigned long long COOC_INVALID = ~0ull;
+
+// ln(x), x > 0 normal: the operation sequence of oracle/glove.c:orc_log_det
+__device__ __forceinline__ float log_det(float x) {
+    uint32_t u = __float_as_uint(x);
+    int e = (int)(u >> 23) - 127;
+    float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421356237f) { m = __fmul_rn(m, 0.5f); e += 1; }
+    const float s = __fdiv_rn(__fsub_rn(m, 1.0f), __fadd_rn(m, 1.0f));
+    const float s2 = __fmul_rn(s, s);
+    float p = 1.0f / 9.0f;
+    p = __fmaf_rn(p, s2, 1.0f / 7.0f);
+    p = __fmaf_rn(p, s2, 1.0f / 5.0f);
+    p = __fmaf_rn(p, s2, 1.0f / 3.0f);
+    p = __fmaf_rn(p, s2, 1.0f);
+    const float lnm = __fmul_rn(__fmul_rn(2.0f, s), p);
+    return __fmaf_rn((float)e, 0.693147180559945f, lnm);
+}
+
+// slot = (walk, position i, offset d in 1..W): keys of the ordered pairs (i, i+d) and (i+d, i)
+__global__ void __launch_bounds__(256) cooc_keys_kernel(const uint32_t *__restrict__ walks, uint64_t n_walks,
+                                                        uint32_t L, uint32_t W,
+                                                        unsigned long long *__restrict__ keys) {
+    const uint64_t total = n_walks * L * W;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = (uint32_t)(idx % W) + 1u;
+        const uint64_t rest = idx / W;
+        const uint32_t i = (uint32_t)(rest % L);
+        const uint64_t w = rest / L;
+        unsigned long long k0 = COOC_INVALID, k1 = COOC_INVALID;
+        if (i + d < L) {
+            const uint32_t a = __ldg(walks + w * L + i), b = __ldg(walks + w * L + i + d);
+            if (a != PAD && b != PAD && a != b) {
+                k0 = ((unsigned long long)a << 32) | b;
+                k1 = ((unsigned long long)b << 32) | a;
+            }
+        }
+        keys[2 * idx] = k0;
+        keys[2 * idx + 1] = k1;
+    }
+}
+
+__global__ void __launch_bounds__(256) cooc_rowptr_kernel(const unsigned long long *__restrict__ keys,
+                                                          uint64_t n_triples, uint64_t n,
+                                                          uint64_t *__restrict__ rowptr) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n) return;
+    const unsigned long long target = (unsigned long long)v << 32;
+    uint64_t lo = 0, hi = n_triples;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(keys + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    rowptr[v] = lo;
+}
+
+struct GloveParams {
+    const unsigned long long *keys;
+    const uint32_t *counts;
+    const uint64_t *rowptr;
+    uint64_t n;
+    uint32_t row_stride, chunks;
+    float alpha, clip, lr, max_count;
+    float *t0, *t1;
+    DeviceCounters *counters;
+};
+
+template <int CH, int NT>
+__global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    float loss_acc = 0.0f;
+    unsigned long long trained = 0;
+    for (;;) {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(&p.counters->work_counter, 1ull);
+        v = __shfl_sync(FULL, v, 0);
+        if (v >= p.n) break;
+        const uint64_t begin = __ldg(p.rowptr + v), end = __ldg(p.rowptr + v + 1);
+        if (begin == end) continue;
+        float *crow = p.t0 + v * p.row_stride;
+        float4 h[CH];
+        load_row<CH>(crow, p.chunks, lane, h);
+        for (uint64_t base = begin; base < end; base += NT) {
+            float4 rows[NT][CH];
+            uint32_t ids[NT], cnt[NT];
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {  // the contexts of a centre are distinct rows
+                const bool on = base + s < end;
+                ids[s] = on ? (uint32_t)__ldg(p.keys + base + s) : PAD;
+                cnt[s] = on ? __ldg(p.counts + base + s) : 1u;
+                if (on) load_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+                if (ids[s] == PAD) continue;
+                const float f = warp_dot<CH>(h, rows[s]);
+                if (fabsf(f) > p.clip) continue;
+                const float x = (float)cnt[s];
+                const float weight = exp_det(__fmul_rn(p.alpha, log_det(__fdiv_rn(x, p.max_count))));
+                const float diff = __fsub_rn(f, log_det(x));
+                const float g = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, weight), diff), p.lr);
+                if (lane == 0) loss_acc += weight * diff * diff;
+                ++trained;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    const float4 old = rows[s][ch];
+                    rows[s][ch].x = __fmaf_rn(-g, h[ch].x, old.x);
+                    rows[s][ch].y = __fmaf_rn(-g, h[ch].y, old.y);
+                    rows[s][ch].z = __fmaf_rn(-g, h[ch].z, old.z);
+                    rows[s][ch].w = __fmaf_rn(-g, h[ch].w, old.w);
+                    h[ch].x = __fmaf_rn(-g, old.x, h[ch].x);
+                    h[ch].y = __fmaf_rn(-g, old.y, h[ch].y);
+                    h[ch].z = __fmaf_rn(-g, old.z, h[ch].z);
+                    h[ch].w = __fmaf_rn(-g, old.w, h[ch].w);
+                }
+                store_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
+            }
+        }
+        store_row<CH>(crow, p.chunks, lane, h);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.counters->pairs, trained);
+        atomicAdd(&p.counters->targets, trained);
+        atomicAdd(&p.counters->loss_sum, (double)loss_acc);
+    }
+}
+
+template <int CH, int NT>
+static cudaError_t launch_glove_one(const GloveParams &p, bool deterministic, int sm_count, cudaStream_t stream) {
+    cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess) return err;
+    if (deterministic) {
+        glove_train_kernel<CH, NT><<<1, 32, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, glove_train_kernel<CH, NT>, 256, 0);
+    if (err != cudaSuccess) return err;
+    uint64_t grid = (uint64_t)sm_count * std::max(per_sm, 1);  // persistent, centres fetched dynamically
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (p.n + 7) / 8));
+    glove_train_kernel<CH, NT><<<(unsigned)grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+#define GLOVE_TRY(call)                            \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) return e_;          \
+    } while (0)
+
+static cudaError_t grow(void **ptr, size_t *have, size_t want) {
+    if (want <= *have) return cudaSuccess;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(ptr, want);
+    if (e == cudaSuccess) *have = want;
+    return e;
+}
+
+// walks per co-occurrence chunk: at most 2^27 key slots (1 GiB of keys, sorted out of place)
+uint64_t glove_chunk_walks(uint32_t walk_length, uint32_t window) {
+    const uint64_t slots_per_walk = 2ull * walk_length * window;
+    return std::max<uint64_t>(1, (1ull << 27) / slots_per_walk);
+}
+
+// Adds the co-occurrences of `n_walks` device-resident walks to the state (merged by key).
+cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_walks, uint32_t L,
+                             uint32_t W, cudaStream_t stream) {
+    typedef unsigned long long u64;
+    const uint64_t slots = 2ull * n_walks * L * W;
+    if (slots == 0) return cudaSuccess;
+    GLOVE_TRY(grow((void **)&g.d_scratch_keys, &g.scratch_keys_bytes, 2 * slots * sizeof(u64)));
+    u64 *raw = g.d_scratch_keys, *sorted = g.d_scratch_keys + slots;
+    const uint64_t grid = std::min<uint64_t>((slots / 2 + 255) / 256, 148ull * 32);
+    cooc_keys_kernel<<<(unsigned)grid, 256, 0, stream>>>(d_walks, n_walks, L, W, raw);
+    GLOVE_TRY(cudaGetLastError());
+
+    size_t need = 0, bytes = 0;
+    GLOVE_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bytes, raw, sorted, slots, 0, 64, stream));
+    need = bytes;
+    // run-length encode into the tail of the merge buffers (sized below)
+    const uint64_t merged_cap = g.n_triples + slots;
+    GLOVE_TRY(grow((void **)&g.d_merge_keys, &g.merge_keys_bytes, 2 * merged_cap * sizeof(u64)));
+    GLOVE_TRY(grow((void **)&g.d_merge_counts, &g.merge_counts_bytes, 2 * merged_cap * sizeof(uint32_t)));
+    GLOVE_TRY(grow((void **)&g.d_scalar, &g.scalar_bytes, 16));
+    u64 *cat_keys = g.d_merge_keys, *out_keys = g.d_merge_keys + merged_cap;
+    uint32_t *cat_counts = g.d_merge_counts, *out_counts = g.d_merge_counts + merged_cap;
+    uint64_t *d_runs = reinterpret_cast<uint64_t *>(g.d_scalar);
+    GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, bytes, sorted, cat_keys + g.n_triples,
+                                                 cat_counts + g.n_triples, d_runs, slots, stream));
+    need = std::max(need, bytes);
+    GLOVE_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, cat_keys, out_keys, cat_counts, out_counts,
+                                              merged_cap, 0, 64, stream));
+    need = std::max(need, bytes);
+    GLOVE_TRY(cub::DeviceReduce::ReduceByKey(nullptr, bytes, out_keys, cat_keys, out_counts, cat_counts, d_runs,
+                                             cub::Sum(), merged_cap, stream));
+    need = std::max(need, bytes);
+    GLOVE_TRY(grow(&g.d_temp, &g.temp_bytes, need));
+
+    bytes = g.temp_bytes;
+    GLOVE_TRY(cub::DeviceRadixSort::SortKeys(g.d_temp, bytes, raw, sorted, slots, 0, 64, stream));
+    // the triples gathered so far sit at the head of the concatenation buffers
+    if (g.n_triples) {
+        GLOVE_TRY(cudaMemcpyAsync(cat_keys, g.d_keys, g.n_triples * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+        GLOVE_TRY(cudaMemcpyAsync(cat_counts, g.d_counts, g.n_triples * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToDevice, stream));
+    }
+    bytes = g.temp_bytes;
+    GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(g.d_temp, bytes, sorted, cat_keys + g.n_triples,
+                                                 cat_counts + g.n_triples, d_runs, slots, stream));
+    uint64_t runs = 0;
+    GLOVE_TRY(cudaMemcpyAsync(&runs, d_runs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    GLOVE_TRY(cudaStreamSynchronize(stream));
+    if (runs) {  // the all-ones key, if present, is the last run
+        u64 last = 0;
+        GLOVE_TRY(cudaMemcpyAsync(&last, cat_keys + g.n_triples + runs - 1, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        GLOVE_TRY(cudaStreamSynchronize(stream));
+        if (last == COOC_INVALID) --runs;
+    }
+    uint64_t total = g.n_triples + runs;
+    if (g.n_triples && runs) {  // merge: sort the concatenation by key, add the counts of equal keys
+        bytes = g.temp_bytes;
+        GLOVE_TRY(cub::DeviceRadixSort::SortPairs(g.d_temp, bytes, cat_keys, out_keys, cat_counts, out_counts,
+                                                  total, 0, 64, stream));
+        bytes = g.temp_bytes;
+        GLOVE_TRY(cub::DeviceReduce::ReduceByKey(g.d_temp, bytes, out_keys, cat_keys, out_counts, cat_counts,
+                                                 d_runs, cub::Sum(), total, stream));
+        GLOVE_TRY(cudaMemcpyAsync(&total, d_runs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        GLOVE_TRY(cudaStreamSynchronize(stream));
+    }
+    GLOVE_TRY(grow((void **)&g.d_keys, &g.keys_bytes, std::max<uint64_t>(total, 1) * sizeof(u64)));
+    GLOVE_TRY(grow((void **)&g.d_counts, &g.counts_bytes, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+    GLOVE_TRY(cudaMemcpyAsync(g.d_keys, cat_keys, total * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+    GLOVE_TRY(cudaMemcpyAsync(g.d_counts, cat_counts, total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    g.n_triples = total;
+    g.finalised = false;
+    return cudaSuccess;
+}
+
+// row offsets by centre and the largest count: needed before training
+cudaError_t glove_finalise(GloveState &g, uint64_t n, cudaStream_t stream) {
+    GLOVE_TRY(grow((void **)&g.d_rowptr, &g.rowptr_bytes, (n + 1) * sizeof(uint64_t)));
+    cooc_rowptr_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, stream>>>(g.d_keys, g.n_triples, n, g.d_rowptr);
+    GLOVE_TRY(cudaGetLastError());
+    g.max_count = 1;
+    if (g.n_triples) {
+        GLOVE_TRY(grow((void **)&g.d_scalar, &g.scalar_bytes, 16));
+        uint32_t *d_max = reinterpret_cast<uint32_t *>(g.d_scalar);
+        size_t bytes = 0;
+        GLOVE_TRY(cub::DeviceReduce::Max(nullptr, bytes, g.d_counts, d_max, g.n_triples, stream));
+        GLOVE_TRY(grow(&g.d_temp, &g.temp_bytes, bytes));
+        bytes = g.temp_bytes;
+        GLOVE_TRY(cub::DeviceReduce::Max(g.d_temp, bytes, g.d_counts, d_max, g.n_triples, stream));
+        GLOVE_TRY(cudaMemcpyAsync(&g.max_count, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
+    GLOVE_TRY(cudaStreamSynchronize(stream));
+    g.finalised = true;
+    return cudaSuccess;
+}
+
+cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, uint32_t embedding_size,
+                        float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
+                        bool deterministic, int sm_count, cudaStream_t stream) {
+    if (g.n_triples == 0) return cudaSuccess;
+    GloveParams p;
+    p.keys = g.d_keys;
+    p.counts = g.d_counts;
+    p.rowptr = g.d_rowptr;
+    p.n = n;
+    p.row_stride = row_stride;
+    p.chunks = (embedding_size + 3u) / 4u;
+    p.alpha = alpha;
+    p.clip = clip;
+    p.lr = lr;
+    p.max_count = (float)g.max_count;
+    p.t0 = t0;
+    p.t1 = t1;
+    p.counters = counters;
+    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, deterministic, sm_count, stream);
+    if (p.chunks <= 64) return launch_glove_one<2, 4>(p, deterministic, sm_count, stream);
+    if (p.chunks <= 128) return launch_glove_one<4, 2>(p, deterministic, sm_count, stream);
+    return cudaErrorInvalidValue;
+}
+
+void glove_free(GloveState &g) {
+    cudaFree(g.d_keys); cudaFree(g.d_counts); cudaFree(g.d_rowptr); cudaFree(g.d_scratch_keys);
+    cudaFree(g.d_merge_keys); cudaFree(g.d_merge_counts); cudaFree(g.d_temp); cudaFree(g.d_scalar);
+    g = GloveState();
+}
+
+}  // namespace b2e

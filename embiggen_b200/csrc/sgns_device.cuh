@@ -24,6 +24,61 @@ __device__ __forceinline__ float exp_det(float y) {
     return __fmul_rn(p, __int_as_float(((int)k + 127) << 23));
 }
 
+// ---- register-staged rows: lane l owns float4 chunks l, l + 32, ... of a row ----
+template <int CH>
+__device__ __forceinline__ void load_row(const float *row, uint32_t chunks, uint32_t lane,
+                                         float4 (&r)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const uint32_t c = lane + 32u * ch;
+        r[ch] = c < chunks ? *reinterpret_cast<const float4 *>(row + 4u * c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void store_row(float *row, uint32_t chunks, uint32_t lane,
+                                          const float4 (&r)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const uint32_t c = lane + 32u * ch;
+        if (c < chunks) *reinterpret_cast<float4 *>(row + 4u * c) = r[ch];
+    }
+}
+
+// lane l owns float4 chunks l, l+32, ...; xor-butterfly 16, 8, 4, 2, 1
+template <int CH>
+__device__ __forceinline__ float warp_dot(const float4 (&a)[CH], const float4 (&b)[CH]) {
+    float p = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        p = __fmaf_rn(a[ch].x, b[ch].x, p);
+        p = __fmaf_rn(a[ch].y, b[ch].y, p);
+        p = __fmaf_rn(a[ch].z, b[ch].z, p);
+        p = __fmaf_rn(a[ch].w, b[ch].w, p);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(FULL, p, off));
+    return p;
+}
+
+template <int CH>
+__device__ __forceinline__ void add_rows(float4 (&a)[CH], const float4 (&b)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        a[ch].x = __fadd_rn(a[ch].x, b[ch].x);
+        a[ch].y = __fadd_rn(a[ch].y, b[ch].y);
+        a[ch].z = __fadd_rn(a[ch].z, b[ch].z);
+        a[ch].w = __fadd_rn(a[ch].w, b[ch].w);
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void zero_rows(float4 (&a)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) a[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre) {
     if (!p.normalize_lr) return p.lr;
     const uint32_t deg = (uint32_t)(__ldg(p.indptr + centre + 1) - __ldg(p.indptr + centre));

@@ -74,11 +74,13 @@ class B200Embedder(AbstractEmbeddingModel):
 class Node2VecB200(B200Embedder):
     """Counterpart of ``Node2VecEnsmallen`` (node2vec.py:13-166)."""
 
-    MODELS = {
+    MODELS = {  # node2vec.py:16-26
         "DeepWalk CBOW": "CBOW",
         "DeepWalk SkipGram": "SkipGram",
+        "DeepWalk GloVe": "GloVe",
         "Node2Vec CBOW": "CBOW",
         "Node2Vec SkipGram": "SkipGram",
+        "Node2Vec GloVe": "GloVe",
     }
 
     def __init__(self, embedding_size: int = 100, random_state: int = 42, ring_bell: bool = False,
@@ -126,19 +128,19 @@ class Node2VecB200(B200Embedder):
         scale = getattr(self, "_walklet_scale", 0)
         return dict(
             model=self.MODELS[self.model_name()], embedding_size=self._embedding_size,
-            epochs=k["epochs"], walk_length=k["walk_length"], iterations=k["iterations"],
+            epochs=k["epochs"], walk_length=k["walk_length"], iterations=k.get("iterations", 1),
             window_size=1 if scale else k["window_size"],
-            number_of_negative_samples=k["number_of_negative_samples"],
-            clipping_value=k["clipping_value"], return_weight=k.get("return_weight", 1.0),
+            number_of_negative_samples=k.get("number_of_negative_samples", 0),
+            clipping_value=k.get("clipping_value", 6.0), glove_alpha=k.get("alpha", 0.75), return_weight=k.get("return_weight", 1.0),
             explore_weight=k.get("explore_weight", 1.0), learning_rate=k["learning_rate"],
             learning_rate_decay=k["learning_rate_decay"],
             negative_sampling_exponent=k["negative_sampling_exponent"],
-            use_scale_free_distribution=k["use_scale_free_distribution"],
-            normalize_learning_rate_by_degree=k["normalize_learning_rate_by_degree"],
+            use_scale_free_distribution=k.get("use_scale_free_distribution", True),
+            normalize_learning_rate_by_degree=k.get("normalize_learning_rate_by_degree", False),
             normalize_by_degree=k["normalize_by_degree"],
             change_node_type_weight=k.get("change_node_type_weight", 1.0),
             change_edge_type_weight=k.get("change_edge_type_weight", 1.0),
-            stochastic_downsample_by_degree=bool(k["stochastic_downsample_by_degree"]),
+            stochastic_downsample_by_degree=bool(k.get("stochastic_downsample_by_degree", False)),
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
             walklet_scale=scale,
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
@@ -182,6 +184,8 @@ class Node2VecB200(B200Embedder):
                 node_types, edge_types = as_types(graph)  # a graph without types walks untyped
                 engine.load_types(node_types if self.is_using_node_types() else None,
                                   edge_types if self.is_using_edge_types() else None)
+            if world > 1 and self.MODELS[self.model_name()] == "GloVe":
+                raise NotImplementedError("GloVe runs on one GPU: the co-occurrence counts are not sharded.")
             if world > 1:
                 c, x, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"])
                 central[:], contextual[:] = c, x
@@ -390,6 +394,75 @@ def _walklets_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
         use_scale_free_distribution=use_scale_free_distribution, dtype=dtype,
         random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
         **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+def _node2vec_glove_init(self, embedding_size=100, alpha=0.75, epochs=100, walk_length=512, window_size=5,
+                         return_weight=0.25, explore_weight=4.0, change_node_type_weight=1.0,
+                         change_edge_type_weight=1.0, max_neighbours=100, learning_rate=0.05,
+                         learning_rate_decay=0.9, central_nodes_embedding_path=None,
+                         contextual_nodes_embedding_path=None, normalize_by_degree=False, dtype="f32",
+                         random_state=42, ring_bell=False, enable_cache=False, verbose=True, **b200_kwargs):
+    """Signature and defaults of node2vec_glove.py:8-30; one walk per node and epoch (:104-106)."""
+    Node2VecB200.__init__(
+        self, embedding_size=embedding_size, alpha=alpha, epochs=epochs, walk_length=walk_length,
+        iterations=1, window_size=window_size, return_weight=return_weight, explore_weight=explore_weight,
+        change_node_type_weight=change_node_type_weight, change_edge_type_weight=change_edge_type_weight,
+        max_neighbours=max_neighbours, learning_rate=learning_rate, learning_rate_decay=learning_rate_decay,
+        central_nodes_embedding_path=central_nodes_embedding_path,
+        contextual_nodes_embedding_path=contextual_nodes_embedding_path,
+        normalize_by_degree=normalize_by_degree, dtype=dtype, random_state=random_state,
+        ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+def _deepwalk_glove_init(self, embedding_size=100, alpha=0.75, epochs=100, walk_length=512, window_size=5,
+                         max_neighbours=100, learning_rate=0.05, learning_rate_decay=0.99,
+                         central_nodes_embedding_path=None, contextual_nodes_embedding_path=None,
+                         normalize_by_degree=False, dtype="f32", random_state=42, ring_bell=False,
+                         enable_cache=False, verbose=True, **b200_kwargs):
+    """Signature and defaults of deepwalk_glove.py:8-26."""
+    Node2VecB200.__init__(
+        self, embedding_size=embedding_size, alpha=alpha, epochs=epochs, walk_length=walk_length,
+        iterations=1, window_size=window_size, max_neighbours=max_neighbours,
+        learning_rate=learning_rate, learning_rate_decay=learning_rate_decay,
+        central_nodes_embedding_path=central_nodes_embedding_path,
+        contextual_nodes_embedding_path=contextual_nodes_embedding_path,
+        normalize_by_degree=normalize_by_degree, dtype=dtype, random_state=random_state,
+        ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        **{**_B200_DEFAULTS, **b200_kwargs})
+
+
+_GLOVE_HIDDEN = ("change_node_type_weight", "change_edge_type_weight", "number_of_negative_samples",
+                 "iterations")
+
+
+class Node2VecGloVeB200(Node2VecB200):
+    """Node2Vec GloVe on B200 (counterpart of node2vec_glove.py:5-140); not registered, like
+    Walklets, so that the registry keeps the four models north_star names."""
+
+    __init__ = _node2vec_glove_init
+
+    def parameters(self) -> Dict[str, Any]:
+        """Drops the same keys as node2vec_glove.py:124-138."""
+        return {k: v for k, v in super().parameters().items() if k not in _GLOVE_HIDDEN}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "Node2Vec GloVe"
+
+
+class DeepWalkGloVeB200(Node2VecB200):
+    """DeepWalk GloVe on B200 (counterpart of deepwalk_glove.py)."""
+
+    __init__ = _deepwalk_glove_init
+
+    def parameters(self) -> Dict[str, Any]:
+        return {k: v for k, v in super().parameters().items()
+                if k not in _GLOVE_HIDDEN + ("return_weight", "explore_weight")}
+
+    @classmethod
+    def model_name(cls) -> str:
+        return "DeepWalk GloVe"
 
 
 @abstract_class

@@ -45,7 +45,7 @@ KWARG_SCHEMA = {
     "contextual_nodes_embedding_path": ["str", "None"], "normalize_by_degree": "bool",
     "stochastic_downsample_by_degree": "bool", "normalize_learning_rate_by_degree": "bool",
     "use_scale_free_distribution": "bool", "random_state": "int", "dtype": "str",
-    "verbose": "bool",
+    "verbose": "bool", "alpha": "float",
     # B200 extras
     "negative_sampling_exponent": "float", "scale_by_sqrt_dim": "bool", "deterministic": "bool",
     "chunk_walks": "int", "max_concurrent_walks": "int", "sync_interval": "int", "device": ["int", "None"],

@@ -73,6 +73,7 @@ class Engine:
                  normalize_learning_rate_by_degree: bool = False,
                  normalize_by_degree: bool = False,
                  change_node_type_weight: float = 1.0, change_edge_type_weight: float = 1.0,
+                 glove_alpha: float = 0.75,
                  stochastic_downsample_by_degree: bool = False,
                  scale_by_sqrt_dim: bool = False, walklet_scale: int = 0, deterministic: bool = False,
                  chunk_walks: int = 0, max_concurrent_walks: int = 0, device: int = 0):
@@ -93,6 +94,7 @@ class Engine:
             use_scale_free_distribution=int(bool(use_scale_free_distribution)),
             normalize_learning_rate_by_degree=int(bool(normalize_learning_rate_by_degree)),
             normalize_by_degree=int(bool(normalize_by_degree)),
+            glove_alpha=glove_alpha,
             change_node_type_weight=change_node_type_weight,
             change_edge_type_weight=change_edge_type_weight,
             stochastic_downsample_by_degree=int(bool(stochastic_downsample_by_degree)),
@@ -193,6 +195,25 @@ class Engine:
         check(self._lib.b2e_fit(self._handle, seed, t0.ctypes.data, t1.ctypes.data,
                                 losses.ctypes.data))
         return t0, t1, [float(x) for x in losses[: self.config.epochs]]
+
+    # ---- GloVe pieces (model "GloVe"): co-occurrence of walks, one SGD pass over the triples ----
+    def cooccurrence(self, seed: int, first_walk: int, n_walks: int, walk_id_stride: int = 1,
+                     accumulate: bool = False) -> int:
+        out = ctypes.c_uint64()
+        check(self._lib.b2e_cooccurrence(self._handle, seed, first_walk, n_walks, walk_id_stride,
+                                         int(accumulate), ctypes.byref(out)))
+        self._n_triples = int(out.value)
+        return self._n_triples
+
+    def export_cooccurrence(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        m = getattr(self, "_n_triples", 0)
+        centre, context, count = (np.empty(max(m, 1), dtype=np.uint32) for _ in range(3))
+        check(self._lib.b2e_cooccurrence_export(self._handle, centre.ctypes.data, context.ctypes.data,
+                                                count.ctypes.data))
+        return centre[:m], context[:m], count[:m]
+
+    def glove_train(self, learning_rate: float) -> None:
+        check(self._lib.b2e_glove_train(self._handle, learning_rate))
 
     # ---- K2 parity/debug export ----
     def walks(self, seed: int, first_walk: int, n_walks: int, walk_id_stride: int = 1) -> np.ndarray:

@@ -34,7 +34,7 @@ typedef enum {
     B2E_ERR_STATE = -3    /* call order violated (e.g. fit before load_csr) */
 } b2e_status;
 
-typedef enum { B2E_SKIPGRAM = 0, B2E_CBOW = 1 } b2e_model;
+typedef enum { B2E_SKIPGRAM = 0, B2E_CBOW = 1, B2E_GLOVE = 2 } b2e_model;
 
 /*
  * Mirrors the constructor kwargs of Node2VecSkipGramEnsmallen / Node2VecCBOWEnsmallen
@@ -56,6 +56,7 @@ typedef struct {
     float learning_rate;
     float learning_rate_decay;
     float negative_sampling_exponent;           /* alias table over deg^alpha; north_star: 0.75 */
+    float glove_alpha;             /* GloVe: weight (count / max count)^alpha (node2vec_glove.py:37) */
     float change_node_type_weight; /* walk weight x this when the node type changes (b2e_load_types) */
     float change_edge_type_weight; /* ... when the edge type changes; 1 = untyped walks */
     uint32_t use_scale_free_distribution;       /* 0 => uniform negatives */
@@ -118,6 +119,20 @@ int b2e_load_csr_weighted(b2e_handle *handle, const int64_t *indptr, const uint3
  * never loaded has no effect (the graph walks untyped).
  */
 int b2e_load_types(b2e_handle *handle, const uint32_t *node_types, const uint32_t *edge_types);
+
+/*
+ * GloVe (model B2E_GLOVE; replaces `ensmallen.models.GloVe.fit_transform` behind
+ * node2vec_glove.py / deepwalk_glove.py).  b2e_fit runs the whole path; the pieces, for parity
+ * tests: b2e_cooccurrence walks `n_walks` walks and counts the ordered pairs of different
+ * tokens at most `window_size` apart (accumulate != 0 adds to the resident counts instead of
+ * replacing them); b2e_cooccurrence_export copies the triples, sorted by (centre, context);
+ * b2e_glove_train is one pass of SGD over the resident triples (counters: pairs = triples
+ * trained, loss_sum = sum of weight * (dot - ln count)^2).
+ */
+int b2e_cooccurrence(b2e_handle *handle, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
+                     uint64_t walk_id_stride, int accumulate, uint64_t *n_triples);
+int b2e_cooccurrence_export(b2e_handle *handle, uint32_t *centre, uint32_t *context, uint32_t *count);
+int b2e_glove_train(b2e_handle *handle, float learning_rate);
 
 uint64_t b2e_number_of_sources(const b2e_handle *handle);
 uint64_t b2e_row_stride(const b2e_handle *handle); /* floats per table row on the device */

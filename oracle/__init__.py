@@ -97,6 +97,13 @@ def lib():
         l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), P(u32), f32, f32,
                                       u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, P(u32),
                                       P(WalkCounters)]
+        l.orc_log_det.restype = f32
+        l.orc_log_det.argtypes = [f32]
+        l.orc_exp_det.restype = f32
+        l.orc_exp_det.argtypes = [f32]
+        l.orc_glove_train.restype = ctypes.c_int
+        l.orc_glove_train.argtypes = [P(u32), P(u32), P(u32), u64, u32, u32, u32, f32, f32, f32,
+                                      P(f32), P(f32), P(ctypes.c_double), P(u64)]
         l.orc_alias_build.restype = ctypes.c_int
         l.orc_alias_build.argtypes = [P(ctypes.c_int64), u64, ctypes.c_double, P(u32), P(u32)]
         l.orc_set_threads.restype = None
@@ -345,5 +352,73 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
             pairs += r["pairs"]
             done += count
         losses.append(loss_sum / max(pairs, 1))
+        lr = np.float32(lr * np.float32(learning_rate_decay))
+    return t0, t1, losses
+
+
+# ---- GloVe on walk co-occurrences (oracle/glove.c) ----
+def cooccurrence(walk_array: np.ndarray, window_size: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(centre, context, count) of every ordered pair of different tokens at most ``window_size``
+    positions apart (window trimmed at the borders, PAD skipped), sorted by (centre, context)."""
+    walk_array = np.ascontiguousarray(walk_array, dtype=np.uint32)
+    keys = []
+    for d in range(1, min(window_size, walk_array.shape[1] - 1) + 1):
+        a, b = walk_array[:, :-d].ravel(), walk_array[:, d:].ravel()
+        ok = (a != PAD_TOKEN) & (b != PAD_TOKEN) & (a != b)
+        a, b = a[ok].astype(np.uint64), b[ok].astype(np.uint64)
+        keys.append((a << np.uint64(32)) | b)
+        keys.append((b << np.uint64(32)) | a)
+    if not keys:
+        empty = np.zeros(0, dtype=np.uint32)
+        return empty, empty.copy(), empty.copy()
+    unique, counts = np.unique(np.concatenate(keys), return_counts=True)
+    return ((unique >> np.uint64(32)).astype(np.uint32), (unique & np.uint64(0xFFFFFFFF)).astype(np.uint32),
+            counts.astype(np.uint32))
+
+
+def log_det(x: float) -> float:
+    return float(lib().orc_log_det(x))
+
+
+def glove_train(centre, context, count, t0: np.ndarray, t1: np.ndarray, embedding_size: int,
+                alpha: float, learning_rate: float, clipping_value: float = 6.0,
+                max_count: Optional[int] = None) -> dict:
+    """One sequential pass over the triples (in place); returns loss_sum / trained."""
+    centre = np.ascontiguousarray(centre, dtype=np.uint32)
+    context = np.ascontiguousarray(context, dtype=np.uint32)
+    count = np.ascontiguousarray(count, dtype=np.uint32)
+    if max_count is None:
+        max_count = int(count.max()) if count.shape[0] else 1
+    loss = ctypes.c_double(0.0)
+    trained = ctypes.c_uint64(0)
+    rc = lib().orc_glove_train(_ptr(centre, ctypes.c_uint32), _ptr(context, ctypes.c_uint32),
+                               _ptr(count, ctypes.c_uint32), centre.shape[0], max_count, embedding_size,
+                               t0.shape[1], alpha, clipping_value, learning_rate,
+                               _ptr(t0, ctypes.c_float), _ptr(t1, ctypes.c_float), ctypes.byref(loss),
+                               ctypes.byref(trained))
+    if rc != 0:
+        raise ValueError(f"orc_glove_train failed with status {rc}")
+    return {"loss_sum": loss.value, "trained": trained.value, "max_count": max_count}
+
+
+def glove_fit(indptr, indices, seed: int, embedding_size: int, epochs: int, walk_length: int,
+              window_size: int, alpha: float, learning_rate: float, learning_rate_decay: float,
+              return_weight: float = 1.0, explore_weight: float = 1.0, clipping_value: float = 6.0,
+              iterations: int = 1):
+    """Whole GloVe path: per epoch fresh walks (one per source node and iteration), their
+    co-occurrence, one pass of SGD.  Returns (t0, t1, epoch_mean_loss)."""
+    indptr, indices = _csr(indptr, indices)
+    n = indptr.shape[0] - 1
+    srcs = sources(indptr)
+    t0, t1 = init_tables(n, embedding_size, seed)
+    per_epoch = iterations * srcs.shape[0]
+    lr = np.float32(learning_rate)
+    losses = []
+    for epoch in range(epochs):
+        w, _ = walks(indptr, indices, seed, epoch * per_epoch, per_epoch, walk_length, return_weight,
+                     explore_weight, srcs=srcs)
+        centre, context, count = cooccurrence(w, window_size)
+        r = glove_train(centre, context, count, t0, t1, embedding_size, alpha, float(lr), clipping_value)
+        losses.append(r["loss_sum"] / max(r["trained"], 1))
         lr = np.float32(lr * np.float32(learning_rate_decay))
     return t0, t1, losses

@@ -116,6 +116,8 @@ typedef struct {
 void orc_set_threads(int threads);
 int orc_get_threads(void);
 
+float orc_exp_det(float y); /* exp from IEEE single ops only (Cody-Waite + degree-6 polynomial) */
+float orc_log_det(float x); /* ln  from IEEE single ops only (atanh series), x > 0, normal      */
 float orc_sigmoid(float x);
 float orc_dot(const float *a, const float *b, uint32_t row_stride);
 
@@ -130,6 +132,21 @@ int orc_train(const orc_sgns_cfg *cfg, const uint32_t *walks, uint64_t n_walks,
               uint64_t first_walk, uint64_t walk_id_stride, uint64_t seed, uint64_t n,
               const int64_t *indptr, const uint32_t *thr, const uint32_t *alias, float *t0,
               float *t1, double *loss_sum, uint64_t *pairs, uint64_t *targets);
+
+/*
+ * GloVe on the walk co-occurrences ("next" row f-3; wrappers
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec_glove.py:5-140,
+ * deepwalk_glove.py).  Triples (centre, context, count) sorted by (centre, context); per centre
+ * the row of T0 stays in `h` while its contexts are visited in order:
+ *   f = <h, T1[o]>;  skipped when |f| > clipping_value
+ *   weight = exp(alpha * ln(count / max_count));  g = 2 * weight * (f - ln(count)) * lr
+ *   h' = h - g * T1[o];  T1[o] -= g * h;  h = h'
+ * loss_sum accumulates weight * (f - ln count)^2 over the triples that were not skipped.
+ */
+int orc_glove_train(const uint32_t *centre, const uint32_t *context, const uint32_t *count,
+                    uint64_t n_triples, uint32_t max_count, uint32_t embedding_size,
+                    uint32_t row_stride, float alpha, float clipping_value, float learning_rate,
+                    float *t0, float *t1, double *loss_sum, uint64_t *trained);
 
 #ifdef __cplusplus
 }

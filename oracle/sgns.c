@@ -33,7 +33,7 @@ void orc_set_threads(int threads) { g_threads = threads < 1 ? 1 : threads; }
 int orc_get_threads(void) { return g_threads; }
 
 /* exp(y) from IEEE single ops only: Cody-Waite reduction + degree-6 polynomial */
-static float exp_det(float y) {
+float orc_exp_det(float y) {
     if (y > 80.0f) y = 80.0f;
     if (y < -80.0f) y = -80.0f;
     const float k = rintf(y * 1.44269504088896341f);
@@ -52,7 +52,7 @@ static float exp_det(float y) {
     return p * scale.f;
 }
 
-float orc_sigmoid(float x) { return 1.0f / (1.0f + exp_det(-x)); }
+float orc_sigmoid(float x) { return 1.0f / (1.0f + orc_exp_det(-x)); }
 
 /* warp-shaped dot: lane l owns float4 chunks l, l+32, ...; xor-butterfly 16,8,4,2,1 */
 float orc_dot(const float *a, const float *b, uint32_t row_stride) {

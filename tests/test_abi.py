@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header_layout():
-    # 26 four-byte fields, no padding
-    assert ctypes.sizeof(_lib.B2EConfig) == 104
+    # 27 four-byte fields, no padding
+    assert ctypes.sizeof(_lib.B2EConfig) == 108
     assert ctypes.sizeof(_lib.B2ECounters) == 48
 
 

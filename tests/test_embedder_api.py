@@ -249,3 +249,24 @@ def test_walklets_classes_mirror_the_reference_surface():
     assert not any("Walklets" in name for name in frame.model_name)
     with pytest.raises(NotImplementedError):
         WalkletsSkipGramB200(central_nodes_embedding_path="x.npy")
+
+
+def test_glove_classes_mirror_the_reference_surface():
+    """node2vec_glove.py:5-140, deepwalk_glove.py: signature defaults, hidden parameters."""
+    from embiggen_b200.embedders import DeepWalkGloVeB200, Node2VecGloVeB200
+    m = Node2VecGloVeB200()
+    p = m.parameters()
+    assert (p["alpha"], p["epochs"], p["walk_length"], p["window_size"], p["learning_rate"],
+            p["learning_rate_decay"], p["return_weight"], p["explore_weight"]) == \
+        (0.75, 100, 512, 5, 0.05, 0.9, 0.25, 4.0)
+    for hidden in ("change_node_type_weight", "change_edge_type_weight", "number_of_negative_samples",
+                   "iterations"):
+        assert hidden not in p
+    assert Node2VecGloVeB200(**p).parameters() == p and m.model_name() == "Node2Vec GloVe"
+    d = DeepWalkGloVeB200()
+    q = d.parameters()
+    assert q["learning_rate_decay"] == 0.99 and "return_weight" not in q
+    assert DeepWalkGloVeB200(**q).parameters() == q and d.model_name() == "DeepWalk GloVe"
+    assert type(d.into_smoke_test()) is DeepWalkGloVeB200
+    frame = get_available_models_for_node_embedding()
+    assert not any("GloVe" in name for name in frame.model_name)

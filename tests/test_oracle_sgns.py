@@ -273,3 +273,49 @@ def test_walklet_training_counts_the_pairs_of_its_scale(small_ppi):
         # every ordered pair (i, i +- k) with two different tokens
         a, b = walks[:, :-k], walks[:, k:]
         assert stats["pairs"] == 2 * int((a != b).sum())
+
+
+# ---- GloVe (oracle/glove.c) ----
+def test_cooccurrence_against_a_python_loop(small_ppi):
+    L, w = 12, 3
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 2, 0, 60, L, 0.25, 4.0)
+    walks[5, 7:] = oracle.PAD_TOKEN
+    expected = {}
+    for walk in walks:
+        for i in range(L):
+            for j in range(max(0, i - w), min(L - 1, i + w) + 1):
+                a, b = int(walk[i]), int(walk[j])
+                if j != i and a != oracle.PAD_TOKEN and b != oracle.PAD_TOKEN and a != b:
+                    expected[(a, b)] = expected.get((a, b), 0) + 1
+    centre, context, count = oracle.cooccurrence(walks, w)
+    got = {(int(a), int(b)): int(c) for a, b, c in zip(centre, context, count)}
+    assert got == expected
+    keys = centre.astype(np.uint64) << np.uint64(32) | context
+    assert (np.diff(keys.astype(np.int64)) > 0).all()
+
+
+def test_log_det_and_glove_step_against_float64(small_ppi):
+    for x in (1.0, 2.0, 3.0, 7.0, 1000.0, 0.25, 1e-4, 123456.0):
+        assert abs(oracle.log_det(x) - np.log(x)) <= 3e-7 * max(1.0, abs(np.log(x)))
+    n, D, alpha, lr = small_ppi.get_number_of_nodes(), 12, 0.75, 0.05
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, 3, 0, 200, 16)
+    centre, context, count = oracle.cooccurrence(walks, 3)
+    t0, t1 = oracle.init_tables(n, D, 3)
+    t0 *= 25.0
+    t1 *= 25.0
+    e0, e1 = t0[:, :D].astype(np.float64), t1[:, :D].astype(np.float64)
+    xmax, loss = float(count.max()), 0.0
+    for c, o, x in zip(centre, context, count):
+        f = e0[c] @ e1[o]
+        if abs(f) > 6.0:
+            continue
+        weight, diff = (x / xmax) ** alpha, f - np.log(x)
+        g = 2.0 * weight * diff * lr
+        loss += weight * diff * diff
+        e0[c], e1[o] = e0[c] - g * e1[o], e1[o] - g * e0[c]
+    got = oracle.glove_train(centre, context, count, t0, t1, D, alpha, lr)
+    assert got["trained"] == len(centre) and np.isclose(got["loss_sum"], loss, rtol=1e-5)
+    assert np.allclose(t0[:, :D], e0, atol=3e-6) and np.allclose(t1[:, :D], e1, atol=3e-6)
+    assert (t0[:, D:] == 0).all() and (t1[:, D:] == 0).all()
+    _, _, losses = oracle.glove_fit(small_ppi.indptr, small_ppi.indices, 5, 16, 6, 32, 4, 0.75, 0.05, 0.9)
+    assert losses[-1] < 0.8 * losses[0]
