@@ -704,9 +704,12 @@ extern "C" int b2e_glove_train(b2e_handle *h, float learning_rate) {
     if (!h->glove.finalised) return fail(B2E_ERR_STATE, "b2e_cooccurrence must be called first");
     const b2e_config &c = h->cfg;
     CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    // centres in flight: like SkipGram, about one per 16 nodes on small graphs (staleness)
+    const uint64_t max_warps = c.max_concurrent_walks ? c.max_concurrent_walks
+                                                       : std::max<uint64_t>(16, h->n / 16);
     CUDA_TRY(b2e::glove_train(h->glove, h->n, h->row_stride, c.embedding_size, c.glove_alpha, c.clipping_value,
                               learning_rate, h->d_t0, h->d_t1, h->d_counters, c.deterministic != 0,
-                              h->sm_count, h->train_stream));
+                              h->sm_count, max_warps, h->train_stream));
     if (h->glove.n_triples) ++h->launches;
     return B2E_OK;
 }

@@ -95,7 +95,12 @@ struct GloveParams {
     DeviceCounters *counters;
 };
 
-template <int CH, int NT>
+// ATOMIC (production launch): a context row is shared by many centres trained concurrently, and
+// a plain read-modify-write would lose all but one of their updates (on a small graph that is
+// most of the epoch).  The row update is additive, so it is applied with one 128-bit
+// red.global.add per lane instead; the single-warp launch keeps the fused multiply-add of the
+// oracle.
+template <int CH, int NT, bool ATOMIC>
 __global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     float loss_acc = 0.0f;
@@ -131,19 +136,27 @@ __global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
                 const float g = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, weight), diff), p.lr);
                 if (lane == 0) loss_acc += weight * diff * diff;
                 ++trained;
+                float *target = p.t1 + (uint64_t)ids[s] * p.row_stride;
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) {
                     const float4 old = rows[s][ch];
-                    rows[s][ch].x = __fmaf_rn(-g, h[ch].x, old.x);
-                    rows[s][ch].y = __fmaf_rn(-g, h[ch].y, old.y);
-                    rows[s][ch].z = __fmaf_rn(-g, h[ch].z, old.z);
-                    rows[s][ch].w = __fmaf_rn(-g, h[ch].w, old.w);
+                    if (ATOMIC) {
+                        const uint32_t c = lane + 32u * ch;
+                        if (c < p.chunks)
+                            atomicAdd(reinterpret_cast<float4 *>(target + 4u * c),
+                                      make_float4(-g * h[ch].x, -g * h[ch].y, -g * h[ch].z, -g * h[ch].w));
+                    } else {
+                        rows[s][ch].x = __fmaf_rn(-g, h[ch].x, old.x);
+                        rows[s][ch].y = __fmaf_rn(-g, h[ch].y, old.y);
+                        rows[s][ch].z = __fmaf_rn(-g, h[ch].z, old.z);
+                        rows[s][ch].w = __fmaf_rn(-g, h[ch].w, old.w);
+                    }
                     h[ch].x = __fmaf_rn(-g, old.x, h[ch].x);
                     h[ch].y = __fmaf_rn(-g, old.y, h[ch].y);
                     h[ch].z = __fmaf_rn(-g, old.z, h[ch].z);
                     h[ch].w = __fmaf_rn(-g, old.w, h[ch].w);
                 }
-                store_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
+                if (!ATOMIC) store_row<CH>(target, p.chunks, lane, rows[s]);
             }
         }
         store_row<CH>(crow, p.chunks, lane, h);
@@ -156,19 +169,20 @@ __global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
 }
 
 template <int CH, int NT>
-static cudaError_t launch_glove_one(const GloveParams &p, bool deterministic, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_glove_one(const GloveParams &p, bool deterministic, int sm_count,
+                                    uint64_t max_warps, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     if (deterministic) {
-        glove_train_kernel<CH, NT><<<1, 32, 0, stream>>>(p);
+        glove_train_kernel<CH, NT, false><<<1, 32, 0, stream>>>(p);
         return cudaGetLastError();
     }
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, glove_train_kernel<CH, NT>, 256, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, glove_train_kernel<CH, NT, true>, 256, 0);
     if (err != cudaSuccess) return err;
     uint64_t grid = (uint64_t)sm_count * std::max(per_sm, 1);  // persistent, centres fetched dynamically
-    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (p.n + 7) / 8));
-    glove_train_kernel<CH, NT><<<(unsigned)grid, 256, 0, stream>>>(p);
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (std::min<uint64_t>(p.n, max_warps) + 7) / 8));
+    glove_train_kernel<CH, NT, true><<<(unsigned)grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -291,7 +305,7 @@ cudaError_t glove_finalise(GloveState &g, uint64_t n, cudaStream_t stream) {
 
 cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, uint32_t embedding_size,
                         float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
-                        bool deterministic, int sm_count, cudaStream_t stream) {
+                        bool deterministic, int sm_count, uint64_t max_warps, cudaStream_t stream) {
     if (g.n_triples == 0) return cudaSuccess;
     GloveParams p;
     p.keys = g.d_keys;
@@ -307,9 +321,9 @@ cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, ui
     p.t0 = t0;
     p.t1 = t1;
     p.counters = counters;
-    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, deterministic, sm_count, stream);
-    if (p.chunks <= 64) return launch_glove_one<2, 4>(p, deterministic, sm_count, stream);
-    if (p.chunks <= 128) return launch_glove_one<4, 2>(p, deterministic, sm_count, stream);
+    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 64) return launch_glove_one<2, 4>(p, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 128) return launch_glove_one<4, 2>(p, deterministic, sm_count, max_warps, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -1,0 +1,33 @@
+"""Small driver for `compute-sanitizer --tool memcheck`: one tiny invocation of every kernel added
+for the SURVEY 8(f) rows (general / typed walks, Walklets split, GloVe, generic SGD with the
+centre skip), plus the production SkipGram / CBOW launches.  Prints 'sanitize ok' at the end."""
+import numpy as np
+
+from embiggen_b200.engine import Engine
+from embiggen_b200.graph import rmat
+
+graph = rmat(10, 6000, n=1000, seed=3)
+n = graph.get_number_of_nodes()
+rng = np.random.default_rng(0)
+node_types = rng.integers(0, 3, n).astype(np.uint32)
+edge_types = rng.integers(0, 3, graph.indices.shape[0]).astype(np.uint32)
+weights = rng.random(graph.indices.shape[0]).astype(np.float32) + 0.1
+
+for model in ("SkipGram", "CBOW"):
+    for extra in (dict(), dict(walklet_scale=3, window_size=1), dict(stochastic_downsample_by_degree=True),
+                  dict(normalize_by_degree=True, change_node_type_weight=3.0, change_edge_type_weight=0.3),
+                  dict(embedding_size=200)):
+        kw = dict(embedding_size=100, walk_length=33, window_size=4, iterations=1, epochs=1,
+                  return_weight=0.5, explore_weight=2.0)
+        kw.update(extra)
+        with Engine(model, **kw) as engine:
+            engine.load_csr(graph.indptr, graph.indices, weights)
+            engine.load_types(node_types, edge_types)
+            t0, t1, losses = engine.fit(7)
+            assert np.isfinite(t0).all() and np.isfinite(t1).all(), (model, extra)
+with Engine("GloVe", embedding_size=100, walk_length=33, window_size=4, iterations=1, epochs=2,
+            chunk_walks=300) as engine:
+    engine.load_csr(graph.indptr, graph.indices)
+    t0, t1, losses = engine.fit(7)
+    assert np.isfinite(t0).all() and np.isfinite(t1).all()
+print("sanitize ok")
