@@ -1,7 +1,12 @@
 """Small driver for `compute-sanitizer --tool memcheck`: one tiny invocation of every kernel added
 for the SURVEY 8(f) rows (general / typed walks, Walklets split, GloVe, generic SGD with the
 centre skip), plus the production SkipGram / CBOW launches.  Prints 'sanitize ok' at the end."""
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 from embiggen_b200.engine import Engine
 from embiggen_b200.graph import rmat
