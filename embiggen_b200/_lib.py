@@ -51,6 +51,22 @@ class B2EConfig(ctypes.Structure):
     ]
 
 
+class B2EPerceptronConfig(ctypes.Structure):
+    """Mirror of ``b2e_perceptron_config`` (include/b2e.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("n_methods", ctypes.c_uint32),
+        ("methods", ctypes.c_uint32 * 12),
+        ("number_of_epochs", ctypes.c_uint32),
+        ("number_of_edges_per_mini_batch", ctypes.c_uint32),
+        ("learning_rate", ctypes.c_float),
+        ("first_order_decay_factor", ctypes.c_float),
+        ("second_order_decay_factor", ctypes.c_float),
+        ("avoid_false_negatives", ctypes.c_uint32),
+        ("use_scale_free_distribution", ctypes.c_uint32),
+    ]
+
+
 class B2ECounters(ctypes.Structure):
     """Mirror of ``b2e_counters`` (include/b2e.h)."""
     _fields_ = [
@@ -101,6 +117,16 @@ SIGNATURES = {
     "b2e_counters_read": (ctypes.c_int, [_H, _P(B2ECounters)]),
     "b2e_counters_reset": (ctypes.c_int, [_H]),
     "b2e_launch_count": (_U64, [_H]),
+    "b2e_features_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _U64, _U32, _P(_H)]),
+    "b2e_features_from_handle": (ctypes.c_int, [_H, ctypes.c_int, _P(_H)]),
+    "b2e_features_destroy": (None, [_H]),
+    "b2e_edge_embedding_size": (ctypes.c_int, [_U32, ctypes.c_void_p, _U32, _P(_U32)]),
+    "b2e_edge_embedding": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, ctypes.c_void_p, _U32,
+                                          ctypes.c_void_p]),
+    "b2e_perceptron_fit": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
+                                          _P(B2EPerceptronConfig), _U64, ctypes.c_void_p, ctypes.c_void_p]),
+    "b2e_perceptron_predict": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, ctypes.c_void_p, _U32,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_csr_from_edges": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _P(_U64)]),
     "b2e_synthetic_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _U64, _U32, _U64, _U64, _U64, _U64,

@@ -6,7 +6,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libb2e.so")
-SOURCES = ["b2e_api.cu", "walk_kernels.cu", "sgns_kernels.cu", "sgns_pipe.cu", "graph_build.cu", "glove.cu"]
+SOURCES = ["b2e_api.cu", "walk_kernels.cu", "sgns_kernels.cu", "sgns_pipe.cu", "graph_build.cu", "glove.cu", "edge_pred.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-shared", "-cudart", "shared",

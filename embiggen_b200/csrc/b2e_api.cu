@@ -32,6 +32,8 @@ static int fail(int status, const std::string &message) {
         CUDA_TRY(cudaSetDevice((h)->cfg.device));                                            \
     } while (0)
 
+int b2e_set_error(int status, const std::string &message) { return fail(status, message); }  // edge_pred.cu
+
 extern "C" const char *b2e_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b2e_abi_version(void) { return B2E_ABI_VERSION; }
 

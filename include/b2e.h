@@ -207,6 +207,58 @@ int b2e_synthetic_csr(int device, int kind, uint64_t n_nodes, uint32_t scale, ui
                       uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, int64_t *indptr,
                       uint32_t *indices, uint64_t indices_capacity, uint64_t *nnz);
 
+/* ---- the step after the path: edge embeddings and a perceptron edge scorer ---- */
+
+/* EdgeTransformer.methods, .../embedding_transformers/edge_transformer.py:337-350, same order */
+typedef enum {
+    B2E_EDGE_HADAMARD = 0, B2E_EDGE_SUM = 1, B2E_EDGE_AVERAGE = 2, B2E_EDGE_L1 = 3,
+    B2E_EDGE_ABSOLUTE_L1 = 4, B2E_EDGE_SQUARED_L2 = 5, B2E_EDGE_L2 = 6, B2E_EDGE_CONCATENATE = 7,
+    B2E_EDGE_MIN = 8, B2E_EDGE_MAX = 9, B2E_EDGE_L2_DISTANCE = 10, B2E_EDGE_COSINE_SIMILARITY = 11
+} b2e_edge_method;
+
+/* node features (n x dim float32) resident in HBM */
+typedef struct b2e_features b2e_features;
+int b2e_features_create(int device, const float *host_features, uint64_t n, uint32_t dim,
+                        b2e_features **features);
+/* zero-copy view of a trained handle's table (0: input table T0, 1: output table T1): the
+ * embedding never leaves HBM between b2e_fit and the scorer; valid while the handle lives */
+int b2e_features_from_handle(b2e_handle *handle, int table, b2e_features **features);
+void b2e_features_destroy(b2e_features *features);
+
+/* width of the concatenation of the methods (Concatenate 2 dim, the two scalar methods 1) */
+int b2e_edge_embedding_size(uint32_t dim, const uint32_t *methods, uint32_t n_methods, uint32_t *size);
+
+/* EdgeTransformer.transform (edge_transformer.py:352-361): out is m x size, row-major, host */
+int b2e_edge_embedding(const b2e_features *features, const uint32_t *src, const uint32_t *dst,
+                       uint64_t m, const uint32_t *methods, uint32_t n_methods, float *out);
+
+/* kwargs of PerceptronEdgePrediction that reach the native model
+ * (.../edge_prediction/edge_prediction_ensmallen/perceptron.py:18-31, :97-109) */
+typedef struct {
+    uint32_t struct_size;
+    uint32_t n_methods;
+    uint32_t methods[12];  /* b2e_edge_method: `edge_embeddings` */
+    uint32_t number_of_epochs;
+    uint32_t number_of_edges_per_mini_batch;
+    float learning_rate;
+    float first_order_decay_factor;
+    float second_order_decay_factor;
+    uint32_t avoid_false_negatives;
+    uint32_t use_scale_free_distribution;
+} b2e_perceptron_config;
+
+/* `models.EdgePredictionPerceptron(...).fit(graph, node_features)` (perceptron.py:133-170):
+ * params receives size weights followed by the bias; epoch_loss (may be NULL) one mean
+ * cross-entropy per epoch */
+int b2e_perceptron_fit(const b2e_features *features, const int64_t *indptr, const uint32_t *indices,
+                       uint64_t n, uint64_t nnz, const b2e_perceptron_config *config, uint64_t seed,
+                       float *params, float *epoch_loss);
+
+/* `.predict(graph, node_features)` on an explicit edge list (perceptron.py:172-215) */
+int b2e_perceptron_predict(const b2e_features *features, const uint32_t *src, const uint32_t *dst,
+                           uint64_t m, const uint32_t *methods, uint32_t n_methods, const float *params,
+                           float *scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,8 @@ def lib():
         l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), P(u32), f32, f32,
                                       u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, P(u32),
                                       P(WalkCounters)]
+        l.orc_philox_range.restype = None
+        l.orc_philox_range.argtypes = [u64, u32, u64, u32, u32, u32, P(u32)]
         l.orc_log_det.restype = f32
         l.orc_log_det.argtypes = [f32]
         l.orc_exp_det.restype = f32
@@ -126,6 +128,13 @@ def philox(seed: int, c0: int, c1: int, c2: int, c3: int) -> Tuple[int, int, int
     out = (ctypes.c_uint32 * 4)()
     lib().orc_philox(seed, c0, c1, c2, c3, out)
     return tuple(int(x) for x in out)
+
+
+def philox_range(seed: int, count: int, c1: int, c2: int, c3: int, first_c0: int = 0) -> np.ndarray:
+    """Blocks (c0 = first_c0 + i, c1, c2, c3), i < count, as a (count, 4) uint32 array."""
+    out = np.empty((count, 4), dtype=np.uint32)
+    lib().orc_philox_range(seed, first_c0, count, c1, c2, c3, _ptr(out, ctypes.c_uint32))
+    return out
 
 
 def set_threads(threads: int) -> None:

@@ -116,6 +116,8 @@ typedef struct {
 void orc_set_threads(int threads);
 int orc_get_threads(void);
 
+void orc_philox_range(uint64_t seed, uint32_t first_c0, uint64_t count, uint32_t c1, uint32_t c2,
+                      uint32_t c3, uint32_t *out);
 float orc_exp_det(float y); /* exp from IEEE single ops only (Cody-Waite + degree-6 polynomial) */
 float orc_log_det(float x); /* ln  from IEEE single ops only (atanh series), x > 0, normal      */
 float orc_sigmoid(float x);

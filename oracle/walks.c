@@ -26,6 +26,14 @@ void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
     orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c0, c1, c2, c3, out);
 }
 
+/* blocks (c0 = first_c0 + i, c1, c2, c3) for i < count; out holds 4 * count words */
+void orc_philox_range(uint64_t seed, uint32_t first_c0, uint64_t count, uint32_t c1, uint32_t c2,
+                      uint32_t c3, uint32_t *out) {
+    for (uint64_t i = 0; i < count; ++i)
+        orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), first_c0 + (uint32_t)i, c1, c2, c3,
+                          out + 4 * i);
+}
+
 uint64_t orc_sources(const int64_t *indptr, uint64_t n, uint32_t *out) {
     uint64_t count = 0;
     for (uint64_t v = 0; v < n; ++v) {
