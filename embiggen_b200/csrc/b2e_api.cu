@@ -154,7 +154,6 @@ static void free_graph(b2e_handle *h) {
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
     cudaFree(h->d_cdf); h->d_cdf = nullptr;
-    cudaFree(h->d_mindeg); h->d_mindeg = nullptr;
     cudaFree(h->d_node_types); h->d_node_types = nullptr;
     cudaFree(h->d_edge_types); h->d_edge_types = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
@@ -303,6 +302,20 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     }
     h->n_src = sources.size();
     h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
+    // normalize_by_degree (.../node2vec_skipgram.py:94-96): the weight of v -> x divided by
+    // max(deg(x), 1), one float32 division per edge, folded into the proposal table -- no extra
+    // rejection however skewed the degrees (oracle: degree_normalised_weights)
+    std::vector<float> normalised;
+    if (c.normalize_by_degree && nnz) {
+        normalised.resize(nnz);
+        for (uint64_t e = 0; e < nnz; ++e) {
+            const uint32_t x = indices[e];
+            if (x >= n) return fail(B2E_ERR_INVALID, "a destination node id is out of range");
+            const float degree = (float)std::max<int64_t>(indptr[x + 1] - indptr[x], 1);
+            normalised[e] = (weights ? weights[e] : 1.0f) / degree;
+        }
+        weights = normalised.data();
+    }
     if (weights) {
         std::vector<uint32_t> cdf(nnz);
         if (!build_edge_cdf(indptr, weights, n, cdf))
@@ -327,12 +340,6 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         CUDA_TRY(cudaMemcpyAsync(h->d_alias, packed.data(), n * sizeof(uint2), cudaMemcpyHostToDevice,
                                  h->walk_stream));
         CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `packed` dies here
-    }
-
-    if (c.normalize_by_degree) {
-        CUDA_TRY(cudaMalloc(&h->d_mindeg, n * sizeof(uint32_t)));
-        CUDA_TRY(launch_min_neighbour_degree(h->d_indptr, h->d_indices, n, h->d_mindeg, h->walk_stream));
-        ++h->launches;
     }
 
     // Is the graph undirected (every edge mirrored)?  Then the second-order walk kernel may
@@ -410,7 +417,6 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     p.indptr = h->d_indptr;
     p.indices = h->d_indices;
     p.cdf = h->d_cdf;
-    p.mindeg = h->d_mindeg;
     p.node_types = h->d_node_types;
     p.edge_types = h->d_edge_types;
     type_thresholds(h->d_node_types ? h->cfg.change_node_type_weight : 1.0f, p.q_node);

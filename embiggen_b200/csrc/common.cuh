@@ -51,7 +51,6 @@ struct WalkParams {
     const int64_t *indptr;
     const uint32_t *indices;
     const uint32_t *cdf;  // per-edge sampling table of a weighted graph, or nullptr
-    const uint32_t *mindeg;  // smallest neighbour degree per node (normalize_by_degree), or nullptr
     const uint32_t *node_types, *edge_types;  // [n] / [nnz] type ids of typed walks, or nullptr
     unsigned long long q_node[2], q_edge[2];  // accept thresholds [same type, changed type]
     const uint32_t *sources;
@@ -112,8 +111,6 @@ void glove_free(GloveState &g);
 
 cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,
                                  uint32_t *out, cudaStream_t stream);
-cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
-                                        uint32_t *out, cudaStream_t stream);
 cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                   uint64_t nnz, int *d_flag, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
@@ -143,7 +140,6 @@ struct b2e_handle {
     int64_t *d_indptr = nullptr;
     uint32_t *d_indices = nullptr;
     uint32_t *d_cdf = nullptr;
-    uint32_t *d_mindeg = nullptr;
     uint32_t *d_node_types = nullptr, *d_edge_types = nullptr;
     b2e::GloveState glove;
     uint32_t *d_walk_raw = nullptr;  // Walklets: the chunk as walked, before it is split by stride

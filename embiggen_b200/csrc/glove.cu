@@ -12,13 +12,15 @@
 //   2. CUB radix sort + run-length encode -> (key, count) of the chunk; chunks are merged by
 //      sort-by-key + reduce-by-key (library calls: this is bookkeeping around the hot kernel)
 //   3. cooc_rowptr_kernel    CSR offsets of the sorted keys by centre (one bisection per node)
-//   4. glove_train_kernel    one warp per centre: the centre row stays in registers while its
-//                            context rows (all distinct) are gathered NT at a time with 128-bit
-//                            loads, scored with the warp-shaped dot of the SGD kernels, updated
-//                            and scattered back (Hogwild across warps).  HBM-bound: 2 * 4D
-//                            bytes per triple.  A single-warp launch reproduces oracle/glove.c
-//                            bit for bit (explicit round-to-nearest intrinsics, log / exp from
-//                            IEEE single operations only).
+//   4. glove_tile_kernel     one warp per tile of 512 consecutive triples (load balance on skewed
+//                            graphs): the centre row stays in registers over a run of equal
+//                            centres while the context rows (all distinct within a centre) are
+//                            gathered NT at a time with 128-bit loads, scored with the
+//                            warp-shaped dot of the SGD kernels and updated with 128-bit
+//                            atomics.  HBM-bound: 2 * 4D bytes per triple.
+//      glove_train_kernel    the single-warp launch (cfg.deterministic): reproduces
+//                            oracle/glove.c bit for bit (explicit round-to-nearest intrinsics,
+//                            log / exp from IEEE single operations only).
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -95,13 +97,10 @@ struct GloveParams {
     DeviceCounters *counters;
 };
 
-// ATOMIC (production launch): a context row is shared by many centres trained concurrently, and
-// a plain read-modify-write would lose all but one of their updates (on a small graph that is
-// most of the epoch).  The row update is additive, so it is applied with one 128-bit
-// red.global.add per lane instead; the single-warp launch keeps the fused multiply-add of the
-// oracle.
-template <int CH, int NT, bool ATOMIC>
-__global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
+// Single-warp launch (cfg.deterministic): centres in ascending order, the operation sequence of
+// oracle/glove.c.  The production launch is glove_tile_kernel below.
+template <int CH, int NT>
+__global__ void __launch_bounds__(32) glove_train_kernel(const GloveParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     float loss_acc = 0.0f;
     unsigned long long trained = 0;
@@ -140,23 +139,16 @@ __global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) {
                     const float4 old = rows[s][ch];
-                    if (ATOMIC) {
-                        const uint32_t c = lane + 32u * ch;
-                        if (c < p.chunks)
-                            atomicAdd(reinterpret_cast<float4 *>(target + 4u * c),
-                                      make_float4(-g * h[ch].x, -g * h[ch].y, -g * h[ch].z, -g * h[ch].w));
-                    } else {
-                        rows[s][ch].x = __fmaf_rn(-g, h[ch].x, old.x);
-                        rows[s][ch].y = __fmaf_rn(-g, h[ch].y, old.y);
-                        rows[s][ch].z = __fmaf_rn(-g, h[ch].z, old.z);
-                        rows[s][ch].w = __fmaf_rn(-g, h[ch].w, old.w);
-                    }
+                    rows[s][ch].x = __fmaf_rn(-g, h[ch].x, old.x);
+                    rows[s][ch].y = __fmaf_rn(-g, h[ch].y, old.y);
+                    rows[s][ch].z = __fmaf_rn(-g, h[ch].z, old.z);
+                    rows[s][ch].w = __fmaf_rn(-g, h[ch].w, old.w);
                     h[ch].x = __fmaf_rn(-g, old.x, h[ch].x);
                     h[ch].y = __fmaf_rn(-g, old.y, h[ch].y);
                     h[ch].z = __fmaf_rn(-g, old.z, h[ch].z);
                     h[ch].w = __fmaf_rn(-g, old.w, h[ch].w);
                 }
-                if (!ATOMIC) store_row<CH>(target, p.chunks, lane, rows[s]);
+                store_row<CH>(target, p.chunks, lane, rows[s]);
             }
         }
         store_row<CH>(crow, p.chunks, lane, h);
@@ -168,21 +160,113 @@ __global__ void __launch_bounds__(256) glove_train_kernel(const GloveParams p) {
     }
 }
 
+// Production launch.  A hub centre owns a large share of the triples of a skewed graph (R-MAT
+// 1 M / 16 M: the pass took as long as the hub's row walked by one warp), so the work unit is a
+// TILE of `GLOVE_TILE` consecutive triples of the flat sorted array instead of a centre: every
+// warp does the same amount of work whatever the degree distribution.  Inside a tile the warp
+// follows the runs of equal centre: at a run boundary it adds `h - h0` (what this run changed)
+// to the centre row with one 128-bit atomic per lane -- rows split over several tiles receive
+// the sum of their tiles' changes -- and loads the next centre.  Context rows are updated
+// with 128-bit atomics too: a context row is shared by many centres trained concurrently and a
+// plain read-modify-write would lose all but one of their updates.
+constexpr uint32_t GLOVE_TILE = 512;
+
+template <int CH>
+__device__ __forceinline__ void flush_centre(float *crow, uint32_t chunks, uint32_t lane, const float4 (&h)[CH],
+                                             const float4 (&h0)[CH]) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const uint32_t c = lane + 32u * ch;
+        if (c < chunks)
+            atomicAdd(reinterpret_cast<float4 *>(crow + 4u * c),
+                      make_float4(h[ch].x - h0[ch].x, h[ch].y - h0[ch].y, h[ch].z - h0[ch].z, h[ch].w - h0[ch].w));
+    }
+}
+
 template <int CH, int NT>
-static cudaError_t launch_glove_one(const GloveParams &p, bool deterministic, int sm_count,
+__global__ void __launch_bounds__(256) glove_tile_kernel(const GloveParams p, uint64_t n_triples) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_tiles = (n_triples + GLOVE_TILE - 1) / GLOVE_TILE;
+    float loss_acc = 0.0f;
+    unsigned long long trained = 0;
+    for (;;) {
+        unsigned long long tile = 0;
+        if (lane == 0) tile = atomicAdd(&p.counters->work_counter, 1ull);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= n_tiles) break;
+        const uint64_t begin = tile * GLOVE_TILE, end = min(begin + GLOVE_TILE, n_triples);
+        uint32_t centre = PAD;
+        float4 h[CH], h0[CH];
+        for (uint64_t base = begin; base < end; base += NT) {
+            float4 rows[NT][CH];
+            uint32_t ids[NT], cnt[NT], cen[NT];
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+                const bool on = base + s < end;
+                const unsigned long long key = on ? __ldg(p.keys + base + s) : ~0ull;
+                ids[s] = on ? (uint32_t)key : PAD;
+                cen[s] = (uint32_t)(key >> 32);
+                cnt[s] = on ? __ldg(p.counts + base + s) : 1u;
+                if (on) load_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+                if (ids[s] == PAD) continue;
+                if (cen[s] != centre) {  // run boundary (warp-uniform)
+                    if (centre != PAD) flush_centre<CH>(p.t0 + (uint64_t)centre * p.row_stride, p.chunks, lane, h, h0);
+                    centre = cen[s];
+                    load_row<CH>(p.t0 + (uint64_t)centre * p.row_stride, p.chunks, lane, h);
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) h0[ch] = h[ch];
+                }
+                const float f = warp_dot<CH>(h, rows[s]);
+                if (fabsf(f) > p.clip) continue;
+                const float x = (float)cnt[s];
+                const float weight = exp_det(__fmul_rn(p.alpha, log_det(__fdiv_rn(x, p.max_count))));
+                const float diff = __fsub_rn(f, log_det(x));
+                const float g = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, weight), diff), p.lr);
+                if (lane == 0) loss_acc += weight * diff * diff;
+                ++trained;
+                float *target = p.t1 + (uint64_t)ids[s] * p.row_stride;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    const float4 old = rows[s][ch];
+                    const uint32_t c = lane + 32u * ch;
+                    if (c < p.chunks)
+                        atomicAdd(reinterpret_cast<float4 *>(target + 4u * c),
+                                  make_float4(-g * h[ch].x, -g * h[ch].y, -g * h[ch].z, -g * h[ch].w));
+                    h[ch].x = __fmaf_rn(-g, old.x, h[ch].x);
+                    h[ch].y = __fmaf_rn(-g, old.y, h[ch].y);
+                    h[ch].z = __fmaf_rn(-g, old.z, h[ch].z);
+                    h[ch].w = __fmaf_rn(-g, old.w, h[ch].w);
+                }
+            }
+        }
+        if (centre != PAD) flush_centre<CH>(p.t0 + (uint64_t)centre * p.row_stride, p.chunks, lane, h, h0);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.counters->pairs, trained);
+        atomicAdd(&p.counters->targets, trained);
+        atomicAdd(&p.counters->loss_sum, (double)loss_acc);
+    }
+}
+
+template <int CH, int NT>
+static cudaError_t launch_glove_one(const GloveParams &p, uint64_t n_triples, bool deterministic, int sm_count,
                                     uint64_t max_warps, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     if (deterministic) {
-        glove_train_kernel<CH, NT, false><<<1, 32, 0, stream>>>(p);
+        glove_train_kernel<CH, NT><<<1, 32, 0, stream>>>(p);
         return cudaGetLastError();
     }
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, glove_train_kernel<CH, NT, true>, 256, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, glove_tile_kernel<CH, NT>, 256, 0);
     if (err != cudaSuccess) return err;
-    uint64_t grid = (uint64_t)sm_count * std::max(per_sm, 1);  // persistent, centres fetched dynamically
-    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (std::min<uint64_t>(p.n, max_warps) + 7) / 8));
-    glove_train_kernel<CH, NT, true><<<(unsigned)grid, 256, 0, stream>>>(p);
+    uint64_t grid = (uint64_t)sm_count * std::max(per_sm, 1);  // persistent, tiles fetched dynamically
+    const uint64_t n_tiles = (n_triples + GLOVE_TILE - 1) / GLOVE_TILE;
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (std::min<uint64_t>(n_tiles, max_warps) + 7) / 8));
+    glove_tile_kernel<CH, NT><<<(unsigned)grid, 256, 0, stream>>>(p, n_triples);
     return cudaGetLastError();
 }
 
@@ -321,9 +405,9 @@ cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, ui
     p.t0 = t0;
     p.t1 = t1;
     p.counters = counters;
-    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, deterministic, sm_count, max_warps, stream);
-    if (p.chunks <= 64) return launch_glove_one<2, 4>(p, deterministic, sm_count, max_warps, stream);
-    if (p.chunks <= 128) return launch_glove_one<4, 2>(p, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 64) return launch_glove_one<2, 4>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 128) return launch_glove_one<4, 2>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -367,39 +367,11 @@ __global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
 }
 
 
-// ---- normalize_by_degree: transition weight divided by the degree of the destination ----
-// (.../node2vec_skipgram.py:94-96): accept iff r1 * deg(x) < thr[class] * mindeg[cur], where
-// mindeg[cur] is the smallest neighbour degree of the current node (the bound rejection sampling
-// needs for 1 / deg(x)).  All products fit 64 bits (thr <= 2^32, degrees < 2^32), so the
-// decisions are the oracle's.
-__global__ void __launch_bounds__(256) min_neighbour_degree_kernel(const int64_t *__restrict__ indptr,
-                                                                   const uint32_t *__restrict__ indices,
-                                                                   uint64_t n, uint32_t *__restrict__ out) {
-    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    uint32_t best = 0xFFFFFFFFu;
-    for (int64_t e = __ldg(indptr + v), end = __ldg(indptr + v + 1); e < end; ++e) {
-        const uint32_t x = __ldg(indices + e);
-        const uint32_t d = (uint32_t)(__ldg(indptr + x + 1) - __ldg(indptr + x));
-        best = min(best, max(d, 1u));  // a dead end weighs like a leaf
-    }
-    out[v] = best;
-}
-
-cudaError_t launch_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n,
-                                        uint32_t *out, cudaStream_t stream) {
-    min_neighbour_degree_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(indptr, indices, n, out);
-    return cudaGetLastError();
-}
-
-__device__ __forceinline__ unsigned long long scaled_threshold(unsigned long long thr, uint32_t bound) {
-    return thr >= 4294967296ull ? ((unsigned long long)bound << 32) : thr * bound;
-}
-
-// General walks (normalize_by_degree and / or typed walks): every transition is a trial loop with
-// ONE Philox block per trial (tag 7): x proposal, z node-type test, w edge-type test, y p/q test
-// with the degree normalisation folded in.  Independent words => the acceptance probability is
-// the product of the three ratios.  Cheap tests first; see oracle/walks.c:walks_general.
+// Typed walks (change_node_type_weight / change_edge_type_weight, .../node2vec_skipgram.py:72-77):
+// every transition is a trial loop with ONE Philox block per trial (tag 7): x proposal, z
+// node-type test, w edge-type test, y p/q test.  Independent words => the acceptance probability
+// is the product of the three ratios.  Cheap tests first; see oracle/walks.c:walks_general.
+// (normalize_by_degree needs no kernel: it is folded into the proposal table at load.)
 template <bool VEC, bool WEIGHTED>
 __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -431,7 +403,6 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
                     if (deg == 0) {
                         alive = false;
                     } else {
-                        const uint32_t bound = p.mindeg ? __ldg(p.mindeg + cur) : 1u;
                         const uint32_t cur_type = use_nt ? __ldg(p.node_types + cur) : 0u;
                         uint32_t trial = 0;
                         int64_t e = off;
@@ -446,23 +417,18 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
                                 accept = rnd.z < p.q_node[__ldg(p.node_types + next) != cur_type ? 1 : 0];
                             if (accept && use_et && t > 1)
                                 accept = rnd.w < p.q_edge[__ldg(p.edge_types + e) != prev_etype ? 1 : 0];
-                            if (accept) {
-                                uint32_t next_deg = 1u;
-                                if (p.mindeg)
-                                    next_deg = max((uint32_t)(__ldg(p.indptr + next + 1) - __ldg(p.indptr + next)), 1u);
-                                const unsigned long long lhs = (unsigned long long)rnd.y * next_deg;
-                                if (t == 1) {
-                                    accept = lhs < scaled_threshold(4294967296ull, bound);
-                                } else if (next == prev) {
-                                    accept = lhs < scaled_threshold(p.thr_return, bound);
-                                } else if (lhs < scaled_threshold(thr_lo, bound)) {
+                            if (accept && t > 1) {
+                                const unsigned long long lhs = rnd.y;
+                                if (next == prev) {
+                                    accept = lhs < p.thr_return;
+                                } else if (lhs < thr_lo) {
                                     accept = true;
-                                } else if (lhs >= scaled_threshold(thr_hi, bound)) {
+                                } else if (lhs >= thr_hi) {
                                     accept = false;
                                 } else {
                                     ++n_searches;
                                     const bool common = row_contains(p.indices + prev_off, prev_deg, next);
-                                    accept = lhs < scaled_threshold(common ? p.thr_common : p.thr_explore, bound);
+                                    accept = lhs < (common ? p.thr_common : p.thr_explore);
                                 }
                             }
                             if (accept) break;
@@ -561,7 +527,7 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     const bool weighted = p.cdf != nullptr;
     const bool typed = (p.node_types && p.q_node[0] != p.q_node[1]) ||
                        (p.edge_types && p.q_edge[0] != p.q_edge[1]);
-    if (p.mindeg || typed) {  // normalize_by_degree / typed walks: one trial loop per transition
+    if (typed) {  // typed walks: one trial loop per transition
         if (vec) { if (weighted) walk_general_kernel<true, true><<<grid, block, 0, stream>>>(p);
                    else walk_general_kernel<true, false><<<grid, block, 0, stream>>>(p); }
         else { if (weighted) walk_general_kernel<false, true><<<grid, block, 0, stream>>>(p);

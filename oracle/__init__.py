@@ -88,13 +88,8 @@ def lib():
         l.orc_walks_weighted.restype = ctypes.c_int
         l.orc_walks_weighted.argtypes = [P(ctypes.c_int64), P(u32), P(u32), u64, P(u32), u64, u64, u64,
                                          u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
-        l.orc_min_neighbour_degree.restype = ctypes.c_int
-        l.orc_min_neighbour_degree.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32)]
-        l.orc_walks_full.restype = ctypes.c_int
-        l.orc_walks_full.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), u64, P(u32), u64, u64, u64,
-                                     u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
         l.orc_walks_typed.restype = ctypes.c_int
-        l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), P(u32), f32, f32,
+        l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), f32, f32,
                                       u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, P(u32),
                                       P(WalkCounters)]
         l.orc_philox_range.restype = None
@@ -177,14 +172,14 @@ def edge_cdf(indptr, weights) -> np.ndarray:
     return cdf
 
 
-def min_neighbour_degree(indptr, indices) -> np.ndarray:
+def degree_normalised_weights(indptr, indices, weights=None) -> np.ndarray:
+    """normalize_by_degree (.../node2vec_skipgram.py:94-96): the weight of v -> x divided by
+    max(deg(x), 1), in float32 (a single IEEE division per edge)."""
     indptr, indices = _csr(indptr, indices)
-    out = np.empty(indptr.shape[0] - 1, dtype=np.uint32)
-    rc = lib().orc_min_neighbour_degree(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
-                                        indptr.shape[0] - 1, _ptr(out, ctypes.c_uint32))
-    if rc != 0:
-        raise ValueError(f"orc_min_neighbour_degree failed with status {rc}")
-    return out
+    degrees = np.maximum(np.diff(indptr), 1).astype(np.float32)
+    base = np.ones(indices.shape[0], dtype=np.float32) if weights is None else \
+        np.ascontiguousarray(weights, dtype=np.float32)
+    return (base / degrees[indices]).astype(np.float32)
 
 
 def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length: int,
@@ -194,8 +189,9 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
           change_node_type_weight: float = 1.0,
           change_edge_type_weight: float = 1.0) -> Tuple[np.ndarray, dict]:
     indptr, indices = _csr(indptr, indices)
+    if normalize_by_degree:
+        weights = degree_normalised_weights(indptr, indices, weights)
     cdf = None if weights is None else edge_cdf(indptr, weights)
-    mindeg = min_neighbour_degree(indptr, indices) if normalize_by_degree else None
     n = indptr.shape[0] - 1
     if srcs is None:
         srcs = sources(indptr)
@@ -209,8 +205,7 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
         edge_types = np.ascontiguousarray(edge_types, dtype=np.uint32)
         assert edge_types.shape[0] == indices.shape[0]
     rc = lib().orc_walks_typed(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
-                               _ptr(cdf, ctypes.c_uint32), _ptr(mindeg, ctypes.c_uint32),
-                               _ptr(node_types, ctypes.c_uint32), _ptr(edge_types, ctypes.c_uint32),
+                               _ptr(cdf, ctypes.c_uint32), _ptr(node_types, ctypes.c_uint32), _ptr(edge_types, ctypes.c_uint32),
                                change_node_type_weight, change_edge_type_weight, n,
                                _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
                                walk_id_stride, walk_length, return_weight, explore_weight,

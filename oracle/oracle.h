@@ -68,21 +68,12 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
                        float return_weight, float explore_weight, uint32_t *out,
                        orc_walk_counters *counters);
 
-/* smallest degree among the neighbours of every node (0xFFFFFFFF for a node without any) */
-int orc_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n, uint32_t *out);
-
-/* orc_walks_weighted plus normalize_by_degree (mindeg from orc_min_neighbour_degree; NULL: off) */
-int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                   const uint32_t *mindeg, uint64_t n, const uint32_t *sources, uint64_t n_src,
-                   uint64_t seed, uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
-                   uint32_t walk_length, float return_weight, float explore_weight, uint32_t *out,
-                   orc_walk_counters *counters);
-
-/* orc_walks_full plus typed walks: node_types[n] / edge_types[nnz] (NULL: untyped) and the
- * weights multiplied in when the node type / the edge type changes */
+/* orc_walks_weighted plus typed walks: node_types[n] / edge_types[nnz] (NULL: untyped) and the
+ * weights multiplied in when the node type / the edge type changes.  normalize_by_degree is a
+ * property of the proposal table: build `cdf` over weight / max(deg(destination), 1). */
 void orc_type_thresholds(float change_weight, uint64_t q[2]);
 int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                    const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                    const uint32_t *node_types, const uint32_t *edge_types,
                     float change_node_type_weight, float change_edge_type_weight, uint64_t n,
                     const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                     uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,

@@ -117,6 +117,12 @@ static uint32_t propose(const uint32_t *cdf_row, uint32_t deg, uint32_t r) {
     return lo < deg ? lo : deg - 1;
 }
 
+static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+                       const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                       uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                       float return_weight, float explore_weight, uint32_t *out,
+                       orc_walk_counters *counters);
+
 int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const uint32_t *sources,
               uint64_t n_src, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
               uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
@@ -130,45 +136,27 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
                        orc_walk_counters *counters) {
-    return orc_walks_full(indptr, indices, cdf, NULL, n, sources, n_src, seed, first_walk, n_walks,
-                          walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+    return walks_plain(indptr, indices, cdf, n, sources, n_src, seed, first_walk, n_walks,
+                       walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
 }
 
 /*
- * `normalize_by_degree` ("Whether to normalize the random walk by the node degree of the
- * destination node degrees", .../node2vec_skipgram.py:94-96): the transition weight of v -> x is
- * divided by deg(x).  Rejection sampling needs a bound of 1 / deg(x) over N(v): the smallest
- * neighbour degree mindeg[v], one value per node computed at load.
- */
-int orc_min_neighbour_degree(const int64_t *indptr, const uint32_t *indices, uint64_t n, uint32_t *out) {
-    if (!indptr || !indices || !out) return -1;
-    for (uint64_t v = 0; v < n; ++v) {
-        uint32_t best = 0xFFFFFFFFu;
-        for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
-            const uint32_t x = indices[e];
-            uint64_t d = (uint64_t)(indptr[x + 1] - indptr[x]);
-            if (d == 0) d = 1; /* a dead end weighs like a leaf: 1 / max(deg, 1) */
-            if (d < best) best = (uint32_t)d;
-        }
-        out[v] = best;
-    }
-    return 0;
-}
-
-/*
- * General walks: normalize_by_degree and / or typed walks ("next" row f-2,
- * .../node2vec_skipgram.py:72-77, 94-96).  Every transition, the first one included, is a trial
- * loop on its own Philox stream (tag 7, ONE block per trial: c2 = t - 1, c3 = trial):
+ * Typed walks ("next" row f-2, .../node2vec_skipgram.py:72-77).  Every transition, the first one
+ * included, is a trial loop on its own Philox stream (tag 7, ONE block per trial: c2 = t - 1,
+ * c3 = trial):
  *   word 0  proposal (uniform, or proportional to the edge weight);
  *   word 2  node-type test: the weight of v -> x is multiplied by change_node_type_weight when
  *           type(x) != type(v); accept iff r2 < q_node[changed];
  *   word 3  edge-type test (from the second transition on): multiplied by
  *           change_edge_type_weight when type(v -> x) != type(prev -> v); accept iff r3 < q_edge[changed];
- *   word 1  p/q test, with normalize_by_degree folded in: accept iff
- *           r1 * max(deg(x), 1) < thr[class] * mindeg[v]   (thr = 2^32 for the first transition).
+ *   word 1  p/q test: accept iff r1 < thr[class]   (thr = 2^32 for the first transition).
  * q[changed] = floor(w / max(1, w) * 2^32), q[same] = floor(1 / max(1, w) * 2^32).  The three
  * tests use independent words, so the acceptance probability is the product of the three
- * ratios and the walk follows  weight * bias_pq * type factors / deg(x)  exactly (up to 2^-32).
+ * ratios and the walk follows  weight * bias_pq * type factors  exactly (up to 2^-32).
+ * `normalize_by_degree` (.../node2vec_skipgram.py:94-96: the transition weight divided by the
+ * degree of the destination) is not a rejection test at all: it is folded into the proposal,
+ * whose per-edge table is built over  weight / max(deg(destination), 1)  (orc_edge_cdf), so it
+ * costs no extra trials however skewed the degrees are.
  * Integer arithmetic only; the cheap tests come first and the adjacency search is counted only
  * when it is reached and undecided.
  */
@@ -182,7 +170,7 @@ void orc_type_thresholds(float change_weight, uint64_t q[2]) {
 }
 
 static int walks_general(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                         const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                         const uint32_t *node_types, const uint32_t *edge_types,
                          float change_node_type_weight, float change_edge_type_weight,
                          const uint32_t *sources, uint64_t n_src, uint64_t seed,
                          uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
@@ -212,7 +200,6 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
             const int64_t off = indptr[cur];
             const uint64_t deg = (uint64_t)(indptr[cur + 1] - off);
             if (deg == 0) break;
-            const unsigned __int128 bound = mindeg ? mindeg[cur] : 1u;
             uint32_t next, trial = 0;
             int64_t e;
             for (;;) {
@@ -227,12 +214,7 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
                 if (accept && use_et && t > 1 && (uint64_t)rnd[3] >= qe[edge_types[e] != prev_etype])
                     accept = 0;
                 if (accept) {
-                    uint64_t next_deg = 1;
-                    if (mindeg) {
-                        next_deg = (uint64_t)(indptr[next + 1] - indptr[next]);
-                        if (next_deg == 0) next_deg = 1;
-                    }
-                    const unsigned __int128 lhs = (unsigned __int128)rnd[1] * next_deg;
+                    const uint64_t lhs = rnd[1];
                     uint64_t limit = 4294967296ull; /* first transition: no p/q bias */
                     if (t > 1) {
                         int cls;
@@ -242,14 +224,14 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
                             const int64_t poff = indptr[prev];
                             const uint64_t pdeg = (uint64_t)(indptr[prev + 1] - poff);
                             cls = row_contains(indices + poff, pdeg, next) ? 1 : 2;
-                            if (lhs >= thr_lo * bound && lhs < thr_hi * bound) {
+                            if (lhs >= thr_lo && lhs < thr_hi) {
                                 ++n_searches;
                                 n_probe += probe_sectors(pdeg);
                             }
                         }
                         limit = thr[cls];
                     }
-                    accept = lhs < limit * bound;
+                    accept = lhs < limit;
                 }
                 if (accept) break;
                 ++trial;
@@ -271,7 +253,7 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
 }
 
 int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                    const uint32_t *mindeg, const uint32_t *node_types, const uint32_t *edge_types,
+                    const uint32_t *node_types, const uint32_t *edge_types,
                     float change_node_type_weight, float change_edge_type_weight, uint64_t n,
                     const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                     uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
@@ -280,24 +262,20 @@ int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32
     if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
     const int typed = (node_types && change_node_type_weight != 1.0f) ||
                       (edge_types && change_edge_type_weight != 1.0f);
-    if (!mindeg && !typed)
-        return orc_walks_full(indptr, indices, cdf, NULL, n, sources, n_src, seed, first_walk, n_walks,
-                              walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
-    return walks_general(indptr, indices, cdf, mindeg, node_types, edge_types, change_node_type_weight,
+    if (!typed)
+        return orc_walks_weighted(indptr, indices, cdf, n, sources, n_src, seed, first_walk, n_walks,
+                                  walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
+    return walks_general(indptr, indices, cdf, node_types, edge_types, change_node_type_weight,
                          change_edge_type_weight, sources, n_src, seed, first_walk, n_walks,
                          walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
 }
 
-int orc_walks_full(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
-                   const uint32_t *mindeg, uint64_t n, const uint32_t *sources, uint64_t n_src,
-                   uint64_t seed, uint64_t first_walk, uint64_t n_walks, uint64_t walk_id_stride,
-                   uint32_t walk_length, float return_weight, float explore_weight, uint32_t *out,
-                   orc_walk_counters *counters) {
+static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+                       const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
+                       uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
+                       float return_weight, float explore_weight, uint32_t *out,
+                       orc_walk_counters *counters) {
     if (!indptr || !indices || !sources || !out || n_src == 0 || walk_length == 0) return -1;
-    if (mindeg)
-        return walks_general(indptr, indices, cdf, mindeg, NULL, NULL, 1.0f, 1.0f, sources, n_src, seed,
-                             first_walk, n_walks, walk_id_stride, walk_length, return_weight,
-                             explore_weight, out, counters);
     (void)n;
     const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
     const int second_order = !(return_weight == 1.0f && explore_weight == 1.0f);

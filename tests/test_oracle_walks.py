@@ -241,17 +241,14 @@ def test_unit_weights_reproduce_nothing_else_than_valid_walks(small_ppi_weighted
 
 
 # ---- normalize_by_degree: transition weight / deg(destination) (node2vec_skipgram.py:94-96) ----
-def test_min_neighbour_degree():
+def test_degree_normalised_weights():
     graph = dense_test_graph()
-    degrees = np.diff(graph.indptr)
-    expected = np.array([degrees[neighbours(graph, v)].min() for v in range(12)], dtype=np.uint32)
-    assert np.array_equal(oracle.min_neighbour_degree(graph.indptr, graph.indices), expected)
-    dead = tiny_graphs()["directed_dead_end"]
-    got = oracle.min_neighbour_degree(dead.indptr, dead.indices)
-    deg = np.maximum(np.diff(dead.indptr), 1)
-    for v in range(dead.get_number_of_nodes()):
-        nv = neighbours(dead, v)
-        assert got[v] == (deg[nv].min() if len(nv) else 0xFFFFFFFF)
+    degrees = np.diff(graph.indptr).astype(np.float32)
+    got = oracle.degree_normalised_weights(graph.indptr, graph.indices)
+    assert got.dtype == np.float32 and np.array_equal(got, np.float32(1.0) / degrees[graph.indices])
+    dead = tiny_graphs()["directed_dead_end"]           # a dead end weighs like a leaf
+    got = oracle.degree_normalised_weights(dead.indptr, dead.indices, np.full(dead.indices.shape[0], 3.0))
+    assert np.array_equal(got, np.float32(3.0) / np.maximum(np.diff(dead.indptr), 1).astype(np.float32)[dead.indices])
 
 
 @pytest.mark.parametrize("rw,ew", [(1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
@@ -264,7 +261,9 @@ def test_normalize_by_degree_matches_analytic_pmf(rw, ew, weighted):
     degrees = np.diff(graph.indptr).astype(np.float64)
     walks, counters = oracle.walks(graph.indptr, graph.indices, 31, 0, 480_000, 3, rw, ew,
                                    weights=weights, normalize_by_degree=True)
-    assert counters["capped"] == 0 and counters["first_order"] == 0
+    assert counters["capped"] == 0
+    if (rw, ew) == (1.0, 1.0):  # folded into the proposal: no trial at all for a first-order walk
+        assert counters["trials"] == 0
     for v in (0, 4, 2):
         lo, hi = graph.indptr[v], graph.indptr[v + 1]
         nxt = walks[walks[:, 0] == v, 1]
