@@ -48,6 +48,9 @@ def timed(stream, fn, repeat=3):
     return float(np.median(out))
 
 
+ONLY = os.environ.get("B2E_ROWS", "")  # e.g. B2E_ROWS=glove restricts the run (profiling)
+
+
 def main():
     torch.cuda.set_device(0)
     device = torch.device("cuda", 0)
@@ -70,7 +73,7 @@ def main():
         "weighted + normalized + typed": dict(weights=True, normalize_by_degree=True, change_node_type_weight=3.0,
                                               change_edge_type_weight=0.3, types=True),
     }
-    for name, opt in variants.items():
+    for name, opt in ({} if ONLY else variants).items():
         opt = dict(opt)
         use_weights, use_types = opt.pop("weights", False), opt.pop("types", False)
         with Engine("SkipGram", embedding_size=D, walk_length=L, window_size=W, iterations=1,
@@ -100,7 +103,7 @@ def main():
         "Walklets SkipGram scale 2": dict(model="SkipGram", walklet_scale=2, window_size=1),
         "Walklets CBOW scale 3": dict(model="CBOW", walklet_scale=3, window_size=1),
     }
-    for name, opt in sgd.items():
+    for name, opt in ({} if ONLY else sgd).items():
         opt = dict(opt)
         model = opt.pop("model")
         kw = dict(embedding_size=D, walk_length=L, window_size=W, iterations=1, return_weight=2.0,
@@ -148,6 +151,8 @@ def main():
         emit(row="f-3 GloVe SGD", triples=triples, ms_per_pass=ms, triples_per_s=triples / ms * 1e3,
              algorithmic_gbs=bytes_ / ms / 1e6, frac=bytes_ / ms / 1e6 / PEAK)
 
+    if ONLY:
+        return
     # ---- (f)-4: edge embeddings and the perceptron on resident features ----
     features = rng.normal(size=(n, D)).astype(np.float32)
     m = 4_000_000
