@@ -717,7 +717,7 @@ extern "C" int b2e_glove_train(b2e_handle *h, float learning_rate) {
                                                        : std::max<uint64_t>(16, h->n / 16);
     CUDA_TRY(b2e::glove_train(h->glove, h->n, h->row_stride, c.embedding_size, c.glove_alpha, c.clipping_value,
                               learning_rate, h->d_t0, h->d_t1, h->d_counters, c.deterministic != 0,
-                              h->sm_count, max_warps, h->train_stream));
+                              h->sm_count, max_warps, h->variant, h->train_stream));
     if (h->glove.n_triples) ++h->launches;
     return B2E_OK;
 }

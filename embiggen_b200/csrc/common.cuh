@@ -106,7 +106,8 @@ cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_
 cudaError_t glove_finalise(GloveState &g, uint64_t n, cudaStream_t stream);
 cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, uint32_t embedding_size,
                         float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
-                        bool deterministic, int sm_count, uint64_t max_warps, cudaStream_t stream);
+                        bool deterministic, int sm_count, uint64_t max_warps, uint32_t variant,
+                        cudaStream_t stream);
 void glove_free(GloveState &g);
 
 cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,

@@ -97,6 +97,15 @@ struct GloveParams {
     DeviceCounters *counters;
 };
 
+// weight = (x / x_max)^alpha and ln x depend on the count alone: lane s computes them for triple
+// base + s of the batch (once, instead of 32 times) and the warp reads them back by shuffle
+__device__ __forceinline__ void count_terms(const GloveParams &p, uint64_t base, uint64_t end, uint32_t lane,
+                                            float &weight, float &log_count) {
+    const float x = base + lane < end ? (float)__ldg(p.counts + base + lane) : 1.0f;
+    weight = exp_det(__fmul_rn(p.alpha, log_det(__fdiv_rn(x, p.max_count))));
+    log_count = log_det(x);
+}
+
 // Single-warp launch (cfg.deterministic): centres in ascending order, the operation sequence of
 // oracle/glove.c.  The production launch is glove_tile_kernel below.
 template <int CH, int NT>
@@ -116,22 +125,22 @@ __global__ void __launch_bounds__(32) glove_train_kernel(const GloveParams p) {
         load_row<CH>(crow, p.chunks, lane, h);
         for (uint64_t base = begin; base < end; base += NT) {
             float4 rows[NT][CH];
-            uint32_t ids[NT], cnt[NT];
+            uint32_t ids[NT];
 #pragma unroll
             for (int s = 0; s < NT; ++s) {  // the contexts of a centre are distinct rows
                 const bool on = base + s < end;
                 ids[s] = on ? (uint32_t)__ldg(p.keys + base + s) : PAD;
-                cnt[s] = on ? __ldg(p.counts + base + s) : 1u;
                 if (on) load_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
             }
+            float my_weight, my_log;  // lane s < NT holds the two count-only terms of triple s
+            count_terms(p, base, end, lane, my_weight, my_log);
 #pragma unroll
             for (int s = 0; s < NT; ++s) {
                 if (ids[s] == PAD) continue;
                 const float f = warp_dot<CH>(h, rows[s]);
                 if (fabsf(f) > p.clip) continue;
-                const float x = (float)cnt[s];
-                const float weight = exp_det(__fmul_rn(p.alpha, log_det(__fdiv_rn(x, p.max_count))));
-                const float diff = __fsub_rn(f, log_det(x));
+                const float weight = __shfl_sync(FULL, my_weight, s);
+                const float diff = __fsub_rn(f, __shfl_sync(FULL, my_log, s));
                 const float g = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, weight), diff), p.lr);
                 if (lane == 0) loss_acc += weight * diff * diff;
                 ++trained;
@@ -199,16 +208,17 @@ __global__ void __launch_bounds__(256) glove_tile_kernel(const GloveParams p, ui
         float4 h[CH], h0[CH];
         for (uint64_t base = begin; base < end; base += NT) {
             float4 rows[NT][CH];
-            uint32_t ids[NT], cnt[NT], cen[NT];
+            uint32_t ids[NT], cen[NT];
 #pragma unroll
             for (int s = 0; s < NT; ++s) {
                 const bool on = base + s < end;
                 const unsigned long long key = on ? __ldg(p.keys + base + s) : ~0ull;
                 ids[s] = on ? (uint32_t)key : PAD;
                 cen[s] = (uint32_t)(key >> 32);
-                cnt[s] = on ? __ldg(p.counts + base + s) : 1u;
                 if (on) load_row<CH>(p.t1 + (uint64_t)ids[s] * p.row_stride, p.chunks, lane, rows[s]);
             }
+            float my_weight, my_log;
+            count_terms(p, base, end, lane, my_weight, my_log);
 #pragma unroll
             for (int s = 0; s < NT; ++s) {
                 if (ids[s] == PAD) continue;
@@ -221,9 +231,8 @@ __global__ void __launch_bounds__(256) glove_tile_kernel(const GloveParams p, ui
                 }
                 const float f = warp_dot<CH>(h, rows[s]);
                 if (fabsf(f) > p.clip) continue;
-                const float x = (float)cnt[s];
-                const float weight = exp_det(__fmul_rn(p.alpha, log_det(__fdiv_rn(x, p.max_count))));
-                const float diff = __fsub_rn(f, log_det(x));
+                const float weight = __shfl_sync(FULL, my_weight, s);
+                const float diff = __fsub_rn(f, __shfl_sync(FULL, my_log, s));
                 const float g = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, weight), diff), p.lr);
                 if (lane == 0) loss_acc += weight * diff * diff;
                 ++trained;
@@ -389,7 +398,8 @@ cudaError_t glove_finalise(GloveState &g, uint64_t n, cudaStream_t stream) {
 
 cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, uint32_t embedding_size,
                         float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
-                        bool deterministic, int sm_count, uint64_t max_warps, cudaStream_t stream) {
+                        bool deterministic, int sm_count, uint64_t max_warps, uint32_t variant,
+                        cudaStream_t stream) {
     if (g.n_triples == 0) return cudaSuccess;
     GloveParams p;
     p.keys = g.d_keys;
@@ -405,7 +415,11 @@ cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, ui
     p.t0 = t0;
     p.t1 = t1;
     p.counters = counters;
-    if (p.chunks <= 32) return launch_glove_one<1, 8>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
+    // 4 rows per batch: 64 registers, 4 CTAs per SM -- 6.0 G triples/s against 3.8 G with 8 rows
+    // (95 registers, 2 CTAs per SM) on R-MAT 1 M / 16 M; B2E_VARIANT=1 keeps the larger batch
+    if (p.chunks <= 32 && variant == 1 && !deterministic)
+        return launch_glove_one<1, 8>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
+    if (p.chunks <= 32) return launch_glove_one<1, 4>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
     if (p.chunks <= 64) return launch_glove_one<2, 4>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
     if (p.chunks <= 128) return launch_glove_one<4, 2>(p, g.n_triples, deterministic, sm_count, max_warps, stream);
     return cudaErrorInvalidValue;
