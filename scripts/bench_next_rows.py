@@ -170,6 +170,7 @@ def main():
                  d2h_gbs=out.nbytes / seconds / 1e9)
         model = PerceptronEdgePredictionB200(edge_embeddings="Hadamard", number_of_epochs=2,
                                              number_of_edges_per_mini_batch=4096)
+        model.fit(graph, resident)  # first call: module load, allocator warm-up
         t0 = time.perf_counter()
         model.fit(graph, resident)
         seconds = time.perf_counter() - t0

@@ -9,7 +9,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from embiggen_b200.edge_prediction import DeviceFeatures, PerceptronEdgePredictionB200  # noqa: E402
 from embiggen_b200.graph_gpu import rmat_gpu  # noqa: E402
 
-graph = rmat_gpu(18, 2_000_000, n=200_000, seed=42, device=0)
+if os.environ.get("GRAPH") == "big":
+    graph = rmat_gpu(20, 16_000_000, n=1_000_000, seed=42, device=0)
+else:
+    graph = rmat_gpu(18, 2_000_000, n=200_000, seed=42, device=0)
 nnz = graph.indices.shape[0]
 features = np.random.default_rng(0).normal(size=(graph.get_number_of_nodes(), 100)).astype(np.float32)
 with DeviceFeatures(features) as resident:
