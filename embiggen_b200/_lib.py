@@ -57,6 +57,8 @@ class B2EPerceptronConfig(ctypes.Structure):
         ("struct_size", ctypes.c_uint32),
         ("n_methods", ctypes.c_uint32),
         ("methods", ctypes.c_uint32 * 12),
+        ("n_edge_features", ctypes.c_uint32),
+        ("edge_features", ctypes.c_uint32 * 5),
         ("number_of_epochs", ctypes.c_uint32),
         ("number_of_edges_per_mini_batch", ctypes.c_uint32),
         ("learning_rate", ctypes.c_float),
@@ -120,12 +122,15 @@ SIGNATURES = {
     "b2e_features_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _U64, _U32, _P(_H)]),
     "b2e_features_from_handle": (ctypes.c_int, [_H, ctypes.c_int, _P(_H)]),
     "b2e_features_destroy": (None, [_H]),
-    "b2e_edge_embedding_size": (ctypes.c_int, [_U32, ctypes.c_void_p, _U32, _P(_U32)]),
+    "b2e_edge_embedding_size": (ctypes.c_int, [_U32, ctypes.c_void_p, _U32, ctypes.c_void_p, _U32, _P(_U32)]),
+    "b2e_edge_metrics": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64, ctypes.c_void_p,
+                                        ctypes.c_void_p, _U64, ctypes.c_void_p, _U32, ctypes.c_void_p]),
     "b2e_edge_embedding": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, ctypes.c_void_p, _U32,
                                           ctypes.c_void_p]),
     "b2e_perceptron_fit": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
                                           _P(B2EPerceptronConfig), _U64, ctypes.c_void_p, ctypes.c_void_p]),
-    "b2e_perceptron_predict": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, ctypes.c_void_p, _U32,
+    "b2e_perceptron_predict": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64, ctypes.c_void_p,
+                                              ctypes.c_void_p, _U64, ctypes.c_void_p, _U32, ctypes.c_void_p, _U32,
                                               ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_csr_from_edges": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _P(_U64)]),

@@ -29,11 +29,23 @@ constexpr uint32_t TAG_EDGE_SAMPLE = 8u;
 constexpr uint32_t TAG_PERCEPTRON_INIT = 9u;
 constexpr int MAX_METHODS = 12;
 
+constexpr int MAX_METRICS = 5;
+
 struct MethodList {
     uint32_t n;
     uint32_t id[MAX_METHODS];
     uint32_t offset[MAX_METHODS];  // first feature of the method in the concatenation
+    uint32_t n_metrics;            // topological edge features, after the edge embeddings
+    uint32_t metric_id[MAX_METRICS];
+    uint32_t metric_offset[MAX_METRICS];
     uint32_t size;                 // total number of features
+};
+
+// what the topological edge features read: the support graph's sorted CSR
+struct GraphView {
+    const int64_t *indptr;
+    const uint32_t *indices;
+    float inv_max_degree;
 };
 
 __host__ __device__ __forceinline__ uint32_t method_width(uint32_t id, uint32_t dim) {
@@ -78,6 +90,61 @@ __device__ __forceinline__ void scalar_features(const float *__restrict__ a, con
     float norm = sqrtf(aa) * sqrtf(bb);
     if (norm < 1e-6f) norm = 1e-6f;
     cosine = ab / norm;
+}
+
+// ---- topological edge features (perceptron.py:38-46): one pass over the common neighbours ----
+// values: [0] deg(u) / max degree, [1] deg(v) / max degree, [2] Adamic-Adar, [3] Jaccard,
+// [4] resource allocation index, [5] preferential attachment (normalised by max degree^2).
+// Lanes stride over the shorter row and bisect the longer one.
+__device__ __forceinline__ void edge_metric_values(const GraphView &g, uint32_t u, uint32_t v, uint32_t lane,
+                                                   float (&out)[6]) {
+    int64_t a_off = __ldg(g.indptr + u), b_off = __ldg(g.indptr + v);
+    uint32_t a_len = (uint32_t)(__ldg(g.indptr + u + 1) - a_off), b_len = (uint32_t)(__ldg(g.indptr + v + 1) - b_off);
+    const float du = (float)a_len, dv = (float)b_len;
+    if (a_len > b_len) {
+        const int64_t t = a_off; a_off = b_off; b_off = t;
+        const uint32_t l = a_len; a_len = b_len; b_len = l;
+    }
+    float common = 0.f, adamic_adar = 0.f, resource = 0.f;
+    for (uint32_t i = lane; i < a_len; i += 32u) {
+        const uint32_t x = __ldg(g.indices + a_off + i);
+        uint32_t lo = 0, hi = b_len;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(g.indices + b_off + mid) < x) lo = mid + 1; else hi = mid;
+        }
+        if (lo < b_len && __ldg(g.indices + b_off + lo) == x) {
+            const float dx = (float)(uint32_t)(__ldg(g.indptr + x + 1) - __ldg(g.indptr + x));
+            common += 1.f;
+            if (dx > 1.f) adamic_adar += 1.f / logf(dx);
+            if (dx > 0.f) resource += 1.f / dx;
+        }
+    }
+    common = warp_sum(common);
+    adamic_adar = warp_sum(adamic_adar);
+    resource = warp_sum(resource);
+    const float uni = du + dv - common;
+    out[0] = du * g.inv_max_degree;
+    out[1] = dv * g.inv_max_degree;
+    out[2] = adamic_adar;
+    out[3] = uni > 0.f ? common / uni : 0.f;
+    out[4] = resource;
+    out[5] = (du * g.inv_max_degree) * (dv * g.inv_max_degree);
+}
+
+__device__ __forceinline__ uint32_t metric_slot(uint32_t id) {  // first value of the metric in `out`
+    return id == B2E_EDGE_FEATURE_DEGREE ? 0u : id + 1u;
+}
+
+// lane 0 only: the share of <w, f> that comes from the topological features
+__device__ __forceinline__ float metrics_dot(const MethodList &m, const float *w, const float (&values)[6]) {
+    float total = 0.f;
+    for (uint32_t k = 0; k < m.n_metrics; ++k) {
+        const uint32_t slot = metric_slot(m.metric_id[k]);
+        total = fmaf(w[m.metric_offset[k]], values[slot], total);
+        if (m.metric_id[k] == B2E_EDGE_FEATURE_DEGREE) total = fmaf(w[m.metric_offset[k] + 1], values[1], total);
+    }
+    return total;
 }
 
 __device__ __forceinline__ bool needs_scalars(const MethodList &m) {
@@ -140,11 +207,32 @@ __device__ __forceinline__ float forward_dot(const float *__restrict__ a, const 
 
 __device__ __forceinline__ float sigmoidf(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
+// ---- the topological features of an edge list, materialised (graph.get_*_scores) ----
+__global__ void __launch_bounds__(256) edge_metrics_kernel(GraphView g, const uint32_t *__restrict__ src,
+                                                           const uint32_t *__restrict__ dst, uint64_t m,
+                                                           MethodList methods, float *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < m; e += warps) {
+        float values[6];
+        edge_metric_values(g, __ldg(src + e), __ldg(dst + e), lane, values);
+        if (lane == 0) {
+            float *row = out + e * methods.size;
+            for (uint32_t k = 0; k < methods.n_metrics; ++k) {
+                const uint32_t slot = metric_slot(methods.metric_id[k]);
+                row[methods.metric_offset[k]] = values[slot];
+                if (methods.metric_id[k] == B2E_EDGE_FEATURE_DEGREE) row[methods.metric_offset[k] + 1] = values[1];
+            }
+        }
+    }
+}
+
 // ---- predict_proba ----
 __global__ void __launch_bounds__(256) perceptron_predict_kernel(const float *__restrict__ features, uint64_t pitch,
                                                                  uint32_t dim, const uint32_t *__restrict__ src,
                                                                  const uint32_t *__restrict__ dst, uint64_t m,
-                                                                 MethodList methods, const float *__restrict__ params,
+                                                                 MethodList methods, GraphView graph,
+                                                                 const float *__restrict__ params,
                                                                  float *__restrict__ scores) {
     extern __shared__ float w[];  // size weights + bias
     for (uint32_t j = threadIdx.x; j <= methods.size; j += blockDim.x) w[j] = params[j];
@@ -156,7 +244,12 @@ __global__ void __launch_bounds__(256) perceptron_predict_kernel(const float *__
         const float *b = features + (uint64_t)__ldg(dst + e) * pitch;
         float l2 = 0.f, cosine = 0.f;
         if (needs_scalars(methods)) scalar_features(a, b, dim, lane, l2, cosine);
-        const float z = forward_dot(a, b, dim, lane, methods, w, l2, cosine) + w[methods.size];
+        float z = forward_dot(a, b, dim, lane, methods, w, l2, cosine) + w[methods.size];
+        if (methods.n_metrics) {
+            float values[6];
+            edge_metric_values(graph, __ldg(src + e), __ldg(dst + e), lane, values);
+            z += metrics_dot(methods, w, values);  // meaningful on lane 0, which writes the score
+        }
         if (lane == 0) scores[e] = sigmoidf(z);
     }
 }
@@ -172,6 +265,7 @@ struct StepParams {
     uint64_t nnz;
     uint32_t seed_lo, seed_hi, step, batch;
     uint32_t scale_free, avoid_false_negatives;
+    float inv_max_degree;
     const float *params;  // size weights + bias
     float *grad;          // size + 1, accumulated with atomics, cleared by the Adam kernel
     double *loss;         // [0] loss sum, [1] valid samples (of the epoch)
@@ -219,13 +313,25 @@ __global__ void __launch_bounds__(256) perceptron_step_kernel(const StepParams p
         const float *b = p.features + (uint64_t)v * p.pitch;
         float l2 = 0.f, cosine = 0.f;
         if (needs_scalars(methods)) scalar_features(a, b, p.dim, lane, l2, cosine);
-        const float z = forward_dot(a, b, p.dim, lane, methods, w, l2, cosine) + w[methods.size];
+        float z = forward_dot(a, b, p.dim, lane, methods, w, l2, cosine) + w[methods.size];
+        float values[6];
+        if (methods.n_metrics) {
+            const GraphView graph = {p.indptr, p.indices, p.inv_max_degree};
+            edge_metric_values(graph, u, v, lane, values);
+            z = __shfl_sync(0xffffffffu, z + metrics_dot(methods, w, values), 0);
+        }
         const float prob = sigmoidf(z);
         const float delta = (prob - (positive ? 1.0f : 0.0f)) / (float)p.batch;
         if (lane == 0) {
             loss += -__logf((positive ? prob : 1.0f - prob) + 1e-12f);
             valid_count += 1.0f;
             atomicAdd(g + methods.size, delta);
+            for (uint32_t m = 0; m < methods.n_metrics; ++m) {
+                const uint32_t slot = metric_slot(methods.metric_id[m]);
+                atomicAdd(g + methods.metric_offset[m], delta * values[slot]);
+                if (methods.metric_id[m] == B2E_EDGE_FEATURE_DEGREE)
+                    atomicAdd(g + methods.metric_offset[m] + 1, delta * values[1]);
+            }
         }
         for (uint32_t m = 0; m < methods.n; ++m) {
             const uint32_t id = methods.id[m];
@@ -311,10 +417,14 @@ int b2e_set_error(int status, const std::string &message);  // b2e_api.cu
             return b2e_set_error(B2E_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-static int build_methods(const uint32_t *ids, uint32_t count, uint32_t dim, MethodList &out) {
-    if (!ids || count == 0 || count > MAX_METHODS)
-        return b2e_set_error(B2E_ERR_INVALID, "between 1 and 12 edge embedding methods are required");
+static int build_methods(const uint32_t *ids, uint32_t count, uint32_t dim, const uint32_t *metrics,
+                         uint32_t n_metrics, MethodList &out) {
+    if (count > MAX_METHODS || n_metrics > MAX_METRICS || (count && !ids) || (n_metrics && !metrics))
+        return b2e_set_error(B2E_ERR_INVALID, "at most 12 edge embedding methods and 5 edge features");
+    if (count + n_metrics == 0)
+        return b2e_set_error(B2E_ERR_INVALID, "at least one edge embedding method or edge feature is required");
     out.n = count;
+    out.n_metrics = n_metrics;
     out.size = 0;
     for (uint32_t k = 0; k < count; ++k) {
         if (ids[k] > B2E_EDGE_COSINE_SIMILARITY) return b2e_set_error(B2E_ERR_INVALID, "unknown edge embedding method");
@@ -322,10 +432,19 @@ static int build_methods(const uint32_t *ids, uint32_t count, uint32_t dim, Meth
         out.offset[k] = out.size;
         out.size += method_width(ids[k], dim);
     }
+    for (uint32_t k = 0; k < n_metrics; ++k) {
+        if (metrics[k] > B2E_EDGE_FEATURE_PREFERENTIAL_ATTACHMENT)
+            return b2e_set_error(B2E_ERR_INVALID, "unknown edge feature");
+        out.metric_id[k] = metrics[k];
+        out.metric_offset[k] = out.size;
+        out.size += metrics[k] == B2E_EDGE_FEATURE_DEGREE ? 2u : 1u;
+    }
     if ((out.size + 1) * 2 * sizeof(float) > 200 * 1024)
         return b2e_set_error(B2E_ERR_INVALID, "edge embedding too wide for the perceptron kernels");
     return B2E_OK;
 }
+
+
 
 struct DeviceArray {
     void *p = nullptr;
@@ -333,6 +452,31 @@ struct DeviceArray {
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
     template <typename T> T *as() { return static_cast<T *>(p); }
 };
+
+// the support graph of the topological features, uploaded for the duration of a call
+struct DeviceGraph {
+    DeviceArray indptr, indices;
+    GraphView view = {nullptr, nullptr, 0.f};
+    int upload(const int64_t *h_indptr, const uint32_t *h_indices, uint64_t n, uint64_t nnz) {
+        if (!h_indptr || (!h_indices && nnz) || (uint64_t)h_indptr[n] != nnz)
+            return b2e_set_error(B2E_ERR_INVALID, "the edge features need the support graph's CSR");
+        int64_t max_degree = 1;
+        for (uint64_t v = 0; v < n; ++v) max_degree = std::max(max_degree, h_indptr[v + 1] - h_indptr[v]);
+        EP_TRY(indptr.alloc((n + 1) * sizeof(int64_t)));
+        EP_TRY(indices.alloc(nnz * sizeof(uint32_t)));
+        EP_TRY(cudaMemcpy(indptr.p, h_indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        EP_TRY(cudaMemcpy(indices.p, h_indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        view.indptr = indptr.as<int64_t>();
+        view.indices = indices.as<uint32_t>();
+        view.inv_max_degree = 1.0f / (float)max_degree;
+        return B2E_OK;
+    }
+};
+
+static int select_device(const b2e_features *f) {
+    if (f) EP_TRY(cudaSetDevice(f->device));
+    return B2E_OK;
+}
 
 extern "C" int b2e_features_create(int device, const float *host, uint64_t n, uint32_t dim, b2e_features **out) {
     if (!host || !out || n == 0 || dim == 0) return b2e_set_error(B2E_ERR_INVALID, "null or empty node features");
@@ -378,18 +522,19 @@ extern "C" void b2e_features_destroy(b2e_features *f) {
     delete f;
 }
 
-extern "C" int b2e_edge_embedding_size(uint32_t dim, const uint32_t *methods, uint32_t n_methods, uint32_t *size) {
+extern "C" int b2e_edge_embedding_size(uint32_t dim, const uint32_t *methods, uint32_t n_methods,
+                                       const uint32_t *edge_features, uint32_t n_edge_features, uint32_t *size) {
     MethodList list;
     if (!size) return b2e_set_error(B2E_ERR_INVALID, "null argument");
-    if (int rc = build_methods(methods, n_methods, dim, list)) return rc;
+    if (int rc = build_methods(methods, n_methods, dim, edge_features, n_edge_features, list)) return rc;
     *size = list.size;
     return B2E_OK;
 }
 
-static int upload_edges(const b2e_features *f, const uint32_t *src, const uint32_t *dst, uint64_t m,
+static int upload_edges(uint64_t n, const uint32_t *src, const uint32_t *dst, uint64_t m,
                         DeviceArray &d_src, DeviceArray &d_dst) {
     for (uint64_t e = 0; e < m; ++e)
-        if (src[e] >= f->n || dst[e] >= f->n) return b2e_set_error(B2E_ERR_INVALID, "a node id is out of range");
+        if (src[e] >= n || dst[e] >= n) return b2e_set_error(B2E_ERR_INVALID, "a node id is out of range");
     EP_TRY(d_src.alloc(m * sizeof(uint32_t)));
     EP_TRY(d_dst.alloc(m * sizeof(uint32_t)));
     EP_TRY(cudaMemcpy(d_src.p, src, m * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -405,11 +550,12 @@ extern "C" int b2e_edge_embedding(const b2e_features *f, const uint32_t *src, co
                                   const uint32_t *methods, uint32_t n_methods, float *out) {
     if (!f || (m && (!src || !dst || !out))) return b2e_set_error(B2E_ERR_INVALID, "null argument");
     MethodList list;
-    if (int rc = build_methods(methods, n_methods, f->dim, list)) return rc;
+    if (n_methods == 0) return b2e_set_error(B2E_ERR_INVALID, "at least one edge embedding method is required");
+    if (int rc = build_methods(methods, n_methods, f->dim, nullptr, 0, list)) return rc;
     if (m == 0) return B2E_OK;
     EP_TRY(cudaSetDevice(f->device));
     DeviceArray d_src, d_dst, d_out;
-    if (int rc = upload_edges(f, src, dst, m, d_src, d_dst)) return rc;
+    if (int rc = upload_edges(f->n, src, dst, m, d_src, d_dst)) return rc;
     // the materialised embedding is produced in slabs so that it never needs more than 1 GiB
     const uint64_t slab = std::max<uint64_t>(1, (1ull << 28) / list.size);
     EP_TRY(d_out.alloc(std::min(slab, m) * list.size * sizeof(float)));
@@ -423,24 +569,50 @@ extern "C" int b2e_edge_embedding(const b2e_features *f, const uint32_t *src, co
     return B2E_OK;
 }
 
-extern "C" int b2e_perceptron_predict(const b2e_features *f, const uint32_t *src, const uint32_t *dst, uint64_t m,
-                                      const uint32_t *methods, uint32_t n_methods, const float *params,
-                                      float *scores) {
-    if (!f || !params || (m && (!src || !dst || !scores))) return b2e_set_error(B2E_ERR_INVALID, "null argument");
+extern "C" int b2e_edge_metrics(int device, const int64_t *indptr, const uint32_t *indices, uint64_t n, uint64_t nnz,
+                                const uint32_t *src, const uint32_t *dst, uint64_t m, const uint32_t *edge_features,
+                                uint32_t n_edge_features, float *out) {
+    if (m && (!src || !dst || !out)) return b2e_set_error(B2E_ERR_INVALID, "null argument");
     MethodList list;
-    if (int rc = build_methods(methods, n_methods, f->dim, list)) return rc;
+    if (n_edge_features == 0) return b2e_set_error(B2E_ERR_INVALID, "at least one edge feature is required");
+    if (int rc = build_methods(nullptr, 0, 0, edge_features, n_edge_features, list)) return rc;
     if (m == 0) return B2E_OK;
-    EP_TRY(cudaSetDevice(f->device));
+    EP_TRY(cudaSetDevice(device));
+    DeviceGraph graph;
+    if (int rc = graph.upload(indptr, indices, n, nnz)) return rc;
+    DeviceArray d_src, d_dst, d_out;
+    if (int rc = upload_edges(n, src, dst, m, d_src, d_dst)) return rc;
+    EP_TRY(d_out.alloc(m * list.size * sizeof(float)));
+    edge_metrics_kernel<<<warp_grid(m), 256>>>(graph.view, d_src.as<uint32_t>(), d_dst.as<uint32_t>(), m, list,
+                                               d_out.as<float>());
+    EP_TRY(cudaGetLastError());
+    EP_TRY(cudaMemcpy(out, d_out.p, m * list.size * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2E_OK;
+}
+
+extern "C" int b2e_perceptron_predict(const b2e_features *f, const int64_t *indptr, const uint32_t *indices,
+                                      uint64_t n, uint64_t nnz, const uint32_t *src, const uint32_t *dst, uint64_t m,
+                                      const uint32_t *methods, uint32_t n_methods, const uint32_t *edge_features,
+                                      uint32_t n_edge_features, const float *params, float *scores) {
+    if (!params || (m && (!src || !dst || !scores))) return b2e_set_error(B2E_ERR_INVALID, "null argument");
+    if (n_methods && !f) return b2e_set_error(B2E_ERR_INVALID, "edge embeddings need node features");
+    MethodList list;
+    if (int rc = build_methods(methods, n_methods, f ? f->dim : 0, edge_features, n_edge_features, list)) return rc;
+    if (m == 0) return B2E_OK;
+    if (int rc = select_device(f)) return rc;
+    DeviceGraph graph;
+    if (n_edge_features)
+        if (int rc = graph.upload(indptr, indices, n, nnz)) return rc;
     DeviceArray d_src, d_dst, d_params, d_scores;
-    if (int rc = upload_edges(f, src, dst, m, d_src, d_dst)) return rc;
+    if (int rc = upload_edges(f ? f->n : n, src, dst, m, d_src, d_dst)) return rc;
     EP_TRY(d_params.alloc((list.size + 1) * sizeof(float)));
     EP_TRY(d_scores.alloc(m * sizeof(float)));
     EP_TRY(cudaMemcpy(d_params.p, params, (list.size + 1) * sizeof(float), cudaMemcpyHostToDevice));
     const size_t smem = (list.size + 1) * sizeof(float);
     EP_TRY(cudaFuncSetAttribute(perceptron_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    perceptron_predict_kernel<<<warp_grid(m), 256, smem>>>(f->d, f->pitch, f->dim, d_src.as<uint32_t>(),
-                                                           d_dst.as<uint32_t>(), m, list, d_params.as<float>(),
-                                                           d_scores.as<float>());
+    perceptron_predict_kernel<<<warp_grid(m), 256, smem>>>(f ? f->d : nullptr, f ? f->pitch : 0, f ? f->dim : 0,
+                                                           d_src.as<uint32_t>(), d_dst.as<uint32_t>(), m, list,
+                                                           graph.view, d_params.as<float>(), d_scores.as<float>());
     EP_TRY(cudaGetLastError());
     EP_TRY(cudaMemcpy(scores, d_scores.p, m * sizeof(float), cudaMemcpyDeviceToHost));
     return B2E_OK;
@@ -449,18 +621,23 @@ extern "C" int b2e_perceptron_predict(const b2e_features *f, const uint32_t *src
 extern "C" int b2e_perceptron_fit(const b2e_features *f, const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                   uint64_t nnz, const b2e_perceptron_config *cfg, uint64_t seed, float *params_out,
                                   float *epoch_loss) {
-    if (!f || !indptr || !indices || !cfg || !params_out) return b2e_set_error(B2E_ERR_INVALID, "null argument");
+    if (!indptr || !indices || !cfg || !params_out) return b2e_set_error(B2E_ERR_INVALID, "null argument");
     if (cfg->struct_size != sizeof(b2e_perceptron_config))
         return b2e_set_error(B2E_ERR_INVALID, "b2e_perceptron_config size mismatch (ABI)");
-    if (n != f->n) return b2e_set_error(B2E_ERR_INVALID, "the graph and the node features disagree on the number of nodes");
+    if (cfg->n_methods && !f) return b2e_set_error(B2E_ERR_INVALID, "edge embeddings need node features");
+    if (f && n != f->n) return b2e_set_error(B2E_ERR_INVALID, "the graph and the node features disagree on the number of nodes");
     if (nnz == 0 || (uint64_t)indptr[n] != nnz) return b2e_set_error(B2E_ERR_INVALID, "the graph has no edges");
     if (cfg->number_of_edges_per_mini_batch == 0) return b2e_set_error(B2E_ERR_INVALID, "empty mini-batch");
     if (!(cfg->first_order_decay_factor >= 0.f && cfg->first_order_decay_factor < 1.f) ||
         !(cfg->second_order_decay_factor >= 0.f && cfg->second_order_decay_factor < 1.f))
         return b2e_set_error(B2E_ERR_INVALID, "decay factors must be in [0, 1)");
     MethodList list;
-    if (int rc = build_methods(cfg->methods, cfg->n_methods, f->dim, list)) return rc;
-    EP_TRY(cudaSetDevice(f->device));
+    if (int rc = build_methods(cfg->methods, cfg->n_methods, f ? f->dim : 0, cfg->edge_features,
+                               cfg->n_edge_features, list))
+        return rc;
+    if (int rc = select_device(f)) return rc;
+    int64_t max_degree = 1;
+    for (uint64_t v = 0; v < n; ++v) max_degree = std::max(max_degree, indptr[v + 1] - indptr[v]);
     const uint32_t count = list.size + 1;
     DeviceArray d_indptr, d_indices, d_edge_src, d_params, d_m, d_v, d_grad, d_loss;
     EP_TRY(d_indptr.alloc((n + 1) * sizeof(int64_t)));
@@ -482,9 +659,10 @@ extern "C" int b2e_perceptron_fit(const b2e_features *f, const int64_t *indptr, 
     EP_TRY(cudaGetLastError());
 
     StepParams p;
-    p.features = f->d;
-    p.pitch = f->pitch;
-    p.dim = f->dim;
+    p.features = f ? f->d : nullptr;
+    p.pitch = f ? f->pitch : 0;
+    p.dim = f ? f->dim : 0;
+    p.inv_max_degree = 1.0f / (float)max_degree;
     p.indptr = d_indptr.as<int64_t>();
     p.indices = d_indices.as<uint32_t>();
     p.edge_src = d_edge_src.as<uint32_t>();

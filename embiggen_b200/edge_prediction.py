@@ -5,10 +5,11 @@ and a perceptron edge scorer on node features that stay in HBM.
   ``EdgeTransformer`` (/root/reference/embiggen/embedding_transformers/edge_transformer.py:
   337-361 the method table, :423-490 ``fit``, :511-600 ``transform``) for node ids with an
   aligned mapping; node / edge type features are not supported.
-* :class:`PerceptronEdgePredictionB200` -- the ``edge_embeddings`` half of
-  ``PerceptronEdgePrediction`` (/root/reference/embiggen/edge_prediction/
-  edge_prediction_ensmallen/perceptron.py:15-300): same kwargs and defaults; the topological
-  ``edge_features`` (Jaccard, Adamic-Adar, ...) are not implemented by this engine.
+* :class:`PerceptronEdgePredictionB200` -- ``PerceptronEdgePrediction``
+  (/root/reference/embiggen/edge_prediction/edge_prediction_ensmallen/perceptron.py:15-300):
+  same kwargs and defaults, ``edge_embeddings`` and the topological ``edge_features`` (Degree,
+  AdamicAdar, JaccardCoefficient, ResourceAllocationIndex, PreferentialAttachment; not
+  Cooccurrence).
 * :func:`binary_auroc` -- tie-aware AUROC of the scores (``express_measures.binary_auroc``,
   abstract_classifier_model.py:2073), on the host: scores are 4 bytes per edge, the embedding
   is what must not move.
@@ -26,6 +27,8 @@ from .graph import as_csr
 
 EDGE_METHODS = ["Hadamard", "Sum", "Average", "L1", "AbsoluteL1", "SquaredL2", "L2", "Concatenate",
                 "Min", "Max", "L2Distance", "CosineSimilarity"]
+EDGE_FEATURES = ["Degree", "AdamicAdar", "JaccardCoefficient", "ResourceAllocationIndex",
+                 "PreferentialAttachment"]  # perceptron.py:38-46; "Cooccurrence" is not implemented
 # perceptron.py:51-61 names some methods differently from the transformer
 _PERCEPTRON_ALIASES = {"EuclideanDistance": "L2Distance", "Add": "Sum", "Sub": "L1",
                        "Maximum": "Max", "Minimum": "Min"}
@@ -45,6 +48,38 @@ def _method_ids(methods: Union[str, Sequence[str]], aliases: Optional[Dict[str, 
     if not ids:
         raise ValueError("At least one edge embedding method is required.")
     return np.asarray(ids, dtype=np.uint32)
+
+
+def _feature_ids(names: Optional[Union[str, Sequence[str]]]) -> np.ndarray:
+    if names is None:
+        names = []
+    if isinstance(names, str):
+        names = [names]
+    ids = []
+    for name in names:
+        if name == "Cooccurrence":
+            raise NotImplementedError("The Cooccurrence edge feature is not implemented by the B200 engine.")
+        if name not in EDGE_FEATURES:
+            raise ValueError(f"The provided edge feature {name!r} is not in {EDGE_FEATURES}.")
+        ids.append(EDGE_FEATURES.index(name))
+    return np.asarray(ids, dtype=np.uint32)
+
+
+def edge_metrics(graph, sources, destinations, edge_features: Union[str, Sequence[str]],
+                 device: int = 0) -> np.ndarray:
+    """The topological edge features of an edge list, computed on the GPU from the graph's CSR
+    (what ``graph.get_jaccard_coefficient_scores`` & co. return, graph_visualizer.py:2465,2677)."""
+    indptr, indices, _ = as_csr(graph)
+    ids = _feature_ids(edge_features)
+    if len(ids) == 0:
+        raise ValueError("At least one edge feature is required.")
+    src, dst = _edges(sources, destinations)
+    width = sum(2 if i == 0 else 1 for i in ids)
+    out = np.empty((src.shape[0], width), dtype=np.float32)
+    check(_lib.load().b2e_edge_metrics(device, indptr.ctypes.data, indices.ctypes.data, indptr.shape[0] - 1,
+                                       indices.shape[0], src.ctypes.data, dst.ctypes.data, src.shape[0],
+                                       ids.ctypes.data, len(ids), out.ctypes.data))
+    return out
 
 
 def _edges(sources, destinations):
@@ -128,7 +163,7 @@ class EdgeTransformerB200:
             raise ValueError("Transformer was not fitted yet.")
         size = ctypes.c_uint32()
         check(_lib.load().b2e_edge_embedding_size(self._features.shape[1], self._method_ids.ctypes.data,
-                                                  len(self._method_ids), ctypes.byref(size)))
+                                                  len(self._method_ids), None, 0, ctypes.byref(size)))
         return int(size.value)
 
     def transform(self, sources, destinations) -> np.ndarray:
@@ -145,25 +180,27 @@ class EdgeTransformerB200:
 class PerceptronEdgePredictionB200:
     """Perceptron edge scorer over edge embeddings (Adam, scale-free negative sampling)."""
 
-    def __init__(self, edge_features: Optional[Union[str, List[str]]] = None,
-                 edge_embeddings: Optional[Union[str, List[str]]] = "Hadamard",
+    def __init__(self, edge_features: Optional[Union[str, List[str]]] = "JaccardCoefficient",
+                 edge_embeddings: Optional[Union[str, List[str]]] = None,
                  cooccurrence_iterations: int = 100, cooccurrence_window_size: int = 10,
                  number_of_epochs: int = 1000, number_of_edges_per_mini_batch: int = 4096,
                  learning_rate: float = 0.001, first_order_decay_factor: float = 0.9,
                  second_order_decay_factor: float = 0.999, avoid_false_negatives: bool = False,
                  use_scale_free_distribution: bool = True, random_state: int = 42, verbose: bool = True,
                  device: int = 0):
-        if edge_features:
-            raise NotImplementedError(
-                "The topological edge features (Degree, AdamicAdar, JaccardCoefficient, ...) are not "
-                "implemented by the B200 engine; pass edge_features=None and edge_embeddings=[...].")
-        if not edge_embeddings:
-            raise ValueError("At least one edge embedding method is required.")
+        if isinstance(edge_features, str):
+            edge_features = [edge_features]
         if isinstance(edge_embeddings, str):
             edge_embeddings = [edge_embeddings]
-        self._method_ids = _method_ids(edge_embeddings, _PERCEPTRON_ALIASES)
+        if not edge_features and not edge_embeddings:
+            raise ValueError("At least one edge feature or edge embedding method is required.")
+        self._feature_ids = _feature_ids(edge_features)
+        self._method_ids = _method_ids(edge_embeddings, _PERCEPTRON_ALIASES) if edge_embeddings \
+            else np.zeros(0, dtype=np.uint32)
+        self._support = None
         self._model_kwargs = dict(
-            edge_features=None, edge_embeddings=list(edge_embeddings),
+            edge_features=list(edge_features) if edge_features else None,
+            edge_embeddings=list(edge_embeddings) if edge_embeddings else None,
             cooccurrence_iterations=cooccurrence_iterations,
             cooccurrence_window_size=cooccurrence_window_size, number_of_epochs=number_of_epochs,
             number_of_edges_per_mini_batch=number_of_edges_per_mini_batch, learning_rate=learning_rate,
@@ -199,7 +236,7 @@ class PerceptronEdgePredictionB200:
 
     @classmethod
     def smoke_test_parameters(cls) -> Dict[str, Any]:
-        return dict(number_of_epochs=1)
+        return dict(number_of_epochs=1, edge_features="Degree")  # perceptron.py:125-131
 
     def get_losses(self) -> List[float]:
         return list(self._losses)
@@ -214,6 +251,7 @@ class PerceptronEdgePredictionB200:
         k = self._model_kwargs
         config = B2EPerceptronConfig(
             struct_size=ctypes.sizeof(B2EPerceptronConfig), n_methods=len(self._method_ids),
+            n_edge_features=len(self._feature_ids),
             number_of_epochs=k["number_of_epochs"],
             number_of_edges_per_mini_batch=k["number_of_edges_per_mini_batch"],
             learning_rate=k["learning_rate"], first_order_decay_factor=k["first_order_decay_factor"],
@@ -222,52 +260,69 @@ class PerceptronEdgePredictionB200:
             use_scale_free_distribution=int(bool(k["use_scale_free_distribution"])))
         for i, method in enumerate(self._method_ids):
             config.methods[i] = int(method)
+        for i, feature in enumerate(self._feature_ids):
+            config.edge_features[i] = int(feature)
         return config
 
-    def fit(self, graph, node_features) -> "PerceptronEdgePredictionB200":
-        """``graph``: anything :func:`embiggen_b200.graph.as_csr` accepts; ``node_features``: a
-        matrix, a list of matrices (concatenated) or :class:`DeviceFeatures`."""
+    def _ids(self):
+        return (self._method_ids.ctypes.data if len(self._method_ids) else None, len(self._method_ids),
+                self._feature_ids.ctypes.data if len(self._feature_ids) else None, len(self._feature_ids))
+
+    def fit(self, graph, node_features=None) -> "PerceptronEdgePredictionB200":
+        """``graph``: anything :func:`embiggen_b200.graph.as_csr` accepts (it is also the support
+        of the edge features); ``node_features``: a matrix, a list of matrices (concatenated) or
+        :class:`DeviceFeatures`, needed only with ``edge_embeddings``."""
         indptr, indices, _ = as_csr(graph)
         if indices.shape[0] == 0:
             raise ValueError("The provided graph does not have any edge.")
-        features, owned = _as_device_features(node_features, self._device)
+        if len(self._method_ids) and node_features is None:
+            raise ValueError("The edge embeddings need node features.")
+        features, owned = (None, False) if not len(self._method_ids) else \
+            _as_device_features(node_features, self._device)
         try:
             config = self._config()
             size = ctypes.c_uint32()
             lib = _lib.load()
-            check(lib.b2e_edge_embedding_size(features.shape[1], self._method_ids.ctypes.data,
-                                              len(self._method_ids), ctypes.byref(size)))
+            check(lib.b2e_edge_embedding_size(features.shape[1] if features else 0, *self._ids(),
+                                              ctypes.byref(size)))
             params = np.empty(size.value + 1, dtype=np.float32)
             losses = np.zeros(max(1, config.number_of_epochs), dtype=np.float32)
-            check(lib.b2e_perceptron_fit(features._handle, indptr.ctypes.data, indices.ctypes.data,
-                                         indptr.shape[0] - 1, indices.shape[0], ctypes.byref(config),
-                                         int(self._random_state) & 0xFFFFFFFFFFFFFFFF,
+            check(lib.b2e_perceptron_fit(features._handle if features else None, indptr.ctypes.data,
+                                         indices.ctypes.data, indptr.shape[0] - 1, indices.shape[0],
+                                         ctypes.byref(config), int(self._random_state) & 0xFFFFFFFFFFFFFFFF,
                                          params.ctypes.data, losses.ctypes.data))
         finally:
             if owned:
                 features.close()
         self._params = params
+        self._support = (indptr, indices)
         self._losses = [float(x) for x in losses[:config.number_of_epochs]]
         return self
 
-    def predict_proba(self, sources, destinations, node_features) -> np.ndarray:
+    def predict_proba(self, sources, destinations, node_features=None, support=None) -> np.ndarray:
+        """Scores of an edge list; ``support`` (default: the graph given to ``fit``) is the graph
+        the edge features are computed on (perceptron.py:172-215)."""
         if self._params is None:
             raise ValueError("The model was not fitted yet.")
         src, dst = _edges(sources, destinations)
-        features, owned = _as_device_features(node_features, self._device)
+        indptr, indices = self._support if support is None else as_csr(support)[:2]
+        if len(self._method_ids) and node_features is None:
+            raise ValueError("The edge embeddings need node features.")
+        features, owned = (None, False) if not len(self._method_ids) else \
+            _as_device_features(node_features, self._device)
         try:
             scores = np.empty(src.shape[0], dtype=np.float32)
-            check(_lib.load().b2e_perceptron_predict(features._handle, src.ctypes.data, dst.ctypes.data,
-                                                     src.shape[0], self._method_ids.ctypes.data,
-                                                     len(self._method_ids), self._params.ctypes.data,
-                                                     scores.ctypes.data))
+            check(_lib.load().b2e_perceptron_predict(
+                features._handle if features else None, indptr.ctypes.data, indices.ctypes.data,
+                indptr.shape[0] - 1, indices.shape[0], src.ctypes.data, dst.ctypes.data, src.shape[0],
+                *self._ids(), self._params.ctypes.data, scores.ctypes.data))
         finally:
             if owned:
                 features.close()
         return scores
 
-    def predict(self, sources, destinations, node_features) -> np.ndarray:
-        return self.predict_proba(sources, destinations, node_features) > 0.5
+    def predict(self, sources, destinations, node_features=None, support=None) -> np.ndarray:
+        return self.predict_proba(sources, destinations, node_features, support) > 0.5
 
 
 def binary_auroc(labels, scores) -> float:

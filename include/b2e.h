@@ -216,6 +216,16 @@ typedef enum {
     B2E_EDGE_MIN = 8, B2E_EDGE_MAX = 9, B2E_EDGE_L2_DISTANCE = 10, B2E_EDGE_COSINE_SIMILARITY = 11
 } b2e_edge_method;
 
+/* `edge_features` of PerceptronEdgePrediction (perceptron.py:38-46), computed from the support
+ * graph's sorted CSR: Degree = (deg u, deg v) / max degree (two values), Adamic-Adar = sum over
+ * the common neighbours of 1 / ln deg, Jaccard = common / union, resource allocation index =
+ * sum of 1 / deg, preferential attachment = deg u * deg v / max degree^2.  (Cooccurrence is not
+ * implemented.) */
+typedef enum {
+    B2E_EDGE_FEATURE_DEGREE = 0, B2E_EDGE_FEATURE_ADAMIC_ADAR = 1, B2E_EDGE_FEATURE_JACCARD_COEFFICIENT = 2,
+    B2E_EDGE_FEATURE_RESOURCE_ALLOCATION_INDEX = 3, B2E_EDGE_FEATURE_PREFERENTIAL_ATTACHMENT = 4
+} b2e_edge_feature;
+
 /* node features (n x dim float32) resident in HBM */
 typedef struct b2e_features b2e_features;
 int b2e_features_create(int device, const float *host_features, uint64_t n, uint32_t dim,
@@ -225,8 +235,16 @@ int b2e_features_create(int device, const float *host_features, uint64_t n, uint
 int b2e_features_from_handle(b2e_handle *handle, int table, b2e_features **features);
 void b2e_features_destroy(b2e_features *features);
 
-/* width of the concatenation of the methods (Concatenate 2 dim, the two scalar methods 1) */
-int b2e_edge_embedding_size(uint32_t dim, const uint32_t *methods, uint32_t n_methods, uint32_t *size);
+/* width of the concatenation: the methods (Concatenate 2 dim, the two scalar methods 1), then
+ * the edge features (Degree 2, the others 1) */
+int b2e_edge_embedding_size(uint32_t dim, const uint32_t *methods, uint32_t n_methods,
+                            const uint32_t *edge_features, uint32_t n_edge_features, uint32_t *size);
+
+/* the edge features of an edge list, materialised (`graph.get_jaccard_coefficient_scores` and
+ * friends, .../visualizations/graph_visualizer.py:2465,2677): out is m x width, host */
+int b2e_edge_metrics(int device, const int64_t *indptr, const uint32_t *indices, uint64_t n, uint64_t nnz,
+                     const uint32_t *src, const uint32_t *dst, uint64_t m, const uint32_t *edge_features,
+                     uint32_t n_edge_features, float *out);
 
 /* EdgeTransformer.transform (edge_transformer.py:352-361): out is m x size, row-major, host */
 int b2e_edge_embedding(const b2e_features *features, const uint32_t *src, const uint32_t *dst,
@@ -238,6 +256,8 @@ typedef struct {
     uint32_t struct_size;
     uint32_t n_methods;
     uint32_t methods[12];  /* b2e_edge_method: `edge_embeddings` */
+    uint32_t n_edge_features;
+    uint32_t edge_features[5]; /* b2e_edge_feature: `edge_features`, appended after the embeddings */
     uint32_t number_of_epochs;
     uint32_t number_of_edges_per_mini_batch;
     float learning_rate;
@@ -254,10 +274,13 @@ int b2e_perceptron_fit(const b2e_features *features, const int64_t *indptr, cons
                        uint64_t n, uint64_t nnz, const b2e_perceptron_config *config, uint64_t seed,
                        float *params, float *epoch_loss);
 
-/* `.predict(graph, node_features)` on an explicit edge list (perceptron.py:172-215) */
-int b2e_perceptron_predict(const b2e_features *features, const uint32_t *src, const uint32_t *dst,
-                           uint64_t m, const uint32_t *methods, uint32_t n_methods, const float *params,
-                           float *scores);
+/* `.predict(graph, node_features)` on an explicit edge list (perceptron.py:172-215); the
+ * support graph's CSR is needed only with edge features, the node features only with edge
+ * embeddings (either may be NULL otherwise; the same holds for b2e_perceptron_fit's features) */
+int b2e_perceptron_predict(const b2e_features *features, const int64_t *indptr, const uint32_t *indices,
+                           uint64_t n, uint64_t nnz, const uint32_t *src, const uint32_t *dst, uint64_t m,
+                           const uint32_t *methods, uint32_t n_methods, const uint32_t *edge_features,
+                           uint32_t n_edge_features, const float *params, float *scores);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ nnz = graph.indices.shape[0]
 features = np.random.default_rng(0).normal(size=(graph.get_number_of_nodes(), 100)).astype(np.float32)
 with DeviceFeatures(features) as resident:
     for batch in (int(b) for b in os.environ.get("BATCHES", "1024,4096,16384,65536").split(",")):
-        model = PerceptronEdgePredictionB200(edge_embeddings="Hadamard", number_of_epochs=1,
+        model = PerceptronEdgePredictionB200(edge_features=None, edge_embeddings="Hadamard", number_of_epochs=1,
                                              number_of_edges_per_mini_batch=batch)
         model.fit(graph, resident)
         t0 = time.perf_counter()

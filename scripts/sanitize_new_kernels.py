@@ -35,4 +35,18 @@ with Engine("GloVe", embedding_size=100, walk_length=33, window_size=4, iteratio
     engine.load_csr(graph.indptr, graph.indices)
     t0, t1, losses = engine.fit(7)
     assert np.isfinite(t0).all() and np.isfinite(t1).all()
+from embiggen_b200.edge_prediction import (EdgeTransformerB200, PerceptronEdgePredictionB200,  # noqa: E402
+                                           edge_metrics)
+features = rng.normal(size=(n, 20)).astype(np.float32)
+src, dst = rng.integers(0, n, 3000), rng.integers(0, n, 3000)
+transformer = EdgeTransformerB200(["Hadamard", "Concatenate", "CosineSimilarity", "L2Distance", "Min"])
+transformer.fit(features)
+assert np.isfinite(transformer.transform(src, dst)).all()
+assert np.isfinite(edge_metrics(graph, src, dst, ["Degree", "AdamicAdar", "JaccardCoefficient",
+                                                  "ResourceAllocationIndex", "PreferentialAttachment"])).all()
+for kw in (dict(), dict(edge_features=["Degree", "AdamicAdar"], edge_embeddings=["L1", "CosineSimilarity"],
+                        avoid_false_negatives=True)):
+    model = PerceptronEdgePredictionB200(number_of_epochs=2, number_of_edges_per_mini_batch=256, **kw)
+    model.fit(graph, features)
+    assert np.isfinite(model.predict_proba(src, dst, features)).all()
 print("sanitize ok")

@@ -50,7 +50,7 @@ def test_perceptron_fit_tracks_the_oracle(small_ppi, methods, scale_free, avoid)
     expected, expected_loss = ep.perceptron_fit(
         features, small_ppi.indptr, small_ppi.indices, methods, 42, 2, 300, learning_rate=0.01,
         avoid_false_negatives=avoid, scale_free=scale_free)           # 2 x 20 steps
-    model = PerceptronEdgePredictionB200(edge_embeddings=methods, avoid_false_negatives=avoid,
+    model = PerceptronEdgePredictionB200(edge_features=None, edge_embeddings=methods, avoid_false_negatives=avoid,
                                          use_scale_free_distribution=scale_free, random_state=42, **kw)
     model.fit(small_ppi, features)
     got = model.get_weights()
@@ -58,7 +58,8 @@ def test_perceptron_fit_tracks_the_oracle(small_ppi, methods, scale_free, avoid)
     assert np.abs(got - expected).max() <= 2e-3, np.abs(got - expected).max()
     assert np.allclose(model.get_losses(), expected_loss, rtol=1e-2)
     # zero steps: the initialisation alone is bit-exact
-    init = PerceptronEdgePredictionB200(edge_embeddings=methods, number_of_epochs=0, random_state=42)
+    init = PerceptronEdgePredictionB200(edge_features=None, edge_embeddings=methods, number_of_epochs=0,
+                                        random_state=42)
     init.fit(small_ppi, features)
     assert np.array_equal(init.get_weights(), ep.perceptron_init(42, len(expected) - 1))
     src = rng.integers(0, features.shape[0], 700)
@@ -82,7 +83,7 @@ def test_scorer_on_a_resident_embedding_predicts_held_out_edges():
         engine.load_csr(graph.indptr, graph.indices)
         central, _, _ = engine.fit(42)
         resident = DeviceFeatures(engine=engine, table=0)
-        model = PerceptronEdgePredictionB200(edge_embeddings="Hadamard", number_of_epochs=20,
+        model = PerceptronEdgePredictionB200(edge_features=None, edge_embeddings="Hadamard", number_of_epochs=20,
                                              number_of_edges_per_mini_batch=1024, learning_rate=0.02)
         model.fit(graph, resident)
         edges_src = np.concatenate([test_pos[0], test_neg[:, 0]])
@@ -99,12 +100,72 @@ def test_scorer_on_a_resident_embedding_predicts_held_out_edges():
     assert gpu_auroc > 0.8 and abs(gpu_auroc - oracle_auroc) <= 0.005
 
 
+def test_edge_metrics_against_the_oracle(small_ppi, rmat_graph):
+    from conftest import tiny_graphs
+    from embiggen_b200.edge_prediction import edge_metrics
+    rng = np.random.default_rng(5)
+    for graph in (small_ppi, rmat_graph, tiny_graphs()["two_components_isolated"], tiny_graphs()["star"]):
+        n = graph.get_number_of_nodes()
+        src, dst = rng.integers(0, n, 400), rng.integers(0, n, 400)
+        rows = np.repeat(np.arange(n), np.diff(graph.indptr))
+        src[:100], dst[:100] = rows[:100], graph.indices[:100]   # real edges too
+        for names in (ep.EDGE_FEATURES, ["JaccardCoefficient"], ["PreferentialAttachment", "Degree", "AdamicAdar"]):
+            expected = ep.edge_metrics(names, graph.indptr, graph.indices, src, dst)
+            got = edge_metrics(graph, src, dst, names)
+            assert got.shape == expected.shape
+            assert np.allclose(got, expected, rtol=2e-6, atol=1e-7), names
+
+
+@pytest.mark.parametrize("edge_features,edge_embeddings", [
+    ("JaccardCoefficient", None), (["Degree", "AdamicAdar", "ResourceAllocationIndex"], None),
+    (["PreferentialAttachment", "JaccardCoefficient"], ["Hadamard", "L2Distance"])])
+def test_perceptron_with_edge_features_tracks_the_oracle(small_ppi, edge_features, edge_embeddings):
+    rng = np.random.default_rng(4)
+    features = rng.normal(size=(small_ppi.get_number_of_nodes(), 16)).astype(np.float32) if edge_embeddings else None
+    names = [edge_features] if isinstance(edge_features, str) else edge_features
+    expected, expected_loss = ep.perceptron_fit(
+        features, small_ppi.indptr, small_ppi.indices, edge_embeddings or [], 42, 2, 300, learning_rate=0.01,
+        edge_features=names)
+    model = PerceptronEdgePredictionB200(edge_features=edge_features, edge_embeddings=edge_embeddings,
+                                         number_of_epochs=2, number_of_edges_per_mini_batch=300,
+                                         learning_rate=0.01, random_state=42)
+    model.fit(small_ppi, features)
+    got = model.get_weights()
+    assert got.shape == expected.shape and np.abs(got - expected).max() <= 2e-3
+    assert np.allclose(model.get_losses(), expected_loss, rtol=1e-2)
+    src = rng.integers(0, 1064, 500)
+    dst = rng.integers(0, 1064, 500)
+    scores = model.predict_proba(src, dst, features)
+    reference = ep.perceptron_predict(features, src, dst, edge_embeddings or [], got, names,
+                                      small_ppi.indptr, small_ppi.indices)
+    assert np.allclose(scores, reference, atol=1e-5)
+
+
+def test_default_perceptron_separates_edges_from_random_pairs(small_ppi):
+    """The reference's default configuration (Jaccard only, no node features at all)."""
+    model = PerceptronEdgePredictionB200(number_of_epochs=30, number_of_edges_per_mini_batch=512, learning_rate=0.05)
+    model.fit(small_ppi)
+    n = small_ppi.get_number_of_nodes()
+    rows = np.repeat(np.arange(n), np.diff(small_ppi.indptr))
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, n, 3000), rng.integers(0, n, 3000)
+    scores = np.concatenate([model.predict_proba(rows, small_ppi.indices), model.predict_proba(a, b)])
+    labels = np.concatenate([np.ones(len(rows)), np.zeros(3000)])
+    auroc = binary_auroc(labels, scores)
+    print(f"default perceptron (Jaccard) AUROC edges vs random pairs: {auroc:.4f}")
+    assert auroc > 0.6 and model.get_losses()[-1] < model.get_losses()[0]
+
+
 def test_error_paths(small_ppi):
     features = np.ones((small_ppi.get_number_of_nodes() - 1, 4), dtype=np.float32)
     with pytest.raises(ValueError):
-        PerceptronEdgePredictionB200(number_of_epochs=1).fit(small_ppi, features)  # node count mismatch
+        PerceptronEdgePredictionB200(edge_features=None, edge_embeddings="Hadamard", number_of_epochs=1).fit(
+            small_ppi, features)  # node count mismatch
+    with pytest.raises(ValueError):
+        PerceptronEdgePredictionB200(edge_features=None, edge_embeddings="Hadamard").fit(small_ppi)  # no features
     with pytest.raises(ValueError):
         DeviceFeatures(np.full((3, 2), np.nan, dtype=np.float32))
     with pytest.raises(ValueError):
-        PerceptronEdgePredictionB200(number_of_epochs=1, first_order_decay_factor=1.0).fit(
+        PerceptronEdgePredictionB200(edge_features=None, edge_embeddings="Hadamard", number_of_epochs=1,
+                                     first_order_decay_factor=1.0).fit(
             small_ppi, np.ones((small_ppi.get_number_of_nodes(), 4), dtype=np.float32))
