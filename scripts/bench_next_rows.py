@@ -162,9 +162,11 @@ def main():
             transformer = EdgeTransformerB200(methods)
             transformer.fit(resident)
             transformer.transform(src[:1000], dst[:1000])
-            t0 = time.perf_counter()
-            out = transformer.transform(src, dst)
-            seconds = time.perf_counter() - t0
+            seconds = float("inf")
+            for _ in range(2):  # wall clock of a host round trip: best of two
+                t0 = time.perf_counter()
+                out = transformer.transform(src, dst)
+                seconds = min(seconds, time.perf_counter() - t0)
             emit(row="f-4 edge embedding (host edge list in, host matrix out)", methods=methods, edges=m,
                  width=out.shape[1], seconds=seconds, edges_per_s=m / seconds,
                  d2h_gbs=out.nbytes / seconds / 1e9)
@@ -177,9 +179,11 @@ def main():
         samples = 2 * (nnz // 4096) * 4096
         emit(row="f-4 perceptron fit (2 epochs, mini-batch 4096, Hadamard)", samples=samples, seconds=seconds,
              samples_per_s=samples / seconds, steps_per_s=2 * (nnz // 4096) / seconds, losses=model.get_losses())
-        t0 = time.perf_counter()
-        scores = model.predict_proba(src, dst, resident)
-        seconds = time.perf_counter() - t0
+        seconds = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            scores = model.predict_proba(src, dst, resident)
+            seconds = min(seconds, time.perf_counter() - t0)
         emit(row="f-4 perceptron predict (host edge list in, host scores out)", edges=m, seconds=seconds,
              edges_per_s=m / seconds, row_gather_gbs=m * 2 * 4 * D / seconds / 1e9,
              finite=bool(np.isfinite(scores).all()))
