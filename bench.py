@@ -259,7 +259,7 @@ def run_reference(args, cfg):
     value = pairs_total / total
     sample_text = (f"each step = {sample} walks of the workload (walks + SGD), OpenMP Hogwild "
                    f"over {threads} threads")
-    print(json.dumps({
+    emit_result({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True,
@@ -271,7 +271,7 @@ def run_reference(args, cfg):
                          "sample": sample_text},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def run_ours(args, cfg):
@@ -481,13 +481,38 @@ def run_ours(args, cfg):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(graph, cfg, budget_s=args.cpu_budget)
-        print(json.dumps(result), flush=True)
+        emit_result(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Everything else a library may print there (NCCL's
+    version banner ignores NCCL_DEBUG_FILE at NCCL_DEBUG=VERSION, torchrun children, CUDA
+    warnings) is sent to stderr: file descriptor 1 is pointed at stderr for the whole run and
+    the result is written to a saved duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_result(record):
+    line = (json.dumps(record) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    claim_stdout()
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=10)
