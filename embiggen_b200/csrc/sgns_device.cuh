@@ -85,6 +85,11 @@ __device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre
     return __fdiv_rn(p.lr, (float)deg);
 }
 
+// bit i of the mask staged behind a shared-memory walk of L tokens (rounded up to 32)
+__device__ __forceinline__ bool staged_skip(const uint32_t *walk, uint32_t L, uint32_t i) {
+    return (walk[((L + 31u) & ~31u) + (i >> 5)] >> (i & 31u)) & 1u;
+}
+
 // stochastic_downsample_by_degree: the centre at position i is skipped with probability
 // deg(c) / (max degree + 1); one Philox block per centre, the same on every lane.
 __device__ __forceinline__ bool skip_centre(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
@@ -103,9 +108,10 @@ struct PairCursor {
 };
 
 // advance to the next pair of the walk; false when the walk is exhausted.  STAGED: `walk` is a
-// shared-memory copy of the walk (plain loads) instead of global memory (read-only path).  The
-// pipelined kernels (STAGED) are never launched with stochastic_downsample_by_degree (it is
-// routed to the generic kernel), so the skip test exists only in the non-staged instantiation.
+// shared-memory copy of the walk (plain loads) instead of global memory (read-only path).  With
+// stochastic_downsample_by_degree the pipelined kernels (STAGED) read the skip decision from a
+// bit mask staged behind the walk (sgns_pipe.cu: stage_skip_mask); the generic kernel evaluates
+// it in place.
 template <bool STAGED = false>
 __device__ __forceinline__ bool next_pair(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
                                           const uint32_t *__restrict__ walk, uint32_t L, uint32_t W,
@@ -117,7 +123,10 @@ __device__ __forceinline__ bool next_pair(const TrainParams &p, uint32_t wid_lo,
             const uint32_t c = STAGED ? walk[i] : __ldg(walk + i);
             if (c == PAD) return false;
             s.i = i;
-            if (!STAGED && skip_centre(p, wid_lo, wid_hi, i, c)) { s.j = s.hi = 0; continue; }
+            if (STAGED ? (p.downsample && staged_skip(walk, L, i)) : skip_centre(p, wid_lo, wid_hi, i, c)) {
+                s.j = s.hi = 0;
+                continue;
+            }
             s.c = c;
             s.hi = i + W < L - 1 ? i + W : L - 1;
             s.j = i > W ? i - W : 0u;
@@ -140,7 +149,7 @@ __device__ __forceinline__ uint32_t next_centre(const TrainParams &p, uint32_t w
     for (; i < L; ++i) {
         c = STAGED ? walk[i] : __ldg(walk + i);
         if (c == PAD) return L;
-        if (!STAGED && skip_centre(p, wid_lo, wid_hi, i, c)) continue;
+        if (STAGED ? (p.downsample && staged_skip(walk, L, i)) : skip_centre(p, wid_lo, wid_hi, i, c)) continue;
         const uint32_t lo = i > W ? i - W : 0u;
         const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
         for (uint32_t j = lo; j <= hi; ++j) {

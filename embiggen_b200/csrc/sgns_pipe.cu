@@ -64,6 +64,26 @@ __device__ __forceinline__ float reduce16(float (&v)[16], uint32_t lane) {
     return __fadd_rn(v[0], __shfl_xor_sync(FULL, v[0], 1));
 }
 
+// stochastic_downsample_by_degree: one bit per walk position, set when the centre there is
+// skipped; lane t evaluates position t (one Philox block per position instead of one per lane
+// and position), the words live right behind the staged walk
+__device__ __forceinline__ void stage_skip_mask(const TrainParams &p, uint32_t wid_lo, uint32_t wid_hi,
+                                                uint32_t *walk, uint32_t L, uint32_t lane) {
+    if (!p.downsample) return;
+    uint32_t *mask = walk + ((L + 31u) & ~31u);
+    for (uint32_t base = 0; base < L; base += 32u) {
+        const uint32_t t = base + lane;
+        bool skip = false;
+        if (t < L) {
+            const uint32_t c = walk[t];  // written by this very lane just above
+            skip = c != PAD && skip_centre(p, wid_lo, wid_hi, t, c);
+        }
+        const uint32_t word = __ballot_sync(FULL, skip);
+        if (lane == 0) mask[base >> 5] = word;
+    }
+    __syncwarp();
+}
+
 // per-warp carve-up of dynamic shared memory; everything exists in two stages
 struct PipeSmem {
     float *rows_base;    // [2][K + 2][row_stride]: target rows, then the centre row of T0
@@ -80,7 +100,7 @@ struct PipeSmem {
 __host__ __device__ __forceinline__ uint32_t pipe_warp_bytes(uint32_t negatives, uint32_t chunks,
                                                              uint32_t walk_length) {
     return 2u * (negatives + 2u) * chunks * 16u + 2u * 32u * 8u + 2u * PIPE_SLOTS * 4u +
-           ((walk_length + 31u) & ~31u) * 4u;
+           ((walk_length + 31u) & ~31u) * 4u + ((walk_length + 31u) / 32u) * 4u;  // walk + centre skip mask
 }
 
 // what a thread needs to address its 16 B chunk of any row
@@ -229,6 +249,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
             const uint32_t *src = p.walks + w * (uint64_t)L;
             __syncwarp();
             for (uint32_t t = lane; t < L; t += 32u) sm.walk[t] = __ldg(src + t);
+            stage_skip_mask(p, wid_lo, wid_hi, sm.walk, L, lane);
             __syncwarp();
         }
         const uint32_t *walk = sm.walk;
@@ -390,6 +411,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
             const uint32_t *src = p.walks + w * (uint64_t)L;
             __syncwarp();
             for (uint32_t t = lane; t < L; t += 32u) sm.walk[t] = __ldg(src + t);
+            stage_skip_mask(p, wid_lo, wid_hi, sm.walk, L, lane);
             __syncwarp();
         }
         const uint32_t *walk = sm.walk;
@@ -568,7 +590,6 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
 
 bool pipe_supported(const TrainParams &p, uint32_t model) {
     if (p.chunks > 32u || p.negatives + 1u > PIPE_SLOTS || p.walk_length > 1024u) return false;
-    if (p.downsample) return false;  // the centre skip test lives in the generic kernel only
     return model == B2E_SKIPGRAM || 2u * p.window + 1u <= 32u;
 }
 

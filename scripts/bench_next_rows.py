@@ -99,7 +99,7 @@ def main():
     # ---- (f)-2 / (f)-3: SGD variants, pairs/s of one launch ----
     sgd = {
         "SkipGram pipelined (reference point)": dict(model="SkipGram"),
-        "SkipGram stochastic_downsample_by_degree (generic kernel)": dict(model="SkipGram", stochastic_downsample_by_degree=True),
+        "SkipGram stochastic_downsample_by_degree": dict(model="SkipGram", stochastic_downsample_by_degree=True),
         "Walklets SkipGram scale 2": dict(model="SkipGram", walklet_scale=2, window_size=1),
         "Walklets CBOW scale 3": dict(model="CBOW", walklet_scale=3, window_size=1),
     }
