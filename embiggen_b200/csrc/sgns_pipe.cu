@@ -100,7 +100,8 @@ struct PipeSmem {
 __host__ __device__ __forceinline__ uint32_t pipe_warp_bytes(uint32_t negatives, uint32_t chunks,
                                                              uint32_t walk_length) {
     return 2u * (negatives + 2u) * chunks * 16u + 2u * 32u * 8u + 2u * PIPE_SLOTS * 4u +
-           ((walk_length + 31u) & ~31u) * 4u + ((walk_length + 31u) / 32u) * 4u;  // walk + centre skip mask
+           ((walk_length + 31u) & ~31u) * 4u +              // the walk
+           ((((walk_length + 31u) / 32u) * 4u + 15u) & ~15u);  // centre skip mask, slab stays 16 B aligned
 }
 
 // what a thread needs to address its 16 B chunk of any row
