@@ -106,13 +106,23 @@ __device__ __forceinline__ void edge_metric_values(const GraphView &g, uint32_t 
         const uint32_t l = a_len; a_len = b_len; b_len = l;
     }
     float common = 0.f, adamic_adar = 0.f, resource = 0.f;
+    uint32_t from = 0;  // a lane's successive keys ascend: its lower bounds do too
     for (uint32_t i = lane; i < a_len; i += 32u) {
         const uint32_t x = __ldg(g.indices + a_off + i);
-        uint32_t lo = 0, hi = b_len;
+        // gallop from the previous lower bound, then bisect the bracket: O(log gap) probes
+        // instead of O(log deg), which is what makes hub-hub pairs (the bulk of a scale-free
+        // mini-batch) affordable
+        uint32_t lo = from, step = 1;
+        while (lo + step < b_len && __ldg(g.indices + b_off + lo + step) < x) {
+            lo += step;
+            step <<= 1;
+        }
+        uint32_t hi = min(lo + step, b_len);
         while (lo < hi) {
             const uint32_t mid = lo + ((hi - lo) >> 1);
             if (__ldg(g.indices + b_off + mid) < x) lo = mid + 1; else hi = mid;
         }
+        from = lo;
         if (lo < b_len && __ldg(g.indices + b_off + lo) == x) {
             const float dx = (float)(uint32_t)(__ldg(g.indptr + x + 1) - __ldg(g.indptr + x));
             common += 1.f;
