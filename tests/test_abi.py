@@ -33,6 +33,40 @@ def test_config_struct_matches_header_layout():
     assert ctypes.sizeof(_lib.B2ECounters) == 48
 
 
+def header_struct(name):
+    """[(C type, field name, array length or None)] of `typedef struct { ... } name;` in the header."""
+    header = open(os.path.join(ROOT, "include", "b2e.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    body = re.search(r"typedef struct \{([^}]*)\}\s*" + name + r"\s*;", header).group(1)
+    fields = []
+    for declaration in body.split(";"):
+        match = re.match(r"\s*(\w+)\s+(\w+)(?:\[(\d+)\])?\s*$", declaration)
+        if match:
+            fields.append((match.group(1), match.group(2), int(match.group(3)) if match.group(3) else None))
+    return fields
+
+
+@pytest.mark.parametrize("name,mirror", [("b2e_config", _lib.B2EConfig), ("b2e_counters", _lib.B2ECounters),
+                                         ("b2e_perceptron_config", _lib.B2EPerceptronConfig)])
+def test_ctypes_mirrors_follow_the_header_field_by_field(name, mirror):
+    ctypes_of = {"uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "uint64_t": ctypes.c_uint64,
+                 "float": ctypes.c_float, "double": ctypes.c_double}
+    declared = header_struct(name)
+    assert [field for _, field, _ in declared] == [field for field, _ in mirror._fields_]
+    for (c_type, field, length), (_, python_type) in zip(declared, mirror._fields_):
+        expected = ctypes_of[c_type] * length if length else ctypes_of[c_type]
+        assert python_type is expected or (length and python_type._type_ is ctypes_of[c_type]
+                                           and python_type._length_ == length), field
+
+
+def test_integration_stub_lists_the_config_fields_in_header_order():
+    """INTEGRATION.md shows the ctypes stub a maintainer would write: keep it in step."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = text[text.index("class b2e_config(ctypes.Structure)"):text.index("def fit_transform(graph")]
+    names = re.findall(r'"(\w+)"', stub)
+    assert names == [field for _, field, _ in header_struct("b2e_config")]
+
+
 def test_abi_version_and_error_channel():
     lib = _lib.load()
     assert lib.b2e_abi_version() == 1
