@@ -96,6 +96,17 @@ __device__ __forceinline__ void scalar_features(const float *__restrict__ a, con
 // values: [0] deg(u) / max degree, [1] deg(v) / max degree, [2] Adamic-Adar, [3] Jaccard,
 // [4] resource allocation index, [5] preferential attachment (normalised by max degree^2).
 // Lanes stride over the shorter row and bisect the longer one.
+__device__ __forceinline__ void finish_metric_values(const GraphView &g, float du, float dv, float common,
+                                                     float adamic_adar, float resource, float (&out)[6]) {
+    const float uni = du + dv - common;
+    out[0] = du * g.inv_max_degree;
+    out[1] = dv * g.inv_max_degree;
+    out[2] = adamic_adar;
+    out[3] = uni > 0.f ? common / uni : 0.f;
+    out[4] = resource;
+    out[5] = (du * g.inv_max_degree) * (dv * g.inv_max_degree);
+}
+
 __device__ __forceinline__ void edge_metric_values(const GraphView &g, uint32_t u, uint32_t v, uint32_t lane,
                                                    float (&out)[6]) {
     int64_t a_off = __ldg(g.indptr + u), b_off = __ldg(g.indptr + v);
@@ -133,13 +144,58 @@ __device__ __forceinline__ void edge_metric_values(const GraphView &g, uint32_t 
     common = warp_sum(common);
     adamic_adar = warp_sum(adamic_adar);
     resource = warp_sum(resource);
-    const float uni = du + dv - common;
-    out[0] = du * g.inv_max_degree;
-    out[1] = dv * g.inv_max_degree;
-    out[2] = adamic_adar;
-    out[3] = uni > 0.f ? common / uni : 0.f;
-    out[4] = resource;
-    out[5] = (du * g.inv_max_degree) * (dv * g.inv_max_degree);
+    finish_metric_values(g, du, dv, common, adamic_adar, resource, out);
+}
+
+// The same pass by a whole CTA for the `count` samples its warps drew (perceptron_step_kernel):
+// a scale-free mini-batch is full of hub-hub negatives whose two rows are long, and a step lasts
+// as long as its slowest sample, so all 256 threads stride over the shorter row of one sample
+// after the other.  sums[s] = {common, Adamic-Adar, resource allocation} of sample s.
+__device__ __forceinline__ void cta_common_neighbours(const GraphView &g, const uint32_t *s_u, const uint32_t *s_v,
+                                                      const uint32_t *s_valid, uint32_t count, float (*sums)[3]) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t s = 0; s < count; ++s) {
+        if (!s_valid[s]) continue;  // CTA-uniform
+        int64_t a_off = __ldg(g.indptr + s_u[s]), b_off = __ldg(g.indptr + s_v[s]);
+        uint32_t a_len = (uint32_t)(__ldg(g.indptr + s_u[s] + 1) - a_off);
+        uint32_t b_len = (uint32_t)(__ldg(g.indptr + s_v[s] + 1) - b_off);
+        if (a_len > b_len) {
+            const int64_t t = a_off; a_off = b_off; b_off = t;
+            const uint32_t l = a_len; a_len = b_len; b_len = l;
+        }
+        float common = 0.f, adamic_adar = 0.f, resource = 0.f;
+        uint32_t from = 0;
+        for (uint32_t i = threadIdx.x; i < a_len; i += blockDim.x) {
+            const uint32_t x = __ldg(g.indices + a_off + i);
+            uint32_t lo = from, step = 1;
+            while (lo + step < b_len && __ldg(g.indices + b_off + lo + step) < x) {
+                lo += step;
+                step <<= 1;
+            }
+            uint32_t hi = min(lo + step, b_len);
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (__ldg(g.indices + b_off + mid) < x) lo = mid + 1; else hi = mid;
+            }
+            from = lo;
+            if (lo < b_len && __ldg(g.indices + b_off + lo) == x) {
+                const float dx = (float)(uint32_t)(__ldg(g.indptr + x + 1) - __ldg(g.indptr + x));
+                common += 1.f;
+                if (dx > 1.f) adamic_adar += 1.f / logf(dx);
+                if (dx > 0.f) resource += 1.f / dx;
+            }
+        }
+        if (a_len > (threadIdx.x & ~31u)) {  // warp-uniform: warps past the end of the row have nothing to add
+            common = warp_sum(common);
+            adamic_adar = warp_sum(adamic_adar);
+            resource = warp_sum(resource);
+            if (lane == 0 && common > 0.f) {
+                atomicAdd(&sums[s][0], common);
+                atomicAdd(&sums[s][1], adamic_adar);
+                atomicAdd(&sums[s][2], resource);
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t metric_slot(uint32_t id) {  // first value of the metric in `out`
@@ -296,40 +352,58 @@ __global__ void __launch_bounds__(256) perceptron_step_kernel(const StepParams p
     extern __shared__ float smem[];
     float *w = smem;                         // size + 1
     float *g = smem + methods.size + 1;      // size + 1
+    __shared__ uint32_t s_u[8], s_v[8], s_valid[8];
+    __shared__ float s_sums[8][3];
     for (uint32_t j = threadIdx.x; j <= methods.size; j += blockDim.x) { w[j] = p.params[j]; g[j] = 0.f; }
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const GraphView graph = {p.indptr, p.indices, p.inv_max_degree};
     float loss = 0.f, valid_count = 0.f;
-    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < p.batch; k += warps) {
+    // a CTA takes 8 consecutive samples per round, one per warp (CTA-uniform trip count)
+    for (uint32_t base = blockIdx.x * 8u; base < p.batch; base += gridDim.x * 8u) {
+        const uint32_t k = base + warp;
         const uint4 r = philox4x32_10(p.seed_lo, p.seed_hi, k, p.step, 0u, TAG_EDGE_SAMPLE << 24);
         const bool positive = (k & 1u) == 0u;
         const uint64_t ex = __umul64hi((uint64_t)r.x << 32, p.nnz), ey = __umul64hi((uint64_t)r.y << 32, p.nnz);
-        uint32_t u, v;
-        if (positive) {
-            u = __ldg(p.edge_src + ex);
-            v = __ldg(p.indices + ex);
-        } else if (p.scale_free) {
-            u = __ldg(p.edge_src + ex);
-            v = __ldg(p.indices + ey);
-        } else {
-            u = __umulhi(r.x, p.n);
-            v = __umulhi(r.y, p.n);
+        uint32_t u = 0, v = 0;
+        bool valid = k < p.batch;
+        if (valid) {
+            if (positive) {
+                u = __ldg(p.edge_src + ex);
+                v = __ldg(p.indices + ex);
+            } else if (p.scale_free) {
+                u = __ldg(p.edge_src + ex);
+                v = __ldg(p.indices + ey);
+            } else {
+                u = __umulhi(r.x, p.n);
+                v = __umulhi(r.y, p.n);
+            }
+            valid = positive || u != v;
+            if (valid && !positive && p.avoid_false_negatives) valid = !is_edge(p, u, v);
         }
-        bool valid = positive || u != v;
-        if (valid && !positive && p.avoid_false_negatives) valid = !is_edge(p, u, v);
-        if (!valid) continue;  // warp-uniform
+        float values[6];
+        if (methods.n_metrics) {  // CTA-uniform
+            if (lane == 0) {
+                s_u[warp] = u; s_v[warp] = v; s_valid[warp] = valid ? 1u : 0u;
+                s_sums[warp][0] = s_sums[warp][1] = s_sums[warp][2] = 0.f;
+            }
+            __syncthreads();
+            cta_common_neighbours(graph, s_u, s_v, s_valid, 8u, s_sums);
+            __syncthreads();
+            if (valid) {
+                const float du = (float)(uint32_t)(__ldg(p.indptr + u + 1) - __ldg(p.indptr + u));
+                const float dv = (float)(uint32_t)(__ldg(p.indptr + v + 1) - __ldg(p.indptr + v));
+                finish_metric_values(graph, du, dv, s_sums[warp][0], s_sums[warp][1], s_sums[warp][2], values);
+            }
+            __syncthreads();  // s_* are rewritten in the next round
+        }
+        if (!valid) continue;  // warp-uniform; no CTA-wide barrier below this line
         const float *a = p.features + (uint64_t)u * p.pitch;
         const float *b = p.features + (uint64_t)v * p.pitch;
         float l2 = 0.f, cosine = 0.f;
         if (needs_scalars(methods)) scalar_features(a, b, p.dim, lane, l2, cosine);
         float z = forward_dot(a, b, p.dim, lane, methods, w, l2, cosine) + w[methods.size];
-        float values[6];
-        if (methods.n_metrics) {
-            const GraphView graph = {p.indptr, p.indices, p.inv_max_degree};
-            edge_metric_values(graph, u, v, lane, values);
-            z = __shfl_sync(0xffffffffu, z + metrics_dot(methods, w, values), 0);
-        }
+        if (methods.n_metrics) z += metrics_dot(methods, w, values);
         const float prob = sigmoidf(z);
         const float delta = (prob - (positive ? 1.0f : 0.0f)) / (float)p.batch;
         if (lane == 0) {
