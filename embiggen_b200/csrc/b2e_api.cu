@@ -224,22 +224,41 @@ static bool build_alias(const int64_t *indptr, uint64_t n, double alpha, std::ve
     return true;
 }
 
-// per-edge sampling table of a weighted graph; normative construction: oracle/walks.c
-static bool build_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, std::vector<uint32_t> &cdf) {
+// per-row Vose alias tables of a weighted graph, {thr, alias index inside the row} per edge;
+// normative construction: oracle/walks.c (orc_edge_alias), reproduced bit for bit
+static bool build_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, std::vector<uint2> &table) {
+    std::vector<double> scaled;
+    std::vector<uint32_t> small, large;
     for (uint64_t v = 0; v < n; ++v) {
-        const int64_t begin = indptr[v], end = indptr[v + 1];
+        const int64_t begin = indptr[v];
+        const uint64_t d = (uint64_t)(indptr[v + 1] - begin);
+        uint2 *row = table.data() + begin;
         double total = 0.0;
-        for (int64_t e = begin; e < end; ++e) {
-            if (!(weights[e] >= 0.0f)) return false;
-            total += (double)weights[e];
+        uint64_t heaviest = 0;
+        for (uint64_t i = 0; i < d; ++i) {
+            const float w = weights[begin + i];
+            if (!(w >= 0.0f)) return false;
+            total += (double)w;
+            if (w > weights[begin + heaviest]) heaviest = i;
         }
-        double running = 0.0;
-        for (int64_t e = begin; e < end; ++e) {
-            running += (double)weights[e];
-            const double t = total > 0.0 ? floor(running / total * 4294967296.0) : 4294967295.0;
-            cdf[e] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        scaled.resize(d);
+        small.clear();
+        large.clear();
+        for (uint64_t i = 0; i < d; ++i) {
+            scaled[i] = total > 0.0 ? (double)weights[begin + i] * (double)d / total : 1.0;
+            row[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i);
+            if (scaled[i] < 1.0) small.push_back((uint32_t)i); else large.push_back((uint32_t)i);
         }
-        if (end > begin) cdf[end - 1] = 0xFFFFFFFFu;
+        while (!small.empty() && !large.empty()) {
+            const uint32_t s = small.back(); small.pop_back();
+            const uint32_t l = large.back(); large.pop_back();
+            const double t = floor(scaled[s] * 4294967296.0);
+            row[s] = make_uint2(t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t, l);
+            scaled[l] = (scaled[l] + scaled[s]) - 1.0;
+            if (scaled[l] < 1.0) small.push_back(l); else large.push_back(l);
+        }
+        for (const uint32_t s : small)  // leftovers of weight zero are never proposed
+            if (total > 0.0 && weights[begin + s] == 0.0f) row[s] = make_uint2(0u, (uint32_t)heaviest);
     }
     return true;
 }
@@ -317,11 +336,11 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         weights = normalised.data();
     }
     if (weights) {
-        std::vector<uint32_t> cdf(nnz);
-        if (!build_edge_cdf(indptr, weights, n, cdf))
+        std::vector<uint2> cdf(nnz);
+        if (!build_edge_alias(indptr, weights, n, cdf))
             return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
-        CUDA_TRY(cudaMalloc(&h->d_cdf, nnz * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpyAsync(h->d_cdf, cdf.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
+        CUDA_TRY(cudaMalloc(&h->d_cdf, nnz * sizeof(uint2)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cdf, cdf.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
                                  h->walk_stream));
         CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `cdf` dies here
     }

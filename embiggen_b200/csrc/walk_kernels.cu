@@ -27,18 +27,16 @@ __device__ __forceinline__ bool row_contains(const uint32_t *__restrict__ row, u
 }
 
 // index of a proposal inside a row: uniform, or proportional to the edge weights through the
-// per-edge table built at load time (first entry whose cdf exceeds the random word)
+// row's Vose alias table built at load time -- O(1): one 8-byte gather; the high word of r * deg
+// picks the slot, its low word is the coin (oracle/walks.c: propose)
 template <bool WEIGHTED>
-__device__ __forceinline__ uint32_t propose(const uint32_t *__restrict__ cdf, int64_t off, uint32_t deg,
+__device__ __forceinline__ uint32_t propose(const uint2 *__restrict__ table, int64_t off, uint32_t deg,
                                             uint32_t r) {
-    if (!WEIGHTED) return __umulhi(r, deg);
-    const uint32_t *row = cdf + off;
-    uint32_t lo = 0, hi = deg;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(row + mid) > r) hi = mid; else lo = mid + 1;
-    }
-    return lo < deg ? lo : deg - 1;
+    const unsigned long long u = (unsigned long long)r * deg;
+    const uint32_t i = (uint32_t)(u >> 32);
+    if (!WEIGHTED) return i;
+    const uint2 e = __ldg(table + off + i);
+    return (uint32_t)u < e.x ? i : e.y;
 }
 
 template <bool SECOND, bool VEC, bool WEIGHTED>

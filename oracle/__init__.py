@@ -83,8 +83,8 @@ def lib():
         l.orc_walks.restype = ctypes.c_int
         l.orc_walks.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32), u64, u64, u64, u64, u64,
                                 u32, f32, f32, P(u32), P(WalkCounters)]
-        l.orc_edge_cdf.restype = ctypes.c_int
-        l.orc_edge_cdf.argtypes = [P(ctypes.c_int64), P(f32), u64, P(u32)]
+        l.orc_edge_alias.restype = ctypes.c_int
+        l.orc_edge_alias.argtypes = [P(ctypes.c_int64), P(f32), u64, P(u32)]
         l.orc_walks_weighted.restype = ctypes.c_int
         l.orc_walks_weighted.argtypes = [P(ctypes.c_int64), P(u32), P(u32), u64, P(u32), u64, u64, u64,
                                          u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
@@ -160,16 +160,17 @@ def thresholds(return_weight: float, explore_weight: float) -> np.ndarray:
     return out
 
 
-def edge_cdf(indptr, weights) -> np.ndarray:
-    """Per-edge sampling table of a weighted graph (normative construction in walks.c)."""
+def edge_alias(indptr, weights) -> np.ndarray:
+    """Per-row Vose alias tables of a weighted graph, shape (nnz, 2): {thr, alias index inside
+    the row} (oracle/walks.c: orc_edge_alias)."""
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     weights = np.ascontiguousarray(weights, dtype=np.float32)
-    cdf = np.empty(weights.shape[0], dtype=np.uint32)
-    rc = lib().orc_edge_cdf(_ptr(indptr, ctypes.c_int64), _ptr(weights, ctypes.c_float),
-                            indptr.shape[0] - 1, _ptr(cdf, ctypes.c_uint32))
+    table = np.empty((weights.shape[0], 2), dtype=np.uint32)
+    rc = lib().orc_edge_alias(_ptr(indptr, ctypes.c_int64), _ptr(weights, ctypes.c_float),
+                              indptr.shape[0] - 1, _ptr(table, ctypes.c_uint32))
     if rc != 0:
-        raise ValueError(f"orc_edge_cdf failed with status {rc}")
-    return cdf
+        raise ValueError(f"orc_edge_alias failed with status {rc} (negative or NaN weight?)")
+    return table
 
 
 def degree_normalised_weights(indptr, indices, weights=None) -> np.ndarray:
@@ -191,7 +192,7 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
     indptr, indices = _csr(indptr, indices)
     if normalize_by_degree:
         weights = degree_normalised_weights(indptr, indices, weights)
-    cdf = None if weights is None else edge_cdf(indptr, weights)
+    cdf = None if weights is None else edge_alias(indptr, weights)
     n = indptr.shape[0] - 1
     if srcs is None:
         srcs = sources(indptr)

@@ -58,8 +58,9 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
               uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
               float explore_weight, uint32_t *out, orc_walk_counters *counters);
 
-/* per-edge sampling table of a weighted graph (see walks.c); cdf has nnz entries */
-int orc_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *cdf);
+/* per-row alias tables of a weighted graph (see walks.c): two words per edge, {thr, alias index
+ * inside the row}.  The `cdf` arguments below take this table (NULL: unweighted). */
+int orc_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *table);
 
 /* orc_walks with proposals proportional to the edge weights (cdf from orc_edge_cdf; NULL: uniform) */
 int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,

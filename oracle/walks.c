@@ -21,6 +21,7 @@
 #include "philox.h"
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 void orc_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
     orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c0, c1, c2, c3, out);
@@ -79,42 +80,73 @@ static uint64_t probe_sectors(uint64_t len) {
 
 /*
  * Edge weights ("next" row f-2; the reference's classes advertise them:
- * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:119-129).  Normative
- * construction of the per-row sampling table: running = left-to-right double sum of the row's
- * weights; cdf[i] = min(2^32 - 1, floor(running_i / total * 2^32)), last entry 2^32 - 1.  A
- * proposal with random word r picks the first entry whose cdf exceeds r (the last one if none),
- * i.e. edge i with probability w_i / total up to 2^-32; second order keeps the p/q accept test
- * (KnightKing: proposal proportional to the static weight, acceptance by the dynamic bias).
+ * /root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:119-129).  Proposals are
+ * drawn proportionally to the static weight in O(1) through a per-row Vose alias table; second
+ * order keeps the p/q accept test on top (KnightKing: proposal by the static weight, acceptance
+ * by the dynamic bias).  Normative construction, per row of d edges (the product's host-side
+ * builder must reproduce it bit for bit): scaled_i = w_i * d / total with total the
+ * left-to-right double sum of the row; small / large are LIFO stacks filled in ascending edge
+ * order; thr_i = min(floor(prob_i * 2^32), 2^32 - 1); leftovers keep thr = 2^32 - 1 and alias =
+ * self, except a leftover of weight zero, which gets thr = 0 and the row's heaviest edge as alias
+ * (a zero-weight edge is never proposed); a row of total weight zero is uniform.  The table holds
+ * two words per edge: {thr, alias index inside the row}.
+ * Sampling with ONE random word r: u = r * d (64 bit); i = u >> 32; the low word of u is the
+ * coin: edge = low < thr_i ? i : alias_i.
  */
-int orc_edge_cdf(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *cdf) {
-    if (!indptr || !weights || !cdf) return -1;
-    for (uint64_t v = 0; v < n; ++v) {
-        const int64_t begin = indptr[v], end = indptr[v + 1];
+int orc_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *table) {
+    if (!indptr || !weights || !table) return -1;
+    uint64_t max_degree = 0;
+    for (uint64_t v = 0; v < n; ++v)
+        if ((uint64_t)(indptr[v + 1] - indptr[v]) > max_degree) max_degree = (uint64_t)(indptr[v + 1] - indptr[v]);
+    double *scaled = (double *)malloc((max_degree + 1) * sizeof(double));
+    uint32_t *small = (uint32_t *)malloc((max_degree + 1) * sizeof(uint32_t));
+    uint32_t *large = (uint32_t *)malloc((max_degree + 1) * sizeof(uint32_t));
+    if (!scaled || !small || !large) { free(scaled); free(small); free(large); return -3; }
+    int status = 0;
+    for (uint64_t v = 0; v < n && status == 0; ++v) {
+        const int64_t begin = indptr[v];
+        const uint64_t d = (uint64_t)(indptr[v + 1] - begin);
+        uint32_t *row = table + 2 * begin;
         double total = 0.0;
-        for (int64_t e = begin; e < end; ++e) {
-            if (!(weights[e] >= 0.0f)) return -2; /* negative or NaN */
-            total += (double)weights[e];
+        uint64_t heaviest = 0;
+        for (uint64_t i = 0; i < d; ++i) {
+            const float w = weights[begin + i];
+            if (!(w >= 0.0f)) { status = -2; break; } /* negative or NaN */
+            total += (double)w;
+            if (w > weights[begin + heaviest]) heaviest = i;
         }
-        double running = 0.0;
-        for (int64_t e = begin; e < end; ++e) {
-            running += (double)weights[e];
-            double t = total > 0.0 ? floor(running / total * 4294967296.0) : 4294967295.0;
-            cdf[e] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        if (status) break;
+        uint64_t ns = 0, nl = 0;
+        for (uint64_t i = 0; i < d; ++i) {
+            scaled[i] = total > 0.0 ? (double)weights[begin + i] * (double)d / total : 1.0;
+            row[2 * i] = 0xFFFFFFFFu;
+            row[2 * i + 1] = (uint32_t)i;
+            if (scaled[i] < 1.0) small[ns++] = (uint32_t)i; else large[nl++] = (uint32_t)i;
         }
-        if (end > begin) cdf[end - 1] = 0xFFFFFFFFu;
+        while (ns > 0 && nl > 0) {
+            const uint32_t s = small[--ns];
+            const uint32_t l = large[--nl];
+            const double t = floor(scaled[s] * 4294967296.0);
+            row[2 * s] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            row[2 * s + 1] = l;
+            scaled[l] = (scaled[l] + scaled[s]) - 1.0;
+            if (scaled[l] < 1.0) small[ns++] = l; else large[nl++] = l;
+        }
+        for (uint64_t k = 0; k < ns; ++k) { /* leftovers of weight zero are never proposed */
+            const uint32_t s = small[k];
+            if (total > 0.0 && weights[begin + s] == 0.0f) { row[2 * s] = 0; row[2 * s + 1] = (uint32_t)heaviest; }
+        }
     }
-    return 0;
+    free(scaled); free(small); free(large);
+    return status;
 }
 
-/* index of the proposal inside a row: uniform (cdf == NULL) or weighted */
-static uint32_t propose(const uint32_t *cdf_row, uint32_t deg, uint32_t r) {
-    if (!cdf_row) return orc_mulhi(r, deg);
-    uint32_t lo = 0, hi = deg;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (cdf_row[mid] > r) hi = mid; else lo = mid + 1;
-    }
-    return lo < deg ? lo : deg - 1;
+/* index of the proposal inside a row: uniform (table == NULL) or by the row's alias table */
+static uint32_t propose(const uint32_t *table_row, uint32_t deg, uint32_t r) {
+    const uint64_t u = (uint64_t)r * deg;
+    const uint32_t i = (uint32_t)(u >> 32);
+    if (!table_row) return i;
+    return (uint32_t)u < table_row[2 * i] ? i : table_row[2 * i + 1];
 }
 
 static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
@@ -155,7 +187,7 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
  * ratios and the walk follows  weight * bias_pq * type factors  exactly (up to 2^-32).
  * `normalize_by_degree` (.../node2vec_skipgram.py:94-96: the transition weight divided by the
  * degree of the destination) is not a rejection test at all: it is folded into the proposal,
- * whose per-edge table is built over  weight / max(deg(destination), 1)  (orc_edge_cdf), so it
+ * whose per-edge table is built over  weight / max(deg(destination), 1)  (orc_edge_alias), so it
  * costs no extra trials however skewed the degrees are.
  * Integer arithmetic only; the cheap tests come first and the adjacency search is counted only
  * when it is reached and undecided.
@@ -206,7 +238,7 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
                 uint32_t rnd[4];
                 orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
                                   (ORC_TAG_WALK3 << 24) | trial, rnd);
-                e = off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, rnd[0]);
+                e = off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, rnd[0]);
                 next = indices[e];
                 ++n_trials;
                 int accept = 1;
@@ -307,7 +339,7 @@ static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uin
                 const uint32_t s = t - 1;
                 orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, s >> 2, ORC_TAG_WALK1 << 24,
                                   rnd);
-                next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, rnd[s & 3])];
+                next = indices[off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, rnd[s & 3])];
                 ++c.first_order;
             } else {
                 const int64_t poff = indptr[prev];
@@ -318,7 +350,7 @@ static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uin
                         orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
                                           (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
                     const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
-                    next = indices[off + propose(cdf ? cdf + off : NULL, (uint32_t)deg, r0)];
+                    next = indices[off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, r0)];
                     ++c.trials;
                     int cls;
                     if (next == prev) {

@@ -180,17 +180,31 @@ def weighted_test_graph():
     return graph, weights
 
 
-def test_edge_cdf_is_the_quantised_cumulative_distribution():
+def test_edge_alias_tables_reproduce_the_weights():
+    """pmf implied by a row's alias table == weights / total (to 2^-31 per entry); zero-weight
+    edges are never proposed; a row of total weight zero is uniform."""
     graph, weights = weighted_test_graph()
-    cdf = oracle.edge_cdf(graph.indptr, weights)
+    table = oracle.edge_alias(graph.indptr, weights)
+    assert table.shape == (graph.indices.shape[0], 2) and table.dtype == np.uint32
     for v in range(graph.get_number_of_nodes()):
         lo, hi = graph.indptr[v], graph.indptr[v + 1]
+        d = hi - lo
+        thr, alias = table[lo:hi, 0].astype(np.float64), table[lo:hi, 1].astype(np.int64)
+        assert (alias < d).all()
+        # coin: low word < thr keeps the slot (thr = 2^32 - 1 means "always" up to 2^-32)
+        keep = np.where(thr >= 2.0 ** 32 - 1, 1.0, thr / 2.0 ** 32)
+        pmf = keep / d
+        np.add.at(pmf, alias, (1.0 - keep) / d)
         row = weights[lo:hi].astype(np.float64)
-        expected = np.minimum(np.floor(np.cumsum(row) / row.sum() * 2.0 ** 32), 2.0 ** 32 - 1)
-        assert cdf[hi - 1] == 0xFFFFFFFF
-        assert np.array_equal(cdf[lo:hi - 1], expected[:-1].astype(np.uint32))
+        if row.sum() == 0:                     # node 11: its only edge weighs zero -> uniform row
+            assert np.allclose(pmf, 1.0 / d)
+            continue
+        assert np.allclose(pmf, row / row.sum(), atol=1e-9)
+        assert (pmf[row == 0] == 0).all()
     with pytest.raises(ValueError):
-        oracle.edge_cdf(graph.indptr, -weights)
+        oracle.edge_alias(graph.indptr, -weights)
+    zero = oracle.edge_alias(graph.indptr, np.zeros_like(weights))
+    assert (zero[:, 0] == 0xFFFFFFFF).all()   # uniform rows
 
 
 def test_weighted_first_order_follows_the_weights():
