@@ -153,7 +153,7 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
 static void free_graph(b2e_handle *h) {
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
-    cudaFree(h->d_cdf); h->d_cdf = nullptr;
+    cudaFree(h->d_edge_alias); h->d_edge_alias = nullptr;
     cudaFree(h->d_node_types); h->d_node_types = nullptr;
     cudaFree(h->d_edge_types); h->d_edge_types = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
@@ -336,13 +336,13 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         weights = normalised.data();
     }
     if (weights) {
-        std::vector<uint2> cdf(nnz);
-        if (!build_edge_alias(indptr, weights, n, cdf))
+        std::vector<uint2> edge_alias(nnz);
+        if (!build_edge_alias(indptr, weights, n, edge_alias))
             return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
-        CUDA_TRY(cudaMalloc(&h->d_cdf, nnz * sizeof(uint2)));
-        CUDA_TRY(cudaMemcpyAsync(h->d_cdf, cdf.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
+        CUDA_TRY(cudaMalloc(&h->d_edge_alias, nnz * sizeof(uint2)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_edge_alias, edge_alias.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
                                  h->walk_stream));
-        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `cdf` dies here
+        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `edge_alias` dies here
     }
     CUDA_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
@@ -435,7 +435,7 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     WalkParams p;
     p.indptr = h->d_indptr;
     p.indices = h->d_indices;
-    p.cdf = h->d_cdf;
+    p.edge_alias = h->d_edge_alias;
     p.node_types = h->d_node_types;
     p.edge_types = h->d_edge_types;
     type_thresholds(h->d_node_types ? h->cfg.change_node_type_weight : 1.0f, p.q_node);

@@ -50,7 +50,7 @@ struct DeviceCounters {
 struct WalkParams {
     const int64_t *indptr;
     const uint32_t *indices;
-    const uint2 *cdf;  // per-row alias tables of a weighted graph ({thr, alias} per edge), or nullptr
+    const uint2 *edge_alias;  // per-row alias tables of a weighted graph ({thr, alias} per edge), or nullptr
     const uint32_t *node_types, *edge_types;  // [n] / [nnz] type ids of typed walks, or nullptr
     unsigned long long q_node[2], q_edge[2];  // accept thresholds [same type, changed type]
     const uint32_t *sources;
@@ -140,7 +140,7 @@ struct b2e_handle {
     uint32_t row_stride = 0;
     int64_t *d_indptr = nullptr;
     uint32_t *d_indices = nullptr;
-    uint2 *d_cdf = nullptr;
+    uint2 *d_edge_alias = nullptr;
     uint32_t *d_node_types = nullptr, *d_edge_types = nullptr;
     b2e::GloveState glove;
     uint32_t *d_walk_raw = nullptr;  // Walklets: the chunk as walked, before it is split by stride

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                                                     TAG_WALK1 << 24);
                             const uint32_t r = (s & 3u) == 0 ? rnd.x : (s & 3u) == 1 ? rnd.y
                                              : (s & 3u) == 2 ? rnd.z : rnd.w;
-                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r));
+                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r));
                         } else {
                             const uint32_t *prow = p.indices + prev_off;
                             uint32_t trial = 0;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                                                         (TAG_WALK2 << 24) | (trial >> 1));
                                 const uint32_t r0 = (trial & 1u) ? rnd.z : rnd.x;
                                 const unsigned long long r1 = (trial & 1u) ? rnd.w : rnd.y;
-                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.cdf, off, deg, r0));
+                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r0));
                                 ++n_trials;
                                 bool accept;
                                 if (next == prev) {
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
                         for (;;) {
                             const uint4 rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
                                                             (TAG_WALK3 << 24) | trial);
-                            e = off + propose<WEIGHTED>(p.cdf, off, deg, rnd.x);
+                            e = off + propose<WEIGHTED>(p.edge_alias, off, deg, rnd.x);
                             next = __ldg(p.indices + e);
                             ++n_trials;
                             bool accept = true;
@@ -522,7 +522,7 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     const unsigned block = 256;
     const unsigned grid = (unsigned)((p.n_walks + block - 1) / block);
     const bool vec = (p.walk_length % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16u) == 0;
-    const bool weighted = p.cdf != nullptr;
+    const bool weighted = p.edge_alias != nullptr;
     const bool typed = (p.node_types && p.q_node[0] != p.q_node[1]) ||
                        (p.edge_types && p.q_edge[0] != p.q_edge[1]);
     if (typed) {  // typed walks: one trial loop per transition

@@ -192,7 +192,7 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
     indptr, indices = _csr(indptr, indices)
     if normalize_by_degree:
         weights = degree_normalised_weights(indptr, indices, weights)
-    cdf = None if weights is None else edge_alias(indptr, weights)
+    table = None if weights is None else edge_alias(indptr, weights)
     n = indptr.shape[0] - 1
     if srcs is None:
         srcs = sources(indptr)
@@ -206,7 +206,7 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
         edge_types = np.ascontiguousarray(edge_types, dtype=np.uint32)
         assert edge_types.shape[0] == indices.shape[0]
     rc = lib().orc_walks_typed(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
-                               _ptr(cdf, ctypes.c_uint32), _ptr(node_types, ctypes.c_uint32), _ptr(edge_types, ctypes.c_uint32),
+                               _ptr(table, ctypes.c_uint32), _ptr(node_types, ctypes.c_uint32), _ptr(edge_types, ctypes.c_uint32),
                                change_node_type_weight, change_edge_type_weight, n,
                                _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
                                walk_id_stride, walk_length, return_weight, explore_weight,

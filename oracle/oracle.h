@@ -59,11 +59,11 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
               float explore_weight, uint32_t *out, orc_walk_counters *counters);
 
 /* per-row alias tables of a weighted graph (see walks.c): two words per edge, {thr, alias index
- * inside the row}.  The `cdf` arguments below take this table (NULL: unweighted). */
+ * inside the row}.  The `table` arguments below take this table (NULL: unweighted). */
 int orc_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, uint32_t *table);
 
-/* orc_walks with proposals proportional to the edge weights (cdf from orc_edge_cdf; NULL: uniform) */
-int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+/* orc_walks with proposals proportional to the edge weights (table from orc_edge_alias; NULL: uniform) */
+int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *table, uint64_t n,
                        const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
@@ -71,9 +71,9 @@ int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uin
 
 /* orc_walks_weighted plus typed walks: node_types[n] / edge_types[nnz] (NULL: untyped) and the
  * weights multiplied in when the node type / the edge type changes.  normalize_by_degree is a
- * property of the proposal table: build `cdf` over weight / max(deg(destination), 1). */
+ * property of the proposal table: build `table` over weight / max(deg(destination), 1). */
 void orc_type_thresholds(float change_weight, uint64_t q[2]);
-int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *table,
                     const uint32_t *node_types, const uint32_t *edge_types,
                     float change_node_type_weight, float change_edge_type_weight, uint64_t n,
                     const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,

@@ -149,7 +149,7 @@ static uint32_t propose(const uint32_t *table_row, uint32_t deg, uint32_t r) {
     return (uint32_t)u < table_row[2 * i] ? i : table_row[2 * i + 1];
 }
 
-static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *table, uint64_t n,
                        const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
@@ -163,12 +163,12 @@ int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const 
                               walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
 }
 
-int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *table, uint64_t n,
                        const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
                        orc_walk_counters *counters) {
-    return walks_plain(indptr, indices, cdf, n, sources, n_src, seed, first_walk, n_walks,
+    return walks_plain(indptr, indices, table, n, sources, n_src, seed, first_walk, n_walks,
                        walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
 }
 
@@ -201,7 +201,7 @@ void orc_type_thresholds(float change_weight, uint64_t q[2]) {
     }
 }
 
-static int walks_general(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+static int walks_general(const int64_t *indptr, const uint32_t *indices, const uint32_t *table,
                          const uint32_t *node_types, const uint32_t *edge_types,
                          float change_node_type_weight, float change_edge_type_weight,
                          const uint32_t *sources, uint64_t n_src, uint64_t seed,
@@ -238,7 +238,7 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
                 uint32_t rnd[4];
                 orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
                                   (ORC_TAG_WALK3 << 24) | trial, rnd);
-                e = off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, rnd[0]);
+                e = off + propose(table ? table + 2 * off : NULL, (uint32_t)deg, rnd[0]);
                 next = indices[e];
                 ++n_trials;
                 int accept = 1;
@@ -284,7 +284,7 @@ static int walks_general(const int64_t *indptr, const uint32_t *indices, const u
     return 0;
 }
 
-int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf,
+int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32_t *table,
                     const uint32_t *node_types, const uint32_t *edge_types,
                     float change_node_type_weight, float change_edge_type_weight, uint64_t n,
                     const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
@@ -295,14 +295,14 @@ int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32
     const int typed = (node_types && change_node_type_weight != 1.0f) ||
                       (edge_types && change_edge_type_weight != 1.0f);
     if (!typed)
-        return orc_walks_weighted(indptr, indices, cdf, n, sources, n_src, seed, first_walk, n_walks,
+        return orc_walks_weighted(indptr, indices, table, n, sources, n_src, seed, first_walk, n_walks,
                                   walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
-    return walks_general(indptr, indices, cdf, node_types, edge_types, change_node_type_weight,
+    return walks_general(indptr, indices, table, node_types, edge_types, change_node_type_weight,
                          change_edge_type_weight, sources, n_src, seed, first_walk, n_walks,
                          walk_id_stride, walk_length, return_weight, explore_weight, out, counters);
 }
 
-static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *cdf, uint64_t n,
+static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uint32_t *table, uint64_t n,
                        const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
                        float return_weight, float explore_weight, uint32_t *out,
@@ -339,7 +339,7 @@ static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uin
                 const uint32_t s = t - 1;
                 orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, s >> 2, ORC_TAG_WALK1 << 24,
                                   rnd);
-                next = indices[off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, rnd[s & 3])];
+                next = indices[off + propose(table ? table + 2 * off : NULL, (uint32_t)deg, rnd[s & 3])];
                 ++c.first_order;
             } else {
                 const int64_t poff = indptr[prev];
@@ -350,7 +350,7 @@ static int walks_plain(const int64_t *indptr, const uint32_t *indices, const uin
                         orc_philox4x32_10(seed_lo, seed_hi, wid_lo, wid_hi, t - 1,
                                           (ORC_TAG_WALK2 << 24) | (trial >> 1), rnd);
                     const uint32_t r0 = rnd[2 * (trial & 1u)], r1 = rnd[2 * (trial & 1u) + 1];
-                    next = indices[off + propose(cdf ? cdf + 2 * off : NULL, (uint32_t)deg, r0)];
+                    next = indices[off + propose(table ? table + 2 * off : NULL, (uint32_t)deg, r0)];
                     ++c.trials;
                     int cls;
                     if (next == prev) {
