@@ -327,8 +327,10 @@ cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_
     GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, bytes, sorted, cat_keys + g.n_triples,
                                                  cat_counts + g.n_triples, d_runs, slots, stream));
     need = std::max(need, bytes);
-    GLOVE_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, cat_keys, out_keys, cat_counts, out_counts,
-                                              merged_cap, 0, 64, stream));
+    // merging two sorted lists is one linear pass (sorting the concatenation would be eight)
+    GLOVE_TRY(cub::DeviceMerge::MergePairs(nullptr, bytes, g.d_keys, g.d_counts, (int64_t)g.n_triples,
+                                           cat_keys + g.n_triples, cat_counts + g.n_triples, (int64_t)slots,
+                                           out_keys, out_counts, ::cuda::std::less<>{}, stream));
     need = std::max(need, bytes);
     GLOVE_TRY(cub::DeviceReduce::ReduceByKey(nullptr, bytes, out_keys, cat_keys, out_counts, cat_counts, d_runs,
                                              cub::Sum(), merged_cap, stream));
@@ -337,12 +339,7 @@ cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_
 
     bytes = g.temp_bytes;
     GLOVE_TRY(cub::DeviceRadixSort::SortKeys(g.d_temp, bytes, raw, sorted, slots, 0, 64, stream));
-    // the triples gathered so far sit at the head of the concatenation buffers
-    if (g.n_triples) {
-        GLOVE_TRY(cudaMemcpyAsync(cat_keys, g.d_keys, g.n_triples * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
-        GLOVE_TRY(cudaMemcpyAsync(cat_counts, g.d_counts, g.n_triples * sizeof(uint32_t),
-                                  cudaMemcpyDeviceToDevice, stream));
-    }
+    // the chunk's (key, count) list goes behind the room of the triples gathered so far
     bytes = g.temp_bytes;
     GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(g.d_temp, bytes, sorted, cat_keys + g.n_triples,
                                                  cat_counts + g.n_triples, d_runs, slots, stream));
@@ -355,21 +352,26 @@ cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_
         GLOVE_TRY(cudaStreamSynchronize(stream));
         if (last == COOC_INVALID) --runs;
     }
-    uint64_t total = g.n_triples + runs;
-    if (g.n_triples && runs) {  // merge: sort the concatenation by key, add the counts of equal keys
+    if (runs == 0) return cudaSuccess;  // nothing new: the resident triples stand
+    uint64_t total = runs;
+    const u64 *result_keys = cat_keys;  // g.n_triples == 0: the chunk's list is the result
+    const uint32_t *result_counts = cat_counts;
+    if (g.n_triples) {  // both lists are sorted: merge, then add the counts of equal keys
+        total = g.n_triples + runs;
         bytes = g.temp_bytes;
-        GLOVE_TRY(cub::DeviceRadixSort::SortPairs(g.d_temp, bytes, cat_keys, out_keys, cat_counts, out_counts,
-                                                  total, 0, 64, stream));
+        GLOVE_TRY(cub::DeviceMerge::MergePairs(g.d_temp, bytes, g.d_keys, g.d_counts, (int64_t)g.n_triples,
+                                               cat_keys + g.n_triples, cat_counts + g.n_triples, (int64_t)runs,
+                                               out_keys, out_counts, ::cuda::std::less<>{}, stream));
         bytes = g.temp_bytes;
         GLOVE_TRY(cub::DeviceReduce::ReduceByKey(g.d_temp, bytes, out_keys, cat_keys, out_counts, cat_counts,
                                                  d_runs, cub::Sum(), total, stream));
         GLOVE_TRY(cudaMemcpyAsync(&total, d_runs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
         GLOVE_TRY(cudaStreamSynchronize(stream));
     }
-    GLOVE_TRY(grow((void **)&g.d_keys, &g.keys_bytes, std::max<uint64_t>(total, 1) * sizeof(u64)));
-    GLOVE_TRY(grow((void **)&g.d_counts, &g.counts_bytes, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
-    GLOVE_TRY(cudaMemcpyAsync(g.d_keys, cat_keys, total * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
-    GLOVE_TRY(cudaMemcpyAsync(g.d_counts, cat_counts, total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    GLOVE_TRY(grow((void **)&g.d_keys, &g.keys_bytes, total * sizeof(u64)));
+    GLOVE_TRY(grow((void **)&g.d_counts, &g.counts_bytes, total * sizeof(uint32_t)));
+    GLOVE_TRY(cudaMemcpyAsync(g.d_keys, result_keys, total * sizeof(u64), cudaMemcpyDeviceToDevice, stream));
+    GLOVE_TRY(cudaMemcpyAsync(g.d_counts, result_counts, total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     g.n_triples = total;
     g.finalised = false;
     return cudaSuccess;

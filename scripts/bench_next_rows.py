@@ -146,6 +146,12 @@ def main():
         slots = 2 * glove_walks * L * W
         emit(row="f-3 GloVe co-occurrence", walks=glove_walks, key_slots=slots, triples=triples, seconds=cooc_s,
              walk_pairs_per_s=slots / cooc_s)
+        t0 = time.perf_counter()
+        many = engine.cooccurrence(SEED, 0, 4 * glove_walks)  # four chunks: three sorted-list merges
+        seconds = time.perf_counter() - t0
+        emit(row="f-3 GloVe co-occurrence, 4 chunks merged", walks=4 * glove_walks, key_slots=4 * slots,
+             triples=many, seconds=seconds, walk_pairs_per_s=4 * slots / seconds)
+        triples = engine.cooccurrence(SEED, 0, glove_walks)
         ms = timed(ts, lambda: engine.glove_train(0.05))
         bytes_ = triples * 2 * 4 * D + triples * 12
         emit(row="f-3 GloVe SGD", triples=triples, ms_per_pass=ms, triples_per_s=triples / ms * 1e3,
