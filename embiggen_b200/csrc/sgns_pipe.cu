@@ -311,6 +311,12 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
         float lr = p.lr;
         while (ok_cur) {
             cp_async_wait_all();  // rows of `cur` (this stage) and alias entries of `nxt` are here
+            // Memory ordering between lanes: the copies above were waited for by the lane that
+            // issued them, and the ids / alias slots of the other stage were last read in the
+            // previous iteration.  The warp is converged here anyway (ballot / match follow); the
+            // barrier makes the ordering a guarantee of the memory model instead of a property of
+            // the hardware.
+            __syncwarp();
             // ---- pair p+1: resolve ids, copy its rows unless pair p is about to update one ----
             uint32_t neg_nxt = PAD, vmask_nxt = 0, ids_nxt = 0xFFFFFF00u | lane;
             bool deferred = false;
@@ -461,6 +467,7 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
 
         while (i_cur < L) {
             cp_async_wait_all();
+            __syncwarp();  // inter-lane memory ordering, see skipgram_pipe_kernel
             // ---- centre p+1: resolve ids, copy its target rows, prefetch the entering row ----
             uint32_t neg_nxt = PAD, vmask_nxt = 0, ids_nxt = 0xFFFFFF00u | lane;
             bool deferred = false;
