@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: node2vec/DeepWalk walks + one SkipGram/CBOW SGD pass.
+"""Benchmark of the hot path: node2vec/DeepWalk walks + SkipGram/CBOW SGD over them.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --steps K --warmup W    # CPU baseline (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the path on the host cores
 
-A *step* is one pass of the hot path over one batch: walks from every start node once
-(n_src walks, one `iteration` of the reference's kwargs) followed by SGD over those walks.
-Workload = BASELINE.json configs[1] (C2): DeepWalk SkipGram on Erdos-Renyi 1M nodes / 10M
-edges, D=100, L=128, w=4, K=10.  `value` = context pairs/s (whole job, device-resident,
-walk kernel of step k+1 overlapped with the SGD kernel of step k); walk steps/s is reported
-beside it under "walk".  One JSON line on stdout (rank 0).
+Workload (default): BASELINE.json's headline shape, config C5 -- Node2Vec SkipGram p=0.5 q=2 on
+a synthetic R-MAT graph of 100 M nodes / 2 B edges, D=100, L=128, w=4, K=10 -- which fits one
+B200 (125 GB of 180).  When the host has too little memory for it the run falls back to C3 (the
+same model on R-MAT 10 M / 200 M) and says so in `config.workload`.
+
+A *step* is one pass of the hot path over one batch: `chunk` walks per GPU (2^20) from
+consecutive start nodes, then SGD over those walks; the walk kernel of step k+1 overlaps the SGD
+kernel of step k on a second stream.  `value` = context pairs/s of the whole job, device
+resident (CUDA events, max over ranks); with N > 1 GPUs the replicas are averaged every
+`--sync-interval` steps by the peer-memory exchange kernel, inside the timed region.  `e2e` = the
+named job in full through the reference-facing call -- host CSR in, one epoch over every start
+node, host tables out.  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -25,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: graph spec, model, kwargs
+    # name: graph spec, model, kwargs (BASELINE.json configs[1..4])
     "C2": dict(graph=("er", 1_000_000, 10_000_000), model="SkipGram", embedding_size=100,
                return_weight=1.0, explore_weight=1.0, iterations=10,
                label="DeepWalk SkipGram p=q=1, Erdos-Renyi 1M nodes / 10M edges"),
@@ -52,22 +58,62 @@ CONFIGS = {
 COMMON = dict(walk_length=128, window_size=4, number_of_negative_samples=10, learning_rate=0.01,
               learning_rate_decay=0.9, clipping_value=6.0)
 SEED = 42
+HEADLINE, FALLBACK = "C5", "C3"
+HEADLINE_HOST_GB = 150  # C5 on the host: 17 GB of CSR (+ its tmpfs copy) and 80 GB of tables
 GATHER_CEILING = 40.6e9  # measured random 4-byte gathers/s of a B200 over a 1.6 GB array
 METRIC = "skipgram_context_pairs_per_s"
 
 
-def load_graph(spec, device=None, world=1, local_rank=0, barrier=None):
-    """Synthetic graph of the named shape (generator seed 42), cached as raw .npy files (tmpfs
-    when available) and memory-mapped, so that the ranks of one node share one copy.
+def host_memory_gb():
+    try:
+        with open("/proc/meminfo") as handle:
+            for line in handle:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
 
-    With a GPU the graph is generated and its CSR built on the device (same graph as the numpy
-    generators, tests/test_gpu_graph_build.py); the CPU reference arm falls back to numpy.
-    With several ranks only local rank 0 generates; the others wait at `barrier` and map it."""
-    from embiggen_b200.graph import CSRGraph, erdos_renyi, rmat
+
+def choose_config(requested):
+    """(name, note): the headline shape unless the host cannot hold it (both arms decide alike)."""
+    if requested != "auto":
+        return requested, None
+    available = host_memory_gb()
+    if available >= HEADLINE_HOST_GB or os.environ.get("B2E_FORCE_HEADLINE"):
+        return HEADLINE, None
+    return FALLBACK, (f"fallback from {HEADLINE}: {available:.0f} GB of host memory available, "
+                      f"{HEADLINE_HOST_GB} GB needed for the 100M-node tables on the CPU arm")
+
+
+def config_dict(name, cfg, note):
+    """The `config` object: the same in both arms (the driver compares them)."""
+    n = cfg["graph"][3] if cfg["graph"][0] == "rmat" else cfg["graph"][1]
+    tables_mb = 2 * n * cfg["embedding_size"] * 4 / 1e6
+    return {"workload": cfg["label"] + (f" [{note}]" if note else ""), "name": name,
+            "objective": cfg["model"], "embedding_size": cfg["embedding_size"],
+            "return_weight": cfg["return_weight"], "explore_weight": cfg["explore_weight"], **COMMON,
+            "l2": f"inputs larger than L2 (tables {tables_mb:.0f} MB, rows gathered at random; no flush)"}
+
+
+def cache_paths(spec):
     tag = "_".join(str(x) for x in spec)
     default_cache = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
     base = os.path.join(os.environ.get("B2E_CACHE", default_cache), f"b2e_graph_{tag}")
-    paths = (base + ".indptr.npy", base + ".indices.npy")
+    return tag, (base + ".indptr.npy", base + ".indices.npy")
+
+
+def load_graph(spec, device=None, local_rank=0, barrier=None):
+    """Synthetic graph of the named shape (generator seed 42), cached as raw .npy files (tmpfs
+    when available) and memory-mapped, so that the ranks of one node -- and the two arms of one
+    driver run -- share one copy.
+
+    Ours (`device` given): generated and built on the GPU (csrc/graph_build.cu).  The reference
+    arm (`device` None): generated on the host cores by oracle/graphgen.c; it never loads the
+    product library.  All generators implement one definition and tests compare them.  With several
+    ranks only local rank 0 generates; the others wait at `barrier` and map the files."""
+    from embiggen_b200.graph import CSRGraph
+    tag, paths = cache_paths(spec)
 
     def cached():
         if all(os.path.exists(p) for p in paths):
@@ -75,29 +121,37 @@ def load_graph(spec, device=None, world=1, local_rank=0, barrier=None):
         return None
 
     graph = cached()
+    seconds = 0.0
     if graph is None and local_rank == 0:
+        begin = time.perf_counter()
+        n = spec[3] if spec[0] == "rmat" else spec[1]
         if device is not None:
             from embiggen_b200.graph_gpu import erdos_renyi_gpu, rmat_gpu
-            graph = erdos_renyi_gpu(spec[1], spec[2], seed=42, device=device) if spec[0] == "er" else \
+            built = erdos_renyi_gpu(spec[1], spec[2], seed=42, device=device) if spec[0] == "er" else \
                 rmat_gpu(spec[1], spec[2], n=spec[3], seed=42, device=device)
+            arrays = (built.indptr, built.indices)
+            del built
         else:
-            graph = erdos_renyi(spec[1], spec[2], seed=42) if spec[0] == "er" else \
-                rmat(spec[1], spec[2], n=spec[3], seed=42)
-        if world > 1 or graph.indices.shape[0] <= 1_000_000_000:  # one rank alone keeps 2 B edges in RAM
-            try:
-                for path, array in zip(paths, (graph.indptr, graph.indices)):
-                    tmp = path + f".{os.getpid()}.tmp.npy"
-                    np.save(tmp, array)
-                    os.replace(tmp, path)
-            except OSError:
-                pass
+            import oracle
+            oracle.set_threads(os.cpu_count() or 1)
+            arrays = oracle.synthetic_csr("er", n, spec[2], seed=42) if spec[0] == "er" else \
+                oracle.synthetic_csr("rmat", n, spec[2], scale=spec[1], seed=42)
+        seconds = time.perf_counter() - begin
+        try:
+            for path, array in zip(paths, arrays):
+                tmp = path + f".{os.getpid()}.tmp.npy"
+                np.save(tmp, array)
+                os.replace(tmp, path)
+            del arrays
+        except OSError:
+            graph = CSRGraph(arrays[0], arrays[1], name=tag)
     if barrier is not None:
         barrier()
     if graph is None:
         graph = cached()
     if graph is None:
         raise RuntimeError("the graph cache written by local rank 0 is not visible on this rank")
-    return graph
+    return graph, seconds
 
 
 def measured_traffic(config_name, walks_per_launch):
@@ -167,7 +221,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(clocks)}
 
 
-def skipgram_bytes(counters, embedding_size, walk_length, centres):
+def skipgram_bytes(counters, embedding_size, centres):
     """Algorithmic bytes of the SGD kernel from the device counters.
 
     Every scored target row is read and written once (2 * 4D), every centre row likewise,
@@ -184,88 +238,151 @@ def cbow_bytes(counters, embedding_size, centres):
     return (counters["pairs"] + counters["targets"]) * row + centres * 4 + negatives_drawn * 32
 
 
-def cpu_baseline(graph, cfg, budget_s=15.0, threads=None):
-    """Times the CPU oracle (multi-threaded Hogwild) on a bounded sample of the workload."""
-    import oracle
-    threads = threads or os.cpu_count() or 1
-    oracle.set_threads(threads)
-    n = graph.get_number_of_nodes()
-    D = cfg["embedding_size"]
-    thr, alias = oracle.alias_build(graph.indptr, 0.75)
-    t0, t1 = oracle.init_tables(n, D, SEED)
-    srcs = oracle.sources(graph.indptr)
+class CpuPath:
+    """The path on the host cores: oracle/ (plain C + OpenMP Hogwild, `fast_math` arithmetic: a
+    vectorised dot and libm exp instead of the warp-shaped bit-exact forms the parity tests use)."""
 
-    def run(first, count):
+    def __init__(self, graph, cfg, threads=None):
+        import oracle
+        self.oracle, self.graph, self.cfg = oracle, graph, cfg
+        self.threads = threads or os.cpu_count() or 1
+        oracle.set_threads(self.threads)
+        self.n = graph.get_number_of_nodes()
+        self.D = cfg["embedding_size"]
+        self.thr, self.alias = oracle.alias_build(graph.indptr, 0.75)
+        self.t0, self.t1 = oracle.init_tables(self.n, self.D, SEED)
+        self.srcs = oracle.sources(graph.indptr)
+
+    def step(self, first, count):
+        """walks + SGD over `count` walks; (walk steps, pairs, walk seconds, SGD seconds)"""
+        o, cfg = self.oracle, self.cfg
         begin = time.perf_counter()
-        walks, wc = oracle.walks(graph.indptr, graph.indices, SEED, first, count,
-                                 COMMON["walk_length"], cfg["return_weight"],
-                                 cfg["explore_weight"], srcs=srcs)
+        walks, wc = o.walks(self.graph.indptr, self.graph.indices, SEED, first, count, COMMON["walk_length"],
+                            cfg["return_weight"], cfg["explore_weight"], srcs=self.srcs, undirected=True)
         mid = time.perf_counter()
-        stats = oracle.train(cfg["model"], walks, t0, t1, SEED, n, D, COMMON["window_size"],
-                             COMMON["number_of_negative_samples"], COMMON["learning_rate"],
-                             COMMON["clipping_value"], first_walk=first, thr=thr, alias=alias)
+        stats = o.train(cfg["model"], walks, self.t0, self.t1, SEED, self.n, self.D, COMMON["window_size"],
+                        COMMON["number_of_negative_samples"], COMMON["learning_rate"],
+                        COMMON["clipping_value"], first_walk=first, thr=self.thr, alias=self.alias,
+                        fast_math=True)
         end = time.perf_counter()
         return wc["steps"], stats["pairs"], mid - begin, end - mid
 
-    _, pairs, tw, tt = run(0, 64 * threads)  # calibration (also warms the caches)
+    def close(self):
+        self.oracle.set_threads(1)
+
+
+def cpu_baseline(graph, cfg, budget_s=15.0):
+    """Times the CPU path on a bounded sample of the workload (rank 0, N = 1 only)."""
+    path = CpuPath(graph, cfg)
+    threads = path.threads
+    _, pairs, tw, tt = path.step(0, 64 * threads)  # calibration (also warms the caches)
     rate = pairs / max(tw + tt, 1e-9)
     per_walk = pairs / (64 * threads)
     count = int(max(64 * threads, min(2_000_000, budget_s * rate / per_walk)))
-    steps, pairs, tw, tt = run(64 * threads, count)
-    oracle.set_threads(1)
+    steps, pairs, tw, tt = path.step(64 * threads, count)
+    path.close()
     return {
         "value": pairs / (tw + tt), "unit": "pairs/s", "cores": threads, "kind": "port",
         "sample": f"{count} walks of the same workload ({pairs} pairs, {steps} walk steps): "
-                  f"walks {tw:.2f} s + SGD {tt:.2f} s, OpenMP Hogwild over {threads} threads",
+                  f"walks {tw:.2f} s + SGD {tt:.2f} s, OpenMP Hogwild over {threads} threads, "
+                  "vectorised float32 arithmetic (oracle fast_math)",
         "walk_steps_per_s": steps / max(tw, 1e-9), "sgd_pairs_per_s": pairs / max(tt, 1e-9),
     }
 
 
-def run_reference(args, cfg):
-    """--impl reference: the CPU implementation of the path on the host cores.
+def ensmallen_probe():
+    """The reference's own engine, when the wheel exists on this box (it never has so far)."""
+    for extra in (os.path.join(ROOT, "baseline", "_ref"),):
+        if os.path.isdir(extra) and extra not in sys.path:
+            sys.path.insert(0, extra)
+    try:
+        import ensmallen  # noqa: F401
+        return True, getattr(ensmallen, "__version__", "unknown")
+    except Exception as error:  # ModuleNotFoundError here and on the GPU boxes (profiles/r02a_gpu_box_probe.txt)
+        return False, f"{type(error).__name__}: {error}"
 
-    The reference's own arithmetic lives in the `ensmallen` wheel, which is not vendored
-    and not installable offline, so the timed implementation is the oracle port.
-    """
+
+def run_ensmallen(args, name, cfg, note):
+    """`Node2VecSkipGramEnsmallen(...).fit_transform` on the same graph, timed wall-clock on all host
+    cores.  Only reachable where `import ensmallen` works; whole-job pairs/s."""
+    import ensmallen
+    from embiggen.embedders.ensmallen_embedders import Node2VecCBOWEnsmallen, Node2VecSkipGramEnsmallen
+    graph, _ = load_graph(cfg["graph"])
+    n = graph.get_number_of_nodes()
+    rows = np.repeat(np.arange(n, dtype=np.uint32), np.diff(graph.indptr))
+    keep = rows < graph.indices
+    path = os.path.join(os.environ.get("B2E_CACHE", "/tmp"), f"b2e_edges_{name}.tsv")
+    np.savetxt(path, np.stack([rows[keep], np.asarray(graph.indices)[keep]], axis=1), fmt="%d", delimiter="\t")
+    g = ensmallen.Graph.from_csv(edge_path=path, directed=False, edge_list_header=False, sources_column_number=0,
+                                 destinations_column_number=1, edge_list_numeric_node_ids=True,
+                                 number_of_nodes=n, name=name)
+    model_class = Node2VecSkipGramEnsmallen if cfg["model"] == "SkipGram" else Node2VecCBOWEnsmallen
+    kwargs = dict(embedding_size=cfg["embedding_size"], epochs=1, iterations=cfg["iterations"],
+                  return_weight=cfg["return_weight"], explore_weight=cfg["explore_weight"], max_neighbours=None,
+                  verbose=False, **COMMON)
+    from embiggen_b200.engine import pairs_per_walk
+    walks = cfg["iterations"] * int((np.diff(graph.indptr) > 0).sum())
+    pairs = walks * pairs_per_walk(COMMON["walk_length"], COMMON["window_size"])
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        begin = time.perf_counter()
+        model_class(**kwargs).fit_transform(g, return_dataframe=False)
+        times.append(time.perf_counter() - begin)
+    value = pairs / float(np.median(times))
+    threads = os.cpu_count() or 1
+    sample = f"one epoch over every start node ({walks} walks), wall clock, median of {len(times)}, rayon over {threads} threads"
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.median(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(name, cfg, note),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "ensmallen", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def run_reference(args, name, cfg, note):
+    """--impl reference: the path on the host cores, all of them.
+
+    The reference's own arithmetic lives in the `ensmallen` wheel, which is neither vendored nor
+    installable offline (probe logged under profiles/); when it is importable it is what gets
+    timed, otherwise the oracle port.  Nothing here loads libb2e.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    graph = load_graph(cfg["graph"])
-    threads = os.cpu_count() or 1
-    oracle.set_threads(threads)
-    n = graph.get_number_of_nodes()
-    D = cfg["embedding_size"]
-    thr, alias = oracle.alias_build(graph.indptr, 0.75)
-    t0, t1 = oracle.init_tables(n, D, SEED)
-    srcs = oracle.sources(graph.indptr)
-    sample = max(64 * threads, args.reference_walks)
+    have_wheel, wheel_note = ensmallen_probe()
+    if have_wheel and not os.environ.get("B2E_REFERENCE_PORT"):
+        try:
+            emit_result(run_ensmallen(args, name, cfg, note))
+            return
+        except Exception as error:
+            wheel_note = f"ensmallen importable but the run failed ({type(error).__name__}: {error})"
+    graph, generation_s = load_graph(cfg["graph"])
+    path = CpuPath(graph, cfg)
+    threads = path.threads
+    calibration = 64 * threads
+    _, pairs, tw, tt = path.step(0, calibration)
+    per_step_s = args.reference_step_seconds
+    sample = int(np.clip(per_step_s * (pairs / max(tw + tt, 1e-9)) / (pairs / calibration), 1024, 1 << 18))
+    if args.reference_walks:
+        sample = args.reference_walks
     times, pairs_total, steps_total = [], 0, 0
     for step in range(args.warmup + args.steps):
-        begin = time.perf_counter()
-        walks, wc = oracle.walks(graph.indptr, graph.indices, SEED, step * sample, sample,
-                                 COMMON["walk_length"], cfg["return_weight"],
-                                 cfg["explore_weight"], srcs=srcs)
-        stats = oracle.train(cfg["model"], walks, t0, t1, SEED, n, D, COMMON["window_size"],
-                             COMMON["number_of_negative_samples"], COMMON["learning_rate"],
-                             COMMON["clipping_value"], first_walk=step * sample, thr=thr,
-                             alias=alias)
-        elapsed = time.perf_counter() - begin
+        steps, pairs, tw, tt = path.step(calibration + step * sample, sample)
         if step >= args.warmup:
-            times.append(elapsed)
-            pairs_total += stats["pairs"]
-            steps_total += wc["steps"]
+            times.append(tw + tt)
+            pairs_total += pairs
+            steps_total += steps
+    path.close()
     total = sum(times)
     value = pairs_total / total
-    sample_text = (f"each step = {sample} walks of the workload (walks + SGD), OpenMP Hogwild "
-                   f"over {threads} threads")
+    sample_text = (f"each step = {sample} walks of the workload (walks + SGD), OpenMP Hogwild over "
+                   f"{threads} threads, vectorised float32 arithmetic (oracle fast_math); "
+                   f"graph generated on the host in {generation_s:.0f} s (0 = cached); ensmallen: {wheel_note}")
     emit_result({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["label"], "name": args.config, **COMMON,
-                   "embedding_size": D},
+        "config": config_dict(name, cfg, note),
         "walk_steps_per_s": steps_total / total,
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": sample_text},
@@ -274,7 +391,7 @@ def run_reference(args, cfg):
     })
 
 
-def run_ours(args, cfg):
+def run_ours(args, name, cfg, note):
     import torch
     import torch.distributed as dist
     from embiggen_b200.engine import Engine
@@ -291,30 +408,34 @@ def run_ours(args, cfg):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
-    graph = load_graph(cfg["graph"], device=local_rank, world=world, local_rank=local_rank,
-                       barrier=dist.barrier if world > 1 else None)
+    graph, generation_s = load_graph(cfg["graph"], device=local_rank, local_rank=local_rank,
+                                     barrier=dist.barrier if world > 1 else None)
+    n = graph.get_number_of_nodes()
     D = cfg["embedding_size"]
     L, w, K = COMMON["walk_length"], COMMON["window_size"], COMMON["number_of_negative_samples"]
     engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
                     return_weight=cfg["return_weight"], explore_weight=cfg["explore_weight"],
                     chunk_walks=args.chunk_walks, device=local_rank, **COMMON)
+    begin = time.perf_counter()
     engine.load_csr(graph.indptr, graph.indices)
+    load_s = time.perf_counter() - begin
     n_src = engine.number_of_sources
     chunk = min(engine.chunk_capacity, n_src)  # walks per rank and step
     walk_stream, train_stream = torch.cuda.Stream(device), torch.cuda.Stream(device)
     engine.set_streams(walk_stream, train_stream)
     engine.init_tables(SEED)
-    tables = engine.device_tables() if world > 1 else None
+    if world > 1:
+        engine.open_exchange()
     lr = COMMON["learning_rate"]
+    exchange_s = []
 
     def first_id(step):  # weak scaling: every rank walks `chunk` ids of a world*chunk batch
         return step * chunk * world + rank
 
     def average_tables():
-        engine.sync()
-        for t in tables:
-            dist.all_reduce(t, op=dist.ReduceOp.AVG)
-        torch.cuda.synchronize(device)
+        begin = time.perf_counter()
+        engine.average()
+        exchange_s.append(time.perf_counter() - begin)
 
     def run_steps(first_step, count, events=None):
         """walk(k+1) on the walk stream overlaps train(k) on the train stream."""
@@ -329,7 +450,7 @@ def run_ours(args, cfg):
             engine.train_chunk(SEED, k & 1, lr)
             if events is not None:
                 events[k - first_step][1].record(train_stream)
-            if world > 1 and args.sync_interval and (k + 1) % args.sync_interval == 0:
+            if world > 1 and args.sync_interval and (k + 1 - first_step) % args.sync_interval == 0:
                 average_tables()
 
     def barrier():
@@ -342,8 +463,9 @@ def run_ours(args, cfg):
     run_steps(0, args.warmup)
     barrier()
 
-    # ---- timed region: exactly K steps (K walk launches + K SGD launches [+ all-reduces]) ----
+    # ---- timed region: exactly K steps (K walk launches + K SGD launches [+ exchange kernels]) ----
     engine.reset_counters()
+    exchange_s.clear()
     launches_before = engine.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -360,6 +482,7 @@ def run_ours(args, cfg):
     counters = engine.counters()
     launches = engine.launch_count - launches_before
     sgd_ms = [a.elapsed_time(b) for a, b in per_launch]
+    timed_exchanges = list(exchange_s)
 
     totals = torch.tensor([elapsed_ms, float(counters["pairs"]), float(counters["walk_steps"]),
                            float(launches)], dtype=torch.float64, device=device)
@@ -386,39 +509,41 @@ def run_ours(args, cfg):
     peak, peak_source = measured_peak_gbs()
     centres = chunk * L  # every token of every walk is a centre once
     if cfg["model"] == "SkipGram":
-        per_launch_bytes = skipgram_bytes(counters, D, L, centres * args.steps) / args.steps
+        per_launch_bytes = skipgram_bytes(counters, D, centres * args.steps) / args.steps
     else:
         per_launch_bytes = cbow_bytes(counters, D, centres * args.steps) / args.steps
     sgd_avg_ms = float(np.mean(sgd_ms))
     achieved = per_launch_bytes / (sgd_avg_ms * 1e-3) / 1e9
     steps_per_launch = walk_counters["walk_steps"] / len(walk_events)
-    trials = walk_counters["walk_trials"] / max(walk_counters["walk_steps"], 1)
-    walk_bytes_per_step = 36 + 32 * max(trials, 1.0)  # + probe sectors (needs the oracle's count)
+    per_step = lambda key: walk_counters[key] / max(walk_counters["walk_steps"], 1)  # noqa: E731
+    second_order = not (cfg["return_weight"] == 1.0 and cfg["explore_weight"] == 1.0)
+    trials, searches, probes = per_step("walk_trials"), per_step("walk_searches"), per_step("walk_probes")
+    # 32 B for the row bounds + 4 B of output per step, one 32 B sector per proposal
+    # and per gather of an adjacency check (filter word, row bounds, bisection step: counted on the
+    # device); DeepWalk has exactly one proposal per step and no checks
+    walk_bytes_per_step = 36 + 32 * (trials if second_order else 1.0) + 32 * probes
     walk_avg_ms = float(np.mean(walk_ms))
     walk_achieved = steps_per_launch * walk_bytes_per_step / (walk_avg_ms * 1e-3) / 1e9
     # A walk is a chain of dependent random gathers; when the CSR does not fit L2 the memory
     # system serves at most GATHER_CEILING random 4-byte gathers per second
-    # (scripts/microbench_gather.cu, profiles/r01_microbench_random_gathers.txt).  Every step
-    # needs at least its row bounds, its proposals and one probe per adjacency search.
-    searches = walk_counters["walk_searches"] / max(walk_counters["walk_steps"], 1)
-    gathers_per_step = 1.0 + max(trials, 1.0) + searches
+    # (scripts/microbench_gather.cu, profiles/r01_microbench_random_gathers.txt).
+    gathers_per_step = 1.0 + (trials if second_order else 1.0) + probes
     walk_gathers = steps_per_launch * gathers_per_step / (walk_avg_ms * 1e-3)
 
     kernel_name = ("skipgram_pipe_kernel" if cfg["model"] == "SkipGram" else "cbow_pipe_kernel") + \
         f"<{K + 1}>"
-    traffic, traffic_source = measured_traffic(args.config, chunk)
+    traffic, traffic_source = measured_traffic(name, chunk)
     result = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": cfg["label"], "name": args.config, "embedding_size": D, **COMMON,
-                   "walks_per_step_per_gpu": chunk, "pairs_per_step_per_gpu":
-                   counters["pairs"] / args.steps, "l2": "inputs larger than L2 (tables "
-                   f"{2 * graph.get_number_of_nodes() * D * 4 / 1e6:.0f} MB, random rows)",
-                   "parallelism": f"dp{world}: start nodes sharded, CSR + tables replicated, "
-                                  f"all-reduce AVG every {args.sync_interval} step(s)"
-                   if world > 1 else "single GPU"},
+        "config": config_dict(name, cfg, note),
+        "run": {"walks_per_step_per_gpu": chunk, "pairs_per_step_per_gpu": counters["pairs"] / args.steps,
+                "start_nodes": n_src, "graph_generation_s": generation_s, "load_csr_s": load_s,
+                "parallelism": (f"dp{world}: start nodes sharded, CSR + tables replicated, replicas averaged "
+                                f"by the peer-memory exchange kernel every {args.sync_interval} step(s)")
+                if world > 1 else "single GPU"},
         "walk_steps_per_s": walk_steps_all / (elapsed_ms * 1e-3),
         "gpu_launches": int(launches_all),
         "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved,
@@ -427,57 +552,80 @@ def run_ours(args, cfg):
                      "peak_source": peak_source, "avg_launch_ms": sgd_avg_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes},
         "walk": {"kernel": "walk_kernel", "steps_per_s_alone": steps_per_launch / (walk_avg_ms * 1e-3),
-                 "avg_launch_ms": walk_avg_ms, "trials_per_step": trials,
+                 "avg_launch_ms": walk_avg_ms, "trials_per_step": trials, "searches_per_step": searches,
+                 "probe_gathers_per_step": probes,
+                 "filter_rejects_per_search": walk_counters["walk_filter_rejects"] / max(walk_counters["walk_searches"], 1),
                  "bytes_per_step": walk_bytes_per_step, "achieved_gbs": walk_achieved,
                  "frac": walk_achieved / peak,
-                 "gathers_per_step_lower_bound": gathers_per_step,
-                 "gathers_per_s_lower_bound": walk_gathers,
-                 "gather_ceiling_per_s": GATHER_CEILING,
-                 "gather_frac_lower_bound": walk_gathers / GATHER_CEILING},
+                 "gathers_per_step": gathers_per_step, "gathers_per_s": walk_gathers,
+                 "gather_ceiling_per_s": GATHER_CEILING, "gather_frac": walk_gathers / GATHER_CEILING},
         "clocks": clocks,
         "mean_pair_loss": counters["loss_sum"] / max(counters["pairs"], 1),
     }
+    if world > 1:
+        live = 2 * n * D * 4
+        mean_s = float(np.mean(timed_exchanges)) if timed_exchanges else None
+        result["exchange"] = {
+            "kernel": f"exchange_average_kernel<{world}>", "sync_interval_steps": args.sync_interval,
+            "syncs_in_timed_region": len(timed_exchanges), "ms_per_sync": None if mean_s is None else 1e3 * mean_s,
+            "bytes_in_per_gpu_per_sync": live * (world - 1) / world,
+            "gbs_in_per_gpu": None if not mean_s else live * (world - 1) / world / mean_s / 1e9,
+            "note": "host wall clock of sync + barrier + kernel + barrier on rank 0; live row bytes only"}
 
-    # ---- e2e: the reference-facing call with HOST buffers in and out, on every rank: CSR H2D +
-    # init + K steps per GPU (+ the all-reduces) + tables D2H; max over ranks ----
+    # ---- e2e: the named job in full through the reference-facing call with HOST buffers in and
+    # out: CSR H2D + init + one epoch over every start node (sharded over the ranks, replicas
+    # averaged every sync_interval chunks) + tables D2H (rank 0); max over ranks ----
     if not args.no_e2e:
-        del engine, tables
+        engine.close()
+        del engine
         torch.cuda.synchronize(device)
-        e2e_engine = Engine(cfg["model"], embedding_size=D, epochs=1,
-                            iterations=args.steps * world, return_weight=cfg["return_weight"],
-                            explore_weight=cfg["explore_weight"], chunk_walks=args.chunk_walks,
-                            device=local_rank, **COMMON)
-        n = graph.get_number_of_nodes()
-        out0 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
-        out1 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
+        e2e_engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
+                            return_weight=cfg["return_weight"], explore_weight=cfg["explore_weight"],
+                            chunk_walks=args.chunk_walks, device=local_rank, **COMMON)
+        out0 = out1 = None
+        if rank == 0:
+            out0 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
+            out1 = torch.empty((n, D), dtype=torch.float32, pin_memory=True).numpy()
         if world > 1:
             dist.barrier()
         begin = time.perf_counter()
         e2e_engine.load_csr(graph.indptr, graph.indices)
         if world > 1:
-            t0, t1, _ = e2e_engine.fit_distributed(SEED, args.sync_interval)
-            out0[:], out1[:] = t0, t1
+            e2e_engine.fit_distributed(SEED, args.sync_interval, gather="rank0", table0=out0, table1=out1)
         else:
             e2e_engine.fit(SEED, out0, out1)
         e2e_engine.sync()
         e2e_s = time.perf_counter() - begin
-        stats = torch.tensor([e2e_s, float(e2e_engine.counters()["pairs"])], dtype=torch.float64,
-                             device=device)
+        digest = e2e_engine.tables_digest()
+        job_counters = e2e_engine.counters()
+        stats = torch.tensor([e2e_s, float(job_counters["pairs"])], dtype=torch.float64, device=device)
         if world > 1:
             slowest = stats[:1].clone()
             dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
             dist.all_reduce(stats[1:], op=dist.ReduceOp.SUM)
             stats[0] = slowest[0]
+            digests = [None] * world
+            dist.all_gather_object(digests, digest)
+            assert all(d["bits"] == digests[0]["bits"] for d in digests), "replicas differ after the last exchange"
+            assert all(d["non_finite"] == 0 for d in digests), "non-finite values in the tables"
+        assert digest["non_finite"] == 0, "non-finite values in the tables"
         e2e_s, e2e_pairs = float(stats[0]), float(stats[1])
+        chunks_per_gpu = -(-(cfg["iterations"] * n_src) // (chunk * world))
         h2d = graph.indptr.nbytes + graph.indices.nbytes + 12 * n  # + sources, alias table
+        d2h = 2 * n * D * 4
         result["e2e"] = {"value": e2e_pairs / e2e_s, "unit": "pairs/s",
-                         "h2d_bytes_per_step": h2d / args.steps,
-                         "d2h_bytes_per_step": (out0.nbytes + out1.nbytes) / args.steps,
-                         "seconds": e2e_s,
+                         "h2d_bytes_per_step": h2d / chunks_per_gpu,
+                         "d2h_bytes_per_step": d2h / chunks_per_gpu,
+                         "seconds": e2e_s, "steps_per_gpu": chunks_per_gpu, "pairs": e2e_pairs,
+                         "exchanges": getattr(e2e_engine, "exchange_count", 0),
+                         "exchange_seconds": getattr(e2e_engine, "exchange_seconds", 0.0),
+                         "tables_checked": "finite" + (", replicas bit-identical on all ranks" if world > 1 else ""),
                          "call": ("b2e_load_csr + b2e_fit" if world == 1 else
-                                  "Engine.load_csr + Engine.fit_distributed on every rank") +
-                                 f" (host buffers in/out, {args.steps} steps per GPU, epochs=1)"}
+                                  "Engine.load_csr + Engine.fit_distributed on every rank, tables to the host on rank 0") +
+                                 f" (host CSR in, host tables out; the whole named job: epochs=1, "
+                                 f"iterations={cfg['iterations']}, {cfg['iterations'] * n_src} walks)"}
         e2e_engine.close()
+        del out0, out1
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(graph, cfg, budget_s=args.cpu_budget)
@@ -518,20 +666,22 @@ def main():
     parser.add_argument("--steps", type=int, default=10)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    parser.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    parser.add_argument("--config", default="auto", choices=["auto"] + sorted(CONFIGS))
     parser.add_argument("--chunk-walks", type=int, default=1 << 20)
-    parser.add_argument("--sync-interval", type=int, default=1)
-    parser.add_argument("--reference-walks", type=int, default=8192)
+    parser.add_argument("--sync-interval", type=int, default=4)
+    parser.add_argument("--reference-walks", type=int, default=0)
+    parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--cpu-budget", type=float, default=15.0)
     parser.add_argument("--no-e2e", action="store_true")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 0)
-    cfg = CONFIGS[args.config]
+    name, note = choose_config(args.config)
+    cfg = CONFIGS[name]
     if args.impl == "reference":
-        run_reference(args, cfg)
+        run_reference(args, name, cfg, note)
     else:
-        run_ours(args, cfg)
+        run_ours(args, name, cfg, note)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2e.so")
 
+ABI_VERSION = 2  # B2E_ABI_VERSION of include/b2e.h
 B2E_OK = 0
 B2E_ERR_INVALID = -1
 B2E_ERR_CUDA = -2
@@ -75,6 +76,8 @@ class B2ECounters(ctypes.Structure):
         ("walk_steps", ctypes.c_uint64),
         ("walk_trials", ctypes.c_uint64),
         ("walk_searches", ctypes.c_uint64),
+        ("walk_probes", ctypes.c_uint64),
+        ("walk_filter_rejects", ctypes.c_uint64),
         ("pairs", ctypes.c_uint64),
         ("targets", ctypes.c_uint64),
         ("loss_sum", ctypes.c_double),
@@ -112,6 +115,12 @@ SIGNATURES = {
     "b2e_train_host_walks": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, _U64, _U64, _U64, _F32]),
     "b2e_sync": (ctypes.c_int, [_H]),
     "b2e_device_tables": (ctypes.c_int, [_H, _P(ctypes.c_void_p), _P(ctypes.c_void_p)]),
+    "b2e_exchange_handles": (ctypes.c_int, [_H, ctypes.c_void_p]),
+    "b2e_exchange_open": (ctypes.c_int, [_H, _U32, _U32, ctypes.c_void_p]),
+    "b2e_exchange_open_local": (ctypes.c_int, [_H, _U32, _U32, _P(_H)]),
+    "b2e_exchange_average": (ctypes.c_int, [_H]),
+    "b2e_exchange_close": (ctypes.c_int, [_H]),
+    "b2e_tables_digest": (ctypes.c_int, [_H, _P(ctypes.c_double), _P(_U64)]),
     "b2e_chunk_capacity": (ctypes.c_int, [_H, _P(_U64)]),
     "b2e_export_tables": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_import_tables": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
@@ -159,7 +168,7 @@ def load() -> ctypes.CDLL:
             function = getattr(lib, name)
             function.restype = restype
             function.argtypes = argtypes
-        if lib.b2e_abi_version() != 1:
+        if lib.b2e_abi_version() != ABI_VERSION:
             raise ImportError("libb2e.so ABI version mismatch; rebuild the extension.")
         _lib = lib
     return _lib

@@ -77,6 +77,26 @@ static void thresholds(float return_weight, float explore_weight, unsigned long 
     }
 }
 
+// folded return edge (oracle/walks.c: orc_fold_thresholds): accept thresholds against the envelope
+// of the non-return classes, and the excess E of the return edge in units of 2^-20 envelopes
+static void fold_thresholds(float return_weight, float explore_weight, unsigned long long out[3],
+                            uint64_t *excess) {
+    const double rw = (double)return_weight, ew = (double)explore_weight;
+    const double wenv = ew > 1.0 ? ew : 1.0;
+    const double w[3] = {wenv, 1.0, ew};
+    for (int i = 0; i < 3; ++i) {
+        if (w[i] >= wenv) {
+            out[i] = 4294967296ull;
+        } else {
+            const double t = floor(w[i] / wenv * 4294967296.0);
+            out[i] = t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t;
+        }
+    }
+    double e = rw > wenv ? floor((rw - wenv) / wenv * 1048576.0) : 0.0;
+    if (e > 2147483648.0) e = 2147483648.0;
+    *excess = (uint64_t)e;
+}
+
 extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (!config || !out) return fail(B2E_ERR_INVALID, "null argument");
     if (config->struct_size != sizeof(b2e_config))
@@ -127,7 +147,6 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     h->row_stride = (c.embedding_size + 31u) / 32u * 32u;
     if (const char *env = getenv("B2E_PREFETCH")) h->prefetch = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
-    if (const char *env = getenv("B2E_WALK_SM")) h->walk_state_machine = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
     for (int s = 0; s < 2; ++s) {
@@ -150,13 +169,28 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     return B2E_OK;
 }
 
+static void close_peers(b2e_handle *h) {
+    for (uint32_t g = 0; g < B2E_MAX_WORLD; ++g) {
+        if (h->peers_are_ipc && g != h->rank) {
+            if (h->peer_t0[g]) cudaIpcCloseMemHandle(h->peer_t0[g]);
+            if (h->peer_t1[g]) cudaIpcCloseMemHandle(h->peer_t1[g]);
+        }
+        h->peer_t0[g] = h->peer_t1[g] = nullptr;
+    }
+    h->world = 1;
+    h->rank = 0;
+    h->peers_are_ipc = false;
+}
+
 static void free_graph(b2e_handle *h) {
+    close_peers(h);
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
     cudaFree(h->d_edge_alias); h->d_edge_alias = nullptr;
     cudaFree(h->d_node_types); h->d_node_types = nullptr;
     cudaFree(h->d_edge_types); h->d_edge_types = nullptr;
     cudaFree(h->d_sources); h->d_sources = nullptr;
+    cudaFree(h->d_filter); h->d_filter = nullptr;
     cudaFree(h->d_alias); h->d_alias = nullptr;
     cudaFree(h->d_t0); h->d_t0 = nullptr;
     cudaFree(h->d_t1); h->d_t1 = nullptr;
@@ -288,6 +322,21 @@ extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t
     return b2e_load_csr_weighted(h, indptr, indices, nullptr, n, nnz);
 }
 
+// a failed load leaves the handle without a graph (require_graph() then fails cleanly)
+static int load_failed(b2e_handle *h, int rc) {
+    cudaDeviceSynchronize();
+    free_graph(h);
+    h->n = h->nnz = h->n_src = 0;
+    return rc;
+}
+
+#define LOAD_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return load_failed(h, fail(B2E_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+    } while (0)
+
 extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
                                      const float *weights, uint64_t n, uint64_t nnz) {
     REQUIRE_HANDLE(h);
@@ -298,19 +347,9 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
         return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
     const b2e_config &c = h->cfg;
-    CUDA_TRY(cudaDeviceSynchronize());
-    free_graph(h);
-    h->n = n;
-    h->nnz = nnz;
 
-    // start the big copies first, do the host-side derivations underneath them
-    CUDA_TRY(cudaMalloc(&h->d_indptr, (n + 1) * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc(&h->d_indices, nnz * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemcpyAsync(h->d_indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                             h->walk_stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                             h->walk_stream));
-
+    // host-side validation and derivations that need only indptr come first: nothing of the
+    // previous graph is touched until the offsets are known to be sane
     std::vector<uint32_t> sources;
     sources.reserve(n);
     uint64_t max_degree = 0;
@@ -319,17 +358,62 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
         if (indptr[v + 1] > indptr[v]) sources.push_back((uint32_t)v);
         max_degree = std::max<uint64_t>(max_degree, (uint64_t)(indptr[v + 1] - indptr[v]));
     }
+    if (weights)
+        for (uint64_t e = 0; e < nnz; ++e)
+            if (!(weights[e] >= 0.0f)) return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
+
+    CUDA_TRY(cudaDeviceSynchronize());
+    free_graph(h);
+    h->n = n;
+    h->nnz = nnz;
     h->n_src = sources.size();
     h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
+
+    // K1: the two big copies, then the content check on the device (ids in range, rows strictly
+    // ascending: the kernels index with these ids and bisect these rows without looking again)
+    LOAD_TRY(cudaMalloc(&h->d_indptr, (n + 1) * sizeof(int64_t)));
+    LOAD_TRY(cudaMalloc(&h->d_indices, nnz * sizeof(uint32_t)));
+    LOAD_TRY(cudaMemcpyAsync(h->d_indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                             h->walk_stream));
+    LOAD_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                             h->walk_stream));
+    int *d_flags = nullptr;
+    LOAD_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
+    LOAD_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->walk_stream));
+    LOAD_TRY(launch_csr_check(h->d_indptr, h->d_indices, n, d_flags, h->sm_count, h->walk_stream));
+    ++h->launches;
+
+    // K3 on the host while the copies are in flight
+    h->h_alias_thr.clear();
+    h->h_alias_idx.clear();
+    std::vector<uint2> packed;
+    if (c.use_scale_free_distribution) {
+        if (!build_alias(indptr, n, (double)c.negative_sampling_exponent, h->h_alias_thr, h->h_alias_idx)) {
+            cudaFree(d_flags);
+            return load_failed(h, fail(B2E_ERR_INVALID, "alias table: total weight is zero"));
+        }
+        packed.resize(n);
+        for (uint64_t i = 0; i < n; ++i) packed[i] = make_uint2(h->h_alias_thr[i], h->h_alias_idx[i]);
+    }
+
+    int flags[2] = {0, 1};
+    LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
+    LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
+    if (flags[0]) {
+        cudaFree(d_flags);
+        return load_failed(h, fail(B2E_ERR_INVALID, flags[0] & 1
+                                        ? "a destination node id is out of range"
+                                        : "neighbour lists must be sorted strictly ascending within each row"));
+    }
+
     // normalize_by_degree (.../node2vec_skipgram.py:94-96): the weight of v -> x divided by
     // max(deg(x), 1), one float32 division per edge, folded into the proposal table -- no extra
     // rejection however skewed the degrees (oracle: degree_normalised_weights)
     std::vector<float> normalised;
-    if (c.normalize_by_degree && nnz) {
+    if (c.normalize_by_degree) {
         normalised.resize(nnz);
         for (uint64_t e = 0; e < nnz; ++e) {
             const uint32_t x = indices[e];
-            if (x >= n) return fail(B2E_ERR_INVALID, "a destination node id is out of range");
             const float degree = (float)std::max<int64_t>(indptr[x + 1] - indptr[x], 1);
             normalised[e] = (weights ? weights[e] : 1.0f) / degree;
         }
@@ -337,47 +421,54 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     }
     if (weights) {
         std::vector<uint2> edge_alias(nnz);
-        if (!build_edge_alias(indptr, weights, n, edge_alias))
-            return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
-        CUDA_TRY(cudaMalloc(&h->d_edge_alias, nnz * sizeof(uint2)));
-        CUDA_TRY(cudaMemcpyAsync(h->d_edge_alias, edge_alias.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
+        if (!build_edge_alias(indptr, weights, n, edge_alias)) {
+            cudaFree(d_flags);
+            return load_failed(h, fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers"));
+        }
+        LOAD_TRY(cudaMalloc(&h->d_edge_alias, nnz * sizeof(uint2)));
+        LOAD_TRY(cudaMemcpyAsync(h->d_edge_alias, edge_alias.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
                                  h->walk_stream));
-        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `edge_alias` dies here
+        LOAD_TRY(cudaStreamSynchronize(h->walk_stream));  // `edge_alias` dies here
     }
-    CUDA_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
+    LOAD_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
+    LOAD_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
                              cudaMemcpyHostToDevice, h->walk_stream));
-
-    h->h_alias_thr.clear();
-    h->h_alias_idx.clear();
-    if (c.use_scale_free_distribution) {
-        if (!build_alias(indptr, n, (double)c.negative_sampling_exponent, h->h_alias_thr, h->h_alias_idx))
-            return fail(B2E_ERR_INVALID, "alias table: total weight is zero");
-        std::vector<uint2> packed(n);
-        for (uint64_t i = 0; i < n; ++i) packed[i] = make_uint2(h->h_alias_thr[i], h->h_alias_idx[i]);
-        CUDA_TRY(cudaMalloc(&h->d_alias, n * sizeof(uint2)));
-        CUDA_TRY(cudaMemcpyAsync(h->d_alias, packed.data(), n * sizeof(uint2), cudaMemcpyHostToDevice,
+    if (!packed.empty()) {
+        LOAD_TRY(cudaMalloc(&h->d_alias, n * sizeof(uint2)));
+        LOAD_TRY(cudaMemcpyAsync(h->d_alias, packed.data(), n * sizeof(uint2), cudaMemcpyHostToDevice,
                                  h->walk_stream));
-        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));  // `packed` dies here
     }
 
-    // Is the graph undirected (every edge mirrored)?  Then the second-order walk kernel may
-    // check adjacency in the shorter of the two rows.  Verified here, never assumed.
+    // Second-order walks: is the graph undirected (every edge mirrored)?  Verified here, never
+    // assumed: it allows the adjacency check in the shorter of the two rows and the folded return
+    // edge.  The row filters answer most adjacency checks with one gather (walk_kernels.cu).
     h->undirected = false;
-    if (h->second_order && !getenv("B2E_ASSUME_DIRECTED")) {
-        int *d_flag = nullptr, flag = 1;
-        CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
-        CUDA_TRY(cudaMemcpyAsync(d_flag, &flag, sizeof(int), cudaMemcpyHostToDevice, h->walk_stream));
-        CUDA_TRY(launch_symmetry_check(h->d_indptr, h->d_indices, n, nnz, d_flag, h->walk_stream));
-        CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
-        CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
-        cudaFree(d_flag);
-        h->undirected = flag != 0;
-        ++h->launches;
+    h->fold_excess = 0;
+    if (h->second_order) {
+        if (!getenv("B2E_ASSUME_DIRECTED")) {
+            LOAD_TRY(cudaMemcpyAsync(d_flags + 1, flags + 1, sizeof(int), cudaMemcpyHostToDevice, h->walk_stream));
+            LOAD_TRY(launch_symmetry_check(h->d_indptr, h->d_indices, n, nnz, d_flags + 1, h->walk_stream));
+            LOAD_TRY(cudaMemcpyAsync(flags + 1, d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
+            LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
+            h->undirected = flags[1] != 0;
+            ++h->launches;
+        }
+        uint64_t excess = 0;
+        fold_thresholds(c.return_weight, c.explore_weight, h->thr_fold, &excess);
+        if (h->undirected && !weights && !getenv("B2E_NO_FOLD")) h->fold_excess = excess;
+        if (!getenv("B2E_NO_FILTER")) {
+            const uint64_t words = row_filter_words(nnz);
+            LOAD_TRY(cudaMalloc(&h->d_filter, words * sizeof(unsigned long long)));
+            LOAD_TRY(cudaMemsetAsync(h->d_filter, 0, words * sizeof(unsigned long long), h->walk_stream));
+            LOAD_TRY(launch_row_filter_build(h->d_indptr, h->d_indices, n, h->d_filter, h->sm_count,
+                                             h->walk_stream));
+            ++h->launches;
+        }
     }
+    cudaFree(d_flags);
 
-    CUDA_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
+    LOAD_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
+    LOAD_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
 
     const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
     // an explicit chunk_walks is honoured as given (parity tests feed host walks of that size)
@@ -387,9 +478,9 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     // Walklets: a slot holds the k sub-walks of every walk, k * ceil(L / k) >= L tokens per walk
     const uint64_t slot_tokens = walklet(c) ? (uint64_t)c.walklet_scale * sub_walk_length(c) : c.walk_length;
     for (int s = 0; s < 2; ++s)
-        CUDA_TRY(cudaMalloc(&h->d_walks[s], cap * slot_tokens * sizeof(uint32_t)));
-    if (walklet(c)) CUDA_TRY(cudaMalloc(&h->d_walk_raw, cap * c.walk_length * sizeof(uint32_t)));
-    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+        LOAD_TRY(cudaMalloc(&h->d_walks[s], cap * slot_tokens * sizeof(uint32_t)));
+    if (walklet(c)) LOAD_TRY(cudaMalloc(&h->d_walk_raw, cap * c.walk_length * sizeof(uint32_t)));
+    LOAD_TRY(cudaStreamSynchronize(h->walk_stream));  // `sources`, `packed` die here
     return B2E_OK;
 }
 
@@ -448,13 +539,17 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     p.n_walks = n_walks;
     p.walk_id_stride = walk_id_stride;
     p.walk_length = h->cfg.walk_length;
-    p.thr_return = h->thr[0];
-    p.thr_common = h->thr[1];
-    p.thr_explore = h->thr[2];
+    // typed walks keep the plain envelope (their trial loop has its own Philox layout)
+    const bool typed = (h->d_node_types && p.q_node[0] != p.q_node[1]) || (h->d_edge_types && p.q_edge[0] != p.q_edge[1]);
+    const unsigned long long *thr = h->fold_excess && !typed ? h->thr_fold : h->thr;
+    p.fold_excess = typed ? 0 : h->fold_excess;
+    p.filter = h->d_filter;
+    p.thr_return = thr[0];
+    p.thr_common = thr[1];
+    p.thr_explore = thr[2];
     p.out = d_out;
     p.counters = h->d_counters;
     p.undirected = h->undirected ? 1u : 0u;
-    p.state_machine = h->walk_state_machine;
     p.sm_count = h->sm_count;
     CUDA_TRY(launch_walks(p, h->second_order, stream));
     if (n_walks) ++h->launches;
@@ -608,6 +703,125 @@ extern "C" int b2e_device_tables(b2e_handle *h, void **table0, void **table1) {
     return B2E_OK;
 }
 
+// ---- the exchange step (csrc/exchange.cu) ----
+extern "C" int b2e_exchange_handles(b2e_handle *h, void *ipc_handles) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!ipc_handles) return fail(B2E_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B2E_IPC_HANDLE_BYTES, "B2E_IPC_HANDLE_BYTES");
+    cudaIpcMemHandle_t *out = static_cast<cudaIpcMemHandle_t *>(ipc_handles);
+    CUDA_TRY(cudaIpcGetMemHandle(out, h->d_t0));
+    CUDA_TRY(cudaIpcGetMemHandle(out + 1, h->d_t1));
+    return B2E_OK;
+}
+
+static int check_world(uint32_t world, uint32_t rank) {
+    if (world < 1 || world > B2E_MAX_WORLD) return fail(B2E_ERR_INVALID, "world must be in [1, B2E_MAX_WORLD]");
+    if (rank >= world) return fail(B2E_ERR_INVALID, "rank must be below world");
+    return B2E_OK;
+}
+
+extern "C" int b2e_exchange_open(b2e_handle *h, uint32_t world, uint32_t rank, const void *all_ipc_handles) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (int rc = check_world(world, rank)) return rc;
+    if (!all_ipc_handles) return fail(B2E_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaDeviceSynchronize());
+    close_peers(h);
+    const cudaIpcMemHandle_t *handles = static_cast<const cudaIpcMemHandle_t *>(all_ipc_handles);
+    h->world = world;
+    h->rank = rank;
+    h->peers_are_ipc = true;
+    for (uint32_t g = 0; g < world; ++g) {
+        if (g == rank) {
+            h->peer_t0[g] = h->d_t0;
+            h->peer_t1[g] = h->d_t1;
+            continue;
+        }
+        void *t0 = nullptr, *t1 = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&t0, handles[2 * g], cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            h->peer_t0[g] = static_cast<float *>(t0);
+            e = cudaIpcOpenMemHandle(&t1, handles[2 * g + 1], cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e != cudaSuccess) {
+            close_peers(h);
+            return fail(B2E_ERR_CUDA, std::string("cudaIpcOpenMemHandle (replica of rank ") + std::to_string(g) +
+                                          "): " + cudaGetErrorString(e));
+        }
+        h->peer_t1[g] = static_cast<float *>(t1);
+    }
+    return B2E_OK;
+}
+
+extern "C" int b2e_exchange_open_local(b2e_handle *h, uint32_t world, uint32_t rank, b2e_handle *const *replicas) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (int rc = check_world(world, rank)) return rc;
+    if (!replicas) return fail(B2E_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaDeviceSynchronize());
+    close_peers(h);
+    for (uint32_t g = 0; g < world; ++g) {
+        const b2e_handle *r = g == rank ? h : replicas[g];
+        if (!r || !r->d_t0 || r->n != h->n || r->row_stride != h->row_stride)
+            return fail(B2E_ERR_INVALID, "every replica must hold tables of the same shape");
+        if (r->cfg.device != h->cfg.device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->cfg.device, r->cfg.device));
+            if (!can) return fail(B2E_ERR_CUDA, "no peer access between the devices of the replicas");
+            cudaError_t e = cudaDeviceEnablePeerAccess(r->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(B2E_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    h->world = world;
+    h->rank = rank;
+    for (uint32_t g = 0; g < world; ++g) {
+        const b2e_handle *r = g == rank ? h : replicas[g];
+        h->peer_t0[g] = r->d_t0;
+        h->peer_t1[g] = r->d_t1;
+    }
+    return B2E_OK;
+}
+
+extern "C" int b2e_exchange_average(b2e_handle *h) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (h->world < 2) return B2E_OK;
+    CUDA_TRY(launch_exchange_average(h->peer_t0, h->peer_t1, h->world, h->rank, h->n, h->row_stride,
+                                     (h->cfg.embedding_size + 3u) / 4u, h->sm_count, h->train_stream));
+    ++h->launches;
+    return B2E_OK;
+}
+
+extern "C" int b2e_exchange_close(b2e_handle *h) {
+    REQUIRE_HANDLE(h);
+    CUDA_TRY(cudaDeviceSynchronize());
+    close_peers(h);
+    return B2E_OK;
+}
+
+extern "C" int b2e_tables_digest(b2e_handle *h, double *sums, uint64_t *words) {
+    REQUIRE_HANDLE(h);
+    if (int rc = require_graph(h)) return rc;
+    if (!sums || !words) return fail(B2E_ERR_INVALID, "null argument");
+    if (int rc = b2e_sync(h)) return rc;
+    void *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 56));
+    cudaError_t e = launch_tables_digest(h->d_t0, h->d_t1, h->n, h->row_stride, h->cfg.embedding_size, d_out,
+                                         h->sm_count, h->train_stream);
+    unsigned char host[56];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_out, 56, cudaMemcpyDeviceToHost, h->train_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->train_stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(B2E_ERR_CUDA, std::string("b2e_tables_digest: ") + cudaGetErrorString(e));
+    ++h->launches;
+    memcpy(sums, host, 32);
+    memcpy(words, host + 32, 24);
+    return B2E_OK;
+}
+
 extern "C" int b2e_export_tables(b2e_handle *h, float *table0, float *table1) {
     REQUIRE_HANDLE(h);
     if (int rc = require_graph(h)) return rc;
@@ -661,6 +875,8 @@ extern "C" int b2e_counters_read(b2e_handle *h, b2e_counters *out) {
     out->walk_steps = c.walk_steps;
     out->walk_trials = c.walk_trials;
     out->walk_searches = c.walk_searches;
+    out->walk_probes = c.walk_probes;
+    out->walk_filter_rejects = c.walk_filter_rejects;
     out->pairs = c.pairs;
     out->targets = c.targets;
     out->loss_sum = c.loss_sum;

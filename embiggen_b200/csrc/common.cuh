@@ -18,6 +18,7 @@ constexpr uint32_t TAG_INIT0 = 4u;  // table 0 initialisation
 constexpr uint32_t TAG_INIT1 = 5u;  // table 1 initialisation
 constexpr uint32_t TAG_WALK3 = 7u;  // general walks (normalize_by_degree, typed): 1 trial per block
 constexpr uint32_t TAG_SKIP = 6u;   // stochastic_downsample_by_degree, one draw per centre
+constexpr uint32_t TAG_FOLD = 12u;  // second-order trials with the return edge folded: 1 trial per block
 constexpr uint32_t MAX_TRIALS = 1u << 20;
 constexpr uint32_t PAD = B2E_PAD_TOKEN;
 
@@ -41,6 +42,8 @@ struct DeviceCounters {
     unsigned long long walk_steps;
     unsigned long long walk_trials;
     unsigned long long walk_searches;
+    unsigned long long walk_probes;         // gathers spent on adjacency checks (filter words, row bounds, bisection)
+    unsigned long long walk_filter_rejects; // adjacency checks answered "not a neighbour" by the row filter alone
     unsigned long long pairs;
     unsigned long long targets;
     double loss_sum;
@@ -62,7 +65,8 @@ struct WalkParams {
     uint32_t *out;
     DeviceCounters *counters;
     uint32_t undirected;     // every edge has its mirror (verified at load): allows the short-row check
-    uint32_t state_machine;  // second-order walks as a per-lane state machine (0: plain kernel)
+    const unsigned long long *filter;  // per-row blocked Bloom filters over the neighbour lists, or nullptr
+    unsigned long long fold_excess;    // E > 0: the return edge is folded out of the envelope (TAG_FOLD)
     int sm_count;
 };
 
@@ -114,6 +118,17 @@ cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t
                                  uint32_t *out, cudaStream_t stream);
 cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                   uint64_t nnz, int *d_flag, cudaStream_t stream);
+// *d_flags |= 1: a destination id >= n; |= 2: a row that is not strictly ascending
+cudaError_t launch_csr_check(const int64_t *indptr, const uint32_t *indices, uint64_t n, int *d_flags,
+                             int sm_count, cudaStream_t stream);
+uint64_t row_filter_words(uint64_t nnz);
+cudaError_t launch_row_filter_build(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                    unsigned long long *filter, int sm_count, cudaStream_t stream);
+cudaError_t launch_exchange_average(float *const t0[], float *const t1[], uint32_t world, uint32_t rank,
+                                    uint64_t n, uint32_t row_stride, uint32_t chunks, int sm_count,
+                                    cudaStream_t stream);
+cudaError_t launch_tables_digest(const float *t0, const float *t1, uint64_t n, uint32_t row_stride,
+                                 uint32_t dim, void *d_out, int sm_count, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,
                                uint32_t row_stride, uint64_t seed, cudaStream_t stream);
 // max_warps caps how many walks are trained concurrently (Hogwild staleness on small graphs)
@@ -146,6 +161,9 @@ struct b2e_handle {
     uint32_t *d_walk_raw = nullptr;  // Walklets: the chunk as walked, before it is split by stride
     uint32_t max_degree = 0;
     uint32_t *d_sources = nullptr;
+    unsigned long long *d_filter = nullptr;  // row filters of the adjacency check (second-order walks)
+    uint64_t fold_excess = 0;                // see WalkParams
+    unsigned long long thr_fold[3] = {0, 0, 0};
     uint2 *d_alias = nullptr;
     float *d_t0 = nullptr, *d_t1 = nullptr;
     uint32_t *d_walks[2] = {nullptr, nullptr};
@@ -158,9 +176,12 @@ struct b2e_handle {
     unsigned long long thr[3] = {0, 0, 0};
     bool second_order = false;
     bool undirected = false;
-    uint32_t walk_state_machine = 0;  // B2E_WALK_SM=1 selects walk_sm_kernel
     uint32_t prefetch = 1;
     uint32_t variant = 0;
     uint64_t launches = 0;
     std::vector<uint32_t> h_alias_thr, h_alias_idx;
+    // the exchange step: replicas of the tables on the other GPUs of the node
+    uint32_t world = 1, rank = 0;
+    float *peer_t0[B2E_MAX_WORLD] = {nullptr}, *peer_t1[B2E_MAX_WORLD] = {nullptr};
+    bool peers_are_ipc = false;
 };

@@ -538,11 +538,30 @@ struct DeviceArray {
 };
 
 // the support graph of the topological features, uploaded for the duration of a call
+// ids in range and rows strictly ascending (walk_kernels.cu: csr_check_kernel): the common-neighbour
+// pass and the samplers index and gallop through these arrays without looking again
+static int check_csr_contents(const int64_t *h_indptr, const int64_t *d_indptr, const uint32_t *d_indices,
+                              uint64_t n) {
+    for (uint64_t v = 0; v < n; ++v)
+        if (h_indptr[v + 1] < h_indptr[v]) return b2e_set_error(B2E_ERR_INVALID, "indptr must be non-decreasing");
+    int *d_flags = nullptr, flags = 0;
+    EP_TRY(cudaMalloc(&d_flags, sizeof(int)));
+    cudaError_t e = cudaMemset(d_flags, 0, sizeof(int));
+    if (e == cudaSuccess) e = launch_csr_check(d_indptr, d_indices, n, d_flags, 148, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_flags);
+    EP_TRY(e);
+    if (flags & 1) return b2e_set_error(B2E_ERR_INVALID, "a destination node id is out of range");
+    if (flags & 2)
+        return b2e_set_error(B2E_ERR_INVALID, "neighbour lists must be sorted strictly ascending within each row");
+    return B2E_OK;
+}
+
 struct DeviceGraph {
     DeviceArray indptr, indices;
     GraphView view = {nullptr, nullptr, 0.f};
     int upload(const int64_t *h_indptr, const uint32_t *h_indices, uint64_t n, uint64_t nnz) {
-        if (!h_indptr || (!h_indices && nnz) || (uint64_t)h_indptr[n] != nnz)
+        if (!h_indptr || (!h_indices && nnz) || h_indptr[0] != 0 || (uint64_t)h_indptr[n] != nnz)
             return b2e_set_error(B2E_ERR_INVALID, "the edge features need the support graph's CSR");
         int64_t max_degree = 1;
         for (uint64_t v = 0; v < n; ++v) max_degree = std::max(max_degree, h_indptr[v + 1] - h_indptr[v]);
@@ -550,6 +569,7 @@ struct DeviceGraph {
         EP_TRY(indices.alloc(nnz * sizeof(uint32_t)));
         EP_TRY(cudaMemcpy(indptr.p, h_indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
         EP_TRY(cudaMemcpy(indices.p, h_indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (int rc = check_csr_contents(h_indptr, indptr.as<int64_t>(), indices.as<uint32_t>(), n)) return rc;
         view.indptr = indptr.as<int64_t>();
         view.indices = indices.as<uint32_t>();
         view.inv_max_degree = 1.0f / (float)max_degree;
@@ -680,6 +700,8 @@ extern "C" int b2e_perceptron_predict(const b2e_features *f, const int64_t *indp
                                       uint32_t n_edge_features, const float *params, float *scores) {
     if (!params || (m && (!src || !dst || !scores))) return b2e_set_error(B2E_ERR_INVALID, "null argument");
     if (n_methods && !f) return b2e_set_error(B2E_ERR_INVALID, "edge embeddings need node features");
+    if (f && n_edge_features && n != f->n)
+        return b2e_set_error(B2E_ERR_INVALID, "the graph and the node features disagree on the number of nodes");
     MethodList list;
     if (int rc = build_methods(methods, n_methods, f ? f->dim : 0, edge_features, n_edge_features, list)) return rc;
     if (m == 0) return B2E_OK;
@@ -710,7 +732,8 @@ extern "C" int b2e_perceptron_fit(const b2e_features *f, const int64_t *indptr, 
         return b2e_set_error(B2E_ERR_INVALID, "b2e_perceptron_config size mismatch (ABI)");
     if (cfg->n_methods && !f) return b2e_set_error(B2E_ERR_INVALID, "edge embeddings need node features");
     if (f && n != f->n) return b2e_set_error(B2E_ERR_INVALID, "the graph and the node features disagree on the number of nodes");
-    if (nnz == 0 || (uint64_t)indptr[n] != nnz) return b2e_set_error(B2E_ERR_INVALID, "the graph has no edges");
+    if (nnz == 0 || indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
+        return b2e_set_error(B2E_ERR_INVALID, "the graph has no edges");
     if (cfg->number_of_edges_per_mini_batch == 0) return b2e_set_error(B2E_ERR_INVALID, "empty mini-batch");
     if (!(cfg->first_order_decay_factor >= 0.f && cfg->first_order_decay_factor < 1.f) ||
         !(cfg->second_order_decay_factor >= 0.f && cfg->second_order_decay_factor < 1.f))
@@ -734,6 +757,7 @@ extern "C" int b2e_perceptron_fit(const b2e_features *f, const int64_t *indptr, 
     EP_TRY(d_loss.alloc(2 * sizeof(double)));
     EP_TRY(cudaMemcpy(d_indptr.p, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     EP_TRY(cudaMemcpy(d_indices.p, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (int rc = check_csr_contents(indptr, d_indptr.as<int64_t>(), d_indices.as<uint32_t>(), n)) return rc;
     EP_TRY(cudaMemset(d_m.p, 0, count * sizeof(float)));
     EP_TRY(cudaMemset(d_v.p, 0, count * sizeof(float)));
     EP_TRY(cudaMemset(d_grad.p, 0, count * sizeof(float)));

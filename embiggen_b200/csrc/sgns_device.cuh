@@ -81,8 +81,9 @@ __device__ __forceinline__ void zero_rows(float4 (&a)[CH]) {
 
 __device__ __forceinline__ float centre_lr(const TrainParams &p, uint32_t centre) {
     if (!p.normalize_lr) return p.lr;
+    // a sink of a directed graph is the last real token of its walk and still serves as a centre
     const uint32_t deg = (uint32_t)(__ldg(p.indptr + centre + 1) - __ldg(p.indptr + centre));
-    return __fdiv_rn(p.lr, (float)deg);
+    return __fdiv_rn(p.lr, (float)(deg ? deg : 1u));
 }
 
 // bit i of the mask staged behind a shared-memory walk of L tokens (rounded up to 32)

@@ -16,14 +16,157 @@
 
 namespace b2e {
 
+// sorted-row membership by lower-bound bisection; every load is counted as one probe
 __device__ __forceinline__ bool row_contains(const uint32_t *__restrict__ row, uint32_t len,
-                                             uint32_t key) {
+                                             uint32_t key, unsigned long long &probes) {
     uint32_t lo = 0, hi = len;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
+        ++probes;
         if (__ldg(row + mid) < key) lo = mid + 1; else hi = mid;
     }
-    return lo < len && __ldg(row + lo) == key;
+    if (lo >= len) return false;
+    ++probes;
+    return __ldg(row + lo) == key;
+}
+
+// ---- row filters: a blocked Bloom filter per neighbour list ----
+//
+// The adjacency check "is x a neighbour of prev" decides between the COMMON and EXPLORE classes.
+// On a sparse graph the answer is almost always "no", and finding that out by bisecting a sorted
+// hub row costs log2(deg) dependent sector gathers.  A filter answers most of them with ONE
+// 8-byte gather: one byte of filter per directed edge, laid over the row's own edge range --
+// row v owns the 32 B sectors that bytes [indptr[v], indptr[v + 1]) touch, so no second offset
+// array is needed (boundary sectors are shared with the neighbouring rows, which can only set
+// more bits) -- a key picks one sector by hash, one of its four words, and three bits in it.
+// No false negatives: "not in the filter" is final; "maybe" falls through to the exact search.
+// Rows shorter than FILTER_MIN_DEG are searched directly (one or two sectors).  The filter never
+// changes a decision, so the walks stay bit-identical to the oracle, which has no filter.
+constexpr uint32_t FILTER_MIN_DEG = 16;
+constexpr uint32_t SHORT_ROW_MIN_DEG = 64;  // from here on fetch the proposal's row and bisect the shorter
+
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+struct FilterSlot { uint64_t word; unsigned long long mask; };
+
+__device__ __forceinline__ FilterSlot filter_slot(int64_t off, uint32_t deg, uint32_t key) {
+    const uint64_t first = (uint64_t)off >> 5, last = ((uint64_t)off + deg - 1u) >> 5;
+    const uint32_t h1 = fmix32(key), h2 = fmix32(key ^ 0x9E3779B9u);
+    const uint64_t sector = first + __umulhi(h1, (uint32_t)(last - first) + 1u);
+    FilterSlot s;
+    s.word = sector * 4u + (h2 & 3u);
+    s.mask = (1ull << ((h2 >> 2) & 63u)) | (1ull << ((h2 >> 8) & 63u)) | (1ull << ((h2 >> 14) & 63u));
+    return s;
+}
+
+uint64_t row_filter_words(uint64_t nnz) { return ((nnz + 31u) / 32u) * 4u + 4u; }
+
+// lane l looks at row base + l; rows of at least `min_deg` edges are then walked by the whole warp
+template <typename RowFn, typename EdgeFn>
+__device__ __forceinline__ void for_each_row(const int64_t *__restrict__ indptr, uint64_t n, uint32_t min_deg,
+                                             RowFn small_row, EdgeFn edge) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n;
+         base += warps * 32u) {
+        const uint64_t v = base + lane;
+        int64_t off = 0;
+        uint32_t deg = 0;
+        if (v < n) {
+            off = __ldg(indptr + v);
+            deg = (uint32_t)(__ldg(indptr + v + 1) - off);
+        }
+        const bool big = deg >= min_deg;
+        if (!big && deg) small_row(v, off, deg);
+        uint32_t todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int64_t o = __shfl_sync(0xffffffffu, off, src);
+            const uint32_t d = __shfl_sync(0xffffffffu, deg, src);
+            for (uint32_t e = lane; e < d; e += 32u) edge(base + src, o, d, e);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) row_filter_build_kernel(const int64_t *__restrict__ indptr,
+                                                               const uint32_t *__restrict__ indices, uint64_t n,
+                                                               unsigned long long *filter) {
+    for_each_row(indptr, n, FILTER_MIN_DEG, [](uint64_t, int64_t, uint32_t) {},
+                 [&](uint64_t, int64_t off, uint32_t deg, uint32_t e) {
+                     const FilterSlot s = filter_slot(off, deg, __ldg(indices + off + e));
+                     atomicOr(filter + s.word, s.mask);
+                 });
+}
+
+cudaError_t launch_row_filter_build(const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                    unsigned long long *filter, int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 16);
+    row_filter_build_kernel<<<grid, 256, 0, stream>>>(indptr, indices, n, filter);
+    return cudaGetLastError();
+}
+
+// Every destination id below n and every row strictly ascending?  The walk kernels, the symmetry
+// check and the SGD kernels index with these ids without looking again.
+__global__ void __launch_bounds__(256) csr_check_kernel(const int64_t *__restrict__ indptr,
+                                                        const uint32_t *__restrict__ indices, uint64_t n,
+                                                        int *flags) {
+    int bad = 0;
+    for_each_row(indptr, n, 32u,
+                 [&](uint64_t, int64_t off, uint32_t deg) {
+                     uint32_t last = __ldg(indices + off);
+                     if (last >= n) bad |= 1;
+                     for (uint32_t e = 1; e < deg; ++e) {
+                         const uint32_t x = __ldg(indices + off + e);
+                         if (x >= n) bad |= 1;
+                         if (x <= last) bad |= 2;
+                         last = x;
+                     }
+                 },
+                 [&](uint64_t, int64_t off, uint32_t deg, uint32_t e) {
+                     const uint32_t x = __ldg(indices + off + e);
+                     if (x >= n) bad |= 1;
+                     if (e + 1u < deg && __ldg(indices + off + e + 1) <= x) bad |= 2;
+                 });
+    if (bad) atomicOr(flags, bad);
+}
+
+cudaError_t launch_csr_check(const int64_t *indptr, const uint32_t *indices, uint64_t n, int *d_flags,
+                             int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 16);
+    csr_check_kernel<<<grid, 256, 0, stream>>>(indptr, indices, n, d_flags);
+    return cudaGetLastError();
+}
+
+// Is x a neighbour of prev?  Filter first, then the exact search: on an undirected graph
+// (x in N(prev) <=> prev in N(x)) the shorter of the two rows is bisected, and the bounds of
+// x's row, fetched for that, are handed back so that an accepted x does not fetch them again.
+struct RowBounds { int64_t off; uint32_t deg; bool valid; };
+
+__device__ __forceinline__ bool adjacent(const WalkParams &p, int64_t prev_off, uint32_t prev_deg,
+                                         uint32_t prev, uint32_t x, RowBounds &xrow,
+                                         unsigned long long &probes, unsigned long long &rejects) {
+    if (p.filter && prev_deg >= FILTER_MIN_DEG) {
+        const FilterSlot s = filter_slot(prev_off, prev_deg, x);
+        ++probes;
+        if ((__ldg(p.filter + s.word) & s.mask) != s.mask) {
+            ++rejects;
+            return false;
+        }
+    }
+    if (p.undirected && prev_deg >= SHORT_ROW_MIN_DEG) {
+        xrow.off = __ldg(p.indptr + x);
+        xrow.deg = (uint32_t)(__ldg(p.indptr + x + 1) - xrow.off);
+        xrow.valid = true;
+        ++probes;
+        if (xrow.deg < prev_deg) return row_contains(p.indices + xrow.off, xrow.deg, prev, probes);
+    }
+    return row_contains(p.indices + prev_off, prev_deg, x, probes);
 }
 
 // index of a proposal inside a row: uniform, or proportional to the edge weights through the
@@ -39,10 +182,14 @@ __device__ __forceinline__ uint32_t propose(const uint2 *__restrict__ table, int
     return (uint32_t)u < e.x ? i : e.y;
 }
 
-template <bool SECOND, bool VEC, bool WEIGHTED>
+// FOLD (unweighted, undirected, return_weight > max(1, explore_weight)): the return edge is cut
+// down to the envelope of the other classes and its excess becomes a virtual slot of the row --
+// one Philox block per trial (tag 12): x decides slot vs row, y proposes, z accepts; see
+// oracle/walks.c (orc_fold_thresholds) for the normative statement.
+template <bool SECOND, bool VEC, bool WEIGHTED, bool FOLD>
 __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
+    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0, n_probes = 0, n_rejects = 0;
     if (i < p.n_walks) {
         const uint64_t wid = p.first_walk + i * p.walk_id_stride;
         const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
@@ -53,6 +200,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
         uint32_t cur = __ldg(p.sources + (wid % p.n_src));
         int64_t prev_off = 0;
         uint32_t prev = PAD, prev_deg = 0;
+        RowBounds row = {0, 0, false};  // bounds of cur's row when an adjacency check already fetched them
         bool alive = true;
         uint4 rnd = make_uint4(0, 0, 0, 0);
         uint32_t tok[4];
@@ -65,8 +213,16 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                 if (t >= L) { tok[u] = PAD; continue; }
                 uint32_t next = PAD;
                 if (alive) {
-                    const int64_t off = __ldg(p.indptr + cur);
-                    const uint32_t deg = (uint32_t)(__ldg(p.indptr + cur + 1) - off);
+                    int64_t off;
+                    uint32_t deg;
+                    if (SECOND && row.valid) {
+                        off = row.off;
+                        deg = row.deg;
+                    } else {
+                        off = __ldg(p.indptr + cur);
+                        deg = (uint32_t)(__ldg(p.indptr + cur + 1) - off);
+                    }
+                    row.valid = false;
                     if (deg == 0) {
                         alive = false;
                     } else {
@@ -79,29 +235,51 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
                                              : (s & 3u) == 2 ? rnd.z : rnd.w;
                             next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r));
                         } else {
-                            const uint32_t *prow = p.indices + prev_off;
+                            const unsigned long long t_out =
+                                FOLD ? (p.fold_excess << 32) / (((unsigned long long)deg << 20) + p.fold_excess) : 0ull;
                             uint32_t trial = 0;
                             for (;;) {
-                                if ((trial & 1u) == 0)
-                                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
-                                                        (TAG_WALK2 << 24) | (trial >> 1));
-                                const uint32_t r0 = (trial & 1u) ? rnd.z : rnd.x;
-                                const unsigned long long r1 = (trial & 1u) ? rnd.w : rnd.y;
-                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r0));
+                                uint32_t r0;
+                                unsigned long long r1;
                                 ++n_trials;
+                                if constexpr (FOLD) {
+                                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                        (TAG_FOLD << 24) | trial);
+                                    if (rnd.x < t_out) {  // the virtual slot: back to where we came from
+                                        next = prev;
+                                        row.off = prev_off;
+                                        row.deg = prev_deg;
+                                        row.valid = true;
+                                        break;
+                                    }
+                                    r0 = rnd.y;
+                                    r1 = rnd.z;
+                                } else {
+                                    if ((trial & 1u) == 0)
+                                        rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                            (TAG_WALK2 << 24) | (trial >> 1));
+                                    r0 = (trial & 1u) ? rnd.z : rnd.x;
+                                    r1 = (trial & 1u) ? rnd.w : rnd.y;
+                                }
+                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r0));
                                 bool accept;
+                                RowBounds xrow = {0, 0, false};
                                 if (next == prev) {
                                     accept = r1 < p.thr_return;
+                                    xrow.off = prev_off;
+                                    xrow.deg = prev_deg;
+                                    xrow.valid = true;
                                 } else if (r1 < thr_lo) {
                                     accept = true;   // every non-return class accepts
                                 } else if (r1 >= thr_hi) {
                                     accept = false;  // every non-return class rejects
                                 } else {
                                     ++n_searches;
-                                    const bool common = row_contains(prow, prev_deg, next);
+                                    const bool common = adjacent(p, prev_off, prev_deg, prev, next, xrow,
+                                                                 n_probes, n_rejects);
                                     accept = r1 < (common ? p.thr_common : p.thr_explore);
                                 }
-                                if (accept) break;
+                                if (accept) { row = xrow; break; }
                                 ++trial;
                                 if (trial >= MAX_TRIALS) break;
                             }
@@ -130,237 +308,17 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
         n_steps += __shfl_xor_sync(0xffffffffu, n_steps, off);
         n_trials += __shfl_xor_sync(0xffffffffu, n_trials, off);
         n_searches += __shfl_xor_sync(0xffffffffu, n_searches, off);
+        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, off);
+        n_rejects += __shfl_xor_sync(0xffffffffu, n_rejects, off);
     }
     if ((threadIdx.x & 31) == 0 && p.counters) {
         atomicAdd(&p.counters->walk_steps, n_steps);
         if (SECOND) {
             atomicAdd(&p.counters->walk_trials, n_trials);
             atomicAdd(&p.counters->walk_searches, n_searches);
+            atomicAdd(&p.counters->walk_probes, n_probes);
+            atomicAdd(&p.counters->walk_filter_rejects, n_rejects);
         }
-    }
-}
-
-
-// ---- second-order walks as a per-lane state machine ----
-//
-// In the plain kernel a warp advances at the pace of its slowest lane: every step waits for
-// the lane with the most rejected trials, every trial for the lane with the longest adjacency
-// search.  Here every lane carries its own walk through the states below and performs exactly
-// ONE dependent gather per loop iteration, so no lane ever idles on a neighbour's retry and the
-// loads of all 32 lanes are issued by the same instruction (maximum memory-level parallelism).
-// Finished lanes fetch the next walk (grid-stride), so warps stay full until the chunk ends.
-//
-//   SRC   : start node of the walk                      (sources[wid mod n_src])
-//   ROW   : row bounds of the current node              (indptr[cur], indptr[cur + 1])
-//   TRIAL : one proposal                                (indices[off + idx]) -> accept / reject /
-//           needs an adjacency check
-//   XROW  : (undirected graphs) row bounds of the proposal, to search the shorter of
-//           N(prev) and N(x): x in N(prev) <=> prev in N(x); reused if x is accepted
-//   SEARCH: one bisection step of the adjacency check
-//
-// Decisions are the oracle's (same Philox words, same integer thresholds), only their schedule
-// differs, so the walks stay bit-identical.
-enum WalkState : uint32_t { W_SRC = 0, W_ROW = 1, W_TRIAL = 2, W_XROW = 3, W_SEARCH = 4, W_DONE = 5 };
-
-template <bool UNDIRECTED, bool VEC>
-__global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
-    const uint64_t threads = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t L = p.walk_length;
-    const unsigned long long thr_lo = min(p.thr_common, p.thr_explore);
-    const unsigned long long thr_hi = max(p.thr_common, p.thr_explore);
-    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
-
-    uint32_t state = i < p.n_walks ? W_SRC : W_DONE;
-    uint64_t wid = 0;
-    uint32_t t = 0, cur = PAD, prev = PAD, deg = 0, pdeg = 0, trial = 0;
-    int64_t off = 0, poff = 0;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    uint32_t x = PAD;                  // proposal under examination
-    unsigned long long r1 = 0;         // its accept word
-    int64_t xoff = 0;                  // its row, when XROW fetched it
-    uint32_t xdeg = 0;
-    bool have_xrow = false;
-    int64_t sbase = 0;                 // bisection: row base, bounds, key
-    uint32_t slo = 0, shi = 0, skey = 0;
-    uint32_t tok[4] = {PAD, PAD, PAD, PAD};
-    uint32_t *out = nullptr;
-
-    // append one token to the walk; groups of four leave as one 16-byte store
-    auto emit = [&](uint32_t token) {
-        const uint32_t slot = t & 3u;  // explicit selects keep the group in registers
-        if (slot == 0) tok[0] = token; else if (slot == 1) tok[1] = token;
-        else if (slot == 2) tok[2] = token; else tok[3] = token;
-        ++t;
-        const uint32_t filled = t & 3u;
-        if (filled == 0) {
-            if (VEC) {
-                *reinterpret_cast<uint4 *>(out + t - 4u) = make_uint4(tok[0], tok[1], tok[2], tok[3]);
-            } else {
-                out[t - 4u] = tok[0]; out[t - 3u] = tok[1]; out[t - 2u] = tok[2]; out[t - 1u] = tok[3];
-            }
-        } else if (t == L) {
-            out[t - filled] = tok[0];
-            if (filled > 1) out[t - filled + 1u] = tok[1];
-            if (filled > 2) out[t - filled + 2u] = tok[2];
-        }
-    };
-
-    while (__any_sync(0xffffffffu, state != W_DONE)) {
-        // ---- phase A: the address of this iteration's gather ----
-        const void *addr = p.sources;
-        bool wide = false;  // two 8-byte entries of indptr vs one 4-byte token
-        switch (state) {
-            case W_SRC:
-                wid = p.first_walk + i * p.walk_id_stride;
-                out = p.out + i * (uint64_t)L;
-                addr = p.sources + (wid % p.n_src);
-                break;
-            case W_ROW:
-                addr = p.indptr + cur;
-                wide = true;
-                break;
-            case W_XROW:
-                addr = p.indptr + x;
-                wide = true;
-                break;
-            case W_TRIAL: {
-                const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
-                uint32_t r0;
-                if (t == 1) {
-                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, 0u, TAG_WALK1 << 24);
-                    r0 = rnd.x;
-                } else {
-                    if ((trial & 1u) == 0)
-                        rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
-                                            (TAG_WALK2 << 24) | (trial >> 1));
-                    r0 = (trial & 1u) ? rnd.z : rnd.x;
-                    r1 = (trial & 1u) ? rnd.w : rnd.y;
-                    ++n_trials;
-                }
-                addr = p.indices + off + __umulhi(r0, deg);
-                break;
-            }
-            case W_SEARCH:
-                addr = p.indices + sbase + (slo + ((shi - slo) >> 1));
-                break;
-            default:
-                break;
-        }
-        // ---- phase B: one gather per lane, issued by the whole warp at once ----
-        uint32_t word = 0;
-        long long first = 0, second = 0;
-        if (state != W_DONE) {
-            if (wide) {
-                first = __ldg(reinterpret_cast<const long long *>(addr));
-                second = __ldg(reinterpret_cast<const long long *>(addr) + 1);
-            } else {
-                word = __ldg(reinterpret_cast<const uint32_t *>(addr));
-            }
-        }
-        // ---- phase C: consume it ----
-        bool accept = false, reject = false, new_row = false;
-        switch (state) {
-            case W_SRC:
-                cur = word;
-                prev = PAD;
-                t = 0;
-                emit(cur);
-                have_xrow = false;
-                state = L > 1 ? W_ROW : W_DONE;
-                break;
-            case W_ROW:
-                off = first;
-                deg = (uint32_t)(second - first);
-                new_row = true;
-                break;
-            case W_TRIAL:
-                x = word;
-                if (t == 1) {
-                    accept = true;
-                } else if (x == prev) {
-                    if (r1 < p.thr_return) accept = true; else reject = true;
-                } else if (r1 < thr_lo) {
-                    accept = true;
-                } else if (r1 >= thr_hi) {
-                    reject = true;
-                } else {
-                    ++n_searches;
-                    if (UNDIRECTED) {
-                        state = W_XROW;
-                    } else {
-                        sbase = poff; slo = 0; shi = pdeg; skey = x;
-                        state = W_SEARCH;
-                    }
-                }
-                break;
-            case W_XROW:
-                xoff = first;
-                xdeg = (uint32_t)(second - first);
-                have_xrow = true;
-                // x in N(prev) <=> prev in N(x) on an undirected graph: bisect the shorter row
-                if (xdeg < pdeg) { sbase = xoff; slo = 0; shi = xdeg; skey = prev; }
-                else { sbase = poff; slo = 0; shi = pdeg; skey = x; }
-                state = W_SEARCH;
-                break;
-            case W_SEARCH: {
-                const uint32_t mid = slo + ((shi - slo) >> 1);
-                bool decided = false, common = false;
-                if (word == skey) { decided = true; common = true; }
-                else if (word < skey) slo = mid + 1;
-                else shi = mid;
-                if (!decided && slo >= shi) decided = true;
-                if (decided) {
-                    if (r1 < (common ? p.thr_common : p.thr_explore)) accept = true; else reject = true;
-                }
-                break;
-            }
-            default:
-                break;
-        }
-        if (reject) {
-            ++trial;
-            have_xrow = false;
-            if (trial >= MAX_TRIALS) accept = true; else state = W_TRIAL;
-        }
-        if (accept) {
-            ++n_steps;
-            prev = cur; poff = off; pdeg = deg;
-            cur = x;
-            emit(x);
-            if (t >= L) {
-                state = W_DONE;
-            } else if (have_xrow) {
-                off = xoff; deg = xdeg;
-                new_row = true;
-            } else {
-                state = W_ROW;
-            }
-            have_xrow = false;
-        }
-        if (new_row) {  // the row of the current node is known: walk on, or pad after a dead end
-            trial = 0;
-            state = W_TRIAL;
-            if (deg == 0) {
-                while (t < L) emit(PAD);
-                state = W_DONE;
-            }
-        }
-        if (state == W_DONE && i < p.n_walks) {  // this lane's walk is complete: fetch the next one
-            i += threads;
-            if (i < p.n_walks) state = W_SRC; else i = p.n_walks;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        n_steps += __shfl_xor_sync(0xffffffffu, n_steps, o);
-        n_trials += __shfl_xor_sync(0xffffffffu, n_trials, o);
-        n_searches += __shfl_xor_sync(0xffffffffu, n_searches, o);
-    }
-    if ((threadIdx.x & 31) == 0 && p.counters) {
-        atomicAdd(&p.counters->walk_steps, n_steps);
-        atomicAdd(&p.counters->walk_trials, n_trials);
-        atomicAdd(&p.counters->walk_searches, n_searches);
     }
 }
 
@@ -373,7 +331,7 @@ __global__ void __launch_bounds__(256) walk_sm_kernel(const WalkParams p) {
 template <bool VEC, bool WEIGHTED>
 __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0;
+    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0, n_probes = 0, n_rejects = 0;
     if (i < p.n_walks) {
         const uint64_t wid = p.first_walk + i * p.walk_id_stride;
         const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
@@ -425,7 +383,9 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
                                     accept = false;
                                 } else {
                                     ++n_searches;
-                                    const bool common = row_contains(p.indices + prev_off, prev_deg, next);
+                                    RowBounds xrow = {0, 0, false};
+                                    const bool common = adjacent(p, prev_off, prev_deg, prev, next, xrow,
+                                                                 n_probes, n_rejects);
                                     accept = lhs < (common ? p.thr_common : p.thr_explore);
                                 }
                             }
@@ -457,11 +417,15 @@ __global__ void __launch_bounds__(256) walk_general_kernel(const WalkParams p) {
         n_steps += __shfl_xor_sync(0xffffffffu, n_steps, off);
         n_trials += __shfl_xor_sync(0xffffffffu, n_trials, off);
         n_searches += __shfl_xor_sync(0xffffffffu, n_searches, off);
+        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, off);
+        n_rejects += __shfl_xor_sync(0xffffffffu, n_rejects, off);
     }
     if ((threadIdx.x & 31) == 0 && p.counters) {
         atomicAdd(&p.counters->walk_steps, n_steps);
         atomicAdd(&p.counters->walk_trials, n_trials);
         atomicAdd(&p.counters->walk_searches, n_searches);
+        atomicAdd(&p.counters->walk_probes, n_probes);
+        atomicAdd(&p.counters->walk_filter_rejects, n_rejects);
     }
 }
 
@@ -507,7 +471,8 @@ __global__ void __launch_bounds__(256) symmetry_kernel(const int64_t *__restrict
     const uint32_t u = (uint32_t)lo, v = __ldg(indices + e);
     const int64_t begin = __ldg(indptr + v);
     const uint32_t len = (uint32_t)(__ldg(indptr + v + 1) - begin);
-    if (!row_contains(indices + begin, len, u)) *symmetric = 0;
+    unsigned long long probes = 0;
+    if (!row_contains(indices + begin, len, u, probes)) *symmetric = 0;
 }
 
 cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices, uint64_t n,
@@ -532,32 +497,15 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
                else walk_general_kernel<false, false><<<grid, block, 0, stream>>>(p); }
         return cudaGetLastError();
     }
-    if (second_order && !weighted && p.state_machine) {
-        // persistent grid: lanes fetch walks grid-stride, so size it to the machine, not the chunk
-        int per_sm = 0;
-        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, p.undirected ? (vec ? walk_sm_kernel<true, true> : walk_sm_kernel<true, false>)
-                                  : (vec ? walk_sm_kernel<false, true> : walk_sm_kernel<false, false>),
-            (int)block, 0);
-        if (err != cudaSuccess) return err;
-        unsigned resident = (unsigned)std::max(1, per_sm) * (unsigned)p.sm_count;
-        const unsigned sm_grid = std::min(grid, resident);
-        if (p.undirected) {
-            if (vec) walk_sm_kernel<true, true><<<sm_grid, block, 0, stream>>>(p);
-            else walk_sm_kernel<true, false><<<sm_grid, block, 0, stream>>>(p);
-        } else {
-            if (vec) walk_sm_kernel<false, true><<<sm_grid, block, 0, stream>>>(p);
-            else walk_sm_kernel<false, false><<<sm_grid, block, 0, stream>>>(p);
-        }
-        return cudaGetLastError();
-    }
-#define B2E_LAUNCH_WALK(S, V, W) walk_kernel<S, V, W><<<grid, block, 0, stream>>>(p)
-    if (second_order) {
-        if (vec) { if (weighted) B2E_LAUNCH_WALK(true, true, true); else B2E_LAUNCH_WALK(true, true, false); }
-        else { if (weighted) B2E_LAUNCH_WALK(true, false, true); else B2E_LAUNCH_WALK(true, false, false); }
+#define B2E_LAUNCH_WALK(S, V, W, F) walk_kernel<S, V, W, F><<<grid, block, 0, stream>>>(p)
+    if (second_order && !weighted && p.fold_excess) {
+        if (vec) B2E_LAUNCH_WALK(true, true, false, true); else B2E_LAUNCH_WALK(true, false, false, true);
+    } else if (second_order) {
+        if (vec) { if (weighted) B2E_LAUNCH_WALK(true, true, true, false); else B2E_LAUNCH_WALK(true, true, false, false); }
+        else { if (weighted) B2E_LAUNCH_WALK(true, false, true, false); else B2E_LAUNCH_WALK(true, false, false, false); }
     } else {
-        if (vec) { if (weighted) B2E_LAUNCH_WALK(false, true, true); else B2E_LAUNCH_WALK(false, true, false); }
-        else { if (weighted) B2E_LAUNCH_WALK(false, false, true); else B2E_LAUNCH_WALK(false, false, false); }
+        if (vec) { if (weighted) B2E_LAUNCH_WALK(false, true, true, false); else B2E_LAUNCH_WALK(false, true, false, false); }
+        else { if (weighted) B2E_LAUNCH_WALK(false, false, true, false); else B2E_LAUNCH_WALK(false, false, false, false); }
     }
 #undef B2E_LAUNCH_WALK
     return cudaGetLastError();

@@ -146,13 +146,14 @@ class Node2VecB200(B200Embedder):
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
             device=device)
 
-    def _output_buffers(self, n: int):
+    def _output_buffers(self, n: int, writes_files: bool = True):
         """float32 host buffers the engine writes; .npy memory maps when paths are given
         (node2vec_skipgram.py:86-93)."""
         buffers = []
         for key in ("central_nodes_embedding_path", "contextual_nodes_embedding_path"):
             path = self._model_kwargs.get(key)
-            if path is None or self._model_kwargs["dtype"] != "f32":
+            # under torch.distributed every rank returns the tables but only rank 0 owns the files
+            if path is None or self._model_kwargs["dtype"] != "f32" or not writes_files:
                 buffers.append(np.empty((n, self._embedding_size), dtype=np.float32))
             else:
                 buffers.append(np.lib.format.open_memmap(
@@ -167,17 +168,17 @@ class Node2VecB200(B200Embedder):
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         n = indptr.shape[0] - 1
-        world = 1
+        world, rank = 1, 0
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
-                world = dist.get_world_size()
+                world, rank = dist.get_world_size(), dist.get_rank()
         except ImportError:
             pass
         # the seed is read here, not at construction: set_random_state() between holdouts takes
         # effect (abstract_classifier_model.py:711-712)
         seed = int(self._random_state) & 0xFFFFFFFFFFFFFFFF
-        central, contextual = self._output_buffers(n)
+        central, contextual = self._output_buffers(n, writes_files=rank == 0)
         with Engine(**self._engine_kwargs(device)) as engine:
             engine.load_csr(indptr, indices, weights)  # weighted graphs walk by weight
             if self.is_using_node_types() or self.is_using_edge_types():
@@ -187,8 +188,8 @@ class Node2VecB200(B200Embedder):
             if world > 1 and self.MODELS[self.model_name()] == "GloVe":
                 raise NotImplementedError("GloVe runs on one GPU: the co-occurrence counts are not sharded.")
             if world > 1:
-                c, x, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"])
-                central[:], contextual[:] = c, x
+                _, _, losses = engine.fit_distributed(seed, self._model_kwargs["sync_interval"],
+                                                      table0=central, table1=contextual)
             else:
                 _, _, losses = engine.fit(seed, central, contextual)
         self._last_losses = losses
@@ -201,8 +202,12 @@ class Node2VecB200(B200Embedder):
             node_embeddings = [e.astype(dtype) for e in node_embeddings]
             for e, key in zip(node_embeddings, ("central_nodes_embedding_path",
                                                 "contextual_nodes_embedding_path")):
-                if self._model_kwargs.get(key) is not None:
-                    np.save(self._model_kwargs[key], e)
+                if self._model_kwargs.get(key) is not None and rank == 0:
+                    # exactly the path the caller named (np.save would append ".npy" to it)
+                    out = np.lib.format.open_memmap(self._model_kwargs[key], mode="w+", dtype=e.dtype,
+                                                    shape=e.shape)
+                    out[:] = e
+                    out.flush()
         if return_dataframe:  # node2vec.py:104-109
             node_names = graph.get_node_names() if hasattr(graph, "get_node_names") else None
             node_embeddings = [pd.DataFrame(e, index=node_names) for e in node_embeddings]

@@ -2,10 +2,12 @@
 ``ensmallen.models.SkipGram / CBOW`` instance
 (/root/reference/embiggen/embedders/ensmallen_embedders/node2vec.py:65-69, used at :99).
 
-PyTorch appears only as plumbing for the multi-GPU path (``torch.distributed`` over NCCL and
-a zero-copy tensor view of the device tables); every kernel is in ``libb2e.so``.
+PyTorch appears only as plumbing for the multi-GPU path (``torch.distributed`` carries the
+IPC handles and the barriers around the exchange step); every kernel, the exchange kernel over
+NVLink peer memory included, is in ``libb2e.so``.
 """
 import ctypes
+import time
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -288,46 +290,113 @@ class Engine:
         device = f"cuda:{self.config.device}"
         return tuple(torch.as_tensor(_DeviceArray(p.value, shape), device=device) for p in (p0, p1))
 
-    # ---- data-parallel path: start nodes sharded, tables averaged by NCCL all-reduce ----
-    def fit_distributed(self, seed: int, sync_interval: int = 4, process_group=None
-                        ) -> Tuple[np.ndarray, np.ndarray, List[float]]:
+    def tables_digest(self) -> dict:
+        """Sums, sums of squares, order-independent bit sums and the count of non-finite values of
+        the live part of the two device tables (equal replicas give equal ``bits``)."""
+        sums = (ctypes.c_double * 4)()
+        words = (ctypes.c_uint64 * 3)()
+        check(self._lib.b2e_tables_digest(self._handle, sums, words))
+        return {"sum": (sums[0], sums[2]), "squares": (sums[1], sums[3]),
+                "bits": (int(words[0]), int(words[1])), "non_finite": int(words[2])}
+
+    # ---- the exchange step: replicas averaged by one kernel over NVLink peer memory ----
+    def open_exchange(self, process_group=None) -> None:
+        """Map the tables of the other ranks of the node (CUDA IPC; one process per GPU)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        mine = ctypes.create_string_buffer(2 * 64)
+        check(self._lib.b2e_exchange_handles(self._handle, mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine.raw, group=process_group)
+        everyone = ctypes.create_string_buffer(b"".join(gathered), 2 * 64 * world)
+        check(self._lib.b2e_exchange_open(self._handle, world, rank, everyone))
+        self._exchange_group = process_group
+        dist.barrier(group=process_group)  # nobody averages before every rank has mapped its peers
+
+    def open_exchange_local(self, replicas: List["Engine"], rank: int) -> None:
+        """Same with replicas that live in this process (tests; ``replicas[rank]`` is ignored)."""
+        handles = (ctypes.c_void_p * len(replicas))(*[r._handle for r in replicas])
+        check(self._lib.b2e_exchange_open_local(self._handle, len(replicas), rank, handles))
+
+    def exchange_average(self) -> None:
+        """Launch this rank's share of the averaging (asynchronous on the train stream); the
+        caller brackets it with barriers, see :meth:`average`."""
+        check(self._lib.b2e_exchange_average(self._handle))
+
+    def close_exchange(self) -> None:
+        check(self._lib.b2e_exchange_close(self._handle))
+
+    def average(self, process_group=None) -> None:
+        """One exchange step: every replica becomes the mean of all replicas."""
+        import torch.distributed as dist
+        self.sync()                        # my SGD chunk is done ...
+        dist.barrier(group=process_group)  # ... and so is everybody else's
+        self.exchange_average()
+        self.sync()
+        dist.barrier(group=process_group)  # every owner has written its rows to every replica
+
+    # ---- data-parallel path: start nodes sharded, tables averaged at a fixed step interval ----
+    def fit_distributed(self, seed: int, sync_interval: int = 4, process_group=None,
+                        gather: str = "all", table0: Optional[np.ndarray] = None,
+                        table1: Optional[np.ndarray] = None
+                        ) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], List[float]]:
         """Every rank holds the CSR and both tables; rank r walks ids = r mod world_size.
 
-        Tables are averaged (all-reduce, AVG) every ``sync_interval`` chunks and at each epoch
-        end.  Returns role-ordered tables like :meth:`fit` (identical on every rank).
+        Replicas are averaged every ``sync_interval`` chunks and at each epoch end.  Returns
+        role-ordered tables like :meth:`fit`; with ``gather="rank0"`` only rank 0 copies them to
+        the host (the others return ``None`` tables: at C5 a host copy is 80 GB per rank).
         """
         import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
         cfg = self.config
-        tables = self.device_tables()
+        if gather not in ("all", "rank0"):
+            raise ValueError("gather must be 'all' or 'rank0'")
         self.init_tables(seed)  # identical on every rank (counter-based init)
+        if world > 1:
+            self.open_exchange(process_group)
         per_epoch = self.walks_per_epoch
         lr = np.float32(cfg.learning_rate)
         losses = []
+        self.exchange_seconds = 0.0
+        self.exchange_count = 0
 
         def average():
-            self.sync()
-            average_replicas(tables, process_group)
-            torch.cuda.synchronize(cfg.device)
+            if world == 1:
+                return
+            begin = time.perf_counter()
+            self.average(process_group)
+            self.exchange_seconds += time.perf_counter() - begin
+            self.exchange_count += 1
 
         for epoch in range(cfg.epochs):
             self.reset_counters()
             steps = list(shard_chunks(per_epoch, self.chunk_capacity, world, rank, epoch * per_epoch))
+            if steps:
+                self.walk_chunk(seed, steps[0][0], steps[0][1], steps[0][2], 0)
             for index, (first, mine, stride) in enumerate(steps):
                 slot = index & 1
-                self.walk_chunk(seed, first, mine, stride, slot)
+                if index + 1 < len(steps):  # walk chunk k + 1 overlaps the SGD over chunk k
+                    self.walk_chunk(seed, steps[index + 1][0], steps[index + 1][1], steps[index + 1][2], slot ^ 1)
                 self.train_chunk(seed, slot, float(lr))
                 if sync_interval and (index + 1) % sync_interval == 0 and index + 1 < len(steps):
                     average()
             average()
             c = self.counters()
-            stats = torch.tensor([c["loss_sum"], float(c["pairs"])], dtype=torch.float64,
-                                 device=f"cuda:{cfg.device}")
+            stats = torch.tensor([c["loss_sum"], float(c["pairs"])], dtype=torch.float64)
+            if dist.get_backend(process_group) == "nccl":
+                stats = stats.to(f"cuda:{cfg.device}")
             dist.all_reduce(stats, group=process_group)
             losses.append(float(stats[0] / max(float(stats[1]), 1.0)))
             lr = np.float32(lr * np.float32(cfg.learning_rate_decay))
-        t0, t1 = self.export_tables()
-        if self.model == "cbow":
-            t0, t1 = t1, t0
+        if world > 1:
+            dist.barrier(group=process_group)
+            self.close_exchange()
+        if gather == "rank0" and rank != 0:
+            return None, None, losses
+        shape = (self.n, cfg.embedding_size)
+        t0 = np.empty(shape, dtype=np.float32) if table0 is None else table0
+        t1 = np.empty(shape, dtype=np.float32) if table1 is None else table1
+        first, second = (t1, t0) if self.model == "cbow" else (t0, t1)
+        check(self._lib.b2e_export_tables(self._handle, first.ctypes.data, second.ctypes.data))
         return t0, t1, losses

@@ -24,8 +24,10 @@
 extern "C" {
 #endif
 
-#define B2E_ABI_VERSION 1
+#define B2E_ABI_VERSION 2
 #define B2E_PAD_TOKEN 0xFFFFFFFFu /* walk token after a dead end (directed graphs only) */
+#define B2E_MAX_WORLD 16          /* replicas one exchange step can average (GPUs of one node) */
+#define B2E_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
 
 typedef enum {
     B2E_OK = 0,
@@ -76,7 +78,9 @@ typedef struct {
 typedef struct {
     uint64_t walk_steps;    /* sampled transitions */
     uint64_t walk_trials;   /* second-order proposals */
-    uint64_t walk_searches; /* adjacency checks that needed a binary search */
+    uint64_t walk_searches; /* adjacency checks the accept test could not decide without the class */
+    uint64_t walk_probes;   /* gathers those checks cost: row-filter words, row bounds, bisection steps */
+    uint64_t walk_filter_rejects; /* checks answered "not a neighbour" by the row filter alone */
     uint64_t pairs;         /* (centre, context) positives trained */
     uint64_t targets;       /* target rows scored (positive + valid negatives) */
     double loss_sum;        /* sum of pair losses since the last b2e_reset_counters */
@@ -168,8 +172,34 @@ int b2e_train_host_walks(b2e_handle *handle, uint64_t seed, const uint32_t *walk
                          float learning_rate);
 int b2e_sync(b2e_handle *handle);
 
-/* device pointers of the two tables (n x row_stride float32) for NCCL averaging by the host */
+/* device pointers of the two tables (n x row_stride float32) */
 int b2e_device_tables(b2e_handle *handle, void **table0, void **table1);
+
+/*
+ * The exchange step of the data-parallel path (north_star subsystem 4; no counterpart in the
+ * reference, whose engine is one shared-memory process): every GPU of the node holds a replica of
+ * both tables, trains its shard of the walks on it, and the replicas are averaged at a fixed step
+ * interval.  One kernel per rank reduces the rows that rank owns over NVLink peer memory and
+ * writes the average back to every replica (csrc/exchange.cu).
+ *   b2e_exchange_handles   writes the CUDA IPC handles of this replica's two tables
+ *                          (2 x B2E_IPC_HANDLE_BYTES) for the other processes of the node;
+ *   b2e_exchange_open      takes the handles of all `world` ranks, rank-major (this rank's own
+ *                          entry is ignored), and maps the peers' tables;
+ *   b2e_exchange_open_local same with replicas that live in this process (handles[world], tests);
+ *   b2e_exchange_average   asynchronous on the train stream; the caller guarantees that every
+ *                          replica has finished its SGD chunk before any rank starts (barrier) and
+ *                          that no rank resumes before all have finished (second barrier);
+ *   b2e_exchange_close     unmaps the peers (also done by b2e_load_csr* and b2e_destroy).
+ * b2e_tables_digest: {sum, sum of squares} of table 0, of table 1 (4 doubles), then the
+ * wrap-around sums of the float bit patterns of the two tables and the number of non-finite values
+ * (3 uint64): equal replicas give equal words.
+ */
+int b2e_exchange_handles(b2e_handle *handle, void *ipc_handles);
+int b2e_exchange_open(b2e_handle *handle, uint32_t world, uint32_t rank, const void *all_ipc_handles);
+int b2e_exchange_open_local(b2e_handle *handle, uint32_t world, uint32_t rank, b2e_handle *const *replicas);
+int b2e_exchange_average(b2e_handle *handle);
+int b2e_exchange_close(b2e_handle *handle);
+int b2e_tables_digest(b2e_handle *handle, double *sums, uint64_t *words);
 int b2e_chunk_capacity(const b2e_handle *handle, uint64_t *walks);
 /* strip the row padding and copy both tables to host buffers (n x embedding_size each) */
 int b2e_export_tables(b2e_handle *handle, float *table0, float *table1);

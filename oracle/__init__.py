@@ -47,6 +47,7 @@ class SgnsCfg(ctypes.Structure):
         ("normalize_learning_rate_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("downsample_bound", ctypes.c_uint32),
+        ("fast_math", ctypes.c_uint32),
     ]
 
 
@@ -82,16 +83,20 @@ def lib():
         l.orc_thresholds.argtypes = [f32, f32, P(u64)]
         l.orc_walks.restype = ctypes.c_int
         l.orc_walks.argtypes = [P(ctypes.c_int64), P(u32), u64, P(u32), u64, u64, u64, u64, u64,
-                                u32, f32, f32, P(u32), P(WalkCounters)]
+                                u32, f32, f32, ctypes.c_int, P(u32), P(WalkCounters)]
+        l.orc_is_undirected.restype = ctypes.c_int
+        l.orc_is_undirected.argtypes = [P(ctypes.c_int64), P(u32), u64]
+        l.orc_fold_thresholds.restype = None
+        l.orc_fold_thresholds.argtypes = [f32, f32, P(u64), P(u64)]
         l.orc_edge_alias.restype = ctypes.c_int
         l.orc_edge_alias.argtypes = [P(ctypes.c_int64), P(f32), u64, P(u32)]
         l.orc_walks_weighted.restype = ctypes.c_int
         l.orc_walks_weighted.argtypes = [P(ctypes.c_int64), P(u32), P(u32), u64, P(u32), u64, u64, u64,
-                                         u64, u64, u32, f32, f32, P(u32), P(WalkCounters)]
+                                         u64, u64, u32, f32, f32, ctypes.c_int, P(u32), P(WalkCounters)]
         l.orc_walks_typed.restype = ctypes.c_int
         l.orc_walks_typed.argtypes = [P(ctypes.c_int64), P(u32), P(u32), P(u32), P(u32), f32, f32,
-                                      u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, P(u32),
-                                      P(WalkCounters)]
+                                      u64, P(u32), u64, u64, u64, u64, u64, u32, f32, f32, ctypes.c_int,
+                                      P(u32), P(WalkCounters)]
         l.orc_philox_range.restype = None
         l.orc_philox_range.argtypes = [u64, u32, u64, u32, u32, u32, P(u32)]
         l.orc_log_det.restype = f32
@@ -115,8 +120,33 @@ def lib():
         l.orc_train.restype = ctypes.c_int
         l.orc_train.argtypes = [P(SgnsCfg), P(u32), u64, u64, u64, u64, u64, P(ctypes.c_int64),
                                 P(u32), P(u32), P(f32), P(f32), P(ctypes.c_double), P(u64), P(u64)]
+        l.orc_synthetic_csr.restype = ctypes.c_int
+        l.orc_synthetic_csr.argtypes = [ctypes.c_int, u64, u32, u64, u64, u64, u64, u64,
+                                        P(ctypes.c_int64), P(u32), P(u64)]
         _lib = l
     return _lib
+
+
+RMAT_PROBABILITIES = (0.57, 0.19, 0.19, 0.05)
+
+
+def synthetic_csr(kind: str, n: int, m: int, scale: int = 0, seed: int = 42,
+                  probabilities=RMAT_PROBABILITIES) -> Tuple[np.ndarray, np.ndarray]:
+    """(indptr, indices) of the seeded Erdos-Renyi (``kind="er"``) or R-MAT (``"rmat"``) graph with
+    ``m`` distinct undirected edges: the same graph as ``embiggen_b200.graph.erdos_renyi / rmat``
+    and the product's GPU builder, generated by oracle/graphgen.c on ``set_threads`` host threads."""
+    a, b, c, _ = probabilities
+    t_a, t_ab, t_abc = int(a * 2 ** 32), int((a + b) * 2 ** 32), int((a + b + c) * 2 ** 32)
+    indptr = np.empty(n + 1, dtype=np.int64)
+    indices = np.empty(2 * m, dtype=np.uint32)
+    nnz = ctypes.c_uint64(0)
+    rc = lib().orc_synthetic_csr({"er": 0, "rmat": 1}[kind], n, scale, m, seed, t_a, t_ab, t_abc,
+                                 _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                                 ctypes.byref(nnz))
+    if rc != 0:
+        raise ValueError(f"orc_synthetic_csr failed with status {rc}")
+    assert nnz.value == 2 * m
+    return indptr, indices
 
 
 def philox(seed: int, c0: int, c1: int, c2: int, c3: int) -> Tuple[int, int, int, int]:
@@ -188,8 +218,13 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
           srcs: Optional[np.ndarray] = None, weights=None,
           normalize_by_degree: bool = False, node_types=None, edge_types=None,
           change_node_type_weight: float = 1.0,
-          change_edge_type_weight: float = 1.0) -> Tuple[np.ndarray, dict]:
+          change_edge_type_weight: float = 1.0,
+          undirected: Optional[bool] = None) -> Tuple[np.ndarray, dict]:
+    """``undirected`` (every edge mirrored) enables the folded return edge (walks.c); None =
+    check the graph, as the product does at load."""
     indptr, indices = _csr(indptr, indices)
+    if undirected is None:
+        undirected = is_undirected(indptr, indices) if return_weight > max(1.0, explore_weight) else False
     if normalize_by_degree:
         weights = degree_normalised_weights(indptr, indices, weights)
     table = None if weights is None else edge_alias(indptr, weights)
@@ -210,10 +245,24 @@ def walks(indptr, indices, seed: int, first_walk: int, n_walks: int, walk_length
                                change_node_type_weight, change_edge_type_weight, n,
                                _ptr(srcs, ctypes.c_uint32), srcs.shape[0], seed, first_walk, n_walks,
                                walk_id_stride, walk_length, return_weight, explore_weight,
-                               _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
+                               int(bool(undirected)), _ptr(out, ctypes.c_uint32), ctypes.byref(counters))
     if rc != 0:
         raise ValueError(f"orc_walks failed with status {rc}")
     return out, counters.as_dict()
+
+
+def is_undirected(indptr, indices) -> bool:
+    indptr, indices = _csr(indptr, indices)
+    return bool(lib().orc_is_undirected(_ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_uint32),
+                                        indptr.shape[0] - 1))
+
+
+def fold_thresholds(return_weight: float, explore_weight: float) -> Tuple[np.ndarray, int]:
+    """(accept thresholds [return, common, explore], excess E) of the folded sampler (walks.c)."""
+    out = np.zeros(3, dtype=np.uint64)
+    excess = ctypes.c_uint64(0)
+    lib().orc_fold_thresholds(return_weight, explore_weight, _ptr(out, ctypes.c_uint64), ctypes.byref(excess))
+    return out, int(excess.value)
 
 
 def alias_build(indptr, alpha: float = 0.75) -> Tuple[np.ndarray, np.ndarray]:
@@ -254,8 +303,10 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
           clipping_value: float = 6.0, first_walk: int = 0, walk_id_stride: int = 1,
           thr: Optional[np.ndarray] = None, alias: Optional[np.ndarray] = None,
           indptr: Optional[np.ndarray] = None, normalize_learning_rate_by_degree: bool = False,
-          scale_by_sqrt_dim: bool = False, stochastic_downsample_by_degree: bool = False) -> dict:
-    """Train in place over row-major walks; returns loss_sum / pairs / targets."""
+          scale_by_sqrt_dim: bool = False, stochastic_downsample_by_degree: bool = False,
+          fast_math: bool = False) -> dict:
+    """Train in place over row-major walks; returns loss_sum / pairs / targets.  ``fast_math``
+    (vectorised dot, libm exp) is for timing the CPU baseline only, never for parity."""
     walk_array = np.ascontiguousarray(walk_array, dtype=np.uint32)
     assert t0.dtype == np.float32 and t1.dtype == np.float32
     assert t0.flags.c_contiguous and t1.flags.c_contiguous
@@ -271,6 +322,7 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
         use_alias=int(thr is not None),
         normalize_learning_rate_by_degree=int(normalize_learning_rate_by_degree),
         scale_by_sqrt_dim=int(scale_by_sqrt_dim),
+        fast_math=int(fast_math),
     )
     if indptr is not None:
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)

@@ -56,7 +56,12 @@ void orc_thresholds(float return_weight, float explore_weight, uint64_t thr[3]);
 int orc_walks(const int64_t *indptr, const uint32_t *indices, uint64_t n, const uint32_t *sources,
               uint64_t n_src, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
               uint64_t walk_id_stride, uint32_t walk_length, float return_weight,
-              float explore_weight, uint32_t *out, orc_walk_counters *counters);
+              float explore_weight, int undirected, uint32_t *out, orc_walk_counters *counters);
+
+/* `undirected` (every edge has its mirror; orc_is_undirected) lets the sampler fold the return
+ * edge out of the rejection envelope when return_weight > max(1, explore_weight): walks.c */
+int orc_is_undirected(const int64_t *indptr, const uint32_t *indices, uint64_t n);
+void orc_fold_thresholds(float return_weight, float explore_weight, uint64_t thrf[3], uint64_t *excess);
 
 /* per-row alias tables of a weighted graph (see walks.c): two words per edge, {thr, alias index
  * inside the row}.  The `table` arguments below take this table (NULL: unweighted). */
@@ -66,7 +71,7 @@ int orc_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, uint
 int orc_walks_weighted(const int64_t *indptr, const uint32_t *indices, const uint32_t *table, uint64_t n,
                        const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                        uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
-                       float return_weight, float explore_weight, uint32_t *out,
+                       float return_weight, float explore_weight, int undirected, uint32_t *out,
                        orc_walk_counters *counters);
 
 /* orc_walks_weighted plus typed walks: node_types[n] / edge_types[nnz] (NULL: untyped) and the
@@ -78,7 +83,7 @@ int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32
                     float change_node_type_weight, float change_edge_type_weight, uint64_t n,
                     const uint32_t *sources, uint64_t n_src, uint64_t seed, uint64_t first_walk,
                     uint64_t n_walks, uint64_t walk_id_stride, uint32_t walk_length,
-                    float return_weight, float explore_weight, uint32_t *out,
+                    float return_weight, float explore_weight, int undirected, uint32_t *out,
                     orc_walk_counters *counters);
 
 /* Vose alias table over deg^alpha; thr/alias have n entries. */
@@ -98,6 +103,7 @@ typedef struct {
     uint32_t normalize_learning_rate_by_degree; /* lr / deg(centre)                         */
     uint32_t scale_by_sqrt_dim;                 /* dot / sqrt(D)  (P)   */
     uint32_t downsample_bound; /* stochastic_downsample_by_degree: max degree + 1, 0 => off */
+    uint32_t fast_math; /* 1: vectorised dot + libm expf: for timing the CPU baseline only (sgns.c) */
 } orc_sgns_cfg;
 
 /*
@@ -117,6 +123,16 @@ float orc_dot(const float *a, const float *b, uint32_t row_stride);
 
 int orc_init_tables(uint64_t n, uint32_t embedding_size, uint32_t row_stride, uint64_t seed,
                     float *t0, float *t1);
+
+/*
+ * Seeded synthetic graphs of the BASELINE.json shapes (graphgen.c): the first n_edges distinct
+ * undirected edges, in draw order, of the Philox stream (seed, draw index); kind 0 = Erdos-Renyi
+ * G(n, m), kind 1 = R-MAT over 2^scale ids with ids >= n rejected and quadrant thresholds
+ * t_a, t_ab, t_abc (floor(p * 2^32)).  indptr has n + 1 entries, indices 2 * n_edges.  Same graph
+ * as embiggen_b200/graph.py (numpy) and the product's GPU builder; OpenMP over orc_set_threads.
+ */
+int orc_synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t n_edges, uint64_t seed, uint64_t t_a,
+                      uint64_t t_ab, uint64_t t_abc, int64_t *indptr, uint32_t *indices, uint64_t *nnz_out);
 
 /*
  * Sequential deterministic training over row-major walks (ascending order).

@@ -18,6 +18,7 @@
 #define ORC_TAG_INIT0 4u /* table 0 initialisation                           */
 #define ORC_TAG_INIT1 5u /* table 1 initialisation                           */
 #define ORC_TAG_WALK3 7u /* general walks (normalize_by_degree, typed): 1 trial per block */
+#define ORC_TAG_FOLD 12u /* second-order trials with the return edge folded: 1 trial per block */
 #define ORC_TAG_SKIP 6u  /* stochastic_downsample_by_degree, one per centre     */
 
 static inline void orc_philox4x32_10(uint32_t seed_lo, uint32_t seed_hi, uint32_t c0, uint32_t c1,

@@ -84,6 +84,8 @@ int orc_init_tables(uint64_t n, uint32_t embedding_size, uint32_t row_stride, ui
     for (int table = 0; table < 2; ++table) {
         float *t = table ? t1 : t0;
         const uint32_t tag = (table ? ORC_TAG_INIT1 : ORC_TAG_INIT0) << 24;
+        /* every element is a pure function of (seed, table, i, j): the thread count cannot matter */
+#pragma omp parallel for num_threads(g_threads) if (g_threads > 1) schedule(static)
         for (uint64_t i = 0; i < n; ++i) {
             uint32_t rnd[4];
             for (uint32_t j = 0; j < row_stride; ++j) {
@@ -135,6 +137,16 @@ static void draw_negatives(const orc_sgns_cfg *cfg, uint64_t seed, uint64_t wid,
  * pre-update rows; then targets are applied in order.  acc receives
  * sum_k g_k * row_k (pre-update).
  */
+/* cfg->fast_math: the dot as a plain vectorisable loop and libm's expf -- the same algorithm at the
+ * speed a CPU implementation would be written for; used only to TIME the CPU baseline (bench.py),
+ * never for parity (it is not bit-comparable with the GPU's warp-shaped arithmetic). */
+static float fast_dot(const float *a, const float *b, uint32_t count) {
+    float sum = 0.0f;
+#pragma omp simd reduction(+ : sum)
+    for (uint32_t e = 0; e < count; ++e) sum += a[e] * b[e];
+    return sum;
+}
+
 static void apply_targets(const orc_sgns_cfg *cfg, float lr, float inv_scale, const float *h,
                           float *t1, const uint32_t *target, const int *valid, uint32_t count,
                           float *acc, train_acc *out) {
@@ -142,7 +154,8 @@ static void apply_targets(const orc_sgns_cfg *cfg, float lr, float inv_scale, co
     float f[MAX_TARGETS];
     for (uint32_t k = 0; k < count; ++k) {
         if (!valid[k]) continue;
-        f[k] = orc_dot(h, t1 + (uint64_t)target[k] * stride, stride);
+        f[k] = cfg->fast_math ? fast_dot(h, t1 + (uint64_t)target[k] * stride, stride)
+                              : orc_dot(h, t1 + (uint64_t)target[k] * stride, stride);
         if (cfg->scale_by_sqrt_dim) f[k] = f[k] * inv_scale;
     }
     for (uint32_t k = 0; k < count; ++k) {
@@ -150,9 +163,18 @@ static void apply_targets(const orc_sgns_cfg *cfg, float lr, float inv_scale, co
         ++out->targets;
         if (fabsf(f[k]) > cfg->clipping_value) continue;
         const float label = k == 0 ? 1.0f : 0.0f;
-        const float g = (label - orc_sigmoid(f[k])) * lr;
+        const float g = (label - (cfg->fast_math ? 1.0f / (1.0f + expf(-f[k])) : orc_sigmoid(f[k]))) * lr;
         out->loss += softplus(k == 0 ? -(double)f[k] : (double)f[k]);
         float *row = t1 + (uint64_t)target[k] * stride;
+        if (cfg->fast_math) {
+#pragma omp simd
+            for (uint32_t e = 0; e < stride; ++e) {
+                const float old = row[e];
+                acc[e] += g * old;
+                row[e] = old + g * h[e];
+            }
+            continue;
+        }
         for (uint32_t e = 0; e < stride; ++e) {
             const float old = row[e];
             acc[e] = fmaf(g, old, acc[e]);
@@ -183,8 +205,10 @@ static void train_one_walk(const orc_sgns_cfg *cfg, const uint32_t *walk, uint64
                 continue;
         }
         float lr = cfg->learning_rate;
-        if (cfg->normalize_learning_rate_by_degree)
-            lr = lr / (float)(uint64_t)(indptr[c + 1] - indptr[c]);
+        if (cfg->normalize_learning_rate_by_degree) { /* a sink (directed graphs) counts as degree 1 */
+            const uint64_t deg = (uint64_t)(indptr[c + 1] - indptr[c]);
+            lr = lr / (float)(deg ? deg : 1);
+        }
         const uint32_t lo = i > w ? i - w : 0;
         const uint32_t hi = i + w < L - 1 ? i + w : L - 1;
         if (cfg->model == 0) {

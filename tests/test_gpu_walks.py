@@ -134,11 +134,11 @@ def test_weighted_embedder_runs_and_rejects_negative_weights(small_ppi_weighted)
         model.fit_transform(negative)
 
 
-def test_state_machine_walk_kernel_bit_exact(monkeypatch, small_ppi, rmat_graph):
-    """walk_sm_kernel (B2E_WALK_SM=1: one gather per lane per iteration, adjacency check in the
-    shorter row on undirected graphs) makes the oracle's decisions on another schedule."""
-    from conftest import tiny_graphs
-    monkeypatch.setenv("B2E_WALK_SM", "1")
+def test_fold_filter_and_short_row_variants(monkeypatch, small_ppi, rmat_graph):
+    """The folded return edge is part of the specification (oracle/walks.c): an undirected graph
+    with return_weight > max(1, explore_weight) walks on Philox tag 12, anything else on tag 2.
+    The row filters and the short-row search are accelerators: switching them off must not
+    change a token or a decision counter, only the number of probes."""
     graphs = [small_ppi, rmat_graph, tiny_graphs()["directed_dead_end"], tiny_graphs()["star"]]
     for graph in graphs:
         for rw, ew in [(0.25, 4.0), (2.0, 0.5), (7.5, 1.0)]:
@@ -149,10 +149,45 @@ def test_state_machine_walk_kernel_bit_exact(monkeypatch, small_ppi, rmat_graph)
                 assert np.array_equal(got, expected)
                 assert (gc["walk_steps"], gc["walk_trials"], gc["walk_searches"]) == \
                     (oc["steps"], oc["trials"], oc["searches"])
-    monkeypatch.setenv("B2E_ASSUME_DIRECTED", "1")  # without the short-row check
-    expected, _ = oracle.walks(rmat_graph.indptr, rmat_graph.indices, 1, 0, 5000, 64, 2.0, 0.5)
+    # the fold halves the trials of C3's p/q on an undirected graph and is a different stream
+    folded, fc = oracle.walks(rmat_graph.indptr, rmat_graph.indices, 1, 0, 5000, 64, 2.0, 0.5)
+    plain, pc = oracle.walks(rmat_graph.indptr, rmat_graph.indices, 1, 0, 5000, 64, 2.0, 0.5, undirected=False)
+    assert not np.array_equal(folded, plain) and fc["trials"] < 0.7 * pc["trials"]
+    base, bc = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
+    assert np.array_equal(base, folded) and bc["walk_filter_rejects"] > 0
+    monkeypatch.setenv("B2E_NO_FILTER", "1")
+    got, gc = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
+    assert np.array_equal(got, folded) and gc["walk_filter_rejects"] == 0
+    assert gc["walk_probes"] > bc["walk_probes"] and gc["walk_searches"] == bc["walk_searches"]
+    monkeypatch.delenv("B2E_NO_FILTER")
+    monkeypatch.setenv("B2E_NO_FOLD", "1")
+    got, gc = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
+    assert np.array_equal(got, plain) and gc["walk_trials"] == pc["trials"]
+    monkeypatch.delenv("B2E_NO_FOLD")
+    monkeypatch.setenv("B2E_ASSUME_DIRECTED", "1")  # no fold, no short-row search
     got, _ = gpu_walks(rmat_graph, 1, 0, 5000, 64, 2.0, 0.5)
-    assert np.array_equal(got, expected)
+    assert np.array_equal(got, plain)
+
+
+def test_load_rejects_malformed_csr_and_leaves_a_clean_handle(er_graph):
+    """b2e_load_csr checks the CSR contents on the device: ids in range, rows strictly ascending
+    (the reference's graph object guarantees both; a raw (indptr, indices) pair does not)."""
+    indptr, indices = er_graph.indptr, er_graph.indices.copy()
+    row = int(np.flatnonzero(np.diff(indptr) >= 3)[0])
+    swapped = indices.copy()
+    swapped[indptr[row]], swapped[indptr[row] + 1] = indices[indptr[row] + 1], indices[indptr[row]]
+    duplicate = indices.copy()
+    duplicate[indptr[row] + 1] = duplicate[indptr[row]]
+    out_of_range = indices.copy()
+    out_of_range[-1] = er_graph.get_number_of_nodes()
+    with Engine("SkipGram", return_weight=2.0, explore_weight=0.5) as engine:
+        for bad, message in ((swapped, "sorted"), (duplicate, "sorted"), (out_of_range, "out of range")):
+            with pytest.raises(ValueError, match=message):
+                engine.load_csr(indptr, bad)
+            with pytest.raises(RuntimeError, match="b2e_load_csr"):
+                engine.init_tables(1)
+        engine.load_csr(indptr, indices)  # the handle is still usable
+        assert engine.walks(1, 0, 10).shape == (10, 128)
 
 
 # ---- normalize_by_degree (b2e_config.normalize_by_degree; walk_norm_kernel) ----

@@ -394,3 +394,60 @@ def test_unit_type_weights_leave_the_walks_unchanged(small_ppi):
     # a very small change weight keeps the walk inside the type of its start node when it can
     stay = (node_types[changed[:, 1:]] == node_types[changed[:, :-1]]).mean()
     assert stay > (node_types[plain[:, 1:]] == node_types[plain[:, :-1]]).mean() + 0.2
+
+
+# ---- folded return edge (oracle/walks.c: orc_fold_thresholds) ----
+def test_fold_thresholds_and_symmetry_probe(small_ppi, rmat_graph):
+    thrf, excess = oracle.fold_thresholds(2.0, 0.5)  # C3: p = 0.5, q = 2
+    assert list(thrf) == [2 ** 32, 2 ** 32, 2 ** 31] and excess == 2 ** 20
+    thrf, excess = oracle.fold_thresholds(7.5, 1.0)
+    assert list(thrf) == [2 ** 32] * 3 and excess == int(6.5 * 2 ** 20)
+    thrf, excess = oracle.fold_thresholds(6.0, 4.0)  # envelope 4: common 1/4, explore 1, excess 1/2
+    assert list(thrf) == [2 ** 32, 2 ** 30, 2 ** 32] and excess == 2 ** 19
+    for rw, ew in [(0.25, 4.0), (1.0, 1.0), (0.5, 2.0), (1.0, 3.0), (3.0, 3.0)]:
+        assert oracle.fold_thresholds(rw, ew)[1] == 0  # nothing to fold: the plain envelope stays
+    assert oracle.is_undirected(small_ppi.indptr, small_ppi.indices)
+    assert oracle.is_undirected(rmat_graph.indptr, rmat_graph.indices)
+    directed = tiny_graphs()["directed_dead_end"]
+    assert not oracle.is_undirected(directed.indptr, directed.indices)
+
+
+@pytest.mark.parametrize("rw,ew", [(2.0, 0.5), (7.5, 1.0), (6.0, 4.0)])
+def test_folded_sampler_follows_the_same_pmf_in_fewer_trials(rmat_graph, rw, ew):
+    """Same analytic pmf (test_second_order_transitions_match_analytic_pmf covers the dense graph
+    with the fold on, since it is undirected); here: the plain and the folded streams agree in
+    distribution on a skewed graph and the fold needs fewer proposals."""
+    g = rmat_graph
+    folded, fc = oracle.walks(g.indptr, g.indices, 5, 0, 60_000, 3, rw, ew, undirected=True)
+    plain, pc = oracle.walks(g.indptr, g.indices, 5, 0, 60_000, 3, rw, ew, undirected=False)
+    assert fc["steps"] == pc["steps"] and fc["trials"] < pc["trials"]
+    # class frequencies of the third token (return / other) agree between the two samplers
+    back = [(w[:, 2] == w[:, 0]).sum() for w in (folded, plain)]
+    table = np.array([[back[0], len(folded) - back[0]], [back[1], len(plain) - back[1]]])
+    assert stats.chi2_contingency(table)[1] > 1e-3
+    # a directed graph never folds, whatever the caller claims about p/q
+    directed = tiny_graphs()["directed_dead_end"]
+    a, _ = oracle.walks(directed.indptr, directed.indices, 5, 0, 200, 8, rw, ew)
+    b, _ = oracle.walks(directed.indptr, directed.indices, 5, 0, 200, 8, rw, ew, undirected=False)
+    assert np.array_equal(a, b)
+
+
+def test_synthetic_graph_generator_matches_the_numpy_definition():
+    """oracle/graphgen.c (OpenMP, hash set) == embiggen_b200/graph.py (numpy, sort): the first m
+    distinct undirected edges of the Philox stream, whatever the thread count."""
+    from embiggen_b200.graph import erdos_renyi, rmat
+    for threads in (1, 4):
+        oracle.set_threads(threads)
+        try:
+            for n, m in [(1000, 5000), (50, 600), (3, 1)]:
+                indptr, indices = oracle.synthetic_csr("er", n, m)
+                g = erdos_renyi(n, m, seed=42)
+                assert np.array_equal(indptr, g.indptr) and np.array_equal(indices, g.indices)
+            for scale, n, m in [(10, 900, 4000), (12, 4096, 30000), (14, 10000, 100_000)]:
+                indptr, indices = oracle.synthetic_csr("rmat", n, m, scale=scale, seed=11)
+                g = rmat(scale, m, n=n, seed=11)
+                assert np.array_equal(indptr, g.indptr) and np.array_equal(indices, g.indices)
+        finally:
+            oracle.set_threads(1)
+    with pytest.raises(ValueError):
+        oracle.synthetic_csr("er", 10, 40)

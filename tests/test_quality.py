@@ -169,16 +169,16 @@ def test_replica_averaging_keeps_the_quality():
         for engine in replicas:
             engine.load_csr(graph.indptr, graph.indices)
             engine.init_tables(seed)
-        tables = [engine.device_tables() for engine in replicas]
+        for rank, engine in enumerate(replicas):
+            engine.open_exchange_local(replicas, rank)
 
-        def average():
+        def average():  # the exchange kernel of every "rank", bracketed by syncs like Engine.average
             for engine in replicas:
                 engine.sync()
-            for k in range(2):
-                mean = (tables[0][k] + tables[1][k]) / 2
-                for rank in range(world):
-                    tables[rank][k].copy_(mean)
-            torch.cuda.synchronize()
+            for engine in replicas:
+                engine.exchange_average()
+            for engine in replicas:
+                engine.sync()
 
         per_epoch = replicas[0].walks_per_epoch
         lr = np.float32(KW["learning_rate"])
@@ -196,6 +196,7 @@ def test_replica_averaging_keeps_the_quality():
         a0, a1 = replicas[0].export_tables()
         b0, _ = replicas[1].export_tables()
         assert np.array_equal(a0, b0)  # replicas agree after the exchange
+        assert replicas[0].tables_digest()["bits"] == replicas[1].tables_digest()["bits"]
     finally:
         for engine in replicas:
             engine.close()
