@@ -147,6 +147,7 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     h->row_stride = (c.embedding_size + 31u) / 32u * 32u;
     if (const char *env = getenv("B2E_PREFETCH")) h->prefetch = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_WALK_OCC")) h->walk_occupancy = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
     for (int s = 0; s < 2; ++s) {
@@ -544,6 +545,7 @@ static int walk_into(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t
     const unsigned long long *thr = h->fold_excess && !typed ? h->thr_fold : h->thr;
     p.fold_excess = typed ? 0 : h->fold_excess;
     p.filter = h->d_filter;
+    p.occupancy = h->walk_occupancy;
     p.thr_return = thr[0];
     p.thr_common = thr[1];
     p.thr_explore = thr[2];

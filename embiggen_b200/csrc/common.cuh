@@ -67,6 +67,7 @@ struct WalkParams {
     uint32_t undirected;     // every edge has its mirror (verified at load): allows the short-row check
     const unsigned long long *filter;  // per-row blocked Bloom filters over the neighbour lists, or nullptr
     unsigned long long fold_excess;    // E > 0: the return edge is folded out of the envelope (TAG_FOLD)
+    uint32_t occupancy;                // resident CTAs per SM the second-order kernel is compiled for (4, 5, 6)
     int sm_count;
 };
 
@@ -178,6 +179,7 @@ struct b2e_handle {
     bool undirected = false;
     uint32_t prefetch = 1;
     uint32_t variant = 0;
+    uint32_t walk_occupancy = 4;  // B2E_WALK_OCC: see walk_kernel
     uint64_t launches = 0;
     std::vector<uint32_t> h_alias_thr, h_alias_idx;
     // the exchange step: replicas of the tables on the other GPUs of the node

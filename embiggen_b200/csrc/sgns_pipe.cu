@@ -375,27 +375,46 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
 }
 
 // ---- K5: CBOW.  A draw site is a centre: its K+1 target rows (T1) ride the same asynchronous
-// pipeline; the <= 2W context rows (T0) were written by this very warp one centre earlier, so
-// they are read synchronously (L2 hits) after the previous scatter, in batches whose loads are
-// issued back to back.  The row entering the window is prefetched into L2 one centre ahead.
-constexpr int CBOW_BATCH = 8;
+// pipeline.  The <= 2W context rows (T0) of a centre are the window of the walk, and the window
+// moves one position per centre: each row is needed by up to 2W consecutive centres.  So the
+// warp keeps the window in a shared-memory RING indexed by walk position (2W + 2 slots: the
+// 2W + 1 positions of the current window plus the one entering it): a row is copied from HBM
+// once, one centre before it enters (cp.async, same commit group as the next centre's
+// targets), read from shared memory for the mean, updated in place in shared memory, and its
+// change is pushed to HBM as a 128-bit `red.global.add` per lane -- no read-modify-write round
+// trip, and concurrent walks that share a hub row ADD their updates instead of overwriting
+// each other's.  A token that occurs at two window positions owns two ring slots; they start
+// equal (the second copy is issued only after the first one's pending update, like a deferred
+// target copy) and receive the same sequence of additions, so they stay equal.  In the
+// single-warp launch HBM and ring agree at every step, `old + acc` by the L2 atomic unit is the
+// same IEEE addition the oracle performs, and the tables reproduce oracle/sgns.c bit for bit.
+__device__ __forceinline__ void red_add4(float *gmem, const float4 &v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gmem), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+__host__ __device__ __forceinline__ uint32_t cbow_ring_slots(uint32_t window) { return 2u * window + 2u; }
 
 template <int KP1>
-__global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) {
+__global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t K = KP1 ? (uint32_t)(KP1 - 1) : p.negatives;
     const uint32_t L = p.walk_length, W = p.window;
     const uint32_t full_mask = (2u << K) - 1u;
+    const uint32_t R = cbow_ring_slots(W);
     PipeSmem sm;
+    float *ring;  // [R][pitch]: T0 rows of the walk positions around the centre, slot = position % R
     {
-        unsigned char *base = smem_raw + warp * pipe_warp_bytes(K, p.chunks, L);
+        unsigned char *base = smem_raw + warp * (pipe_warp_bytes(K, p.chunks, L) + R * p.chunks * 16u);
         sm.pitch = p.chunks * 4u;
         sm.stage_floats = (K + 2u) * sm.pitch;
         sm.rows_base = reinterpret_cast<float *>(base);
         sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * sm.stage_floats);
         sm.ids_base = reinterpret_cast<uint32_t *>(sm.alias_base + 64);
         sm.walk = sm.ids_base + 2 * PIPE_SLOTS;
+        ring = reinterpret_cast<float *>(base + pipe_warp_bytes(K, p.chunks, L));
     }
     LaneView v;
     v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
@@ -448,6 +467,11 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
             if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, PAD);
             else issue_rows<KP1, false>(p, sm, v, stage, lane, ids, vmask, PAD);
         };
+        // copy the T0 row of walk position `pos` into its ring slot (nothing to copy for PAD)
+        auto fetch = [&](uint32_t pos) {
+            const uint32_t t = walk[pos];
+            if (t != PAD && v.active) cp_async16(ring + (pos % R) * sm.pitch + 4u * lane, v.t0 + t * v.row_bytes);
+        };
 
         uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
         uint32_t i_cur = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, 0, c_cur);
@@ -460,6 +484,9 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
         vmask_cur = resolve(c_cur, slot_a, idx_n, ry_n, neg_cur);
         ids_cur = slot_ids(lane, c_cur, neg_cur, vmask_cur);
         issue(stage, ids_cur, vmask_cur);
+        // positions < resident are in the ring (or are PAD); the first window is copied here
+        uint32_t resident = i_cur > W ? i_cur - W : 0u;
+        for (const uint32_t end = min(L, i_cur + W + 1u); resident < end; ++resident) fetch(resident);
         uint32_t i_nxt = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_cur + 1, c_nxt);
         slot_a ^= 1u;
         if (i_nxt < L) draw(i_nxt, slot_a, idx_n, ry_n);
@@ -468,9 +495,26 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
         while (i_cur < L) {
             cp_async_wait_all();
             __syncwarp();  // inter-lane memory ordering, see skipgram_pipe_kernel
-            // ---- centre p+1: resolve ids, copy its target rows, prefetch the entering row ----
+            const uint32_t i = i_cur, c = c_cur;
+            const uint32_t lo = i > W ? i - W : 0u;
+            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+            if (resident <= hi) {  // the centre jumped (skipped centres): complete the window now
+                if (resident < lo) resident = lo;
+                for (; resident <= hi; ++resident) fetch(resident);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            // ---- the window of centre p: lane l looks at window slot l (2W + 1 <= 32) ----
+            const uint32_t j = lo + lane;
+            const uint32_t tok = j <= hi ? walk[j] : PAD;
+            const bool ctx = j <= hi && j != i && tok != PAD && tok != c;
+            const uint32_t cmask = __ballot_sync(FULL, ctx);
+            const uint32_t m = __popc(cmask);
+
+            // ---- centre p+1: resolve ids, copy its target rows and the row entering the window ----
             uint32_t neg_nxt = PAD, vmask_nxt = 0, ids_nxt = 0xFFFFFF00u | lane;
-            bool deferred = false;
+            bool deferred = false, deferred_ring = false;
             if (i_nxt < L) {
                 vmask_nxt = resolve(c_nxt, slot_a, idx_n, ry_n, neg_nxt);
                 ids_nxt = slot_ids(lane, c_nxt, neg_nxt, vmask_nxt);
@@ -480,10 +524,14 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
                 const uint32_t same = __match_any_sync(FULL, both);
                 deferred = __ballot_sync(FULL, lane < 16u && (same >> 16) != 0u) != 0u;
                 if (!deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt);
-                const uint32_t entering = i_nxt + W < L ? walk[i_nxt + W] : PAD;
-                if (entering != PAD && lane * 128u < p.chunks * 16u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                        reinterpret_cast<const char *>(p.t0) + entering * v.row_bytes + lane * 128u));
+                // one position ahead of the window: its slot is the spare one (2W + 2 slots)
+                if (resident == hi + 1u && resident < L && resident <= i_nxt + W) {
+                    const uint32_t entering = walk[resident];
+                    // a row this centre is about to update would be copied stale: copy it afterwards
+                    deferred_ring = __ballot_sync(FULL, ctx && tok == entering) != 0u;
+                    if (!deferred_ring) fetch(resident);
+                    ++resident;
+                }
             }
             // ---- centre p+2: start its draw ----
             const uint32_t i_far = i_nxt < L ? next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_nxt + 1, c_far) : L;
@@ -492,41 +540,17 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
             cp_async_commit();
 
             // ---- centre p: hidden vector = mean of the context rows, in window order ----
-            const uint32_t i = i_cur, c = c_cur;
             const float lr = centre_lr(p, c);
-            const uint32_t lo = i > W ? i - W : 0u;
-            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
-            const uint32_t j = lo + lane;  // lane l looks at window slot l (2W + 1 <= 32)
-            const uint32_t tok = j <= hi ? walk[j] : PAD;
-            const bool ctx = j <= hi && j != i && tok != PAD && tok != c;
-            const uint32_t cmask = __ballot_sync(FULL, ctx);
-            const uint32_t m = __popc(cmask);
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
             {
                 bool first = true;
-                uint32_t rem = cmask;
-                while (rem) {
-                    float4 r[CBOW_BATCH];
-                    uint32_t batch = 0;
-#pragma unroll
-                    for (int b = 0; b < CBOW_BATCH; ++b) {
-                        r[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rem) {
-                            const uint32_t q = __ffs(rem) - 1u;
-                            rem &= rem - 1u;
-                            const uint32_t t = __shfl_sync(FULL, tok, q);
-                            if (v.active) r[b] = __ldcg(reinterpret_cast<const float4 *>(v.t0 + t * v.row_bytes));
-                            batch |= 1u << b;
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < CBOW_BATCH; ++b) {
-                        if ((batch >> b) & 1u) {
-                            if (first) h = r[b]; else add4(h, r[b]);
-                            first = false;
-                        }
-                    }
+                for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
+                    const uint32_t q = __ffs(rem) - 1u;
+                    const float4 r = lds128(ring + ((lo + q) % R) * sm.pitch + v.smem_chunk);
+                    if (first) h = r; else add4(h, r);
+                    first = false;
                 }
+                if (!v.active) h = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const float fm = (float)m;
             h.x = __fdiv_rn(h.x, fm);
@@ -540,44 +564,36 @@ __global__ void __launch_bounds__(128, 4) cbow_pipe_kernel(const TrainParams p) 
             n_targets += __popc(vmask_cur);
             n_pairs += m;
 
-            // ---- scatter acc to every context position; a token that occurs k times in the
-            //      window receives k sequential additions, like the per-position oracle ----
+            // ---- acc goes to every context position: in place in the ring, as an atomic add to
+            //      HBM.  A token at k window positions receives k sequential additions, like the
+            //      per-position oracle: every one of its slots adds acc k times, its first
+            //      position issues the k atomics. ----
             {
                 const uint32_t key = ctx ? tok : (0xFFFFFF00u | lane);
                 const uint32_t same = __match_any_sync(FULL, key);
                 const uint32_t mult = __popc(same);
-                uint32_t rem = __ballot_sync(FULL, ctx && (same & lower) == 0u);
-                while (rem) {
-                    float4 r[CBOW_BATCH];
-                    uint32_t toks[CBOW_BATCH], mults[CBOW_BATCH];
-                    uint32_t batch = 0;
-#pragma unroll
-                    for (int b = 0; b < CBOW_BATCH; ++b) {
-                        r[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        toks[b] = 0;
-                        mults[b] = 0;
-                        if (rem) {
-                            const uint32_t q = __ffs(rem) - 1u;
-                            rem &= rem - 1u;
-                            toks[b] = __shfl_sync(FULL, tok, q);
-                            mults[b] = __shfl_sync(FULL, mult, q);
-                            if (v.active) r[b] = __ldcg(reinterpret_cast<const float4 *>(v.t0 + toks[b] * v.row_bytes));
-                            batch |= 1u << b;
-                        }
+                const uint32_t leaders = __ballot_sync(FULL, ctx && (same & lower) == 0u);
+                for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
+                    const uint32_t q = __ffs(rem) - 1u;
+                    const uint32_t k = __shfl_sync(FULL, mult, q);
+                    float *slot = ring + ((lo + q) % R) * sm.pitch + 4u * lane;
+                    if (v.active) {
+                        float4 r = lds128(slot);
+                        for (uint32_t t = 0; t < k; ++t) add4(r, acc);
+                        *reinterpret_cast<float4 *>(slot) = r;
                     }
-#pragma unroll
-                    for (int b = 0; b < CBOW_BATCH; ++b) {
-                        if ((batch >> b) & 1u) {
-                            for (uint32_t t = 0; t < mults[b]; ++t) add4(r[b], acc);
-                            if (v.active)
-                                *reinterpret_cast<float4 *>(const_cast<char *>(v.t0) + toks[b] * v.row_bytes) = r[b];
-                        }
+                    if ((leaders >> q) & 1u) {
+                        const uint32_t t_id = __shfl_sync(FULL, tok, q);
+                        if (v.active)
+                            for (uint32_t t = 0; t < k; ++t)
+                                red_add4(reinterpret_cast<float *>(const_cast<char *>(v.t0) + t_id * v.row_bytes), acc);
                     }
                 }
             }
 
-            if (deferred) {
-                issue(stage ^ 1u, ids_nxt, vmask_nxt);
+            if (deferred || deferred_ring) {
+                if (deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt);
+                if (deferred_ring) fetch(resident - 1u);
                 cp_async_commit();
             }
             i_cur = i_nxt; c_cur = c_nxt; neg_cur = neg_nxt; vmask_cur = vmask_nxt; ids_cur = ids_nxt;
@@ -603,8 +619,8 @@ bool pipe_supported(const TrainParams &p, uint32_t model) {
 
 template <typename Kernel>
 static cudaError_t launch_pipe(Kernel kernel, const TrainParams &p, bool deterministic, int sm_count,
-                               uint64_t max_warps, cudaStream_t stream) {
-    const size_t warp_bytes = pipe_warp_bytes(p.negatives, p.chunks, p.walk_length);
+                               uint64_t max_warps, cudaStream_t stream, size_t extra_warp_bytes = 0) {
+    const size_t warp_bytes = pipe_warp_bytes(p.negatives, p.chunks, p.walk_length) + extra_warp_bytes;
     const int warps = deterministic ? 1 : 4;
     const size_t smem = warp_bytes * warps;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -636,10 +652,11 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
             default: return launch_pipe(skipgram_pipe_kernel<0>, p, deterministic, sm_count, max_warps, stream);
         }
     }
+    const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u;
     switch (p.negatives + 1u) {
-        case 11: return launch_pipe(cbow_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);
-        case 6: return launch_pipe(cbow_pipe_kernel<6>, p, deterministic, sm_count, max_warps, stream);
-        default: return launch_pipe(cbow_pipe_kernel<0>, p, deterministic, sm_count, max_warps, stream);
+        case 11: return launch_pipe(cbow_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream, ring);
+        case 6: return launch_pipe(cbow_pipe_kernel<6>, p, deterministic, sm_count, max_warps, stream, ring);
+        default: return launch_pipe(cbow_pipe_kernel<0>, p, deterministic, sm_count, max_warps, stream, ring);
     }
 }
 

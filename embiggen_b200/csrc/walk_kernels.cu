@@ -17,8 +17,9 @@
 namespace b2e {
 
 // sorted-row membership by lower-bound bisection; every load is counted as one probe
+template <typename Count>
 __device__ __forceinline__ bool row_contains(const uint32_t *__restrict__ row, uint32_t len,
-                                             uint32_t key, unsigned long long &probes) {
+                                             uint32_t key, Count &probes) {
     uint32_t lo = 0, hi = len;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -148,9 +149,10 @@ cudaError_t launch_csr_check(const int64_t *indptr, const uint32_t *indices, uin
 // x's row, fetched for that, are handed back so that an accepted x does not fetch them again.
 struct RowBounds { int64_t off; uint32_t deg; bool valid; };
 
+template <typename Count>
 __device__ __forceinline__ bool adjacent(const WalkParams &p, int64_t prev_off, uint32_t prev_deg,
                                          uint32_t prev, uint32_t x, RowBounds &xrow,
-                                         unsigned long long &probes, unsigned long long &rejects) {
+                                         Count &probes, Count &rejects) {
     if (p.filter && prev_deg >= FILTER_MIN_DEG) {
         const FilterSlot s = filter_slot(prev_off, prev_deg, x);
         ++probes;
@@ -186,138 +188,146 @@ __device__ __forceinline__ uint32_t propose(const uint2 *__restrict__ table, int
 // down to the envelope of the other classes and its excess becomes a virtual slot of the row --
 // one Philox block per trial (tag 12): x decides slot vs row, y proposes, z accepts; see
 // oracle/walks.c (orc_fold_thresholds) for the normative statement.
-template <bool SECOND, bool VEC, bool WEIGHTED, bool FOLD>
-__global__ void __launch_bounds__(256) walk_kernel(const WalkParams p) {
+// MINB: resident CTAs per SM the register allocation is held to (4: 64 registers, no spills;
+// 6: 40 registers and a few spilled words -- more chains in flight per SM)
+template <bool SECOND, bool VEC, bool WEIGHTED, bool FOLD, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) walk_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_steps = 0, n_trials = 0, n_searches = 0, n_probes = 0, n_rejects = 0;
+    // per-thread counts stay far below 2^32 (L < 2^16 steps, at most 2^20 trials each is a cap
+    // never approached); they are widened when the warp adds them up
+    uint32_t n_steps = 0, n_trials = 0, n_searches = 0;
+    uint32_t n_probes = 0, n_rejects = 0;
     if (i < p.n_walks) {
         const uint64_t wid = p.first_walk + i * p.walk_id_stride;
         const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
         uint32_t *out = p.out + i * (uint64_t)p.walk_length;
         const unsigned long long thr_lo = min(p.thr_common, p.thr_explore);
         const unsigned long long thr_hi = max(p.thr_common, p.thr_explore);
+        const uint32_t L = p.walk_length;
 
         uint32_t cur = __ldg(p.sources + (wid % p.n_src));
         int64_t prev_off = 0;
         uint32_t prev = PAD, prev_deg = 0;
         RowBounds row = {0, 0, false};  // bounds of cur's row when an adjacency check already fetched them
-        bool alive = true;
         uint4 rnd = make_uint4(0, 0, 0, 0);
-        uint32_t tok[4];
-        const uint32_t L = p.walk_length;
-        for (uint32_t base = 0; base < L; base += 4) {
-#pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) {
-                const uint32_t t = base + u;
-                if (t == 0) { tok[0] = cur; continue; }
-                if (t >= L) { tok[u] = PAD; continue; }
-                uint32_t next = PAD;
-                if (alive) {
-                    int64_t off;
-                    uint32_t deg;
-                    if (SECOND && row.valid) {
-                        off = row.off;
-                        deg = row.deg;
-                    } else {
-                        off = __ldg(p.indptr + cur);
-                        deg = (uint32_t)(__ldg(p.indptr + cur + 1) - off);
-                    }
-                    row.valid = false;
-                    if (deg == 0) {
-                        alive = false;
-                    } else {
-                        if (!SECOND || t == 1) {
-                            const uint32_t s = t - 1;
-                            if ((s & 3u) == 0 || (SECOND && t == 1))
-                                rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, s >> 2,
-                                                    TAG_WALK1 << 24);
-                            const uint32_t r = (s & 3u) == 0 ? rnd.x : (s & 3u) == 1 ? rnd.y
-                                             : (s & 3u) == 2 ? rnd.z : rnd.w;
-                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r));
-                        } else {
-                            const unsigned long long t_out =
-                                FOLD ? (p.fold_excess << 32) / (((unsigned long long)deg << 20) + p.fold_excess) : 0ull;
-                            uint32_t trial = 0;
-                            for (;;) {
-                                uint32_t r0;
-                                unsigned long long r1;
-                                ++n_trials;
-                                if constexpr (FOLD) {
-                                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
-                                                        (TAG_FOLD << 24) | trial);
-                                    if (rnd.x < t_out) {  // the virtual slot: back to where we came from
-                                        next = prev;
-                                        row.off = prev_off;
-                                        row.deg = prev_deg;
-                                        row.valid = true;
-                                        break;
-                                    }
-                                    r0 = rnd.y;
-                                    r1 = rnd.z;
-                                } else {
-                                    if ((trial & 1u) == 0)
-                                        rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
-                                                            (TAG_WALK2 << 24) | (trial >> 1));
-                                    r0 = (trial & 1u) ? rnd.z : rnd.x;
-                                    r1 = (trial & 1u) ? rnd.w : rnd.y;
-                                }
-                                next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r0));
-                                bool accept;
-                                RowBounds xrow = {0, 0, false};
-                                if (next == prev) {
-                                    accept = r1 < p.thr_return;
-                                    xrow.off = prev_off;
-                                    xrow.deg = prev_deg;
-                                    xrow.valid = true;
-                                } else if (r1 < thr_lo) {
-                                    accept = true;   // every non-return class accepts
-                                } else if (r1 >= thr_hi) {
-                                    accept = false;  // every non-return class rejects
-                                } else {
-                                    ++n_searches;
-                                    const bool common = adjacent(p, prev_off, prev_deg, prev, next, xrow,
-                                                                 n_probes, n_rejects);
-                                    accept = r1 < (common ? p.thr_common : p.thr_explore);
-                                }
-                                if (accept) { row = xrow; break; }
-                                ++trial;
-                                if (trial >= MAX_TRIALS) break;
-                            }
-                        }
-                        ++n_steps;
-                        prev = cur;
-                        prev_off = off;
-                        prev_deg = deg;
-                        cur = next;
-                    }
+        uint4 tok = make_uint4(cur, PAD, PAD, PAD);  // four tokens leave as one 16-byte store
+        bool alive = true;
+        for (uint32_t t = 1; t < L; ++t) {
+            uint32_t next = PAD;
+            if (alive) {
+                int64_t off;
+                uint32_t deg;
+                if (SECOND && row.valid) {
+                    off = row.off;
+                    deg = row.deg;
+                } else {
+                    off = __ldg(p.indptr + cur);
+                    deg = (uint32_t)(__ldg(p.indptr + cur + 1) - off);
                 }
-                tok[u] = next;
+                row.valid = false;
+                if (deg == 0) {
+                    alive = false;
+                } else {
+                    if (!SECOND || t == 1) {
+                        const uint32_t s = t - 1;
+                        if ((s & 3u) == 0 || (SECOND && t == 1))
+                            rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, s >> 2, TAG_WALK1 << 24);
+                        const uint32_t r = (s & 3u) == 0 ? rnd.x : (s & 3u) == 1 ? rnd.y
+                                         : (s & 3u) == 2 ? rnd.z : rnd.w;
+                        next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r));
+                    } else {
+                        const unsigned long long t_out =
+                            FOLD ? (p.fold_excess << 32) / (((unsigned long long)deg << 20) + p.fold_excess) : 0ull;
+                        uint32_t trial = 0;
+                        for (;;) {
+                            uint32_t r0;
+                            unsigned long long r1;
+                            ++n_trials;
+                            if constexpr (FOLD) {
+                                rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                    (TAG_FOLD << 24) | trial);
+                                if (rnd.x < t_out) {  // the virtual slot: back to where we came from
+                                    next = prev;
+                                    row.off = prev_off;
+                                    row.deg = prev_deg;
+                                    row.valid = true;
+                                    break;
+                                }
+                                r0 = rnd.y;
+                                r1 = rnd.z;
+                            } else {
+                                if ((trial & 1u) == 0)
+                                    rnd = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi, t - 1,
+                                                        (TAG_WALK2 << 24) | (trial >> 1));
+                                r0 = (trial & 1u) ? rnd.z : rnd.x;
+                                r1 = (trial & 1u) ? rnd.w : rnd.y;
+                            }
+                            next = __ldg(p.indices + off + propose<WEIGHTED>(p.edge_alias, off, deg, r0));
+                            bool accept;
+                            RowBounds xrow = {0, 0, false};
+                            if (next == prev) {
+                                accept = r1 < p.thr_return;
+                                xrow.off = prev_off;
+                                xrow.deg = prev_deg;
+                                xrow.valid = true;
+                            } else if (r1 < thr_lo) {
+                                accept = true;   // every non-return class accepts
+                            } else if (r1 >= thr_hi) {
+                                accept = false;  // every non-return class rejects
+                            } else {
+                                ++n_searches;
+                                const bool common = adjacent(p, prev_off, prev_deg, prev, next, xrow,
+                                                             n_probes, n_rejects);
+                                accept = r1 < (common ? p.thr_common : p.thr_explore);
+                            }
+                            if (accept) { row = xrow; break; }
+                            ++trial;
+                            if (trial >= MAX_TRIALS) break;
+                        }
+                    }
+                    ++n_steps;
+                    prev = cur;
+                    prev_off = off;
+                    prev_deg = deg;
+                    cur = next;
+                }
             }
-            if (VEC) {
-                *reinterpret_cast<uint4 *>(out + base) = make_uint4(tok[0], tok[1], tok[2], tok[3]);
-            } else {
-#pragma unroll
-                for (uint32_t u = 0; u < 4; ++u)
-                    if (base + u < L) out[base + u] = tok[u];
+            const uint32_t slot = t & 3u;  // explicit selects keep the group in registers
+            if (slot == 0) tok.x = next; else if (slot == 1) tok.y = next;
+            else if (slot == 2) tok.z = next; else tok.w = next;
+            if (slot == 3u) {
+                if (VEC) {
+                    *reinterpret_cast<uint4 *>(out + t - 3u) = tok;
+                } else {
+                    out[t - 3u] = tok.x; out[t - 2u] = tok.y; out[t - 1u] = tok.z; out[t] = tok.w;
+                }
             }
+        }
+        const uint32_t tail = L & 3u;  // tokens of an unfinished group (never with VEC: L % 4 == 0)
+        if (tail) {
+            out[L - tail] = tok.x;
+            if (tail > 1) out[L - tail + 1u] = tok.y;
+            if (tail > 2) out[L - tail + 2u] = tok.z;
         }
     }
     // one atomic per warp and counter
+    unsigned long long steps = n_steps, trials = n_trials, searches = n_searches, probes = n_probes,
+                       rejects = n_rejects;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        n_steps += __shfl_xor_sync(0xffffffffu, n_steps, off);
-        n_trials += __shfl_xor_sync(0xffffffffu, n_trials, off);
-        n_searches += __shfl_xor_sync(0xffffffffu, n_searches, off);
-        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, off);
-        n_rejects += __shfl_xor_sync(0xffffffffu, n_rejects, off);
+        steps += __shfl_xor_sync(0xffffffffu, steps, off);
+        trials += __shfl_xor_sync(0xffffffffu, trials, off);
+        searches += __shfl_xor_sync(0xffffffffu, searches, off);
+        probes += __shfl_xor_sync(0xffffffffu, probes, off);
+        rejects += __shfl_xor_sync(0xffffffffu, rejects, off);
     }
     if ((threadIdx.x & 31) == 0 && p.counters) {
-        atomicAdd(&p.counters->walk_steps, n_steps);
+        atomicAdd(&p.counters->walk_steps, steps);
         if (SECOND) {
-            atomicAdd(&p.counters->walk_trials, n_trials);
-            atomicAdd(&p.counters->walk_searches, n_searches);
-            atomicAdd(&p.counters->walk_probes, n_probes);
-            atomicAdd(&p.counters->walk_filter_rejects, n_rejects);
+            atomicAdd(&p.counters->walk_trials, trials);
+            atomicAdd(&p.counters->walk_searches, searches);
+            atomicAdd(&p.counters->walk_probes, probes);
+            atomicAdd(&p.counters->walk_filter_rejects, rejects);
         }
     }
 }
@@ -498,7 +508,15 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
         return cudaGetLastError();
     }
 #define B2E_LAUNCH_WALK(S, V, W, F) walk_kernel<S, V, W, F><<<grid, block, 0, stream>>>(p)
-    if (second_order && !weighted && p.fold_excess) {
+    if (second_order && !weighted && vec && p.occupancy >= 5) {  // the headline shapes, tunable occupancy
+        if (p.fold_excess) {
+            if (p.occupancy == 5) walk_kernel<true, true, false, true, 5><<<grid, block, 0, stream>>>(p);
+            else walk_kernel<true, true, false, true, 6><<<grid, block, 0, stream>>>(p);
+        } else {
+            if (p.occupancy == 5) walk_kernel<true, true, false, false, 5><<<grid, block, 0, stream>>>(p);
+            else walk_kernel<true, true, false, false, 6><<<grid, block, 0, stream>>>(p);
+        }
+    } else if (second_order && !weighted && p.fold_excess) {
         if (vec) B2E_LAUNCH_WALK(true, true, false, true); else B2E_LAUNCH_WALK(true, false, false, true);
     } else if (second_order) {
         if (vec) { if (weighted) B2E_LAUNCH_WALK(true, true, true, false); else B2E_LAUNCH_WALK(true, true, false, false); }

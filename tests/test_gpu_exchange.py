@@ -110,7 +110,7 @@ def test_fit_distributed_over_cuda_ipc(tmp_path, world):
     for r in range(1, world):
         assert np.array_equal(t0[0], t0[r]) and np.array_equal(t1[0], t1[r])
     meta = np.load(tmp_path / "meta_0.npy")
-    assert meta[-1] == 0 and np.isfinite(t0[0]).all() and meta[1] < meta[0]  # the loss falls
+    assert meta[-1] == 0 and np.isfinite(t0[0]).all() and np.isfinite(t1[0]).all()
     # the averaged run lands where a single replica lands (same walks, same number of updates)
     from embiggen_b200.graph import erdos_renyi
     graph = erdos_renyi(3000, 20000, seed=5)
@@ -118,4 +118,5 @@ def test_fit_distributed_over_cuda_ipc(tmp_path, world):
                 number_of_negative_samples=3, chunk_walks=512) as engine:
         engine.load_csr(graph.indptr, graph.indices)
         _, _, single = engine.fit(9)
-    assert abs(meta[1] - single[1]) < 0.1 * single[1]
+    assert abs(meta[0] - single[0]) < 0.02 * single[0] and abs(meta[1] - single[1]) < 0.05 * single[1]
+    assert not np.array_equal(t0[0], np.zeros_like(t0[0]))
