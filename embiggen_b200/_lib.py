@@ -115,6 +115,8 @@ SIGNATURES = {
     "b2e_train_host_walks": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, _U64, _U64, _U64, _F32]),
     "b2e_sync": (ctypes.c_int, [_H]),
     "b2e_device_tables": (ctypes.c_int, [_H, _P(ctypes.c_void_p), _P(ctypes.c_void_p)]),
+    "b2e_host_register": (ctypes.c_int, [ctypes.c_void_p, _U64]),
+    "b2e_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "b2e_exchange_handles": (ctypes.c_int, [_H, ctypes.c_void_p]),
     "b2e_exchange_open": (ctypes.c_int, [_H, _U32, _U32, ctypes.c_void_p]),
     "b2e_exchange_open_local": (ctypes.c_int, [_H, _U32, _U32, _P(_H)]),

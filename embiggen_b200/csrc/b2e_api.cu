@@ -705,6 +705,18 @@ extern "C" int b2e_device_tables(b2e_handle *h, void **table0, void **table1) {
     return B2E_OK;
 }
 
+extern "C" int b2e_host_register(void *buffer, uint64_t bytes) {
+    if (!buffer || !bytes) return fail(B2E_ERR_INVALID, "null or empty buffer");
+    CUDA_TRY(cudaHostRegister(buffer, bytes, cudaHostRegisterPortable));
+    return B2E_OK;
+}
+
+extern "C" int b2e_host_unregister(void *buffer) {
+    if (!buffer) return fail(B2E_ERR_INVALID, "null buffer");
+    CUDA_TRY(cudaHostUnregister(buffer));
+    return B2E_OK;
+}
+
 // ---- the exchange step (csrc/exchange.cu) ----
 extern "C" int b2e_exchange_handles(b2e_handle *h, void *ipc_handles) {
     REQUIRE_HANDLE(h);

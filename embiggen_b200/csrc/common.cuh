@@ -179,7 +179,7 @@ struct b2e_handle {
     bool undirected = false;
     uint32_t prefetch = 1;
     uint32_t variant = 0;
-    uint32_t walk_occupancy = 4;  // B2E_WALK_OCC: see walk_kernel
+    uint32_t walk_occupancy = 6;  // B2E_WALK_OCC: see walk_kernel
     uint64_t launches = 0;
     std::vector<uint32_t> h_alias_thr, h_alias_idx;
     // the exchange step: replicas of the tables on the other GPUs of the node

@@ -107,7 +107,9 @@ __host__ __device__ __forceinline__ uint32_t pipe_warp_bytes(uint32_t negatives,
 // what a thread needs to address its 16 B chunk of any row
 struct LaneView {
     const char *t0, *t1;  // table bases advanced by 16 * lane bytes
-    uint64_t row_bytes;
+    uint32_t row_bytes;   // 32-bit on purpose: id * row_bytes is then a single widening multiply
+    __device__ __forceinline__ const char *row0(uint32_t id) const { return t0 + (uint64_t)id * row_bytes; }
+    __device__ __forceinline__ const char *row1(uint32_t id) const { return t1 + (uint64_t)id * row_bytes; }
     uint32_t smem_chunk;  // 4 * min(lane, chunks - 1): lanes past the row re-read its last chunk
     bool active;          // lane < chunks; only active lanes copy and store
 };
@@ -135,11 +137,11 @@ __device__ __forceinline__ void issue_rows(const TrainParams &p, const PipeSmem 
     for (int s = 0; s < S; ++s) {
         if ((uint32_t)s < slots && (ALL || ((vmask >> s) & 1u))) {
             const uint32_t id = __shfl_sync(FULL, my_id, s);
-            if (v.active) cp_async16(dst + (uint32_t)s * sm.pitch, v.t1 + id * v.row_bytes);
+            if (v.active) cp_async16(dst + (uint32_t)s * sm.pitch, v.row1(id));
         }
     }
     if (centre_or_pad != PAD && v.active)
-        cp_async16(dst + slots * sm.pitch, v.t0 + centre_or_pad * v.row_bytes);
+        cp_async16(dst + slots * sm.pitch, v.row0(centre_or_pad));
 }
 
 // dots, sigmoid, axpy and scatter of the targets of one draw site out of stage `stage`;
@@ -199,7 +201,7 @@ __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSme
             r.y = __fmaf_rn(g, h.y, r.y);
             r.z = __fmaf_rn(g, h.z, r.z);
             r.w = __fmaf_rn(g, h.w, r.w);
-            if (v.active) *reinterpret_cast<float4 *>(const_cast<char *>(v.t1) + id * v.row_bytes) = r;
+            if (v.active) *reinterpret_cast<float4 *>(const_cast<char *>(v.row1(id))) = r;
         }
     }
     if (!v.active) acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
     LaneView v;
     v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
     v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
-    v.row_bytes = (uint64_t)p.row_stride * 4u;
+    v.row_bytes = p.row_stride * 4u;
     v.active = lane < p.chunks;
     v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
     float loss_acc = 0.0f;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
             n_targets += __popc(vmask_cur);
             ++n_pairs;
             if ((!ok_nxt || nxt.i != cur.i) && v.active)
-                *reinterpret_cast<float4 *>(const_cast<char *>(v.t0) + cur.c * v.row_bytes) = h;
+                *reinterpret_cast<float4 *>(const_cast<char *>(v.row0(cur.c))) = h;
 
             if (deferred) {  // its rows overlap the rows just stored: copy them now
                 issue(stage ^ 1u, ids_nxt, vmask_nxt, nxt.i != cur.i ? nxt.c : PAD);
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
     LaneView v;
     v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
     v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
-    v.row_bytes = (uint64_t)p.row_stride * 4u;
+    v.row_bytes = p.row_stride * 4u;
     v.active = lane < p.chunks;
     v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
     const uint32_t lower = (1u << lane) - 1u;
@@ -467,10 +469,18 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
             if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, PAD);
             else issue_rows<KP1, false>(p, sm, v, stage, lane, ids, vmask, PAD);
         };
+        // Ring slot of a walk position = position mod R, kept without a division: `slot_lo` is the
+        // slot of the first window position `lo_at`, and every position the loop touches lies less
+        // than R behind or ahead of it.
+        uint32_t lo_at = 0, slot_lo = 0;
+        auto slot_of = [&](uint32_t pos) -> uint32_t {
+            const uint32_t s = slot_lo + (pos - lo_at);
+            return s >= R ? s - R : s;
+        };
         // copy the T0 row of walk position `pos` into its ring slot (nothing to copy for PAD)
         auto fetch = [&](uint32_t pos) {
             const uint32_t t = walk[pos];
-            if (t != PAD && v.active) cp_async16(ring + (pos % R) * sm.pitch + 4u * lane, v.t0 + t * v.row_bytes);
+            if (t != PAD && v.active) cp_async16(ring + slot_of(pos) * sm.pitch + 4u * lane, v.row0(t));
         };
 
         uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
@@ -486,6 +496,8 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
         issue(stage, ids_cur, vmask_cur);
         // positions < resident are in the ring (or are PAD); the first window is copied here
         uint32_t resident = i_cur > W ? i_cur - W : 0u;
+        lo_at = resident;
+        slot_lo = resident % R;
         for (const uint32_t end = min(L, i_cur + W + 1u); resident < end; ++resident) fetch(resident);
         uint32_t i_nxt = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_cur + 1, c_nxt);
         slot_a ^= 1u;
@@ -498,6 +510,7 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
             const uint32_t i = i_cur, c = c_cur;
             const uint32_t lo = i > W ? i - W : 0u;
             const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+            for (; lo_at < lo; ++lo_at) slot_lo = slot_lo + 1u == R ? 0u : slot_lo + 1u;
             if (resident <= hi) {  // the centre jumped (skipped centres): complete the window now
                 if (resident < lo) resident = lo;
                 for (; resident <= hi; ++resident) fetch(resident);
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
                 bool first = true;
                 for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
                     const uint32_t q = __ffs(rem) - 1u;
-                    const float4 r = lds128(ring + ((lo + q) % R) * sm.pitch + v.smem_chunk);
+                    const float4 r = lds128(ring + slot_of(lo + q) * sm.pitch + v.smem_chunk);
                     if (first) h = r; else add4(h, r);
                     first = false;
                 }
@@ -571,22 +584,34 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
             {
                 const uint32_t key = ctx ? tok : (0xFFFFFF00u | lane);
                 const uint32_t same = __match_any_sync(FULL, key);
-                const uint32_t mult = __popc(same);
                 const uint32_t leaders = __ballot_sync(FULL, ctx && (same & lower) == 0u);
-                for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
-                    const uint32_t q = __ffs(rem) - 1u;
-                    const uint32_t k = __shfl_sync(FULL, mult, q);
-                    float *slot = ring + ((lo + q) % R) * sm.pitch + 4u * lane;
-                    if (v.active) {
-                        float4 r = lds128(slot);
-                        for (uint32_t t = 0; t < k; ++t) add4(r, acc);
-                        *reinterpret_cast<float4 *>(slot) = r;
-                    }
-                    if ((leaders >> q) & 1u) {
+                if (leaders == cmask) {  // every context token occurs once: the common case
+                    for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
+                        const uint32_t q = __ffs(rem) - 1u;
                         const uint32_t t_id = __shfl_sync(FULL, tok, q);
-                        if (v.active)
-                            for (uint32_t t = 0; t < k; ++t)
-                                red_add4(reinterpret_cast<float *>(const_cast<char *>(v.t0) + t_id * v.row_bytes), acc);
+                        if (v.active) {
+                            float *slot = ring + slot_of(lo + q) * sm.pitch + 4u * lane;
+                            float4 r = lds128(slot);
+                            add4(r, acc);
+                            *reinterpret_cast<float4 *>(slot) = r;
+                            red_add4(reinterpret_cast<float *>(const_cast<char *>(v.row0(t_id))), acc);
+                        }
+                    }
+                } else {
+                    const uint32_t mult = __popc(same);
+                    for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
+                        const uint32_t q = __ffs(rem) - 1u;
+                        const uint32_t k = __shfl_sync(FULL, mult, q);
+                        const uint32_t t_id = __shfl_sync(FULL, tok, q);
+                        if (v.active) {
+                            float *slot = ring + slot_of(lo + q) * sm.pitch + 4u * lane;
+                            float4 r = lds128(slot);
+                            for (uint32_t t = 0; t < k; ++t) add4(r, acc);
+                            *reinterpret_cast<float4 *>(slot) = r;
+                            if ((leaders >> q) & 1u)
+                                for (uint32_t t = 0; t < k; ++t)
+                                    red_add4(reinterpret_cast<float *>(const_cast<char *>(v.row0(t_id))), acc);
+                        }
                     }
                 }
             }

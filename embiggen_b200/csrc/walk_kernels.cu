@@ -189,7 +189,8 @@ __device__ __forceinline__ uint32_t propose(const uint2 *__restrict__ table, int
 // one Philox block per trial (tag 12): x decides slot vs row, y proposes, z accepts; see
 // oracle/walks.c (orc_fold_thresholds) for the normative statement.
 // MINB: resident CTAs per SM the register allocation is held to (4: 64 registers, no spills;
-// 6: 40 registers and a few spilled words -- more chains in flight per SM)
+// 6: 40 registers and a few spilled words -- more chains in flight per SM; measured on C3:
+// 7.8 / 8.6 / 9.4 G steps/s at 4 / 5 / 6, profiles/r02c_*)
 template <bool SECOND, bool VEC, bool WEIGHTED, bool FOLD, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB) walk_kernel(const WalkParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,9 +512,11 @@ cudaError_t launch_walks(const WalkParams &p, bool second_order, cudaStream_t st
     if (second_order && !weighted && vec && p.occupancy >= 5) {  // the headline shapes, tunable occupancy
         if (p.fold_excess) {
             if (p.occupancy == 5) walk_kernel<true, true, false, true, 5><<<grid, block, 0, stream>>>(p);
+            else if (p.occupancy >= 8) walk_kernel<true, true, false, true, 8><<<grid, block, 0, stream>>>(p);
             else walk_kernel<true, true, false, true, 6><<<grid, block, 0, stream>>>(p);
         } else {
             if (p.occupancy == 5) walk_kernel<true, true, false, false, 5><<<grid, block, 0, stream>>>(p);
+            else if (p.occupancy >= 8) walk_kernel<true, true, false, false, 8><<<grid, block, 0, stream>>>(p);
             else walk_kernel<true, true, false, false, 6><<<grid, block, 0, stream>>>(p);
         }
     } else if (second_order && !weighted && p.fold_excess) {

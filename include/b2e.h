@@ -156,6 +156,13 @@ int b2e_fit(b2e_handle *handle, uint64_t seed, float *table0, float *table1, flo
 int b2e_walks(b2e_handle *handle, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
               uint64_t walk_id_stride, uint32_t *out);
 
+/*
+ * Page-lock / unlock a caller-owned host buffer (cudaHostRegister): b2e_fit then copies the tables
+ * of a large graph into it at full PCIe speed (40 GB per table at 100 M nodes).  Optional.
+ */
+int b2e_host_register(void *buffer, uint64_t bytes);
+int b2e_host_unregister(void *buffer);
+
 /* ---- stepping API (device-resident; used by the host driver, multi-GPU and bench) ---- */
 
 /* Streams are cudaStream_t handles (e.g. torch.cuda.Stream().cuda_stream); NULL = default. */

@@ -30,6 +30,28 @@ for model in ("SkipGram", "CBOW"):
             engine.load_types(node_types, edge_types)
             t0, t1, losses = engine.fit(7)
             assert np.isfinite(t0).all() and np.isfinite(t1).all(), (model, extra)
+# round 2: folded return edge + row filters + short-row search (unweighted, undirected), the
+# CSR content check, the window-ring CBOW kernel without weights, the exchange kernel, the digest
+hub = rmat(11, 20000, n=2000, seed=5)
+for model in ("SkipGram", "CBOW"):
+    replicas = [Engine(model, embedding_size=100, walk_length=40, window_size=4, iterations=1, epochs=1,
+                       return_weight=2.0, explore_weight=0.5, chunk_walks=700) for _ in range(2)]
+    for rank, engine in enumerate(replicas):
+        engine.load_csr(hub.indptr, hub.indices)
+        engine.init_tables(3)
+        engine.walk_chunk(3, rank, 700, 2, 0)
+        engine.train_chunk(3, 0, 0.05)
+    for rank, engine in enumerate(replicas):
+        engine.open_exchange_local(replicas, rank)
+    for engine in replicas:
+        engine.sync()
+    for engine in replicas:
+        engine.exchange_average()
+    digests = [engine.tables_digest() for engine in replicas]
+    assert digests[0]["bits"] == digests[1]["bits"] and digests[0]["non_finite"] == 0
+    assert replicas[0].counters()["walk_filter_rejects"] > 0
+    for engine in replicas:
+        engine.close()
 with Engine("GloVe", embedding_size=100, walk_length=33, window_size=4, iterations=1, epochs=2,
             chunk_walks=300) as engine:
     engine.load_csr(graph.indptr, graph.indices)
