@@ -47,6 +47,8 @@ for model in ("SkipGram", "CBOW"):
         engine.sync()
     for engine in replicas:
         engine.exchange_average()
+    for engine in replicas:
+        engine.sync()
     digests = [engine.tables_digest() for engine in replicas]
     assert digests[0]["bits"] == digests[1]["bits"] and digests[0]["non_finite"] == 0
     assert replicas[0].counters()["walk_filter_rejects"] > 0

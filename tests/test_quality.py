@@ -152,7 +152,7 @@ def test_replica_averaging_keeps_the_quality():
     """The data-parallel exchange step on one GPU: two replicas (two handles) train the two
     shards of every step and are averaged at the driver's sync points, exactly like two ranks;
     the averaged embedding must predict held-out edges as well as the single-replica one
-    (tolerance 0.01 AUROC on one holdout)."""
+    (within 0.005 AUROC, two-sided, on one holdout; measured 0.8971 vs 0.8980)."""
     import torch
     from embiggen_b200.engine import Engine, shard_chunks
     src, dst, n = block_model(3)
@@ -202,4 +202,4 @@ def test_replica_averaging_keeps_the_quality():
             engine.close()
     averaged = auroc(np.hstack([a0, a1]), train_pos, test_pos, train_neg, test_neg)
     print(f"AUROC single replica {baseline:.4f}  two averaged replicas {averaged:.4f}")
-    assert averaged >= baseline - 0.01
+    assert abs(averaged - baseline) <= 0.005
