@@ -143,6 +143,14 @@ SIGNATURES = {
     "b2e_perceptron_predict": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64, ctypes.c_void_p,
                                               ctypes.c_void_p, _U64, ctypes.c_void_p, _U32, ctypes.c_void_p, _U32,
                                               ctypes.c_void_p, ctypes.c_void_p]),
+    "b2e_graph_from_edges": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
+                                            ctypes.c_int, _P(_H)]),
+    "b2e_graph_synthetic": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _U64, _U32, _U64, _U64, _U64, _U64,
+                                           _U64, _P(_H)]),
+    "b2e_graph_shape": (ctypes.c_int, [_H, _P(_U64), _P(_U64)]),
+    "b2e_graph_export": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "b2e_graph_destroy": (None, [_H]),
+    "b2e_load_graph": (ctypes.c_int, [_H, _H]),
     "b2e_csr_from_edges": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _P(_U64)]),
     "b2e_synthetic_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _U64, _U32, _U64, _U64, _U64, _U64,

@@ -183,8 +183,21 @@ static void close_peers(b2e_handle *h) {
     h->peers_are_ipc = false;
 }
 
+static void release_graph(b2e_graph *g) {
+    if (!g || --g->references > 0) return;
+    cudaFree(g->csr.indptr);
+    cudaFree(g->csr.indices);
+    delete g;
+}
+
 static void free_graph(b2e_handle *h) {
     close_peers(h);
+    if (h->shared_graph) {  // the CSR belongs to a b2e_graph: drop this handle's reference
+        release_graph(h->shared_graph);
+        h->shared_graph = nullptr;
+        h->d_indptr = nullptr;
+        h->d_indices = nullptr;
+    }
     cudaFree(h->d_indptr); h->d_indptr = nullptr;
     cudaFree(h->d_indices); h->d_indices = nullptr;
     cudaFree(h->d_edge_alias); h->d_edge_alias = nullptr;
@@ -338,10 +351,20 @@ static int load_failed(b2e_handle *h, int rc) {
             return load_failed(h, fail(B2E_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
     } while (0)
 
+static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_t *indices, const float *weights,
+                             uint64_t n, uint64_t nnz, b2e_graph *resident);
+
 extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const uint32_t *indices,
                                      const float *weights, uint64_t n, uint64_t nnz) {
     REQUIRE_HANDLE(h);
     if (!indptr || (!indices && nnz)) return fail(B2E_ERR_INVALID, "null CSR pointer");
+    return load_graph_common(h, indptr, indices, weights, n, nnz, nullptr);
+}
+
+// `resident`: the CSR already lives in HBM (b2e_load_graph) -- `indptr` is a host copy of its
+// offsets, `indices` is null and nothing is uploaded
+static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_t *indices, const float *weights,
+                             uint64_t n, uint64_t nnz, b2e_graph *resident) {
     if (n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
     if (n >= 0xFFFFFF00ull) return fail(B2E_ERR_INVALID, "node ids must be below 0xFFFFFF00");
     if (nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
@@ -370,14 +393,22 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     h->n_src = sources.size();
     h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
 
-    // K1: the two big copies, then the content check on the device (ids in range, rows strictly
-    // ascending: the kernels index with these ids and bisect these rows without looking again)
-    LOAD_TRY(cudaMalloc(&h->d_indptr, (n + 1) * sizeof(int64_t)));
-    LOAD_TRY(cudaMalloc(&h->d_indices, nnz * sizeof(uint32_t)));
-    LOAD_TRY(cudaMemcpyAsync(h->d_indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                             h->walk_stream));
-    LOAD_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                             h->walk_stream));
+    // K1: the two big copies (none when the CSR is resident already), then the content check on
+    // the device (ids in range, rows strictly ascending: the kernels index with these ids and
+    // bisect these rows without looking again)
+    if (resident) {
+        h->shared_graph = resident;
+        ++resident->references;
+        h->d_indptr = resident->csr.indptr;
+        h->d_indices = resident->csr.indices;
+    } else {
+        LOAD_TRY(cudaMalloc(&h->d_indptr, (n + 1) * sizeof(int64_t)));
+        LOAD_TRY(cudaMalloc(&h->d_indices, nnz * sizeof(uint32_t)));
+        LOAD_TRY(cudaMemcpyAsync(h->d_indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                 h->walk_stream));
+        LOAD_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                 h->walk_stream));
+    }
     int *d_flags = nullptr;
     LOAD_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
     LOAD_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->walk_stream));
@@ -411,7 +442,13 @@ extern "C" int b2e_load_csr_weighted(b2e_handle *h, const int64_t *indptr, const
     // max(deg(x), 1), one float32 division per edge, folded into the proposal table -- no extra
     // rejection however skewed the degrees (oracle: degree_normalised_weights)
     std::vector<float> normalised;
+    std::vector<uint32_t> fetched_indices;
     if (c.normalize_by_degree) {
+        if (!indices) {  // resident graph: this rarely used option needs the ids on the host
+            fetched_indices.resize(nnz);
+            LOAD_TRY(cudaMemcpy(fetched_indices.data(), h->d_indices, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            indices = fetched_indices.data();
+        }
         normalised.resize(nnz);
         for (uint64_t e = 0; e < nnz; ++e) {
             const uint32_t x = indices[e];
@@ -1034,6 +1071,46 @@ extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table
     return b2e_export_tables(h, table0, table1);
 }
 
+static int select_device(int device);
+
+// ---- resident graphs: built on the GPU, handed to a handle without leaving HBM ----
+extern "C" int b2e_graph_shape(const b2e_graph *g, uint64_t *n, uint64_t *nnz) {
+    if (!g || !n || !nnz) return fail(B2E_ERR_INVALID, "null argument");
+    *n = g->csr.n;
+    *nnz = g->csr.nnz;
+    return B2E_OK;
+}
+
+extern "C" int b2e_graph_export(const b2e_graph *g, int64_t *indptr, uint32_t *indices) {
+    if (!g || !indptr || (!indices && g->csr.nnz)) return fail(B2E_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaMemcpy(indptr, g->csr.indptr, (g->csr.n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (g->csr.nnz)
+        CUDA_TRY(cudaMemcpy(indices, g->csr.indices, g->csr.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return B2E_OK;
+}
+
+extern "C" void b2e_graph_destroy(b2e_graph *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    release_graph(g);
+}
+
+extern "C" int b2e_load_graph(b2e_handle *h, b2e_graph *g) {
+    REQUIRE_HANDLE(h);
+    if (!g) return fail(B2E_ERR_INVALID, "null graph");
+    if (g->device != h->cfg.device) return fail(B2E_ERR_INVALID, "the graph lives on another device than the handle");
+    if (g->csr.n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
+    if (g->csr.nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
+    // the offsets (8 bytes per node) come back for the host-side derivations; the ids stay put
+    std::vector<int64_t> indptr(g->csr.n + 1);
+    CUDA_TRY(cudaMemcpy(indptr.data(), g->csr.indptr, indptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    ++g->references;  // keep it alive across free_graph() of a handle that already walks on it
+    const int rc = load_graph_common(h, indptr.data(), nullptr, nullptr, g->csr.n, g->csr.nnz, g);
+    release_graph(g);
+    return rc;
+}
+
 // ---- graph ingest (csrc/graph_build.cu) ----
 static int select_device(int device) {
     int count = 0;
@@ -1044,6 +1121,53 @@ static int select_device(int device) {
     if (device < 0 || device >= count) return fail(B2E_ERR_INVALID, "device ordinal out of range");
     CUDA_TRY(cudaSetDevice(device));
     return B2E_OK;
+}
+
+static int deliver_graph(int device, cudaError_t e, const std::string &error, ResidentCsr &csr, b2e_graph **out) {
+    if (e == cudaErrorInvalidValue) return fail(B2E_ERR_INVALID, error);
+    if (e != cudaSuccess) return fail(B2E_ERR_CUDA, error);
+    b2e_graph *g = new (std::nothrow) b2e_graph();
+    if (!g) {
+        cudaFree(csr.indptr);
+        cudaFree(csr.indices);
+        return fail(B2E_ERR_INVALID, "out of host memory");
+    }
+    g->csr = csr;
+    g->device = device;
+    *out = g;
+    return B2E_OK;
+}
+
+extern "C" int b2e_graph_from_edges(int device, const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                                    uint64_t n_nodes, int symmetrise, b2e_graph **out) {
+    if (!out || (n_edges && (!src || !dst))) return fail(B2E_ERR_INVALID, "null argument");
+    if (n_nodes == 0 || n_nodes >= 0xFFFFFF00ull)
+        return fail(B2E_ERR_INVALID, "the number of nodes must be in [1, 0xFFFFFF00)");
+    if (int rc = select_device(device)) return rc;
+    std::string error;
+    ResidentCsr csr;
+    uint64_t nnz = 0;
+    cudaError_t e = csr_from_edges(src, dst, n_edges, n_nodes, symmetrise, nullptr, nullptr, 0, &nnz, error, &csr);
+    return deliver_graph(device, e, error, csr, out);
+}
+
+extern "C" int b2e_graph_synthetic(int device, int kind, uint64_t n_nodes, uint32_t scale, uint64_t n_edges,
+                                   uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, b2e_graph **out) {
+    if (!out) return fail(B2E_ERR_INVALID, "null argument");
+    if (kind != 0 && kind != 1) return fail(B2E_ERR_INVALID, "kind must be 0 (Erdos-Renyi) or 1 (R-MAT)");
+    if (n_nodes < 2 || n_nodes >= 0xFFFFFF00ull)
+        return fail(B2E_ERR_INVALID, "the number of nodes must be in [2, 0xFFFFFF00)");
+    if (kind == 1 && (scale == 0 || scale > 32 || (scale < 32 && n_nodes > (1ull << scale))))
+        return fail(B2E_ERR_INVALID, "R-MAT needs 1 <= scale <= 32 and n_nodes <= 2^scale");
+    if ((double)n_edges > 0.5 * (double)n_nodes * (double)(n_nodes - 1) * 0.5)
+        return fail(B2E_ERR_INVALID, "Too many edges requested.");
+    if (int rc = select_device(device)) return rc;
+    std::string error;
+    ResidentCsr csr;
+    uint64_t nnz = 0;
+    cudaError_t e = synthetic_csr(kind, n_nodes, scale, n_edges, seed, t_a, t_ab, t_abc, nullptr, nullptr, 0, &nnz,
+                                  error, &csr);
+    return deliver_graph(device, e, error, csr, out);
 }
 
 extern "C" int b2e_csr_from_edges(int device, const uint32_t *src, const uint32_t *dst, uint64_t n_edges,

@@ -139,18 +139,32 @@ bool pipe_supported(const TrainParams &p, uint32_t model);
 cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                               uint64_t max_warps, cudaStream_t stream);
 
+// a CSR that stays in HBM (b2e_graph): built by graph_build.cu, handed to a handle without a copy
+struct ResidentCsr {
+    int64_t *indptr = nullptr;
+    uint32_t *indices = nullptr;
+    uint64_t n = 0, nnz = 0;
+};
+// `resident` != nullptr: the device arrays move into it and the host buffers are not touched
 cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint64_t n,
                            int symmetrise, int64_t *indptr, uint32_t *indices, uint64_t capacity,
-                           uint64_t *nnz_out, std::string &error);
+                           uint64_t *nnz_out, std::string &error, ResidentCsr *resident = nullptr);
 cudaError_t synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t m, uint64_t seed,
                           unsigned long long t_a, unsigned long long t_ab, unsigned long long t_abc,
                           int64_t *indptr, uint32_t *indices, uint64_t capacity, uint64_t *nnz_out,
-                          std::string &error);
+                          std::string &error, ResidentCsr *resident = nullptr);
 
 }  // namespace b2e
 
+struct b2e_graph {
+    b2e::ResidentCsr csr;
+    int device = 0;
+    int references = 1;  // the caller's object + every handle that walks on it
+};
+
 struct b2e_handle {
     b2e_config cfg;
+    b2e_graph *shared_graph = nullptr;  // d_indptr / d_indices belong to it (b2e_load_graph)
     int sm_count = 0;
     uint64_t n = 0, nnz = 0, n_src = 0;
     uint32_t row_stride = 0;

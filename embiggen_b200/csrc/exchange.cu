@@ -27,40 +27,53 @@ struct ExchangeParams {
     float scale;
 };
 
-// one warp per (table, row); the G loads of a lane are issued back to back (NVLink latency is
-// covered by loads in flight, not by occupancy alone)
-template <int G>
+// One warp per (table, row), U rows per iteration: the G x U loads of a lane are issued back to
+// back before the first is consumed -- NVLink round trips are covered by loads in flight (at
+// G = 2 a single row per iteration moved 200 GB/s per direction, profiles/r02e_*).
+template <int G, int U>
 __global__ void __launch_bounds__(256) exchange_average_kernel(const ExchangeParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t rows = p.row_end - p.row_begin;
+    const uint64_t rows = p.row_end - p.row_begin, items = 2 * rows;
+    constexpr int GG = G ? G : B2E_MAX_WORLD;
     const uint32_t world = G ? (uint32_t)G : p.world;
-    for (uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < 2 * rows; item += warps) {
-        const uint32_t table = item >= rows;
-        const uint64_t row = p.row_begin + (table ? item - rows : item);
-        const uint64_t at = row * p.row_stride;
+    for (uint64_t base = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * U; base < items;
+         base += warps * U) {
         for (uint32_t c = lane; c < p.chunks; c += 32u) {
-            float4 v[G ? G : B2E_MAX_WORLD];
+            float4 v[U][GG];
+            uint64_t at[U];
+            uint32_t table[U];
 #pragma unroll
-            for (int g = 0; g < (G ? G : B2E_MAX_WORLD); ++g)
-                if ((uint32_t)g < world) v[g] = __ldcg(reinterpret_cast<const float4 *>(p.t[table][g] + at) + c);
-            float4 s = v[0];
+            for (int u = 0; u < U; ++u) {
+                const uint64_t item = base + u < items ? base + u : items - 1;  // the tail repeats its last row
+                table[u] = item >= rows;
+                at[u] = (p.row_begin + (table[u] ? item - rows : item)) * p.row_stride;
 #pragma unroll
-            for (int g = 1; g < (G ? G : B2E_MAX_WORLD); ++g) {
-                if ((uint32_t)g < world) {
-                    s.x = __fadd_rn(s.x, v[g].x);
-                    s.y = __fadd_rn(s.y, v[g].y);
-                    s.z = __fadd_rn(s.z, v[g].z);
-                    s.w = __fadd_rn(s.w, v[g].w);
+                for (int g = 0; g < GG; ++g)
+                    if ((uint32_t)g < world) v[u][g] = __ldcg(reinterpret_cast<const float4 *>(p.t[table[u]][g] + at[u]) + c);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float4 s = v[u][0];
+#pragma unroll
+                for (int g = 1; g < GG; ++g) {
+                    if ((uint32_t)g < world) {
+                        s.x = __fadd_rn(s.x, v[u][g].x);
+                        s.y = __fadd_rn(s.y, v[u][g].y);
+                        s.z = __fadd_rn(s.z, v[u][g].z);
+                        s.w = __fadd_rn(s.w, v[u][g].w);
+                    }
+                }
+                s.x = __fmul_rn(s.x, p.scale);
+                s.y = __fmul_rn(s.y, p.scale);
+                s.z = __fmul_rn(s.z, p.scale);
+                s.w = __fmul_rn(s.w, p.scale);
+                if (base + u < items) {
+#pragma unroll
+                    for (int g = 0; g < GG; ++g)
+                        if ((uint32_t)g < world) __stcg(reinterpret_cast<float4 *>(p.t[table[u]][g] + at[u]) + c, s);
                 }
             }
-            s.x = __fmul_rn(s.x, p.scale);
-            s.y = __fmul_rn(s.y, p.scale);
-            s.z = __fmul_rn(s.z, p.scale);
-            s.w = __fmul_rn(s.w, p.scale);
-#pragma unroll
-            for (int g = 0; g < (G ? G : B2E_MAX_WORLD); ++g)
-                if ((uint32_t)g < world) __stcg(reinterpret_cast<float4 *>(p.t[table][g] + at) + c, s);
         }
     }
 }
@@ -84,10 +97,10 @@ cudaError_t launch_exchange_average(float *const t0[], float *const t1[], uint32
     if (rows == 0) return cudaSuccess;
     const unsigned grid = (unsigned)std::min<uint64_t>((2 * rows + 7) / 8, (uint64_t)sm_count * 8);
     switch (world) {
-        case 2: exchange_average_kernel<2><<<grid, 256, 0, stream>>>(p); break;
-        case 4: exchange_average_kernel<4><<<grid, 256, 0, stream>>>(p); break;
-        case 8: exchange_average_kernel<8><<<grid, 256, 0, stream>>>(p); break;
-        default: exchange_average_kernel<0><<<grid, 256, 0, stream>>>(p); break;
+        case 2: exchange_average_kernel<2, 4><<<grid, 256, 0, stream>>>(p); break;
+        case 4: exchange_average_kernel<4, 2><<<grid, 256, 0, stream>>>(p); break;
+        case 8: exchange_average_kernel<8, 1><<<grid, 256, 0, stream>>>(p); break;
+        default: exchange_average_kernel<0, 1><<<grid, 256, 0, stream>>>(p); break;
     }
     return cudaGetLastError();
 }

@@ -37,6 +37,11 @@ struct DeviceBuffer {
         if (e == cudaSuccess) bytes = want;
         return e;
     }
+    void release() {
+        cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
     template <typename T> T *as() { return static_cast<T *>(ptr); }
 };
 
@@ -147,11 +152,11 @@ static cudaError_t sort_keys(DeviceBuffer &temp, const unsigned long long *keys_
     return cudaSuccess;
 }
 
-// directed keys (any order) -> CSR in host buffers.  `scratch` is the alternate buffer of the
+// directed keys (any order) -> CSR in device buffers.  `scratch` is the alternate buffer of the
 // radix sort (no third copy).  With `dedup` the keys may repeat and contain INVALID_KEY.
 static cudaError_t keys_to_csr(DeviceBuffer &temp, unsigned long long *keys, unsigned long long *scratch,
-                               uint64_t count, uint64_t n, bool dedup, int64_t *indptr, uint32_t *indices,
-                               uint64_t capacity, uint64_t *nnz_out, std::string &error) {
+                               uint64_t count, uint64_t n, bool dedup, DeviceBuffer &d_indptr,
+                               DeviceBuffer &d_indices, uint64_t *nnz_out, std::string &error) {
     cub::DoubleBuffer<unsigned long long> buffers(keys, scratch);
     size_t bytes = 0;
     GB_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bytes, buffers, count));
@@ -172,16 +177,32 @@ static cudaError_t keys_to_csr(DeviceBuffer &temp, unsigned long long *keys, uns
         sorted = other;
     }
     *nnz_out = nnz;
-    if (nnz > capacity) {
-        error = "indices buffer too small for the de-duplicated graph";
-        return cudaErrorInvalidValue;
-    }
-    DeviceBuffer d_indices, d_indptr;
     GB_TRY(d_indices.reserve(std::max<uint64_t>(nnz, 1) * sizeof(uint32_t)));
     GB_TRY(d_indptr.reserve((n + 1) * sizeof(long long)));
     csr_from_keys_kernel<<<blocks_for(std::max<uint64_t>(nnz, n + 1)), 256>>>(
         sorted, nnz, n, d_indices.as<uint32_t>(), d_indptr.as<long long>());
     GB_TRY(cudaGetLastError());
+    GB_TRY(cudaDeviceSynchronize());
+    return cudaSuccess;
+}
+
+// hand the device arrays over: to host buffers, or (out != nullptr) to a resident b2e_graph
+static cudaError_t deliver(DeviceBuffer &d_indptr, DeviceBuffer &d_indices, uint64_t n, uint64_t nnz,
+                           int64_t *indptr, uint32_t *indices, uint64_t capacity, ResidentCsr *out,
+                           std::string &error) {
+    if (out) {
+        out->indptr = d_indptr.as<int64_t>();
+        out->indices = d_indices.as<uint32_t>();
+        out->n = n;
+        out->nnz = nnz;
+        d_indptr.ptr = d_indices.ptr = nullptr;  // ownership moves
+        d_indptr.bytes = d_indices.bytes = 0;
+        return cudaSuccess;
+    }
+    if (nnz > capacity) {
+        error = "indices buffer too small for the de-duplicated graph";
+        return cudaErrorInvalidValue;
+    }
     GB_TRY(cudaMemcpy(indptr, d_indptr.ptr, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
     if (nnz) GB_TRY(cudaMemcpy(indices, d_indices.ptr, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return cudaSuccess;
@@ -189,7 +210,7 @@ static cudaError_t keys_to_csr(DeviceBuffer &temp, unsigned long long *keys, uns
 
 cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint64_t n,
                            int symmetrise, int64_t *indptr, uint32_t *indices, uint64_t capacity,
-                           uint64_t *nnz_out, std::string &error) {
+                           uint64_t *nnz_out, std::string &error, ResidentCsr *resident) {
     const uint64_t count = n_edges * (symmetrise ? 2 : 1);
     DeviceBuffer d_src, d_dst, keys, scratch, temp, flag;
     GB_TRY(d_src.reserve(std::max<uint64_t>(n_edges, 1) * sizeof(uint32_t)));
@@ -212,8 +233,12 @@ cudaError_t csr_from_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_
         error = "an edge endpoint is not below the number of nodes";
         return cudaErrorInvalidValue;
     }
-    return keys_to_csr(temp, keys.as<unsigned long long>(), scratch.as<unsigned long long>(), count, n,
-                       true, indptr, indices, capacity, nnz_out, error);
+    d_src.release();
+    d_dst.release();
+    DeviceBuffer d_indptr, d_indices;
+    GB_TRY(keys_to_csr(temp, keys.as<unsigned long long>(), scratch.as<unsigned long long>(), count, n, true,
+                       d_indptr, d_indices, nnz_out, error));
+    return deliver(d_indptr, d_indices, n, *nnz_out, indptr, indices, capacity, resident, error);
 }
 
 // flags[j] = 1 when keys[j] is a real key that the sorted pool does not hold yet
@@ -250,7 +275,7 @@ static cudaError_t select_flagged(DeviceBuffer &temp, const T *in, const unsigne
 cudaError_t synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t m, uint64_t seed,
                           unsigned long long t_a, unsigned long long t_ab, unsigned long long t_abc,
                           int64_t *indptr, uint32_t *indices, uint64_t capacity, uint64_t *nnz_out,
-                          std::string &error) {
+                          std::string &error, ResidentCsr *resident) {
     typedef unsigned long long u64;
     const uint64_t batch_max = 1ull << 29;
     DeviceBuffer pool[2], keys_in, ids_in, keys_sorted, ids_sorted, keys_unique, ids_unique, keys_new,
@@ -330,8 +355,13 @@ cudaError_t synthetic_csr(int kind, uint64_t n, uint32_t scale, uint64_t m, uint
     pool[cur].ptr = nullptr;
     pool[cur].bytes = 0;
     GB_TRY(alternate.reserve(2 * have * sizeof(u64)));
-    return keys_to_csr(temp, directed.as<u64>(), alternate.as<u64>(), 2 * have, n, false, indptr, indices,
-                       capacity, nnz_out, error);
+    DeviceBuffer d_indptr, d_indices;
+    GB_TRY(keys_to_csr(temp, directed.as<u64>(), alternate.as<u64>(), 2 * have, n, false, d_indptr, d_indices,
+                       nnz_out, error));
+    directed.release();
+    alternate.release();
+    temp.release();
+    return deliver(d_indptr, d_indices, n, *nnz_out, indptr, indices, capacity, resident, error);
 }
 
 }  // namespace b2e

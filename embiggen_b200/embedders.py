@@ -161,13 +161,19 @@ class Node2VecB200(B200Embedder):
         return buffers
 
     def _fit_transform(self, graph, return_dataframe: bool = True) -> EmbeddingResult:
-        indptr, indices, weights = as_csr(graph)
+        resident = hasattr(graph, "_handle") and hasattr(graph, "to_host")  # graph_gpu.DeviceGraph
+        if resident:
+            indptr, indices, weights = None, None, None
+            n_nodes = graph.get_number_of_nodes()
+        else:
+            indptr, indices, weights = as_csr(graph)
+            n_nodes = indptr.shape[0] - 1
         # max_neighbours (approximated walks for hubs) is accepted for compatibility: the walk
         # kernel always samples the exact transition distribution.
         device = self._model_kwargs["device"]
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
-        n = indptr.shape[0] - 1
+        n = n_nodes
         world, rank = 1, 0
         try:
             import torch.distributed as dist
@@ -180,7 +186,10 @@ class Node2VecB200(B200Embedder):
         seed = int(self._random_state) & 0xFFFFFFFFFFFFFFFF
         central, contextual = self._output_buffers(n, writes_files=rank == 0)
         with Engine(**self._engine_kwargs(device)) as engine:
-            engine.load_csr(indptr, indices, weights)  # weighted graphs walk by weight
+            if resident:
+                engine.load_graph(graph)  # the CSR is in HBM already: no copy
+            else:
+                engine.load_csr(indptr, indices, weights)  # weighted graphs walk by weight
             if self.is_using_node_types() or self.is_using_edge_types():
                 node_types, edge_types = as_types(graph)  # a graph without types walks untyped
                 engine.load_types(node_types if self.is_using_node_types() else None,

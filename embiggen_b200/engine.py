@@ -145,6 +145,13 @@ class Engine:
         self.n = n
         self.nnz = nnz
 
+    def load_graph(self, graph) -> None:
+        """K1 without the copy: walk on a :class:`embiggen_b200.graph_gpu.DeviceGraph` (a CSR that
+        was built on this GPU and never left HBM)."""
+        check(self._lib.b2e_load_graph(self._handle, graph._handle))
+        self.n = graph.get_number_of_nodes()
+        self.nnz = graph.get_number_of_directed_edges()
+
     def load_types(self, node_types: Optional[np.ndarray] = None,
                    edge_types: Optional[np.ndarray] = None) -> None:
         """Type ids of typed walks (``change_node_type_weight`` / ``change_edge_type_weight``):

@@ -244,6 +244,24 @@ int b2e_synthetic_csr(int device, int kind, uint64_t n_nodes, uint32_t scale, ui
                       uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, int64_t *indptr,
                       uint32_t *indices, uint64_t indices_capacity, uint64_t *nnz);
 
+/*
+ * Resident graphs: the same builders, but the CSR stays in HBM and is handed to a handle without a
+ * copy ("zero-copy hand-off"; the accessor idiom it replaces is
+ * .../pecanpy_embedders/node2vec.py:139-163, which copies both arrays through the host).  A
+ * b2e_graph is reference counted: b2e_load_graph makes the handle walk on the graph's own device
+ * arrays, b2e_graph_destroy may be called right after it.  b2e_graph_export copies the CSR to host
+ * buffers of n + 1 and nnz entries (b2e_graph_shape).
+ */
+typedef struct b2e_graph b2e_graph;
+int b2e_graph_from_edges(int device, const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                         uint64_t n_nodes, int symmetrise, b2e_graph **graph);
+int b2e_graph_synthetic(int device, int kind, uint64_t n_nodes, uint32_t scale, uint64_t n_edges,
+                        uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, b2e_graph **graph);
+int b2e_graph_shape(const b2e_graph *graph, uint64_t *n_nodes, uint64_t *nnz);
+int b2e_graph_export(const b2e_graph *graph, int64_t *indptr, uint32_t *indices);
+void b2e_graph_destroy(b2e_graph *graph);
+int b2e_load_graph(b2e_handle *handle, b2e_graph *graph);
+
 /* ---- the step after the path: edge embeddings and a perceptron edge scorer ---- */
 
 /* EdgeTransformer.methods, .../embedding_transformers/edge_transformer.py:337-350, same order */

@@ -72,3 +72,37 @@ def test_full_size_shapes():
         upper.sort()
         lower.sort()
         assert np.array_equal(upper, lower)
+
+
+# ---- resident graphs: built on the GPU, handed to the engine without leaving HBM ----
+def test_resident_graph_equals_host_graph_and_walks_identically(small_ppi):
+    import oracle
+    from embiggen_b200.engine import Engine
+    from embiggen_b200.graph_gpu import DeviceGraph, device_graph_from_edges
+    expected = rmat(12, 30000, n=4000, seed=11)
+    resident = rmat_gpu(12, 30000, n=4000, seed=11, resident=True)
+    assert isinstance(resident, DeviceGraph)
+    assert resident.get_number_of_nodes() == 4000 and resident.get_number_of_directed_edges() == 60000
+    assert same_graph(expected, resident.to_host())
+    assert same_graph(erdos_renyi(2000, 12000, seed=7), erdos_renyi_gpu(2000, 12000, seed=7, resident=True).to_host())
+    src = np.repeat(np.arange(1064), np.diff(small_ppi.indptr))
+    assert same_graph(small_ppi, device_graph_from_edges(src, small_ppi.indices, 1064).to_host())
+    # walks on the resident CSR == walks on the uploaded CSR == the oracle's
+    want, _ = oracle.walks(expected.indptr, expected.indices, 3, 0, 3000, 40, 2.0, 0.5)
+    with Engine("SkipGram", walk_length=40, return_weight=2.0, explore_weight=0.5) as engine:
+        engine.load_graph(resident)
+        resident.close()  # reference counted: the engine keeps the arrays alive
+        assert np.array_equal(engine.walks(3, 0, 3000), want)
+        engine.load_csr(expected.indptr, expected.indices)  # and a host graph can replace it
+        assert np.array_equal(engine.walks(3, 0, 3000), want)
+
+
+def test_embedder_accepts_a_resident_graph():
+    from embiggen_b200.embedders import Node2VecSkipGramB200
+    resident = rmat_gpu(12, 30000, n=4000, seed=11, resident=True)
+    host = resident.to_host()
+    kw = dict(embedding_size=16, epochs=1, walk_length=16, iterations=1, verbose=False)
+    a = Node2VecSkipGramB200(**kw).fit_transform(resident, return_dataframe=False).get_all_node_embedding()
+    b = Node2VecSkipGramB200(**kw).fit_transform(host, return_dataframe=False).get_all_node_embedding()
+    assert a[0].shape == (4000, 16) and np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
+    assert np.abs(a[0] - b[0]).max() < 0.05  # same walks, same seed; Hogwild interleaving differs
