@@ -111,6 +111,7 @@ SIGNATURES = {
     "b2e_set_streams": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_init_tables": (ctypes.c_int, [_H, _U64]),
     "b2e_walk_chunk": (ctypes.c_int, [_H, _U64, _U64, _U64, _U64, _U32]),
+    "b2e_adopt_walks": (ctypes.c_int, [_H, _H, _U32]),
     "b2e_train_chunk": (ctypes.c_int, [_H, _U64, _U32, _F32]),
     "b2e_train_host_walks": (ctypes.c_int, [_H, _U64, ctypes.c_void_p, _U64, _U64, _U64, _F32]),
     "b2e_sync": (ctypes.c_int, [_H]),
@@ -147,6 +148,7 @@ SIGNATURES = {
                                             ctypes.c_int, _P(_H)]),
     "b2e_graph_synthetic": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _U64, _U32, _U64, _U64, _U64, _U64,
                                            _U64, _P(_H)]),
+    "b2e_graph_from_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64, _P(_H)]),
     "b2e_graph_shape": (ctypes.c_int, [_H, _P(_U64), _P(_U64)]),
     "b2e_graph_export": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "b2e_graph_destroy": (None, [_H]),

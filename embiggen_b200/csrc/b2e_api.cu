@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 
 #include "common.cuh"
@@ -371,6 +372,17 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
     if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
         return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
     const b2e_config &c = h->cfg;
+    // B2E_LOAD_TIMING=1: where the time of a load goes, on stderr
+    const bool timing = getenv("B2E_LOAD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double mark = now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        const double t = now();
+        fprintf(stderr, "[b2e load] %-28s %8.3f s\n", what, t - mark);
+        mark = t;
+    };
 
     // host-side validation and derivations that need only indptr come first: nothing of the
     // previous graph is touched until the offsets are known to be sane
@@ -386,6 +398,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         for (uint64_t e = 0; e < nnz; ++e)
             if (!(weights[e] >= 0.0f)) return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
 
+    lap("sources, max degree (host)");
     CUDA_TRY(cudaDeviceSynchronize());
     free_graph(h);
     h->n = n;
@@ -414,6 +427,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
     LOAD_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->walk_stream));
     LOAD_TRY(launch_csr_check(h->d_indptr, h->d_indices, n, d_flags, h->sm_count, h->walk_stream));
     ++h->launches;
+    lap("CSR upload + content check");
 
     // K3 on the host while the copies are in flight
     h->h_alias_thr.clear();
@@ -428,6 +442,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         for (uint64_t i = 0; i < n; ++i) packed[i] = make_uint2(h->h_alias_thr[i], h->h_alias_idx[i]);
     }
 
+    lap("alias table (host Vose)");
     int flags[2] = {0, 1};
     LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
     LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
@@ -477,6 +492,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
                                  h->walk_stream));
     }
 
+    lap("edge alias / sources / alias upload");
     // Second-order walks: is the graph undirected (every edge mirrored)?  Verified here, never
     // assumed: it allows the adjacency check in the shorter of the two rows and the folded return
     // edge.  The row filters answer most adjacency checks with one gather (walk_kernels.cu).
@@ -490,6 +506,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
             LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
             h->undirected = flags[1] != 0;
             ++h->launches;
+            lap("symmetry check");
         }
         uint64_t excess = 0;
         fold_thresholds(c.return_weight, c.explore_weight, h->thr_fold, &excess);
@@ -504,6 +521,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         }
     }
     cudaFree(d_flags);
+    lap("row filters");
 
     LOAD_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
     LOAD_TRY(cudaMalloc(&h->d_t1, n * (uint64_t)h->row_stride * sizeof(float)));
@@ -519,6 +537,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         LOAD_TRY(cudaMalloc(&h->d_walks[s], cap * slot_tokens * sizeof(uint32_t)));
     if (walklet(c)) LOAD_TRY(cudaMalloc(&h->d_walk_raw, cap * c.walk_length * sizeof(uint32_t)));
     LOAD_TRY(cudaStreamSynchronize(h->walk_stream));  // `sources`, `packed` die here
+    lap("tables + walk ring allocation");
     return B2E_OK;
 }
 
@@ -617,6 +636,37 @@ extern "C" int b2e_walk_chunk(b2e_handle *h, uint64_t seed, uint64_t first_walk,
     h->slot_first[slot] = first_walk;
     h->slot_count[slot] = n_walks;
     h->slot_stride[slot] = walk_id_stride;
+    return B2E_OK;
+}
+
+// Walklets in one pass: every scale has its own handle (its own tables), but the walks of a chunk
+// are the same for all of them -- `dst` takes the chunk `src` has just walked into `slot` instead
+// of walking it again (split by its own scale, or copied), ordered after src's walk on the device.
+extern "C" int b2e_adopt_walks(b2e_handle *dst, b2e_handle *src, uint32_t slot) {
+    REQUIRE_HANDLE(dst);
+    if (!src) return fail(B2E_ERR_INVALID, "null source handle");
+    if (int rc = require_graph(dst)) return rc;
+    if (int rc = require_graph(src)) return rc;
+    if (slot > 1) return fail(B2E_ERR_INVALID, "slot must be 0 or 1");
+    if (src->cfg.device != dst->cfg.device || src->cfg.walk_length != dst->cfg.walk_length)
+        return fail(B2E_ERR_INVALID, "both handles must sit on one device and use one walk_length");
+    const uint64_t n_walks = src->slot_count[slot];
+    if (n_walks > dst->chunk_cap) return fail(B2E_ERR_INVALID, "the chunk exceeds the capacity of the adopting handle");
+    const uint32_t L = dst->cfg.walk_length;
+    const uint32_t *raw = walklet(src->cfg) ? src->d_walk_raw : src->d_walks[slot];
+    CUDA_TRY(cudaStreamWaitEvent(dst->walk_stream, src->walk_done[slot], 0));
+    CUDA_TRY(cudaStreamWaitEvent(dst->walk_stream, dst->train_done[slot], 0));
+    if (walklet(dst->cfg)) {
+        CUDA_TRY(launch_walklet_split(raw, n_walks, L, dst->cfg.walklet_scale, dst->d_walks[slot], dst->walk_stream));
+        if (n_walks) ++dst->launches;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(dst->d_walks[slot], raw, n_walks * L * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                 dst->walk_stream));
+    }
+    CUDA_TRY(cudaEventRecord(dst->walk_done[slot], dst->walk_stream));
+    dst->slot_first[slot] = src->slot_first[slot];
+    dst->slot_count[slot] = n_walks;
+    dst->slot_stride[slot] = src->slot_stride[slot];
     return B2E_OK;
 }
 
@@ -1074,6 +1124,33 @@ extern "C" int b2e_fit(b2e_handle *h, uint64_t seed, float *table0, float *table
 static int select_device(int device);
 
 // ---- resident graphs: built on the GPU, handed to a handle without leaving HBM ----
+// a host CSR uploaded once, to be shared by several handles (b2e_load_graph checks its contents)
+extern "C" int b2e_graph_from_csr(int device, const int64_t *indptr, const uint32_t *indices, uint64_t n,
+                                  uint64_t nnz, b2e_graph **out) {
+    if (!out || !indptr || (!indices && nnz)) return fail(B2E_ERR_INVALID, "null argument");
+    if (n == 0 || n >= 0xFFFFFF00ull) return fail(B2E_ERR_INVALID, "the number of nodes must be in [1, 0xFFFFFF00)");
+    if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
+        return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
+    for (uint64_t v = 0; v < n; ++v)
+        if (indptr[v + 1] < indptr[v]) return fail(B2E_ERR_INVALID, "indptr must be non-decreasing");
+    if (int rc = select_device(device)) return rc;
+    b2e_graph *g = new (std::nothrow) b2e_graph();
+    if (!g) return fail(B2E_ERR_INVALID, "out of host memory");
+    g->device = device;
+    g->csr.n = n;
+    g->csr.nnz = nnz;
+    cudaError_t e = cudaMalloc(&g->csr.indptr, (n + 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&g->csr.indices, std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(g->csr.indptr, indptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(g->csr.indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        release_graph(g);
+        return fail(B2E_ERR_CUDA, std::string("b2e_graph_from_csr: ") + cudaGetErrorString(e));
+    }
+    *out = g;
+    return B2E_OK;
+}
+
 extern "C" int b2e_graph_shape(const b2e_graph *g, uint64_t *n, uint64_t *nnz) {
     if (!g || !n || !nnz) return fail(B2E_ERR_INVALID, "null argument");
     *n = g->csr.n;

@@ -501,16 +501,59 @@ class WalkletsB200(Node2VecB200):
         return parameters
 
     def _fit_transform(self, graph, return_dataframe: bool = True) -> EmbeddingResult:
+        """All scales in ONE pass over the walks: the graph is uploaded once and shared, every
+        chunk is walked once (by the engine of scale 1) and adopted by the engines of the other
+        scales, each of which owns its pair of tables (engine.fit_scales).  Weighted and typed
+        graphs, other dtypes than f32 and torch.distributed runs take the scale-by-scale path."""
+        from .engine import fit_scales
+        from .graph_gpu import device_graph_from_csr
         window_size = self._model_kwargs["window_size"]
-        node_embeddings, losses = [], []
+        distributed = False
         try:
-            for scale in range(1, window_size + 1):
-                self._walklet_scale = scale
-                result = super()._fit_transform(graph, return_dataframe=return_dataframe)
-                node_embeddings.extend(result.get_all_node_embedding())
-                losses.append(self._last_losses)
-        finally:
-            self._walklet_scale = 0
+            import torch.distributed as dist
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except ImportError:
+            pass
+        resident = hasattr(graph, "_handle") and hasattr(graph, "to_host")
+        weights = None if resident else as_csr(graph)[2]
+        one_pass = (weights is None and not distributed and self._model_kwargs["dtype"] == "f32"
+                    and not self.is_using_node_types() and not self.is_using_edge_types())
+        node_embeddings, losses = [], []
+        if one_pass:
+            device = self._model_kwargs["device"]
+            device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+            shared = graph if resident else device_graph_from_csr(*as_csr(graph)[:2], device=device)
+            n = shared.get_number_of_nodes()
+            seed = int(self._random_state) & 0xFFFFFFFFFFFFFFFF
+            engines = []
+            try:
+                for scale in range(1, window_size + 1):
+                    self._walklet_scale = scale
+                    engines.append(Engine(**self._engine_kwargs(device)))
+                    engines[-1].load_graph(shared)
+                losses = fit_scales(engines, seed)
+                for engine in engines:
+                    t0, t1 = engine.export_tables()
+                    node_embeddings.extend([t1, t0] if engine.model == "cbow" else [t0, t1])
+            finally:
+                self._walklet_scale = 0
+                for engine in engines:
+                    engine.close()
+                if not resident:
+                    shared.close()
+            assert all(e.shape == (n, self._embedding_size) for e in node_embeddings)
+            if return_dataframe:
+                names = graph.get_node_names() if hasattr(graph, "get_node_names") else None
+                node_embeddings = [pd.DataFrame(e, index=names) for e in node_embeddings]
+        else:
+            try:
+                for scale in range(1, window_size + 1):
+                    self._walklet_scale = scale
+                    result = super()._fit_transform(graph, return_dataframe=return_dataframe)
+                    node_embeddings.extend(result.get_all_node_embedding())
+                    losses.append(self._last_losses)
+            finally:
+                self._walklet_scale = 0
         self._last_losses = [float(np.mean(epoch)) for epoch in zip(*losses)]
         return EmbeddingResult(embedding_method_name=self.model_name(), node_embeddings=node_embeddings)
 

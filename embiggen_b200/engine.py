@@ -48,6 +48,41 @@ def shard_chunks(walks_per_epoch: int, chunk_capacity: int, world: int, rank: in
         done += count
 
 
+def fit_scales(engines: List["Engine"], seed: int) -> List[List[float]]:
+    """Walklets in one pass: ``engines[k]`` holds the tables of scale k + 1 (all on one device,
+    one graph, one walk_length); every chunk of every epoch is walked ONCE, by ``engines[0]``, and
+    adopted by the others.  The schedule is b2e_fit's; returns the per-epoch losses per scale."""
+    lead, cfg = engines[0], engines[0].config
+    for engine in engines:
+        engine.init_tables(seed)
+    per_epoch, capacity = lead.walks_per_epoch, min(e.chunk_capacity for e in engines)
+    lr = np.float32(cfg.learning_rate)
+    losses: List[List[float]] = [[] for _ in engines]
+    index = 0
+    for epoch in range(cfg.epochs):
+        for engine in engines:
+            engine.reset_counters()
+        done = 0
+        while done < per_epoch:
+            count = min(capacity, per_epoch - done)
+            slot = index & 1
+            # the adopters of two chunks ago have trained on this slot before it is walked over
+            for engine in engines[1:]:
+                engine.sync()
+            lead.walk_chunk(seed, epoch * per_epoch + done, count, 1, slot)
+            for engine in engines[1:]:
+                engine.adopt_walks(lead, slot)
+            for engine in engines:
+                engine.train_chunk(seed, slot, float(lr))
+            done += count
+            index += 1
+        for k, engine in enumerate(engines):
+            c = engine.counters()
+            losses[k].append(c["loss_sum"] / max(c["pairs"], 1))
+        lr = np.float32(lr * np.float32(cfg.learning_rate_decay))
+    return losses
+
+
 def average_replicas(tables, process_group=None) -> None:
     """In-place average of every rank's replica of the tables (the one exchange step of the
     path).  NCCL reduces with AVG (no extra pass over HBM); gloo (CPU tests) sums then scales."""
@@ -245,6 +280,10 @@ class Engine:
     def walk_chunk(self, seed: int, first_walk: int, n_walks: int, walk_id_stride: int = 1,
                    slot: int = 0) -> None:
         check(self._lib.b2e_walk_chunk(self._handle, seed, first_walk, n_walks, walk_id_stride, slot))
+
+    def adopt_walks(self, source: "Engine", slot: int) -> None:
+        """Take the chunk ``source`` has just walked into ``slot`` instead of walking it again."""
+        check(self._lib.b2e_adopt_walks(self._handle, source._handle, slot))
 
     def train_chunk(self, seed: int, slot: int, learning_rate: float) -> None:
         check(self._lib.b2e_train_chunk(self._handle, seed, slot, learning_rate))

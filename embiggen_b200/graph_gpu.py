@@ -118,6 +118,16 @@ class DeviceGraph:
         return self.get_number_of_disconnected_nodes() > 0
 
 
+def device_graph_from_csr(indptr, indices, name: str = "graph", device: int = 0) -> DeviceGraph:
+    """Upload a host CSR once (to share it between several engines)."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    handle = ctypes.c_void_p()
+    check(_lib.load().b2e_graph_from_csr(device, indptr.ctypes.data, indices.ctypes.data, indptr.shape[0] - 1,
+                                         indices.shape[0], ctypes.byref(handle)))
+    return DeviceGraph(handle, device, name=name)
+
+
 def device_graph_from_edges(src, dst, n: int, symmetrise: bool = True, name: str = "graph",
                             device: int = 0) -> DeviceGraph:
     """:func:`csr_from_edges_gpu`, but the CSR stays in HBM."""

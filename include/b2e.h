@@ -171,6 +171,10 @@ int b2e_init_tables(b2e_handle *handle, uint64_t seed);
 /* walks for one chunk into device buffer `slot` (0 or 1), asynchronous on the walk stream */
 int b2e_walk_chunk(b2e_handle *handle, uint64_t seed, uint64_t first_walk, uint64_t n_walks,
                    uint64_t walk_id_stride, uint32_t slot);
+/* Walklets in one pass (.../walklets.py:7-149: one embedding per scale): `handle` takes the chunk
+ * `source` has just walked into `slot` (split by handle's own walklet_scale) instead of walking it
+ * again; the source must not walk into that slot again before its adopters have trained on it */
+int b2e_adopt_walks(b2e_handle *handle, b2e_handle *source, uint32_t slot);
 /* K4/K5 over the walks in `slot`, asynchronous on the train stream, ordered after the walk */
 int b2e_train_chunk(b2e_handle *handle, uint64_t seed, uint32_t slot, float learning_rate);
 /* train on caller-provided host walks (parity tests feed the oracle's walks) */
@@ -257,6 +261,9 @@ int b2e_graph_from_edges(int device, const uint32_t *src, const uint32_t *dst, u
                          uint64_t n_nodes, int symmetrise, b2e_graph **graph);
 int b2e_graph_synthetic(int device, int kind, uint64_t n_nodes, uint32_t scale, uint64_t n_edges,
                         uint64_t seed, uint64_t t_a, uint64_t t_ab, uint64_t t_abc, b2e_graph **graph);
+/* a host CSR uploaded once, e.g. to be shared by the handles of the Walklets scales */
+int b2e_graph_from_csr(int device, const int64_t *indptr, const uint32_t *indices, uint64_t n_nodes,
+                       uint64_t nnz, b2e_graph **graph);
 int b2e_graph_shape(const b2e_graph *graph, uint64_t *n_nodes, uint64_t *nnz);
 int b2e_graph_export(const b2e_graph *graph, int64_t *indptr, uint32_t *indices);
 void b2e_graph_destroy(b2e_graph *graph);

@@ -239,3 +239,26 @@ def test_walklets_embedder(small_ppi):
         assert len(losses) == 2 and losses[1] < losses[0]
         frames = model.fit_transform(small_ppi).get_all_node_embedding()
         assert list(frames[0].index) == small_ppi.get_node_names()
+
+
+def test_walklets_one_pass_equals_scale_by_scale(small_ppi_weighted, small_ppi):
+    """The one-pass schedule (walk a chunk once, every scale adopts it: engine.fit_scales) trains
+    exactly what the scale-by-scale path trains: in the single-warp launch the tables are equal
+    bit for bit.  A weighted graph takes the scale-by-scale path (same walks by weight)."""
+    from embiggen_b200.embedders import WalkletsCBOWB200, WalkletsSkipGramB200
+    for cls in (WalkletsSkipGramB200, WalkletsCBOWB200):
+        kw = dict(embedding_size=12, window_size=3, epochs=2, walk_length=20, iterations=1, verbose=False,
+                  deterministic=True, chunk_walks=300, return_weight=2.0, explore_weight=0.5)
+        one_pass = cls(**kw).fit_transform(small_ppi, return_dataframe=False).get_all_node_embedding()
+        reference = []
+        model = cls(**kw)
+        for scale in (1, 2, 3):  # the old path, spelled out
+            model._walklet_scale = scale
+            reference.extend(super(type(model).__mro__[1], model)._fit_transform(
+                small_ppi, return_dataframe=False).get_all_node_embedding())
+        model._walklet_scale = 0
+        assert len(one_pass) == len(reference) == 6
+        for a, b in zip(one_pass, reference):
+            assert np.array_equal(a, b)
+        weighted = cls(**kw).fit_transform(small_ppi_weighted, return_dataframe=False).get_all_node_embedding()
+        assert len(weighted) == 6 and all(np.isfinite(t).all() for t in weighted)
