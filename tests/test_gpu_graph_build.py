@@ -101,8 +101,8 @@ def test_embedder_accepts_a_resident_graph():
     from embiggen_b200.embedders import Node2VecSkipGramB200
     resident = rmat_gpu(12, 30000, n=4000, seed=11, resident=True)
     host = resident.to_host()
-    kw = dict(embedding_size=16, epochs=1, walk_length=16, iterations=1, verbose=False)
+    kw = dict(embedding_size=16, epochs=1, walk_length=16, iterations=1, verbose=False, deterministic=True)
     a = Node2VecSkipGramB200(**kw).fit_transform(resident, return_dataframe=False).get_all_node_embedding()
     b = Node2VecSkipGramB200(**kw).fit_transform(host, return_dataframe=False).get_all_node_embedding()
     assert a[0].shape == (4000, 16) and np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
-    assert np.abs(a[0] - b[0]).max() < 0.05  # same walks, same seed; Hogwild interleaving differs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])  # single-warp launch: same bits
