@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(_HERE, "libb2e.so")
 SOURCES = ["b2e_api.cu", "walk_kernels.cu", "sgns_kernels.cu", "sgns_pipe.cu", "graph_build.cu", "glove.cu",
-           "edge_pred.cu", "exchange.cu", "graph_device.cu"]
+           "edge_pred.cu", "exchange.cu", "alias_build.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",

@@ -231,48 +231,6 @@ extern "C" void b2e_destroy(b2e_handle *h) {
     delete h;
 }
 
-// K3: Vose alias table over deg^alpha, built on the host while the CSR copy is in flight.
-static double degree_weight(uint64_t deg, double alpha) {
-    if (deg == 0) return 0.0;
-    const double d = (double)deg;
-    if (alpha == 0.0) return 1.0;
-    if (alpha == 1.0) return d;
-    if (alpha == 0.5) return sqrt(d);
-    if (alpha == 0.75) return sqrt(sqrt(d * d * d));
-    return pow(d, alpha);
-}
-
-static bool build_alias(const int64_t *indptr, uint64_t n, double alpha, std::vector<uint32_t> &thr,
-                        std::vector<uint32_t> &alias) {
-    std::vector<double> scaled(n);
-    std::vector<uint32_t> small, large;
-    small.reserve(n);
-    large.reserve(n);
-    double total = 0.0;
-    for (uint64_t i = 0; i < n; ++i) {
-        scaled[i] = degree_weight((uint64_t)(indptr[i + 1] - indptr[i]), alpha);
-        total += scaled[i];
-    }
-    if (!(total > 0.0)) return false;
-    thr.assign(n, 0xFFFFFFFFu);
-    alias.resize(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        scaled[i] = scaled[i] * (double)n / total;
-        alias[i] = (uint32_t)i;
-        if (scaled[i] < 1.0) small.push_back((uint32_t)i); else large.push_back((uint32_t)i);
-    }
-    while (!small.empty() && !large.empty()) {
-        const uint32_t s = small.back(); small.pop_back();
-        const uint32_t l = large.back(); large.pop_back();
-        const double t = floor(scaled[s] * 4294967296.0);
-        thr[s] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-        alias[s] = l;
-        scaled[l] = (scaled[l] + scaled[s]) - 1.0;
-        if (scaled[l] < 1.0) small.push_back(l); else large.push_back(l);
-    }
-    return true;
-}
-
 // per-row Vose alias tables of a weighted graph, {thr, alias index inside the row} per edge;
 // normative construction: oracle/walks.c (orc_edge_alias), reproduced bit for bit
 static bool build_edge_alias(const int64_t *indptr, const float *weights, uint64_t n, std::vector<uint2> &table) {
@@ -369,7 +327,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
     if (n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
     if (n >= 0xFFFFFF00ull) return fail(B2E_ERR_INVALID, "node ids must be below 0xFFFFFF00");
     if (nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
-    if (indptr[0] != 0 || (uint64_t)indptr[n] != nnz)
+    if (indptr && (indptr[0] != 0 || (uint64_t)indptr[n] != nnz))
         return fail(B2E_ERR_INVALID, "indptr must start at 0 and end at nnz");
     const b2e_config &c = h->cfg;
     // B2E_LOAD_TIMING=1: where the time of a load goes, on stderr
@@ -383,32 +341,18 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         fprintf(stderr, "[b2e load] %-28s %8.3f s\n", what, t - mark);
         mark = t;
     };
-
-    // host-side validation and derivations that need only indptr come first: nothing of the
-    // previous graph is touched until the offsets are known to be sane
-    std::vector<uint32_t> sources;
-    sources.reserve(n);
-    uint64_t max_degree = 0;
-    for (uint64_t v = 0; v < n; ++v) {
-        if (indptr[v + 1] < indptr[v]) return fail(B2E_ERR_INVALID, "indptr must be non-decreasing");
-        if (indptr[v + 1] > indptr[v]) sources.push_back((uint32_t)v);
-        max_degree = std::max<uint64_t>(max_degree, (uint64_t)(indptr[v + 1] - indptr[v]));
-    }
     if (weights)
         for (uint64_t e = 0; e < nnz; ++e)
             if (!(weights[e] >= 0.0f)) return fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers");
 
-    lap("sources, max degree (host)");
     CUDA_TRY(cudaDeviceSynchronize());
     free_graph(h);
     h->n = n;
     h->nnz = nnz;
-    h->n_src = sources.size();
-    h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
 
-    // K1: the two big copies (none when the CSR is resident already), then the content check on
-    // the device (ids in range, rows strictly ascending: the kernels index with these ids and
-    // bisect these rows without looking again)
+    // K1: the two big copies (none when the CSR is resident already), then the checks on the
+    // device: offsets non-decreasing and within nnz; ids in range, rows strictly ascending (the
+    // kernels index with these ids and bisect these rows without looking again)
     if (resident) {
         h->shared_graph = resident;
         ++resident->references;
@@ -423,29 +367,21 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
                                  h->walk_stream));
     }
     int *d_flags = nullptr;
+    int flags[2] = {0, 1};
     LOAD_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
     LOAD_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->walk_stream));
-    LOAD_TRY(launch_csr_check(h->d_indptr, h->d_indices, n, d_flags, h->sm_count, h->walk_stream));
-    ++h->launches;
-    lap("CSR upload + content check");
-
-    // K3 on the host while the copies are in flight
-    h->h_alias_thr.clear();
-    h->h_alias_idx.clear();
-    std::vector<uint2> packed;
-    if (c.use_scale_free_distribution) {
-        if (!build_alias(indptr, n, (double)c.negative_sampling_exponent, h->h_alias_thr, h->h_alias_idx)) {
-            cudaFree(d_flags);
-            return load_failed(h, fail(B2E_ERR_INVALID, "alias table: total weight is zero"));
-        }
-        packed.resize(n);
-        for (uint64_t i = 0; i < n; ++i) packed[i] = make_uint2(h->h_alias_thr[i], h->h_alias_idx[i]);
-    }
-
-    lap("alias table (host Vose)");
-    int flags[2] = {0, 1};
+    LOAD_TRY(check_indptr_device(h->d_indptr, n, nnz, d_flags, h->walk_stream));
     LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
     LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
+    if (flags[0]) {
+        cudaFree(d_flags);
+        return load_failed(h, fail(B2E_ERR_INVALID, "indptr must be non-decreasing"));
+    }
+    LOAD_TRY(launch_csr_check(h->d_indptr, h->d_indices, n, d_flags, h->sm_count, h->walk_stream));
+    h->launches += 2;
+    LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
+    LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
+    lap("CSR upload + content checks");
     if (flags[0]) {
         cudaFree(d_flags);
         return load_failed(h, fail(B2E_ERR_INVALID, flags[0] & 1
@@ -453,11 +389,47 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
                                         : "neighbour lists must be sorted strictly ascending within each row"));
     }
 
+    // K3 on the device: start nodes, maximum degree, alias table over deg^alpha (alias_build.cu)
+    h->h_alias_thr.clear();
+    h->h_alias_idx.clear();
+    {
+        uint32_t *d_sources_all = nullptr;
+        LOAD_TRY(cudaMalloc(&d_sources_all, n * sizeof(uint32_t)));
+        if (c.use_scale_free_distribution && cudaMalloc(&h->d_alias, n * sizeof(uint2)) != cudaSuccess) {
+            cudaFree(d_sources_all);
+            cudaFree(d_flags);
+            return load_failed(h, fail(B2E_ERR_CUDA, "out of device memory (alias table)"));
+        }
+        std::string error;
+        uint64_t n_src = 0, max_degree = 0;
+        cudaError_t e = build_node_tables(h->d_indptr, indptr, n, (double)c.negative_sampling_exponent, d_sources_all,
+                                          &n_src, &max_degree, h->d_alias, h->walk_stream, error);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_sources, std::max<uint64_t>(1, n_src) * sizeof(uint32_t));
+        if (e == cudaSuccess && n_src)
+            e = cudaMemcpy(h->d_sources, d_sources_all, n_src * sizeof(uint32_t), cudaMemcpyDeviceToDevice);
+        cudaFree(d_sources_all);
+        if (e != cudaSuccess) {
+            cudaFree(d_flags);
+            if (error.empty()) error = std::string("start-node list: ") + cudaGetErrorString(e);
+            return load_failed(h, fail(e == cudaErrorInvalidValue ? B2E_ERR_INVALID : B2E_ERR_CUDA, error));
+        }
+        h->n_src = n_src;
+        h->max_degree = (uint32_t)std::min<uint64_t>(max_degree, 0xFFFFFFFEull);
+        h->launches += 8;
+    }
+    lap("start nodes + alias table (GPU)");
+
     // normalize_by_degree (.../node2vec_skipgram.py:94-96): the weight of v -> x divided by
     // max(deg(x), 1), one float32 division per edge, folded into the proposal table -- no extra
     // rejection however skewed the degrees (oracle: degree_normalised_weights)
     std::vector<float> normalised;
     std::vector<uint32_t> fetched_indices;
+    std::vector<int64_t> fetched_indptr;
+    if ((c.normalize_by_degree || weights) && !indptr) {  // resident graph: these options work on the host
+        fetched_indptr.resize(n + 1);
+        LOAD_TRY(cudaMemcpy(fetched_indptr.data(), h->d_indptr, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        indptr = fetched_indptr.data();
+    }
     if (c.normalize_by_degree) {
         if (!indices) {  // resident graph: this rarely used option needs the ids on the host
             fetched_indices.resize(nnz);
@@ -483,16 +455,8 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
                                  h->walk_stream));
         LOAD_TRY(cudaStreamSynchronize(h->walk_stream));  // `edge_alias` dies here
     }
-    LOAD_TRY(cudaMalloc(&h->d_sources, std::max<size_t>(1, sources.size()) * sizeof(uint32_t)));
-    LOAD_TRY(cudaMemcpyAsync(h->d_sources, sources.data(), sources.size() * sizeof(uint32_t),
-                             cudaMemcpyHostToDevice, h->walk_stream));
-    if (!packed.empty()) {
-        LOAD_TRY(cudaMalloc(&h->d_alias, n * sizeof(uint2)));
-        LOAD_TRY(cudaMemcpyAsync(h->d_alias, packed.data(), n * sizeof(uint2), cudaMemcpyHostToDevice,
-                                 h->walk_stream));
-    }
 
-    lap("edge alias / sources / alias upload");
+    lap("edge alias tables (weighted graphs)");
     // Second-order walks: is the graph undirected (every edge mirrored)?  Verified here, never
     // assumed: it allows the adjacency check in the shorter of the two rows and the folded return
     // edge.  The row filters answer most adjacency checks with one gather (walk_kernels.cu).
@@ -536,7 +500,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
     for (int s = 0; s < 2; ++s)
         LOAD_TRY(cudaMalloc(&h->d_walks[s], cap * slot_tokens * sizeof(uint32_t)));
     if (walklet(c)) LOAD_TRY(cudaMalloc(&h->d_walk_raw, cap * c.walk_length * sizeof(uint32_t)));
-    LOAD_TRY(cudaStreamSynchronize(h->walk_stream));  // `sources`, `packed` die here
+    LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
     lap("tables + walk ring allocation");
     return B2E_OK;
 }
@@ -923,19 +887,59 @@ extern "C" int b2e_tables_digest(b2e_handle *h, double *sums, uint64_t *words) {
     return B2E_OK;
 }
 
+// One table to the host without its row padding: packed on the device in slabs (train stream),
+// each slab copied with one contiguous DMA (walk stream, idle here) while the next one is packed.
+static int export_table(b2e_handle *h, const float *d_table, float *host) {
+    const uint32_t dim = h->cfg.embedding_size;
+    if (dim == h->row_stride) {
+        CUDA_TRY(cudaMemcpyAsync(host, d_table, h->n * (uint64_t)dim * sizeof(float), cudaMemcpyDeviceToHost,
+                                 h->train_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->train_stream));
+        return B2E_OK;
+    }
+    const uint64_t slab_rows = std::max<uint64_t>(1, (256ull << 20) / (dim * sizeof(float)));
+    float *stage[2] = {nullptr, nullptr};
+    cudaEvent_t packed[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaMalloc(&stage[b], std::min<uint64_t>(slab_rows, h->n) * dim * sizeof(float));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&packed[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+    }
+    uint64_t slab = 0;
+    for (uint64_t row = 0; row < h->n && e == cudaSuccess; row += slab_rows, ++slab) {
+        const int b = (int)(slab & 1);
+        const uint64_t rows = std::min(slab_rows, h->n - row);
+        if (slab >= 2) e = cudaStreamWaitEvent(h->train_stream, copied[b], 0);  // the slab buffer is free again
+        if (e == cudaSuccess)
+            e = launch_pack_rows(d_table + row * h->row_stride, rows, h->row_stride, dim, stage[b], h->sm_count,
+                                 h->train_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(packed[b], h->train_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->walk_stream, packed[b], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(host + row * dim, stage[b], rows * dim * sizeof(float), cudaMemcpyDeviceToHost,
+                                h->walk_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(copied[b], h->walk_stream);
+        ++h->launches;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->walk_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->train_stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(stage[b]);
+        if (packed[b]) cudaEventDestroy(packed[b]);
+        if (copied[b]) cudaEventDestroy(copied[b]);
+    }
+    if (e != cudaSuccess) return fail(B2E_ERR_CUDA, std::string("b2e_export_tables: ") + cudaGetErrorString(e));
+    return B2E_OK;
+}
+
 extern "C" int b2e_export_tables(b2e_handle *h, float *table0, float *table1) {
     REQUIRE_HANDLE(h);
     if (int rc = require_graph(h)) return rc;
     if (!table0 || !table1) return fail(B2E_ERR_INVALID, "null output buffer");
     if (int rc = b2e_sync(h)) return rc;
-    const size_t width = h->cfg.embedding_size * sizeof(float);
-    const size_t pitch = h->row_stride * sizeof(float);
-    CUDA_TRY(cudaMemcpy2DAsync(table0, width, h->d_t0, pitch, width, h->n, cudaMemcpyDeviceToHost,
-                               h->train_stream));
-    CUDA_TRY(cudaMemcpy2DAsync(table1, width, h->d_t1, pitch, width, h->n, cudaMemcpyDeviceToHost,
-                               h->train_stream));
-    CUDA_TRY(cudaStreamSynchronize(h->train_stream));
-    return B2E_OK;
+    if (int rc = export_table(h, h->d_t0, table0)) return rc;
+    return export_table(h, h->d_t1, table1);
 }
 
 extern "C" int b2e_import_tables(b2e_handle *h, const float *table0, const float *table1) {
@@ -960,7 +964,18 @@ extern "C" int b2e_import_tables(b2e_handle *h, const float *table0, const float
 
 extern "C" int b2e_export_alias(b2e_handle *h, uint32_t *threshold, uint32_t *alias) {
     if (!h || !threshold || !alias) return fail(B2E_ERR_INVALID, "null argument");
-    if (h->h_alias_thr.empty()) return fail(B2E_ERR_STATE, "no alias table (uniform negatives or no graph)");
+    if (!h->d_alias) return fail(B2E_ERR_STATE, "no alias table (uniform negatives or no graph)");
+    if (h->h_alias_thr.empty()) {  // built on the device: fetched on demand (parity tests)
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        std::vector<uint2> packed(h->n);
+        CUDA_TRY(cudaMemcpy(packed.data(), h->d_alias, h->n * sizeof(uint2), cudaMemcpyDeviceToHost));
+        h->h_alias_thr.resize(h->n);
+        h->h_alias_idx.resize(h->n);
+        for (uint64_t i = 0; i < h->n; ++i) {
+            h->h_alias_thr[i] = packed[i].x;
+            h->h_alias_idx[i] = packed[i].y;
+        }
+    }
     memcpy(threshold, h->h_alias_thr.data(), h->n * sizeof(uint32_t));
     memcpy(alias, h->h_alias_idx.data(), h->n * sizeof(uint32_t));
     return B2E_OK;
@@ -1179,11 +1194,17 @@ extern "C" int b2e_load_graph(b2e_handle *h, b2e_graph *g) {
     if (g->device != h->cfg.device) return fail(B2E_ERR_INVALID, "the graph lives on another device than the handle");
     if (g->csr.n == 0) return fail(B2E_ERR_INVALID, "The provided graph is empty.");
     if (g->csr.nnz == 0) return fail(B2E_ERR_INVALID, "The provided graph does not have edges.");
-    // the offsets (8 bytes per node) come back for the host-side derivations; the ids stay put
-    std::vector<int64_t> indptr(g->csr.n + 1);
-    CUDA_TRY(cudaMemcpy(indptr.data(), g->csr.indptr, indptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    // nothing comes back to the host: start nodes, alias table, filters are all built from the
+    // resident arrays (an exponent without an exact form fetches the offsets, see alias_build.cu)
+    std::vector<int64_t> indptr;
+    const double alpha = (double)h->cfg.negative_sampling_exponent;
+    if (h->cfg.use_scale_free_distribution && alpha != 0.0 && alpha != 0.5 && alpha != 0.75 && alpha != 1.0) {
+        indptr.resize(g->csr.n + 1);
+        CUDA_TRY(cudaMemcpy(indptr.data(), g->csr.indptr, indptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
     ++g->references;  // keep it alive across free_graph() of a handle that already walks on it
-    const int rc = load_graph_common(h, indptr.data(), nullptr, nullptr, g->csr.n, g->csr.nnz, g);
+    const int rc = load_graph_common(h, indptr.empty() ? nullptr : indptr.data(), nullptr, nullptr, g->csr.n,
+                                     g->csr.nnz, g);
     release_graph(g);
     return rc;
 }

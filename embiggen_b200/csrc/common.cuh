@@ -122,12 +122,19 @@ cudaError_t launch_symmetry_check(const int64_t *indptr, const uint32_t *indices
 // *d_flags |= 1: a destination id >= n; |= 2: a row that is not strictly ascending
 cudaError_t launch_csr_check(const int64_t *indptr, const uint32_t *indices, uint64_t n, int *d_flags,
                              int sm_count, cudaStream_t stream);
+// alias_build.cu: offsets check (*d_flags |= 4), start nodes + maximum degree + alias table on the device
+cudaError_t check_indptr_device(const int64_t *d_indptr, uint64_t n, uint64_t nnz, int *d_flags, cudaStream_t stream);
+cudaError_t build_node_tables(const int64_t *d_indptr, const int64_t *host_indptr, uint64_t n, double alpha,
+                              uint32_t *d_sources, uint64_t *n_src_out, uint64_t *max_degree_out, uint2 *d_table,
+                              cudaStream_t stream, std::string &error);
 uint64_t row_filter_words(uint64_t nnz);
 cudaError_t launch_row_filter_build(const int64_t *indptr, const uint32_t *indices, uint64_t n,
                                     unsigned long long *filter, int sm_count, cudaStream_t stream);
 cudaError_t launch_exchange_average(float *const t0[], float *const t1[], uint32_t world, uint32_t rank,
                                     uint64_t n, uint32_t row_stride, uint32_t chunks, int sm_count,
                                     cudaStream_t stream);
+cudaError_t launch_pack_rows(const float *table, uint64_t rows, uint32_t row_stride, uint32_t dim, float *dense,
+                             int sm_count, cudaStream_t stream);
 cudaError_t launch_tables_digest(const float *t0, const float *t1, uint64_t n, uint32_t row_stride,
                                  uint32_t dim, void *d_out, int sm_count, cudaStream_t stream);
 cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedding_size,

@@ -105,6 +105,26 @@ cudaError_t launch_exchange_average(float *const t0[], float *const t1[], uint32
     return cudaGetLastError();
 }
 
+// Strip the row padding on the device: `rows` rows of `chunks` float4 each leave their 128 B-aligned
+// pitch for a dense buffer that one contiguous DMA then carries to the host (a pitched 2-D copy of
+// 400-byte rows moved 80 GB in 12 s; packed and double-buffered it is bound by PCIe).
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ table, uint64_t rows,
+                                                        uint32_t row_stride, uint32_t dim, float *__restrict__ dense) {
+    const uint64_t total = rows * dim;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = k / dim;
+        dense[k] = __ldg(table + row * row_stride + (k - row * dim));
+    }
+}
+
+cudaError_t launch_pack_rows(const float *table, uint64_t rows, uint32_t row_stride, uint32_t dim, float *dense,
+                             int sm_count, cudaStream_t stream) {
+    if (rows == 0) return cudaSuccess;
+    pack_rows_kernel<<<(unsigned)sm_count * 8u, 256, 0, stream>>>(table, rows, row_stride, dim, dense);
+    return cudaGetLastError();
+}
+
 // digest of the live part of both tables (replica equality / finiteness checks of the multi-GPU
 // path without moving the tables): per table the sum and the sum of squares in double
 // (informative: atomics reorder them) and the wrap-around integer sum of the float bit patterns

@@ -86,7 +86,8 @@ int orc_walks_typed(const int64_t *indptr, const uint32_t *indices, const uint32
                     float return_weight, float explore_weight, int undirected, uint32_t *out,
                     orc_walk_counters *counters);
 
-/* Vose alias table over deg^alpha; thr/alias have n entries. */
+/* Alias table over deg^alpha (integer construction, alias.c); thr/alias have n entries. */
+int orc_alias_fraction_bits(uint64_t n, uint64_t max_degree, double alpha);
 int orc_alias_build(const int64_t *indptr, uint64_t n, double alpha, uint32_t *thr,
                     uint32_t *alias);
 

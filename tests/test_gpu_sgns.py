@@ -262,3 +262,24 @@ def test_walklets_one_pass_equals_scale_by_scale(small_ppi_weighted, small_ppi):
             assert np.array_equal(a, b)
         weighted = cls(**kw).fit_transform(small_ppi_weighted, return_dataframe=False).get_all_node_embedding()
         assert len(weighted) == 6 and all(np.isfinite(t).all() for t in weighted)
+
+
+def test_alias_table_and_start_nodes_at_scale():
+    """K3 on the GPU (alias_build.cu) against the oracle's sequential sweep on a skewed graph of
+    1 M nodes / 16 M edges (maximum degree ~ 10^5, a third of the nodes isolated), from host
+    arrays and from a resident graph, with exact-form and libm exponents."""
+    from embiggen_b200.graph_gpu import rmat_gpu
+    resident = rmat_gpu(20, 16_000_000, n=1_000_000, seed=3, resident=True)
+    host = resident.to_host()
+    sources = np.flatnonzero(np.diff(host.indptr) > 0).astype(np.uint32)
+    for alpha, graph in ((0.75, resident), (0.75, host), (1.0, host), (0.6, resident), (0.0, host)):
+        thr, alias = oracle.alias_build(host.indptr, float(np.float32(alpha)))
+        with Engine("SkipGram", negative_sampling_exponent=alpha, walk_length=4) as engine:
+            if graph is host:
+                engine.load_csr(host.indptr, host.indices)
+            else:
+                engine.load_graph(resident)
+            g_thr, g_alias = engine.export_alias()
+            assert engine.number_of_sources == len(sources)
+            assert np.array_equal(engine.walks(1, 0, len(sources))[:, 0], sources)  # start-node list
+        assert np.array_equal(g_thr, thr) and np.array_equal(g_alias, alias), alpha

@@ -33,6 +33,61 @@ def test_alias_table_reproduces_target_pmf(rmat_graph, alpha):
     assert pmf[degrees == 0].max(initial=0.0) < 1e-9  # isolated nodes are (almost) never drawn
 
 
+def closed_form_alias(indptr, alpha):
+    """The table of oracle/alias.c in closed form (what the GPU builder computes, alias_build.cu):
+    light node k is topped up by heavy node #{j : S_j < D_k}; heavy node j is exhausted by the
+    first light node whose running deficit exceeds S_j and keeps c + S_j - that running deficit."""
+    import ctypes
+    lib = oracle.lib()
+    lib.orc_alias_fraction_bits.restype = ctypes.c_int
+    lib.orc_alias_fraction_bits.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double]
+    deg = np.diff(indptr).astype(np.uint64)
+    n = len(deg)
+    d = deg.astype(np.float64)
+    w = {0.0: np.ones_like(d), 1.0: d, 0.5: np.sqrt(d), 0.75: np.sqrt(np.sqrt(d * d * d))}.get(alpha)
+    w = np.where(deg > 0, d ** alpha if w is None else w, 0.0)
+    bits = lib.orc_alias_fraction_bits(n, int(deg.max()), alpha)
+    mass = np.floor(np.ldexp(w, bits)).astype(np.uint64)
+    total = int(mass.sum())
+    c = (total + n - 1) // n
+    nz = deg > 0
+    each, first = divmod(c * n - total, int(nz.sum()))
+    rank = np.cumsum(nz) - 1
+    mass[nz] += np.uint64(each) + (rank[nz] < first).astype(np.uint64)
+
+    def threshold(m):
+        r, q = int(m), 0
+        for _ in range(32):
+            r, q = r << 1, q << 1
+            if r >= c:
+                r, q = r - c, q | 1
+        return q
+
+    light, heavy = np.flatnonzero(mass < c), np.flatnonzero(mass >= c)
+    thr = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+    alias = np.arange(n, dtype=np.uint32)
+    deficit, surplus = np.uint64(c) - mass[light], mass[heavy] - np.uint64(c)
+    d_sum, s_sum = np.cumsum(deficit), np.cumsum(surplus)
+    thr[light] = [threshold(m) for m in mass[light]]
+    alias[light] = heavy[np.searchsorted(s_sum, d_sum - deficit, side="left")]
+    k = np.searchsorted(d_sum, s_sum, side="right")
+    exhausted = np.flatnonzero(k < len(light))
+    thr[heavy[exhausted]] = [threshold(c + int(s_sum[j]) - int(d_sum[k[j]])) for j in exhausted]
+    alias[heavy[exhausted]] = heavy[exhausted + 1]
+    return thr, alias
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 0.75, 1.0, 0.6])
+def test_alias_sweep_equals_its_closed_form(rmat_graph, er_graph, small_ppi, alpha):
+    """oracle/alias.c sweeps the light and heavy nodes sequentially; the product builds the same
+    table from two prefix sums.  Here the closed form is restated in numpy and compared with the
+    sweep, so the derivation is checked on the CPU before the GPU test compares the kernels."""
+    for graph in (rmat_graph, er_graph, small_ppi):
+        thr, alias = oracle.alias_build(graph.indptr, alpha)
+        c_thr, c_alias = closed_form_alias(graph.indptr, alpha)
+        assert np.array_equal(thr, c_thr) and np.array_equal(alias, c_alias)
+
+
 def test_alias_sampling_chi_square(small_ppi):
     thr, alias = oracle.alias_build(small_ppi.indptr, 0.75)
     n = len(thr)
