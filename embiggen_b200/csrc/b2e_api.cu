@@ -791,7 +791,9 @@ extern "C" int b2e_exchange_open(b2e_handle *h, uint32_t world, uint32_t rank, c
     if (int rc = require_graph(h)) return rc;
     if (int rc = check_world(world, rank)) return rc;
     if (!all_ipc_handles) return fail(B2E_ERR_INVALID, "null argument");
-    CUDA_TRY(cudaDeviceSynchronize());
+    // nothing mapped yet: no need to drain the device (the caller may have SGD chunks queued and
+    // wants them to run while the peers are being mapped)
+    if (h->world > 1) CUDA_TRY(cudaDeviceSynchronize());
     close_peers(h);
     const cudaIpcMemHandle_t *handles = static_cast<const cudaIpcMemHandle_t *>(all_ipc_handles);
     h->world = world;

@@ -398,9 +398,9 @@ class Engine:
         cfg = self.config
         if gather not in ("all", "rank0"):
             raise ValueError("gather must be 'all' or 'rank0'")
+        self.timings = {}
         self.init_tables(seed)  # identical on every rank (counter-based init)
-        if world > 1:
-            self.open_exchange(process_group)
+        opened = world == 1
         per_epoch = self.walks_per_epoch
         lr = np.float32(cfg.learning_rate)
         losses = []
@@ -408,8 +408,17 @@ class Engine:
         self.exchange_count = 0
 
         def average():
+            nonlocal opened
             if world == 1:
                 return
+            if not opened:
+                # Mapping the peers' tables costs about a second per peer (CUDA IPC over 2 x 51 GB
+                # at C5).  It is done here, at the first exchange, when this rank's first chunks
+                # are already queued on the device: the GPU trains while the host maps.
+                begin = time.perf_counter()
+                self.open_exchange(process_group)
+                self.timings["open_exchange_s"] = time.perf_counter() - begin
+                opened = True
             begin = time.perf_counter()
             self.average(process_group)
             self.exchange_seconds += time.perf_counter() - begin
@@ -435,14 +444,18 @@ class Engine:
             dist.all_reduce(stats, group=process_group)
             losses.append(float(stats[0] / max(float(stats[1]), 1.0)))
             lr = np.float32(lr * np.float32(cfg.learning_rate_decay))
-        if world > 1:
+        if world > 1 and opened:
+            begin = time.perf_counter()
             dist.barrier(group=process_group)
             self.close_exchange()
+            self.timings["close_exchange_s"] = time.perf_counter() - begin
         if gather == "rank0" and rank != 0:
             return None, None, losses
         shape = (self.n, cfg.embedding_size)
         t0 = np.empty(shape, dtype=np.float32) if table0 is None else table0
         t1 = np.empty(shape, dtype=np.float32) if table1 is None else table1
         first, second = (t1, t0) if self.model == "cbow" else (t0, t1)
+        begin = time.perf_counter()
         check(self._lib.b2e_export_tables(self._handle, first.ctypes.data, second.ctypes.data))
+        self.timings["export_tables_s"] = time.perf_counter() - begin
         return t0, t1, losses

@@ -18,7 +18,7 @@ def exists(relative):
 
 
 def test_profiles_index_names_existing_files():
-    names = cited("profiles/README.md", r"`((?:r01|traffic)[\w*.\-]+)`")
+    names = cited("profiles/README.md", r"`((?:r0\d|traffic)[\w*.\-]+)`")
     assert len(names) > 20
     missing = [name for name in names if not exists(os.path.join("profiles", name))]
     assert not missing, missing
