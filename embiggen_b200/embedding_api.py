@@ -15,8 +15,11 @@ reference code whose behaviour it keeps:
 Only what the Node2Vec / DeepWalk SkipGram / CBOW path touches is restated; the classifier
 half of ``AbstractModel`` is out of scope.
 """
+import gzip
 import hashlib
 import json
+import os
+import pickle
 import warnings
 from typing import Any, Dict, List, Optional, Type, Union
 
@@ -329,7 +332,7 @@ if not HAVE_EMBIGGEN:
                 raise ValueError("The embedding size, if provided, should be a strictly positive "
                                  f"integer but {embedding_size} was provided.")  # :37-41
             self._embedding_size = embedding_size
-            self._enable_cache = enable_cache  # accepted; result caching needs cache_decorator
+            self._enable_cache = enable_cache  # see _cache_path: the restatement of the @Cache at :91-95
             self._ring_bell = None
 
         def parameters(self) -> Dict[str, Any]:
@@ -375,6 +378,26 @@ if not HAVE_EMBIGGEN:
                         "embedding algorithms that only use topological information such as CBOW "
                         "and SkipGram are not able to provide meaningful embeddings for these nodes.")
 
+        def _cache_path(self, graph, return_dataframe: bool) -> str:
+            """`enable_cache` (abstract_embedding_model.py:91-95: cache_decorator's
+            "{cache_dir}/{model_name}/{library_name}/{graph name}/{_hash}.pkl.gz", cache_dir =
+            "embedding", overridable with the CACHE_DIR environment variable as there).  The hash
+            covers the parameters (seed included) and the graph's shape and contents."""
+            digest = hashlib.sha256()
+            digest.update(repr(sorted(self.parameters().items())).encode())
+            digest.update(repr((return_dataframe, graph.get_number_of_nodes())).encode())
+            for getter in ("get_cumulative_node_degrees", "get_directed_destination_node_ids"):
+                if hasattr(graph, getter):
+                    array = np.ascontiguousarray(getattr(graph, getter)())
+                    digest.update(repr(array.shape).encode())
+                    digest.update(array[:: max(1, array.shape[0] // (1 << 22))].tobytes())  # <= 4 M samples
+            if hasattr(graph, "has_edge_weights") and graph.has_edge_weights():
+                weights = np.ascontiguousarray(graph.get_directed_edge_weights())
+                digest.update(weights[:: max(1, weights.shape[0] // (1 << 22))].tobytes())
+            directory = os.path.join(os.environ.get("CACHE_DIR", "embedding"), self.model_name(),
+                                     self.library_name(), str(graph.get_name()).replace(os.sep, "_"))
+            return os.path.join(directory, digest.hexdigest()[:32] + ".pkl.gz")
+
         def fit_transform(self, graph, repository: Optional[str] = None,
                           version: Optional[str] = None, return_dataframe: bool = True):  # :200-251
             if isinstance(graph, str):
@@ -389,7 +412,17 @@ if not HAVE_EMBIGGEN:
                     f"{graph.get_number_of_nodes()}, and creating a Dataframe would most likely "
                     "cause an OOM on your system.")
             self._validate_graph(graph)
+            cache_path = self._cache_path(graph, return_dataframe) if self._enable_cache else None
+            if cache_path is not None and os.path.exists(cache_path):
+                with gzip.open(cache_path, "rb") as handle:
+                    return EmbeddingResult.load(pickle.load(handle))
             result = self._fit_transform(graph=graph, return_dataframe=return_dataframe)
+            if cache_path is not None and isinstance(result, EmbeddingResult):
+                os.makedirs(os.path.dirname(cache_path), exist_ok=True)
+                temporary = f"{cache_path}.{os.getpid()}.tmp"
+                with gzip.open(temporary, "wb", compresslevel=1) as handle:
+                    pickle.dump(result.dump(), handle, protocol=pickle.HIGHEST_PROTOCOL)
+                os.replace(temporary, cache_path)
             if not isinstance(result, EmbeddingResult):
                 raise NotImplementedError(
                     f"The embedding result produced by the {self.model_name()} method from the "

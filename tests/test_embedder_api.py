@@ -270,3 +270,36 @@ def test_glove_classes_mirror_the_reference_surface():
     assert type(d.into_smoke_test()) is DeepWalkGloVeB200
     frame = get_available_models_for_node_embedding()
     assert not any("GloVe" in name for name in frame.model_name)
+
+
+def test_enable_cache_stores_and_reuses_the_result(tmp_path, monkeypatch, small_ppi):
+    """`enable_cache` (abstract_embedding_model.py:91-95): the second call with the same graph and
+    parameters is served from "{CACHE_DIR}/{model}/{library}/{graph}/{hash}.pkl.gz"; another seed
+    or another graph is another entry.  (Restatement only: with the real `embiggen` importable its
+    own cache_decorator does this.)"""
+    from embiggen_b200 import embedding_api
+    if embedding_api.HAVE_EMBIGGEN:
+        pytest.skip("the real embiggen base class brings its own cache")
+    from embiggen_b200.embedders import Node2VecSkipGramB200
+    monkeypatch.setenv("CACHE_DIR", str(tmp_path))
+    calls = []
+
+    def fake_fit(self, graph, return_dataframe=True):
+        calls.append(self._random_state)
+        n = graph.get_number_of_nodes()
+        tables = [np.full((n, 4), float(self._random_state), dtype=np.float32) for _ in range(2)]
+        return embedding_api.EmbeddingResult(self.model_name(), node_embeddings=tables)
+
+    monkeypatch.setattr(Node2VecSkipGramB200, "_fit_transform", fake_fit)
+    model = Node2VecSkipGramB200(embedding_size=4, enable_cache=True, random_state=5, verbose=False)
+    first = model.fit_transform(small_ppi, return_dataframe=False)
+    again = model.fit_transform(small_ppi, return_dataframe=False)
+    assert calls == [5]
+    assert np.array_equal(first.get_all_node_embedding()[1], again.get_all_node_embedding()[1])
+    stored = list(tmp_path.rglob("*.pkl.gz"))
+    assert len(stored) == 1 and stored[0].parts[-4:-1] == ("Node2Vec SkipGram", "B200", "small_ppi")
+    model.set_random_state(6)
+    model.fit_transform(small_ppi, return_dataframe=False)
+    Node2VecSkipGramB200(embedding_size=4, enable_cache=False, random_state=6, verbose=False).fit_transform(
+        small_ppi, return_dataframe=False)
+    assert calls == [5, 6, 6] and len(list(tmp_path.rglob("*.pkl.gz"))) == 2
