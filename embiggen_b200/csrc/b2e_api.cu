@@ -1075,15 +1075,102 @@ extern "C" int b2e_glove_train(b2e_handle *h, float learning_rate) {
     return B2E_OK;
 }
 
+// One GloVe epoch whose co-occurrence exceeds one sort (glove.cu, "co-occurrence by centre
+// range"): walk the whole epoch, bucket the token positions by centre range, then count and train
+// range by range in ascending order of centre.  x_max is the largest count of the WHOLE epoch, so
+// with more than one range the ranges are counted twice: once for x_max, once to train.
+static int glove_epoch_by_ranges(b2e_handle *h, uint64_t seed, uint64_t first_walk, uint64_t per_epoch, float lr,
+                                 uint64_t capacity_slots) {
+    const b2e_config &c = h->cfg;
+    GloveState &g = h->glove;
+    const uint32_t L = c.walk_length, W = c.window_size;
+    const uint64_t tokens = per_epoch * L;
+    CUDA_TRY(glove_reserve((void **)&g.d_epoch_walks, &g.epoch_walks_bytes, tokens * sizeof(uint32_t)));
+    CUDA_TRY(glove_reserve((void **)&g.d_histogram, &g.histogram_bytes, h->n * sizeof(uint32_t)));
+    for (uint64_t done = 0; done < per_epoch; done += h->chunk_cap) {
+        const uint64_t count = std::min(h->chunk_cap, per_epoch - done);
+        if (int rc = walk_into(h, seed, first_walk + done, count, 1, g.d_epoch_walks + done * L, h->walk_stream)) return rc;
+    }
+    CUDA_TRY(glove_token_histogram(g.d_epoch_walks, tokens, g.d_histogram, h->n, h->walk_stream));
+    std::vector<uint32_t> histogram(h->n);
+    CUDA_TRY(cudaMemcpyAsync(histogram.data(), g.d_histogram, h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             h->walk_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    h->launches += 2;
+    // ranges of centre ids holding at most capacity_slots key slots each (one node may exceed it)
+    std::vector<uint32_t> bounds(1, 0u);
+    std::vector<unsigned long long> offsets(1, 0ull);
+    uint64_t in_range = 0, placed = 0;
+    for (uint64_t v = 0; v < h->n; ++v) {
+        const uint64_t slots = (uint64_t)histogram[v] * 2ull * W;
+        if (in_range && in_range + slots > capacity_slots) {
+            bounds.push_back((uint32_t)v);
+            offsets.push_back(placed);
+            in_range = 0;
+        }
+        in_range += slots;
+        placed += histogram[v];
+        if (slots >= (1ull << 31))
+            return fail(B2E_ERR_INVALID, "one node alone has 2^31 co-occurrence slots in an epoch: lower walk_length, "
+                                         "window_size or iterations");
+    }
+    bounds.push_back((uint32_t)h->n);
+    offsets.push_back(placed);
+    const uint32_t ranges = (uint32_t)bounds.size() - 1u;
+    g.last_ranges = ranges;
+    CUDA_TRY(glove_reserve((void **)&g.d_bounds, &g.bounds_bytes, bounds.size() * sizeof(uint32_t)));
+    CUDA_TRY(glove_reserve((void **)&g.d_cursor, &g.cursor_bytes, ranges * sizeof(unsigned long long)));
+    CUDA_TRY(glove_reserve((void **)&g.d_positions, &g.positions_bytes, std::max<uint64_t>(placed, 1) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpyAsync(g.d_bounds, bounds.data(), bounds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->walk_stream));
+    CUDA_TRY(cudaMemcpyAsync(g.d_cursor, offsets.data(), ranges * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->walk_stream));
+    CUDA_TRY(glove_bucket_positions(g.d_epoch_walks, tokens, g.d_bounds, ranges, g.d_cursor, g.d_positions, h->walk_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->walk_stream));
+    ++h->launches;
+    uint32_t x_max = 1;
+    if (ranges > 1) {
+        for (uint32_t r = 0; r < ranges; ++r) {
+            CUDA_TRY(glove_range_triples(g, g.d_epoch_walks, L, W, g.d_positions + offsets[r], offsets[r + 1] - offsets[r],
+                                         h->walk_stream));
+            uint32_t local = 0;
+            CUDA_TRY(glove_max_count(g, &local, h->walk_stream));
+            x_max = std::max(x_max, local);
+            h->launches += 2;
+        }
+    }
+    for (uint32_t r = 0; r < ranges; ++r) {
+        CUDA_TRY(glove_range_triples(g, g.d_epoch_walks, L, W, g.d_positions + offsets[r], offsets[r + 1] - offsets[r],
+                                     h->walk_stream));
+        h->launches += 2;
+        if (g.n_triples == 0) continue;
+        CUDA_TRY(glove_finalise(g, h->n, h->walk_stream));
+        if (ranges > 1) g.max_count = x_max;
+        if (int rc = b2e_glove_train(h, lr)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(h->train_stream));  // the triples are replaced by the next range
+    }
+    return B2E_OK;
+}
+
+// key slots one sort may hold (B2E_GLOVE_SLOTS overrides: tests force many ranges on small graphs)
+static uint64_t glove_capacity_slots() {
+    if (const char *env = getenv("B2E_GLOVE_SLOTS")) return std::max<uint64_t>(64, strtoull(env, nullptr, 10));
+    return 1ull << 28;
+}
+
 static int fit_glove(b2e_handle *h, uint64_t seed, float *table0, float *table1, float *epoch_loss) {
     const b2e_config &c = h->cfg;
     if (int rc = b2e_init_tables(h, seed)) return rc;
     const uint64_t per_epoch = (uint64_t)c.iterations * h->n_src;
+    const uint64_t capacity = glove_capacity_slots();
+    const bool by_ranges = 2ull * per_epoch * c.walk_length * c.window_size > capacity;
     float lr = c.learning_rate;
     for (uint32_t epoch = 0; epoch < c.epochs; ++epoch) {
         if (int rc = b2e_counters_reset(h)) return rc;
-        if (int rc = b2e_cooccurrence(h, seed, (uint64_t)epoch * per_epoch, per_epoch, 1, 0, nullptr)) return rc;
-        if (int rc = b2e_glove_train(h, lr)) return rc;
+        if (by_ranges) {
+            if (int rc = glove_epoch_by_ranges(h, seed, (uint64_t)epoch * per_epoch, per_epoch, lr, capacity)) return rc;
+        } else {
+            if (int rc = b2e_cooccurrence(h, seed, (uint64_t)epoch * per_epoch, per_epoch, 1, 0, nullptr)) return rc;
+            if (int rc = b2e_glove_train(h, lr)) return rc;
+        }
         b2e_counters counters;
         if (int rc = b2e_counters_read(h, &counters)) return rc;
         if (epoch_loss) epoch_loss[epoch] = counters.pairs ? (float)(counters.loss_sum / (double)counters.pairs) : 0.0f;

@@ -104,6 +104,11 @@ struct GloveState {
     uint32_t *d_merge_counts = nullptr;
     void *d_temp = nullptr, *d_scalar = nullptr;
     size_t scratch_keys_bytes = 0, merge_keys_bytes = 0, merge_counts_bytes = 0, temp_bytes = 0, scalar_bytes = 0;
+    // co-occurrence by centre range: the walks of an epoch, their token positions bucketed by range
+    uint32_t *d_epoch_walks = nullptr, *d_histogram = nullptr, *d_bounds = nullptr;
+    unsigned long long *d_positions = nullptr, *d_cursor = nullptr;
+    size_t epoch_walks_bytes = 0, histogram_bytes = 0, bounds_bytes = 0, positions_bytes = 0, cursor_bytes = 0;
+    uint32_t last_ranges = 0;  // how many centre ranges the last epoch took (1 = one piece)
 };
 uint64_t glove_chunk_walks(uint32_t walk_length, uint32_t window);
 cudaError_t glove_accumulate(GloveState &g, const uint32_t *d_walks, uint64_t n_walks, uint32_t walk_length,
@@ -113,6 +118,17 @@ cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, ui
                         float alpha, float clip, float lr, float *t0, float *t1, DeviceCounters *counters,
                         bool deterministic, int sm_count, uint64_t max_warps, uint32_t variant,
                         cudaStream_t stream);
+// co-occurrence by centre range (glove.cu): histogram of the epoch's tokens, occurrences bucketed
+// by range, the triples of one range
+cudaError_t glove_token_histogram(const uint32_t *d_walks, uint64_t tokens, uint32_t *d_histogram, uint64_t n,
+                                  cudaStream_t stream);
+cudaError_t glove_bucket_positions(const uint32_t *d_walks, uint64_t tokens, const uint32_t *d_bounds, uint32_t ranges,
+                                   unsigned long long *d_cursor, unsigned long long *d_positions,
+                                   cudaStream_t stream);
+cudaError_t glove_range_triples(GloveState &g, const uint32_t *d_walks, uint32_t L, uint32_t W,
+                                const unsigned long long *d_positions, uint64_t count, cudaStream_t stream);
+cudaError_t glove_reserve(void **ptr, size_t *have, size_t want);
+cudaError_t glove_max_count(GloveState &g, uint32_t *max_count, cudaStream_t stream);
 void glove_free(GloveState &g);
 
 cudaError_t launch_walklet_split(const uint32_t *raw, uint64_t n_walks, uint32_t walk_length, uint32_t scale,

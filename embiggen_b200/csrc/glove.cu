@@ -427,9 +427,145 @@ cudaError_t glove_train(const GloveState &g, uint64_t n, uint32_t row_stride, ui
     return cudaErrorInvalidValue;
 }
 
+// ---- co-occurrence by centre range: the way past 2^31 key slots per epoch ----
+//
+// The reference's GloVe defaults (walk_length = 512, window_size = 5, node2vec_glove.py:8-30) emit
+// 5 120 key slots per start node and epoch: beyond ~0.4 M nodes an epoch's co-occurrence no
+// longer fits one sort.  Every key (centre, context) belongs to exactly one centre, so the
+// epoch is cut into ranges of centre ids: the occurrences of the epoch's walks are bucketed by
+// range once (one counting pass, one scatter pass), and each range is then counted (emit ->
+// sort -> run-length encode) and trained on its own, in ascending order of centre -- the exact
+// counts and the exact order of the one-piece path, for any number of ranges.
+
+// tokens per node over the walks of an epoch
+__global__ void __launch_bounds__(256) token_histogram_kernel(const uint32_t *__restrict__ walks, uint64_t tokens,
+                                                              uint32_t *__restrict__ histogram) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < tokens;
+         p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(walks + p);
+        if (v != PAD) atomicAdd(histogram + v, 1u);
+    }
+}
+
+// position p of a walk token goes to the range that holds its node: bounds[r] <= node < bounds[r + 1]
+__global__ void __launch_bounds__(256) bucket_positions_kernel(const uint32_t *__restrict__ walks, uint64_t tokens,
+                                                               const uint32_t *__restrict__ bounds, uint32_t ranges,
+                                                               unsigned long long *__restrict__ cursor,
+                                                               unsigned long long *__restrict__ positions) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < tokens;
+         p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(walks + p);
+        if (v == PAD) continue;
+        uint32_t lo = 0, hi = ranges;  // last r with bounds[r] <= v
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(bounds + mid) <= v) lo = mid; else hi = mid;
+        }
+        positions[atomicAdd(cursor + lo, 1ull)] = p;
+    }
+}
+
+// occurrence (position p) x window offset: the key (centre, context) or the all-ones key
+__global__ void __launch_bounds__(256) range_keys_kernel(const uint32_t *__restrict__ walks, uint32_t L, uint32_t W,
+                                                         const unsigned long long *__restrict__ positions,
+                                                         uint64_t count, unsigned long long *__restrict__ keys) {
+    const uint64_t total = count * 2ull * W;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t occurrence = idx / (2u * W);
+        const uint32_t slot = (uint32_t)(idx - occurrence * 2u * W);
+        const uint32_t d = (slot >> 1) + 1u;
+        const unsigned long long p = __ldg(positions + occurrence);
+        const uint32_t i = (uint32_t)(p % L);
+        const long long j = (slot & 1u) ? (long long)i - d : (long long)i + d;
+        unsigned long long key = COOC_INVALID;
+        if (j >= 0 && j < (long long)L) {
+            const uint32_t a = __ldg(walks + p), b = __ldg(walks + (p - i) + (uint64_t)j);
+            if (b != PAD && a != b) key = ((unsigned long long)a << 32) | b;
+        }
+        keys[idx] = key;
+    }
+}
+
+cudaError_t glove_token_histogram(const uint32_t *d_walks, uint64_t tokens, uint32_t *d_histogram, uint64_t n,
+                                  cudaStream_t stream) {
+    GLOVE_TRY(cudaMemsetAsync(d_histogram, 0, n * sizeof(uint32_t), stream));
+    if (tokens == 0) return cudaSuccess;
+    token_histogram_kernel<<<148 * 16, 256, 0, stream>>>(d_walks, tokens, d_histogram);
+    return cudaGetLastError();
+}
+
+cudaError_t glove_bucket_positions(const uint32_t *d_walks, uint64_t tokens, const uint32_t *d_bounds, uint32_t ranges,
+                                   unsigned long long *d_cursor, unsigned long long *d_positions,
+                                   cudaStream_t stream) {
+    if (tokens == 0) return cudaSuccess;
+    bucket_positions_kernel<<<148 * 16, 256, 0, stream>>>(d_walks, tokens, d_bounds, ranges, d_cursor, d_positions);
+    return cudaGetLastError();
+}
+
+// The co-occurrence triples of one centre range replace the resident ones (g.n_triples, sorted
+// by (centre, context)); `count` occurrences, 2 W key slots each.
+cudaError_t glove_range_triples(GloveState &g, const uint32_t *d_walks, uint32_t L, uint32_t W,
+                                const unsigned long long *d_positions, uint64_t count, cudaStream_t stream) {
+    typedef unsigned long long u64;
+    g.n_triples = 0;
+    g.finalised = false;
+    const uint64_t slots = count * 2ull * W;
+    if (slots == 0) return cudaSuccess;
+    GLOVE_TRY(grow((void **)&g.d_scratch_keys, &g.scratch_keys_bytes, 2 * slots * sizeof(u64)));
+    u64 *raw = g.d_scratch_keys, *sorted = g.d_scratch_keys + slots;
+    const uint64_t grid = std::min<uint64_t>((slots + 255) / 256, 148ull * 32);
+    range_keys_kernel<<<(unsigned)grid, 256, 0, stream>>>(d_walks, L, W, d_positions, count, raw);
+    GLOVE_TRY(cudaGetLastError());
+    GLOVE_TRY(grow((void **)&g.d_keys, &g.keys_bytes, slots * sizeof(u64)));
+    GLOVE_TRY(grow((void **)&g.d_counts, &g.counts_bytes, slots * sizeof(uint32_t)));
+    GLOVE_TRY(grow((void **)&g.d_scalar, &g.scalar_bytes, 16));
+    uint64_t *d_runs = reinterpret_cast<uint64_t *>(g.d_scalar);
+    size_t bytes = 0, need = 0;
+    GLOVE_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bytes, raw, sorted, slots, 0, 64, stream));
+    need = bytes;
+    GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, bytes, sorted, g.d_keys, g.d_counts, d_runs, slots, stream));
+    need = std::max(need, bytes);
+    GLOVE_TRY(grow(&g.d_temp, &g.temp_bytes, need));
+    bytes = g.temp_bytes;
+    GLOVE_TRY(cub::DeviceRadixSort::SortKeys(g.d_temp, bytes, raw, sorted, slots, 0, 64, stream));
+    bytes = g.temp_bytes;
+    GLOVE_TRY(cub::DeviceRunLengthEncode::Encode(g.d_temp, bytes, sorted, g.d_keys, g.d_counts, d_runs, slots, stream));
+    uint64_t runs = 0;
+    GLOVE_TRY(cudaMemcpyAsync(&runs, d_runs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    GLOVE_TRY(cudaStreamSynchronize(stream));
+    if (runs) {  // the all-ones key, if present, is the last run
+        u64 last = 0;
+        GLOVE_TRY(cudaMemcpyAsync(&last, g.d_keys + runs - 1, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        GLOVE_TRY(cudaStreamSynchronize(stream));
+        if (last == COOC_INVALID) --runs;
+    }
+    g.n_triples = runs;
+    return cudaSuccess;
+}
+
+cudaError_t glove_reserve(void **ptr, size_t *have, size_t want) { return grow(ptr, have, want); }
+
+// largest count of the resident triples (0 when there are none)
+cudaError_t glove_max_count(GloveState &g, uint32_t *max_count, cudaStream_t stream) {
+    *max_count = 0;
+    if (g.n_triples == 0) return cudaSuccess;
+    GLOVE_TRY(grow((void **)&g.d_scalar, &g.scalar_bytes, 16));
+    uint32_t *d_max = reinterpret_cast<uint32_t *>(g.d_scalar);
+    size_t bytes = 0;
+    GLOVE_TRY(cub::DeviceReduce::Max(nullptr, bytes, g.d_counts, d_max, g.n_triples, stream));
+    GLOVE_TRY(grow(&g.d_temp, &g.temp_bytes, bytes));
+    bytes = g.temp_bytes;
+    GLOVE_TRY(cub::DeviceReduce::Max(g.d_temp, bytes, g.d_counts, d_max, g.n_triples, stream));
+    GLOVE_TRY(cudaMemcpyAsync(max_count, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    return cudaStreamSynchronize(stream);
+}
+
 void glove_free(GloveState &g) {
     cudaFree(g.d_keys); cudaFree(g.d_counts); cudaFree(g.d_rowptr); cudaFree(g.d_scratch_keys);
     cudaFree(g.d_merge_keys); cudaFree(g.d_merge_counts); cudaFree(g.d_temp); cudaFree(g.d_scalar);
+    cudaFree(g.d_epoch_walks); cudaFree(g.d_histogram); cudaFree(g.d_bounds); cudaFree(g.d_positions);
+    cudaFree(g.d_cursor);
     g = GloveState();
 }
 

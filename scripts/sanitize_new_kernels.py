@@ -59,6 +59,12 @@ with Engine("GloVe", embedding_size=100, walk_length=33, window_size=4, iteratio
     engine.load_csr(graph.indptr, graph.indices)
     t0, t1, losses = engine.fit(7)
     assert np.isfinite(t0).all() and np.isfinite(t1).all()
+os.environ["B2E_GLOVE_SLOTS"] = "20000"  # co-occurrence by centre ranges
+with Engine("GloVe", embedding_size=100, walk_length=33, window_size=4, iterations=1, epochs=2) as engine:
+    engine.load_csr(graph.indptr, graph.indices)
+    t0, t1, losses = engine.fit(7)
+    assert np.isfinite(t0).all() and np.isfinite(t1).all()
+del os.environ["B2E_GLOVE_SLOTS"]
 from embiggen_b200.edge_prediction import (EdgeTransformerB200, PerceptronEdgePredictionB200,  # noqa: E402
                                            edge_metrics)
 features = rng.normal(size=(n, 20)).astype(np.float32)

@@ -110,3 +110,35 @@ def test_glove_error_paths(small_ppi):
             engine.glove_train(0.05)
     with pytest.raises(ValueError):
         Engine("GloVe", walklet_scale=2)
+
+
+def test_glove_by_centre_ranges_equals_the_one_piece_epoch(monkeypatch, small_ppi, rmat_graph):
+    """Past 2^31 key slots an epoch's co-occurrence is counted and trained by ranges of centre ids
+    (b2e_api.cu: glove_epoch_by_ranges).  B2E_GLOVE_SLOTS forces that path on small graphs: in the
+    single-warp launch the tables equal the one-piece path and the oracle bit for bit, whatever
+    the number of ranges (exact counts, x_max of the whole epoch, centres in ascending order)."""
+    kw = dict(embedding_size=24, epochs=2, walk_length=40, window_size=3, learning_rate=0.05, learning_rate_decay=0.9)
+    for graph in (small_ppi, rmat_graph):
+        t0, t1, expected = oracle.glove_fit(graph.indptr, graph.indices, 9, alpha=0.75, return_weight=0.5,
+                                            explore_weight=2.0, **kw)
+        for slots in (None, 200_000, 3_000):
+            if slots is None:
+                monkeypatch.delenv("B2E_GLOVE_SLOTS", raising=False)
+            else:
+                monkeypatch.setenv("B2E_GLOVE_SLOTS", str(slots))
+            with Engine("GloVe", return_weight=0.5, explore_weight=2.0, iterations=1, deterministic=True, **kw) as engine:
+                engine.load_csr(graph.indptr, graph.indices)
+                c, x, losses = engine.fit(9)
+            assert np.array_equal(c, t0[:, :24]) and np.array_equal(x, t1[:, :24]), slots
+            assert np.allclose(losses, expected, rtol=1e-4)
+        # the production launch on many ranges: finite, and the loss falls like the one-piece run's
+        monkeypatch.setenv("B2E_GLOVE_SLOTS", "50000")
+        with Engine("GloVe", return_weight=0.5, explore_weight=2.0, iterations=1, **dict(kw, epochs=6)) as engine:
+            engine.load_csr(graph.indptr, graph.indices)
+            c, x, ranged = engine.fit(9)
+        monkeypatch.delenv("B2E_GLOVE_SLOTS")
+        with Engine("GloVe", return_weight=0.5, explore_weight=2.0, iterations=1, **dict(kw, epochs=6)) as engine:
+            engine.load_csr(graph.indptr, graph.indices)
+            _, _, whole = engine.fit(9)
+        assert np.isfinite(c).all() and np.isfinite(x).all() and ranged[-1] < 0.6 * ranged[0]
+        assert abs(ranged[-1] - whole[-1]) <= 0.1 * whole[-1]
