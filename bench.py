@@ -600,10 +600,12 @@ def run_ours(args, name, cfg, note):
             "kernel": f"exchange_average_kernel<{world}>", "sync_interval_steps": args.sync_interval,
             "syncs_in_timed_region": len(timed_exchanges), "kernel_ms_per_sync": mean_ms,
             "wall_ms_per_sync": 1e3 * float(np.mean([w for w, _ in timed_exchanges])) if timed_exchanges else None,
-            "bytes_in_per_gpu_per_sync": live * (world - 1) / world,
-            "gbs_in_per_gpu": None if not mean_ms else live * (world - 1) / world / (mean_ms * 1e-3) / 1e9,
+            "nvlink_bytes_per_direction_per_gpu_per_sync": 2 * live * (world - 1) / world,
+            "nvlink_gbs_per_direction_per_gpu": None if not mean_ms else 2 * live * (world - 1) / world / (mean_ms * 1e-3) / 1e9,
             "note": "rank 0; kernel time by CUDA events on the train stream, wall clock = barrier + kernel + "
-                    "barrier; per GPU the live bytes of the rows it owns cross NVLink once in each direction"}
+                    "barrier.  Per GPU and direction NVLink carries 2 x (G-1)/G of the live table bytes per sync: "
+                    "inbound = the peers' replicas of the rows this rank owns (read responses) + the means the "
+                    "peers write into this replica; outbound is the mirror image (NVLink 5: 900 GB/s per direction)"}
 
     # ---- e2e: the named job in full through the reference-facing call with HOST buffers in and
     # out: CSR H2D + init + one epoch over every start node (sharded over the ranks, replicas

@@ -149,6 +149,8 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (const char *env = getenv("B2E_PREFETCH")) h->prefetch = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_WALK_OCC")) h->walk_occupancy = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_BULK")) h->bulk = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_EXCHANGE_ROWS")) h->exchange_rows = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
     for (int s = 0; s < 2; ++s) {
@@ -660,6 +662,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.scale_dot = c.scale_by_sqrt_dim ? 1u : 0u;
     p.prefetch = h->prefetch;
     p.variant = h->variant;
+    p.bulk = h->bulk;
     p.alias = h->d_alias;
     p.indptr = h->d_indptr;
     p.t0 = h->d_t0;
@@ -857,7 +860,8 @@ extern "C" int b2e_exchange_average(b2e_handle *h) {
     if (int rc = require_graph(h)) return rc;
     if (h->world < 2) return B2E_OK;
     CUDA_TRY(launch_exchange_average(h->peer_t0, h->peer_t1, h->world, h->rank, h->n, h->row_stride,
-                                     (h->cfg.embedding_size + 3u) / 4u, h->sm_count, h->train_stream));
+                                     (h->cfg.embedding_size + 3u) / 4u, h->sm_count, h->train_stream,
+                                     h->exchange_rows));
     ++h->launches;
     return B2E_OK;
 }

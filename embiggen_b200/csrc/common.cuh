@@ -84,6 +84,7 @@ struct TrainParams {
     uint32_t downsample;  // stochastic_downsample_by_degree: max degree + 1, 0 = off
     uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
     uint32_t variant;   // tuning variant of the launch (0 = default)
+    uint32_t bulk;      // SkipGram rows by cp.async.bulk + mbarrier instead of per-lane cp.async (experiment)
     const uint2 *alias;  // {threshold, alias} per node
     const int64_t *indptr;
     float *t0, *t1;
@@ -148,7 +149,7 @@ cudaError_t launch_row_filter_build(const int64_t *indptr, const uint32_t *indic
                                     unsigned long long *filter, int sm_count, cudaStream_t stream);
 cudaError_t launch_exchange_average(float *const t0[], float *const t1[], uint32_t world, uint32_t rank,
                                     uint64_t n, uint32_t row_stride, uint32_t chunks, int sm_count,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, uint32_t rows_per_iteration = 0);
 cudaError_t launch_pack_rows(const float *table, uint64_t rows, uint32_t row_stride, uint32_t dim, float *dense,
                              int sm_count, cudaStream_t stream);
 cudaError_t launch_tables_digest(const float *t0, const float *t1, uint64_t n, uint32_t row_stride,
@@ -216,6 +217,8 @@ struct b2e_handle {
     bool undirected = false;
     uint32_t prefetch = 1;
     uint32_t variant = 0;
+    uint32_t bulk = 0;  // B2E_BULK
+    uint32_t exchange_rows = 0;  // B2E_EXCHANGE_ROWS (0: the default of launch_exchange_average)
     uint32_t walk_occupancy = 6;  // B2E_WALK_OCC: see walk_kernel
     uint64_t launches = 0;
     std::vector<uint32_t> h_alias_thr, h_alias_idx;

@@ -43,6 +43,37 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- bulk-copy variant (B2E_BULK=1): one cp.async.bulk (UBLKCP) per row, issued by lane 0 and
+// completed on a per-warp, per-stage mbarrier, instead of one 16 B LDGSTS per lane and row ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "B2E_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra B2E_DONE;\n\t"
+        "bra B2E_WAIT;\n\t"
+        "B2E_DONE:\n\t"
+        "}" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem), b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(gmem), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 __device__ __forceinline__ float4 lds128(const float *smem) {
     return *reinterpret_cast<const float4 *>(smem);
 }
@@ -144,6 +175,33 @@ __device__ __forceinline__ void issue_rows(const TrainParams &p, const PipeSmem 
         cp_async16(dst + slots * sm.pitch, v.row0(centre_or_pad));
 }
 
+// the same copies as issue_rows, as bulk copies: every lane orders its earlier generic-proxy
+// accesses (stores to the rows, reads of the stage) before the async proxy, lane 0 arms the
+// stage's mbarrier with the byte count and issues one bulk copy per row
+template <int KP1>
+__device__ __forceinline__ void issue_rows_bulk(const TrainParams &p, const PipeSmem &sm, uint32_t stage,
+                                                uint32_t lane, uint32_t my_id, uint32_t vmask,
+                                                uint32_t centre_or_pad, uint64_t *bar) {
+    if (lane < PIPE_SLOTS) sm.ids(stage)[lane] = my_id;
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
+        const uint32_t row = p.chunks * 16u;
+        const uint32_t on = vmask & ((1u << slots) - 1u);
+        mbar_expect_tx(bar, (__popc(on) + (centre_or_pad != PAD ? 1u : 0u)) * row);
+        float *dst = sm.rows(stage);
+        const uint32_t *ids = sm.ids(stage);
+        constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if ((uint32_t)s < slots && ((on >> s) & 1u))
+                bulk_copy_g2s(dst + (uint32_t)s * sm.pitch, p.t1 + (uint64_t)ids[s] * p.row_stride, row, bar);
+        if (centre_or_pad != PAD)
+            bulk_copy_g2s(dst + slots * sm.pitch, p.t0 + (uint64_t)centre_or_pad * p.row_stride, row, bar);
+    }
+}
+
 // dots, sigmoid, axpy and scatter of the targets of one draw site out of stage `stage`;
 // returns this lane's chunk of sum g * row (rows as they were before the update)
 template <int KP1, bool ALL>
@@ -215,7 +273,7 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
     a.w = __fadd_rn(a.w, b.w);
 }
 
-template <int KP1>
+template <int KP1, bool BULK = false>
 __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -223,8 +281,19 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
     const uint32_t L = p.walk_length, W = p.window;
     const uint32_t full_mask = (2u << K) - 1u;  // K + 1 ones
     PipeSmem sm;
+    uint64_t *bars = nullptr;  // BULK: one mbarrier per stage, behind the warp's slab
+    uint32_t parity = 0u;      // bit s: phase of stage s's barrier
     {
-        unsigned char *base = smem_raw + warp * pipe_warp_bytes(K, p.chunks, L);
+        unsigned char *base = smem_raw + warp * (pipe_warp_bytes(K, p.chunks, L) + (BULK ? 16u : 0u));
+        if (BULK) {
+            bars = reinterpret_cast<uint64_t *>(base + pipe_warp_bytes(K, p.chunks, L));
+            if (lane == 0) {
+                mbar_init(bars, 1);
+                mbar_init(bars + 1, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+        }
         sm.pitch = p.chunks * 4u;
         sm.stage_floats = (K + 2u) * sm.pitch;
         sm.rows_base = reinterpret_cast<float *>(base);
@@ -283,7 +352,8 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
             return (__ballot_sync(FULL, valid) << 1) | 1u;
         };
         auto issue = [&](uint32_t stage, uint32_t ids, uint32_t vmask, uint32_t centre_or_pad) {
-            if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, centre_or_pad);
+            if (BULK) issue_rows_bulk<KP1>(p, sm, stage, lane, ids, vmask, centre_or_pad, bars + stage);
+            else if (vmask == full_mask) issue_rows<KP1, true>(p, sm, v, stage, lane, ids, vmask, centre_or_pad);
             else issue_rows<KP1, false>(p, sm, v, stage, lane, ids, vmask, centre_or_pad);
         };
 
@@ -313,6 +383,10 @@ __global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams
         float lr = p.lr;
         while (ok_cur) {
             cp_async_wait_all();  // rows of `cur` (this stage) and alias entries of `nxt` are here
+            if (BULK) {           // ... the rows through the stage's mbarrier
+                mbar_wait(bars + stage, (parity >> stage) & 1u);
+                parity ^= 1u << stage;
+            }
             // Memory ordering between lanes: the copies above were waited for by the lane that
             // issued them, and the ids / alias slots of the other stage were last read in the
             // previous iteration.  The warp is converged here anyway (ballot / match follow); the
@@ -510,7 +584,12 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
             const uint32_t i = i_cur, c = c_cur;
             const uint32_t lo = i > W ? i - W : 0u;
             const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
-            for (; lo_at < lo; ++lo_at) slot_lo = slot_lo + 1u == R ? 0u : slot_lo + 1u;
+            {  // the window moved: usually by one position, by more after skipped centres
+                const uint32_t moved = lo - lo_at;
+                slot_lo = moved < R ? slot_lo + moved : (slot_lo + moved) % R;
+                if (slot_lo >= R) slot_lo -= R;
+                lo_at = lo;
+            }
             if (resident <= hi) {  // the centre jumped (skipped centres): complete the window now
                 if (resident < lo) resident = lo;
                 for (; resident <= hi; ++resident) fetch(resident);
@@ -524,6 +603,8 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
             const bool ctx = j <= hi && j != i && tok != PAD && tok != c;
             const uint32_t cmask = __ballot_sync(FULL, ctx);
             const uint32_t m = __popc(cmask);
+            // float offset of window slot `lane` inside the ring: the loops below fetch it by shuffle
+            const uint32_t my_ring = slot_of(lo + lane) * sm.pitch;
 
             // ---- centre p+1: resolve ids, copy its target rows and the row entering the window ----
             uint32_t neg_nxt = PAD, vmask_nxt = 0, ids_nxt = 0xFFFFFF00u | lane;
@@ -559,7 +640,7 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
                 bool first = true;
                 for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
                     const uint32_t q = __ffs(rem) - 1u;
-                    const float4 r = lds128(ring + slot_of(lo + q) * sm.pitch + v.smem_chunk);
+                    const float4 r = lds128(ring + __shfl_sync(FULL, my_ring, q) + v.smem_chunk);
                     if (first) h = r; else add4(h, r);
                     first = false;
                 }
@@ -589,8 +670,9 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
                     for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
                         const uint32_t q = __ffs(rem) - 1u;
                         const uint32_t t_id = __shfl_sync(FULL, tok, q);
+                        const uint32_t at = __shfl_sync(FULL, my_ring, q);
                         if (v.active) {
-                            float *slot = ring + slot_of(lo + q) * sm.pitch + 4u * lane;
+                            float *slot = ring + at + 4u * lane;
                             float4 r = lds128(slot);
                             add4(r, acc);
                             *reinterpret_cast<float4 *>(slot) = r;
@@ -603,8 +685,9 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
                         const uint32_t q = __ffs(rem) - 1u;
                         const uint32_t k = __shfl_sync(FULL, mult, q);
                         const uint32_t t_id = __shfl_sync(FULL, tok, q);
+                        const uint32_t at = __shfl_sync(FULL, my_ring, q);
                         if (v.active) {
-                            float *slot = ring + slot_of(lo + q) * sm.pitch + 4u * lane;
+                            float *slot = ring + at + 4u * lane;
                             float4 r = lds128(slot);
                             for (uint32_t t = 0; t < k; ++t) add4(r, acc);
                             *reinterpret_cast<float4 *>(slot) = r;
@@ -670,6 +753,8 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
                               uint64_t max_warps, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
+    if (model == B2E_SKIPGRAM && p.bulk && p.negatives + 1u == 11u)  // B2E_BULK=1: the UBLKCP experiment
+        return launch_pipe(skipgram_pipe_kernel<11, true>, p, deterministic, sm_count, max_warps, stream, 16);
     if (model == B2E_SKIPGRAM) {
         switch (p.negatives + 1u) {
             case 11: return launch_pipe(skipgram_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);

@@ -130,7 +130,7 @@ def test_glove_by_centre_ranges_equals_the_one_piece_epoch(monkeypatch, small_pp
                 engine.load_csr(graph.indptr, graph.indices)
                 c, x, losses = engine.fit(9)
             assert np.array_equal(c, t0[:, :24]) and np.array_equal(x, t1[:, :24]), slots
-            assert np.allclose(losses, expected, rtol=1e-4)
+            assert np.allclose(losses, expected, rtol=2e-3)  # float32 loss sums, another order
         # the production launch on many ranges: finite, and the loss falls like the one-piece run's
         monkeypatch.setenv("B2E_GLOVE_SLOTS", "50000")
         with Engine("GloVe", return_weight=0.5, explore_weight=2.0, iterations=1, **dict(kw, epochs=6)) as engine:
