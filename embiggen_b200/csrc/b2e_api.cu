@@ -150,6 +150,7 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
     if (const char *env = getenv("B2E_VARIANT")) h->variant = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_WALK_OCC")) h->walk_occupancy = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_BULK")) h->bulk = (uint32_t)atoi(env);
+    if (const char *env = getenv("B2E_SGD_OCC")) h->sgd_occupancy = (uint32_t)atoi(env);
     if (const char *env = getenv("B2E_EXCHANGE_ROWS")) h->exchange_rows = (uint32_t)atoi(env);
     thresholds(c.return_weight, c.explore_weight, h->thr);
     h->second_order = !(c.return_weight == 1.0f && c.explore_weight == 1.0f);
@@ -663,6 +664,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.prefetch = h->prefetch;
     p.variant = h->variant;
     p.bulk = h->bulk;
+    p.sgd_occupancy = h->sgd_occupancy;
     p.alias = h->d_alias;
     p.indptr = h->d_indptr;
     p.t0 = h->d_t0;

@@ -273,8 +273,10 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
     a.w = __fadd_rn(a.w, b.w);
 }
 
-template <int KP1, bool BULK = false>
-__global__ void __launch_bounds__(128, 4) skipgram_pipe_kernel(const TrainParams p) {
+// MINB: CTAs per SM the register allocation is held to (4: 121 registers; 5: 96 registers and
+// 32 bytes of spills, 20 instead of 16 warps per SM keep more row copies in flight)
+template <int KP1, bool BULK = false, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) skipgram_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t K = KP1 ? (uint32_t)(KP1 - 1) : p.negatives;
@@ -755,6 +757,8 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
     if (err != cudaSuccess) return err;
     if (model == B2E_SKIPGRAM && p.bulk && p.negatives + 1u == 11u)  // B2E_BULK=1: the UBLKCP experiment
         return launch_pipe(skipgram_pipe_kernel<11, true>, p, deterministic, sm_count, max_warps, stream, 16);
+    if (model == B2E_SKIPGRAM && p.sgd_occupancy == 5 && p.negatives + 1u == 11u && !deterministic)
+        return launch_pipe(skipgram_pipe_kernel<11, false, 5>, p, deterministic, sm_count, max_warps, stream);
     if (model == B2E_SKIPGRAM) {
         switch (p.negatives + 1u) {
             case 11: return launch_pipe(skipgram_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);
