@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import heldout_sgns_loss
+from conftest import heldout_sgns_loss, tiny_graphs
 from embiggen_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
@@ -298,3 +298,18 @@ def test_bulk_copy_variant_is_bit_exact(monkeypatch, small_ppi, rmat_graph):
                 assert np.array_equal(r["g0"], r["o0"]) and np.array_equal(r["g1"], r["o1"])
             else:
                 assert np.isfinite(r["g0"]).all() and np.isfinite(r["g1"]).all()
+
+
+@pytest.mark.parametrize("model", ["SkipGram", "CBOW"])
+def test_sink_centre_with_degree_normalised_learning_rate_stays_finite(model):
+    """A walk on a directed graph ends on a sink (out-degree 0) and that token still serves as a
+    centre; with normalize_learning_rate_by_degree the rate is lr / max(deg, 1), in the kernels
+    and in the oracle alike (it used to be lr / 0 = inf, poisoning the tables through the shared
+    negative rows)."""
+    graph = tiny_graphs()["directed_dead_end"]
+    for deterministic in (True, False):
+        r = run_pair(graph, model, 8, 6, 2, 3, 1.0, 1.0, 40, lr=0.5, deterministic=deterministic, normalize=True)
+        assert np.isfinite(r["o0"]).all() and np.isfinite(r["o1"]).all()
+        assert np.isfinite(r["g0"]).all() and np.isfinite(r["g1"]).all()
+        if deterministic:
+            assert np.array_equal(r["g0"], r["o0"]) and np.array_equal(r["g1"], r["o1"])
