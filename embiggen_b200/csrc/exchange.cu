@@ -28,8 +28,8 @@ struct ExchangeParams {
 };
 
 // One warp per (table, row), U rows per iteration: the G x U loads of a lane are issued back to
-// back before the first is consumed -- NVLink round trips are covered by loads in flight (at
-// G = 2 a single row per iteration moved 200 GB/s per direction, profiles/r02e_*).
+// back before the first is consumed.  Measured at G = 2 on C5 (80 GB per direction and exchange):
+// 125 ms for U = 1, 4 and 8 alike (profiles/r02m_*): 637 GB/s per direction, bound by the links.
 template <int G, int U>
 __global__ void __launch_bounds__(256) exchange_average_kernel(const ExchangeParams p) {
     const uint32_t lane = threadIdx.x & 31u;
