@@ -84,7 +84,7 @@ struct TrainParams {
     uint32_t downsample;  // stochastic_downsample_by_degree: max degree + 1, 0 = off
     uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
     uint32_t variant;   // tuning variant of the launch (0 = default)
-    uint32_t sgd_occupancy;  // CTAs per SM the SkipGram kernel is compiled for (4 or 5)
+    uint32_t sgd_occupancy;  // CTAs per SM of the SkipGram kernel (0: by table size, see launch_train_pipe)
     uint32_t bulk;      // SkipGram rows by cp.async.bulk + mbarrier instead of per-lane cp.async (experiment)
     const uint2 *alias;  // {threshold, alias} per node
     const int64_t *indptr;
@@ -218,7 +218,7 @@ struct b2e_handle {
     bool undirected = false;
     uint32_t prefetch = 1;
     uint32_t variant = 0;
-    uint32_t sgd_occupancy = 4;  // B2E_SGD_OCC
+    uint32_t sgd_occupancy = 0;  // B2E_SGD_OCC (0: automatic)
     uint32_t bulk = 0;  // B2E_BULK
     uint32_t exchange_rows = 0;  // B2E_EXCHANGE_ROWS (0: the default of launch_exchange_average)
     uint32_t walk_occupancy = 6;  // B2E_WALK_OCC: see walk_kernel

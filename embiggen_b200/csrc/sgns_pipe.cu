@@ -729,7 +729,8 @@ bool pipe_supported(const TrainParams &p, uint32_t model) {
 
 template <typename Kernel>
 static cudaError_t launch_pipe(Kernel kernel, const TrainParams &p, bool deterministic, int sm_count,
-                               uint64_t max_warps, cudaStream_t stream, size_t extra_warp_bytes = 0) {
+                               uint64_t max_warps, cudaStream_t stream, size_t extra_warp_bytes = 0,
+                               int max_per_sm = 0) {
     const size_t warp_bytes = pipe_warp_bytes(p.negatives, p.chunks, p.walk_length) + extra_warp_bytes;
     const int warps = deterministic ? 1 : 4;
     const size_t smem = warp_bytes * warps;
@@ -743,6 +744,7 @@ static cudaError_t launch_pipe(Kernel kernel, const TrainParams &p, bool determi
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
+    if (max_per_sm && per_sm > max_per_sm) per_sm = max_per_sm;
     uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: every CTA resident, walks fetched
     const uint64_t needed = (std::min<uint64_t>(p.n_walks, max_warps) + warps - 1) / warps;
     if (grid > needed) grid = needed;
@@ -757,8 +759,17 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
     if (err != cudaSuccess) return err;
     if (model == B2E_SKIPGRAM && p.bulk && p.negatives + 1u == 11u)  // B2E_BULK=1: the UBLKCP experiment
         return launch_pipe(skipgram_pipe_kernel<11, true>, p, deterministic, sm_count, max_warps, stream, 16);
-    if (model == B2E_SKIPGRAM && p.sgd_occupancy == 5 && p.negatives + 1u == 11u && !deterministic)
+    // CTAs per SM of the SkipGram kernel (B2E_SGD_OCC overrides).  Measured in pairs/s at 5 / 4 / 3 / 2:
+    // C2 543 / 605 / 596 / -, C3 537 / 587 / 583 / -, C5 473 / 503 / 516 / 460 M (profiles/r02p_*):
+    // four while the tables are a few GB, three once random rows spread over tens of GB (fewer
+    // streams keep more DRAM pages open); the switch-over is put at 32 GiB of tables.
+    uint32_t occupancy = p.sgd_occupancy;
+    if (occupancy == 0) occupancy = 2ull * p.n * p.row_stride * sizeof(float) >= (32ull << 30) ? 3u : 4u;
+    if (model == B2E_SKIPGRAM && occupancy == 5 && p.negatives + 1u == 11u && !deterministic)
         return launch_pipe(skipgram_pipe_kernel<11, false, 5>, p, deterministic, sm_count, max_warps, stream);
+    if (model == B2E_SKIPGRAM && (occupancy == 3 || occupancy == 2) && p.negatives + 1u == 11u && !deterministic)
+        return launch_pipe(skipgram_pipe_kernel<11, false, 3>, p, deterministic, sm_count, max_warps, stream, 0,
+                           (int)occupancy);
     if (model == B2E_SKIPGRAM) {
         switch (p.negatives + 1u) {
             case 11: return launch_pipe(skipgram_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream);
