@@ -664,6 +664,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.prefetch = h->prefetch;
     p.variant = h->variant;
     p.bulk = h->bulk;
+    p.no_full_rows = getenv("B2E_NO_FULL_ROWS") ? 1u : 0u;
     p.sgd_occupancy = h->sgd_occupancy;
     p.alias = h->d_alias;
     p.indptr = h->d_indptr;

@@ -85,6 +85,7 @@ struct TrainParams {
     uint32_t prefetch;  // 1: L2-prefetch the rows of the next draw site
     uint32_t variant;   // tuning variant of the launch (0 = default)
     uint32_t sgd_occupancy;  // CTAs per SM of the SkipGram kernel (0: by table size, see launch_train_pipe)
+    uint32_t no_full_rows;  // B2E_NO_FULL_ROWS: keep the generic CBOW kernel for 32-chunk rows (A/B)
     uint32_t bulk;      // SkipGram rows by cp.async.bulk + mbarrier instead of per-lane cp.async (experiment)
     const uint2 *alias;  // {threshold, alias} per node
     const int64_t *indptr;

@@ -474,7 +474,9 @@ __device__ __forceinline__ void red_add4(float *gmem, const float4 &v) {
 
 __host__ __device__ __forceinline__ uint32_t cbow_ring_slots(uint32_t window) { return 2u * window + 2u; }
 
-template <int KP1>
+// FULL: the row fills all 32 lanes (embedding_size in 125..128): the per-lane "do I hold a chunk"
+// predicate is then a compile-time constant
+template <int KP1, bool FULL = false>
 __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -498,8 +500,8 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
     v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
     v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
     v.row_bytes = p.row_stride * 4u;
-    v.active = lane < p.chunks;
-    v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
+    v.active = FULL ? true : lane < p.chunks;
+    v.smem_chunk = FULL ? 4u * lane : 4u * (lane < p.chunks ? lane : p.chunks - 1u);
     const uint32_t lower = (1u << lane) - 1u;
     float loss_acc = 0.0f;
     unsigned long long n_pairs = 0, n_targets = 0;
@@ -778,6 +780,8 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
         }
     }
     const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u;
+    if (p.chunks == 32u && p.negatives + 1u == 11u && !p.no_full_rows)
+        return launch_pipe(cbow_pipe_kernel<11, true>, p, deterministic, sm_count, max_warps, stream, ring);
     switch (p.negatives + 1u) {
         case 11: return launch_pipe(cbow_pipe_kernel<11>, p, deterministic, sm_count, max_warps, stream, ring);
         case 6: return launch_pipe(cbow_pipe_kernel<6>, p, deterministic, sm_count, max_warps, stream, ring);
