@@ -298,6 +298,12 @@ extern "C" int b2e_load_csr(b2e_handle *h, const int64_t *indptr, const uint32_t
     return b2e_load_csr_weighted(h, indptr, indices, nullptr, n, nnz);
 }
 
+// two int flags on the device, freed on every way out of a load
+struct DeviceFlags {
+    int *ptr = nullptr;
+    ~DeviceFlags() { cudaFree(ptr); }
+};
+
 // a failed load leaves the handle without a graph (require_graph() then fails cleanly)
 static int load_failed(b2e_handle *h, int rc) {
     cudaDeviceSynchronize();
@@ -369,24 +375,21 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         LOAD_TRY(cudaMemcpyAsync(h->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                  h->walk_stream));
     }
-    int *d_flags = nullptr;
+    DeviceFlags flag_words;
     int flags[2] = {0, 1};
-    LOAD_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
+    LOAD_TRY(cudaMalloc(&flag_words.ptr, 2 * sizeof(int)));
+    int *const d_flags = flag_words.ptr;
     LOAD_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->walk_stream));
     LOAD_TRY(check_indptr_device(h->d_indptr, n, nnz, d_flags, h->walk_stream));
     LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
     LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
-    if (flags[0]) {
-        cudaFree(d_flags);
-        return load_failed(h, fail(B2E_ERR_INVALID, "indptr must be non-decreasing"));
-    }
+    if (flags[0]) return load_failed(h, fail(B2E_ERR_INVALID, "indptr must be non-decreasing and end at nnz"));
     LOAD_TRY(launch_csr_check(h->d_indptr, h->d_indices, n, d_flags, h->sm_count, h->walk_stream));
     h->launches += 2;
     LOAD_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->walk_stream));
     LOAD_TRY(cudaStreamSynchronize(h->walk_stream));
     lap("CSR upload + content checks");
     if (flags[0]) {
-        cudaFree(d_flags);
         return load_failed(h, fail(B2E_ERR_INVALID, flags[0] & 1
                                         ? "a destination node id is out of range"
                                         : "neighbour lists must be sorted strictly ascending within each row"));
@@ -400,7 +403,6 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
         LOAD_TRY(cudaMalloc(&d_sources_all, n * sizeof(uint32_t)));
         if (c.use_scale_free_distribution && cudaMalloc(&h->d_alias, n * sizeof(uint2)) != cudaSuccess) {
             cudaFree(d_sources_all);
-            cudaFree(d_flags);
             return load_failed(h, fail(B2E_ERR_CUDA, "out of device memory (alias table)"));
         }
         std::string error;
@@ -412,7 +414,6 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
             e = cudaMemcpy(h->d_sources, d_sources_all, n_src * sizeof(uint32_t), cudaMemcpyDeviceToDevice);
         cudaFree(d_sources_all);
         if (e != cudaSuccess) {
-            cudaFree(d_flags);
             if (error.empty()) error = std::string("start-node list: ") + cudaGetErrorString(e);
             return load_failed(h, fail(e == cudaErrorInvalidValue ? B2E_ERR_INVALID : B2E_ERR_CUDA, error));
         }
@@ -450,8 +451,7 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
     if (weights) {
         std::vector<uint2> edge_alias(nnz);
         if (!build_edge_alias(indptr, weights, n, edge_alias)) {
-            cudaFree(d_flags);
-            return load_failed(h, fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers"));
+                return load_failed(h, fail(B2E_ERR_INVALID, "edge weights must be non-negative numbers"));
         }
         LOAD_TRY(cudaMalloc(&h->d_edge_alias, nnz * sizeof(uint2)));
         LOAD_TRY(cudaMemcpyAsync(h->d_edge_alias, edge_alias.data(), nnz * sizeof(uint2), cudaMemcpyHostToDevice,
@@ -487,7 +487,6 @@ static int load_graph_common(b2e_handle *h, const int64_t *indptr, const uint32_
             ++h->launches;
         }
     }
-    cudaFree(d_flags);
     lap("row filters");
 
     LOAD_TRY(cudaMalloc(&h->d_t0, n * (uint64_t)h->row_stride * sizeof(float)));
