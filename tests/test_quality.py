@@ -7,9 +7,9 @@ Hadamard edge features, `binary_auroc`); without the `ensmallen` wheel the same 
 restated here with numpy + scikit-learn and the oracle stands where Ensmallen would.
 
 Tolerance (stated, as the contract asks): over three holdouts the mean AUROC of the GPU embedding
-may not fall more than 0.005 below the oracle's (the 0.005 of north_star, read as "not worse
-than"; the GPU run is usually a few thousandths *better* than the
-8-thread Hogwild oracle), and no single holdout may differ by more than 0.015 either way.
+must be within 0.005 of the oracle's, two-sided (the 0.005 of north_star), and no single holdout
+may differ by more than 0.01 either way (measured in round 2: every holdout within 0.002, means
++0.0005 ... +0.0011; the comparator is the 8-thread Hogwild oracle, itself not deterministic).
 """
 import numpy as np
 import pytest
@@ -111,9 +111,9 @@ def test_gpu_auroc_matches_oracle_auroc(model, rw, ew):
         a_gpu = auroc(ours, train_pos, test_pos, train_neg, test_neg)
         print(f"{model} rw={rw} ew={ew} holdout {trial}: AUROC oracle {a_ref:.4f}  gpu {a_gpu:.4f}")
         assert a_gpu > 0.85
-        assert abs(a_gpu - a_ref) <= 0.015
+        assert abs(a_gpu - a_ref) <= 0.01
         deltas.append(a_gpu - a_ref)
-    assert np.mean(deltas) >= -0.005
+    assert abs(np.mean(deltas)) <= 0.005  # north_star: within 0.005, two-sided
 
 
 @pytest.mark.gpu
