@@ -42,3 +42,16 @@ def test_library_chatter_on_stdout_is_sent_to_stderr():
     assert done.returncode == 0, done.stderr
     assert done.stdout == '{"ok": 1}\n'
     assert "NCCL version x.y" in done.stderr and "python chatter" in done.stderr
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """The CPU arm is the baseline the product is compared with: it may execute oracle/ (the port)
+    but must not load libb2e.so, not even to generate the graph (oracle/graphgen.c does that)."""
+    code = ("import sys, os; sys.path.insert(0, %r); os.chdir(%r); import bench; "
+            "sys.argv = ['bench.py', '--impl', 'reference', '--config', 'small', '--steps', '1', '--warmup', '0', "
+            "'--reference-walks', '64']; bench.main(); maps = open('/proc/self/maps').read(); "
+            "sys.stderr.write('B2E=%%d ORACLE=%%d\\n' %% ('libb2e.so' in maps, 'liboracle.so' in maps))" % (ROOT, ROOT))
+    done = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                          env=dict(os.environ, B2E_CACHE="/tmp"))
+    assert done.returncode == 0, done.stderr[-2000:]
+    assert "B2E=0 ORACLE=1" in done.stderr
