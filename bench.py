@@ -583,6 +583,7 @@ def run_ours(args, name, cfg, note):
                      "peak_source": peak_source, "avg_launch_ms": sgd_avg_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes},
         "walk": {"kernel": "walk_kernel", "steps_per_s_alone": steps_per_launch / (walk_avg_ms * 1e-3),
+                 "steps_per_s_alone_all_gpus": world * steps_per_launch / (walk_avg_ms * 1e-3),  # rank 0's rate x N
                  "avg_launch_ms": walk_avg_ms, "trials_per_step": trials, "searches_per_step": searches,
                  "probe_gathers_per_step": probes,
                  "filter_rejects_per_search": walk_counters["walk_filter_rejects"] / max(walk_counters["walk_searches"], 1),
