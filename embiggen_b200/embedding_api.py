@@ -68,9 +68,8 @@ def normalize_kwargs(model, kwargs: Dict[str, Any]) -> Dict[str, Any]:
     for key, value in list(kwargs.items()):
         names = KWARG_SCHEMA[key]
         names = [names] if isinstance(names, str) else names
-        if isinstance(value, tuple(_TYPES[name] for name in names)) and not (
-                isinstance(value, bool) and "bool" not in names):
-            continue
+        if isinstance(value, tuple(_TYPES[name] for name in names)):
+            continue  # (a Python bool passes for an int here, exactly as in the reference)
         for name in names:
             if name == "None":
                 continue
