@@ -27,6 +27,8 @@ import numpy as np
 import pandas as pd
 
 try:  # the real thing, when the reference package and its dependencies are installed
+    if os.environ.get("B2E_NO_EMBIGGEN"):  # force the restatement (tests/test_reference_own_tests.py)
+        raise ImportError("B2E_NO_EMBIGGEN is set")
     from embiggen.utils.abstract_models import (  # type: ignore
         AbstractEmbeddingModel, AbstractModel, EmbeddingResult, abstract_class)
     HAVE_EMBIGGEN = True
