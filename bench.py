@@ -87,13 +87,18 @@ def choose_config(requested):
                       "which the 100M-node tables need on the CPU arm")
 
 
+# engine options outside the named workload (--shared-negatives); empty by default, so that the
+# `config` of the default run is the one the reference arm prints
+OPTIONS = {}
+
+
 def config_dict(name, cfg, note):
     """The `config` object: the same in both arms (the driver compares them)."""
     n = cfg["graph"][3] if cfg["graph"][0] == "rmat" else cfg["graph"][1]
     tables_mb = 2 * n * cfg["embedding_size"] * 4 / 1e6
     return {"workload": cfg["label"] + (f" [{note}]" if note else ""), "name": name,
             "objective": cfg["model"], "embedding_size": cfg["embedding_size"],
-            "return_weight": cfg["return_weight"], "explore_weight": cfg["explore_weight"], **COMMON,
+            "return_weight": cfg["return_weight"], "explore_weight": cfg["explore_weight"], **COMMON, **OPTIONS,
             "l2": f"inputs larger than L2 (tables {tables_mb:.0f} MB, rows gathered at random; no flush)"}
 
 
@@ -233,6 +238,14 @@ def skipgram_bytes(counters, embedding_size, centres):
     return counters["targets"] * row + centres * (row + 4) + negatives_drawn * 32
 
 
+def shared_skipgram_bytes(counters, embedding_size, centres):
+    """--shared-negatives: per centre its own T0 row and the one T1 row that enters (and, updated,
+    leaves) the window are read and written once, as is every valid negative's row."""
+    row = 2 * 4 * embedding_size
+    valid_negatives = counters["targets"] - counters["pairs"]
+    return valid_negatives * row + centres * (2 * row + 4) + centres * COMMON["number_of_negative_samples"] * 32
+
+
 def cbow_bytes(counters, embedding_size, centres):
     row = 2 * 4 * embedding_size
     negatives_drawn = centres * COMMON["number_of_negative_samples"]
@@ -285,7 +298,7 @@ class CpuPath:
         stats = o.train(cfg["model"], walks, self.t0, self.t1, SEED, self.n, self.D, COMMON["window_size"],
                         COMMON["number_of_negative_samples"], COMMON["learning_rate"],
                         COMMON["clipping_value"], first_walk=first, thr=self.thr, alias=self.alias,
-                        fast_math=True)
+                        fast_math=True, shared_negatives=bool(OPTIONS.get("shared_negatives")))
         end = time.perf_counter()
         return wc["steps"], stats["pairs"], mid - begin, end - mid
 
@@ -437,7 +450,7 @@ def run_ours(args, name, cfg, note):
     L, w, K = COMMON["walk_length"], COMMON["window_size"], COMMON["number_of_negative_samples"]
     engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
                     return_weight=cfg["return_weight"], explore_weight=cfg["explore_weight"],
-                    chunk_walks=args.chunk_walks, device=local_rank, **COMMON)
+                    chunk_walks=args.chunk_walks, device=local_rank, **COMMON, **OPTIONS)
     begin = time.perf_counter()
     engine.load_csr(graph.indptr, graph.indices)
     load_s = time.perf_counter() - begin
@@ -540,7 +553,8 @@ def run_ours(args, name, cfg, note):
     peak, peak_source = measured_peak_gbs()
     centres = chunk * L  # every token of every walk is a centre once
     if cfg["model"] == "SkipGram":
-        per_launch_bytes = skipgram_bytes(counters, D, centres * args.steps) / args.steps
+        per_launch_bytes = (shared_skipgram_bytes if OPTIONS.get("shared_negatives") else skipgram_bytes)(
+            counters, D, centres * args.steps) / args.steps
     else:
         per_launch_bytes = cbow_bytes(counters, D, centres * args.steps) / args.steps
     sgd_avg_ms = float(np.mean(sgd_ms))
@@ -564,6 +578,8 @@ def run_ours(args, name, cfg, note):
     kernel_name = ("skipgram_pipe_kernel" if cfg["model"] == "SkipGram" else "cbow_pipe_kernel") + \
         f"<{K + 1}>"
     traffic, traffic_source = measured_traffic(name, chunk)
+    if OPTIONS.get("shared_negatives"):
+        kernel_name, traffic, traffic_source = f"skipgram_shared_kernel<{K}>", None, "no ncu capture of this kernel"
     result = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -618,7 +634,7 @@ def run_ours(args, name, cfg, note):
         torch.cuda.synchronize(device)
         e2e_engine = Engine(cfg["model"], embedding_size=D, epochs=1, iterations=cfg["iterations"],
                             return_weight=cfg["return_weight"], explore_weight=cfg["explore_weight"],
-                            chunk_walks=args.chunk_walks, device=local_rank, **COMMON)
+                            chunk_walks=args.chunk_walks, device=local_rank, **COMMON, **OPTIONS)
         out0 = out1 = pinned = None
         if rank == 0:
             pinned = PinnedTables(n, D)
@@ -713,11 +729,17 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--cpu-budget", type=float, default=15.0)
     parser.add_argument("--no-e2e", action="store_true")
+    parser.add_argument("--shared-negatives", action="store_true",
+                        help="SkipGram: one set of negatives per centre (opt-in mode, not the named workload)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 0)
     name, note = choose_config(args.config)
     cfg = CONFIGS[name]
+    if args.shared_negatives:
+        if cfg["model"] != "SkipGram":
+            parser.error("--shared-negatives is a SkipGram option")
+        OPTIONS["shared_negatives"] = True
     if args.impl == "reference":
         run_reference(args, name, cfg, note)
     else:

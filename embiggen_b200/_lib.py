@@ -10,7 +10,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2e.so")
 
-ABI_VERSION = 2  # B2E_ABI_VERSION of include/b2e.h
+ABI_VERSION = 3  # B2E_ABI_VERSION of include/b2e.h
 B2E_OK = 0
 B2E_ERR_INVALID = -1
 B2E_ERR_CUDA = -2
@@ -45,6 +45,7 @@ class B2EConfig(ctypes.Structure):
         ("stochastic_downsample_by_degree", ctypes.c_uint32),
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("walklet_scale", ctypes.c_uint32),
+        ("shared_negatives", ctypes.c_uint32),
         ("deterministic", ctypes.c_uint32),
         ("chunk_walks", ctypes.c_uint32),
         ("max_concurrent_walks", ctypes.c_uint32),

@@ -118,6 +118,14 @@ extern "C" int b2e_create(const b2e_config *config, b2e_handle **out) {
         return fail(B2E_ERR_INVALID, "window_size must be in [1, 64]");
     if (c.number_of_negative_samples > 31)
         return fail(B2E_ERR_INVALID, "number_of_negative_samples must be at most 31");
+    if (c.shared_negatives) {
+        if (c.model != B2E_SKIPGRAM)
+            return fail(B2E_ERR_INVALID, "shared_negatives is a SkipGram option (CBOW already draws per centre)");
+        if (c.window_size > 7 || c.number_of_negative_samples > 15 || c.embedding_size > 128 ||
+            sub_walk_length(c) > 1024)
+            return fail(B2E_ERR_INVALID, "shared_negatives needs window_size <= 7, number_of_negative_samples <= 15, "
+                                         "embedding_size <= 128 and walk_length <= 1024");
+    }
     if (c.iterations == 0) return fail(B2E_ERR_INVALID, "iterations must be positive");
     if (!(c.return_weight > 0.0f) || !(c.explore_weight > 0.0f))
         return fail(B2E_ERR_INVALID, "return_weight and explore_weight must be strictly positive");
@@ -663,6 +671,7 @@ static int train_slot(b2e_handle *h, uint64_t seed, uint32_t slot, float learnin
     p.prefetch = h->prefetch;
     p.variant = h->variant;
     p.bulk = h->bulk;
+    p.shared_negatives = c.shared_negatives ? 1u : 0u;
     p.no_full_rows = getenv("B2E_NO_FULL_ROWS") ? 1u : 0u;
     p.sgd_occupancy = h->sgd_occupancy;
     p.alias = h->d_alias;

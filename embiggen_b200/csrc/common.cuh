@@ -86,6 +86,7 @@ struct TrainParams {
     uint32_t variant;   // tuning variant of the launch (0 = default)
     uint32_t sgd_occupancy;  // CTAs per SM of the SkipGram kernel (0: by table size, see launch_train_pipe)
     uint32_t no_full_rows;  // B2E_NO_FULL_ROWS: keep the generic CBOW kernel for 32-chunk rows (A/B)
+    uint32_t shared_negatives;  // SkipGram: one set of negatives per centre (skipgram_shared_kernel)
     uint32_t bulk;      // SkipGram rows by cp.async.bulk + mbarrier instead of per-lane cp.async (experiment)
     const uint2 *alias;  // {threshold, alias} per node
     const int64_t *indptr;
@@ -162,6 +163,7 @@ cudaError_t launch_init_tables(float *t0, float *t1, uint64_t n, uint32_t embedd
 cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                          uint64_t max_warps, cudaStream_t stream);
 bool pipe_supported(const TrainParams &p, uint32_t model);
+bool shared_negatives_supported(const TrainParams &p);
 cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool deterministic, int sm_count,
                               uint64_t max_warps, cudaStream_t stream);
 

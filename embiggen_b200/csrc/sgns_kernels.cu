@@ -360,6 +360,8 @@ cudaError_t launch_train(const TrainParams &p, uint32_t model, bool deterministi
                          uint64_t max_warps, cudaStream_t stream) {
     if (p.n_walks == 0) return cudaSuccess;
     // production path: shared-memory pipelined kernel; B2E_VARIANT >= 1 keeps the register path
+    if (model == B2E_SKIPGRAM && p.shared_negatives)  // one kernel, no register-staged twin
+        return launch_train_pipe(p, model, deterministic, sm_count, max_warps, stream);
     if (p.variant == 0 && pipe_supported(p, model))
         return launch_train_pipe(p, model, deterministic, sm_count, max_warps, stream);
     if (model == B2E_SKIPGRAM) return launch_model<B2E_SKIPGRAM>(p, deterministic, sm_count, max_warps, stream);

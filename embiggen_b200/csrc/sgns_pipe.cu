@@ -154,15 +154,16 @@ __device__ __forceinline__ uint32_t slot_ids(uint32_t lane, uint32_t context, ui
     return ((vmask >> lane) & 1u) ? id : (0xFFFFFF00u | lane);
 }
 
-// KP1 = K + 1 when known at compile time (0: runtime, up to PIPE_SLOTS); ALL: every slot is on
-template <int KP1, bool ALL>
+// KP1 = K + 1 when known at compile time (0: runtime, up to PIPE_SLOTS); ALL: every slot is on;
+// SHARED (skipgram_shared_kernel): the slots are the K negatives alone, KP1 stands for K
+template <int KP1, bool ALL, bool SHARED = false>
 __device__ __forceinline__ void issue_rows(const TrainParams &p, const PipeSmem &sm, const LaneView &v,
                                            uint32_t stage, uint32_t lane, uint32_t my_id,
                                            uint32_t vmask, uint32_t centre_or_pad) {
     if (lane < PIPE_SLOTS) sm.ids(stage)[lane] = my_id;
     __syncwarp();  // ids are read back by every lane when the pair is trained
     float *dst = sm.rows(stage) + 4u * lane;
-    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
+    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + (SHARED ? 0u : 1u);
     constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -204,14 +205,15 @@ __device__ __forceinline__ void issue_rows_bulk(const TrainParams &p, const Pipe
 
 // dots, sigmoid, axpy and scatter of the targets of one draw site out of stage `stage`;
 // returns this lane's chunk of sum g * row (rows as they were before the update)
-template <int KP1, bool ALL>
+// SHARED: every slot is a negative that stands for `weight` pairs (skipgram_shared_kernel)
+template <int KP1, bool ALL, bool SHARED = false>
 __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSmem &sm, const LaneView &v,
                                              uint32_t stage, uint32_t lane, uint32_t vmask, float lr,
-                                             const float4 &h, float &loss_acc) {
+                                             const float4 &h, float &loss_acc, float weight = 1.0f) {
     // Lanes past the end of the row read its last chunk instead of branching; their h is zero,
     // so they add nothing to a score; their stores are predicated off and their acc is dropped.
     const float *rows = sm.rows(stage) + v.smem_chunk;
-    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + 1u;
+    const uint32_t slots = KP1 ? (uint32_t)KP1 : p.negatives + (SHARED ? 0u : 1u);
     constexpr int S = KP1 ? KP1 : PIPE_SLOTS;
     float part[16];
 #pragma unroll
@@ -235,9 +237,14 @@ __device__ __forceinline__ float4 train_site(const TrainParams &p, const PipeSme
     if (my_on && !(fabsf(f) > p.clip)) {
         const float e = exp_det(-f);
         const float sigmoid = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-        g_mine = __fmul_rn(__fsub_rn(my_slot == 0 ? 1.0f : 0.0f, sigmoid), lr);
         // -log sigmoid(f) = log(1 + e^-f);  -log sigmoid(-f) = log(1 + e^-f) + f
-        if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e) + (my_slot == 0 ? 0.0f : f);
+        if (SHARED) {
+            g_mine = __fmul_rn(__fmul_rn(__fsub_rn(0.0f, sigmoid), lr), weight);
+            if ((lane & 1u) == 0) loss_acc += weight * (__logf(1.0f + e) + f);
+        } else {
+            g_mine = __fmul_rn(__fsub_rn(my_slot == 0 ? 1.0f : 0.0f, sigmoid), lr);
+            if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e) + (my_slot == 0 ? 0.0f : f);
+        }
         apply = true;
     }
     const uint32_t amask = __ballot_sync(FULL, apply);  // bits 2s, 2s+1: slot s is applied
@@ -724,6 +731,292 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
     }
 }
 
+// ---- K4b (opt-in, `shared_negatives`): SkipGram with one set of negatives per CENTRE.  The m
+// pairs of a centre all score against the same h = T0[c]; when they also share their K negatives
+// the m x K block of negative scores collapses to K (each negative stands for m pairs, its
+// gradient carries the factor m), and a centre moves m + K + 1 rows instead of m (K + 1) + 1.
+// The positives are the T1 rows of the window, and the window slides: they live in the ring of
+// the CBOW kernel (a row is copied from HBM once, scored and updated in shared memory by up to
+// 2W centres, every update written through as one 128-bit red.global.add per lane); the K
+// negatives and the centre's T0 row ride the two-stage pipeline.  Rows that the centre being
+// trained is about to write (its negatives, its context rows, its own T0 row) are never copied
+// early: such copies are issued after its stores, as in the kernels above.  Semantics and
+// floating point: oracle/sgns.c, train_centre_shared; the single-warp launch reproduces it bit
+// for bit.  Needs 2W + 1 <= 16 and K <= 15 (two id sets are compared in one MATCH).
+template <int KT>
+__global__ void __launch_bounds__(128, 3) skipgram_shared_kernel(const TrainParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t K = KT ? (uint32_t)KT : p.negatives;
+    const uint32_t L = p.walk_length, W = p.window;
+    const uint32_t full_mask = (1u << K) - 1u;  // K ones
+    const uint32_t R = cbow_ring_slots(W);
+    PipeSmem sm;
+    float *ring;  // [R][pitch]: T1 rows of the walk positions around the centre
+    {
+        unsigned char *base = smem_raw + warp * (pipe_warp_bytes(K, p.chunks, L) + R * p.chunks * 16u);
+        sm.pitch = p.chunks * 4u;
+        sm.stage_floats = (K + 2u) * sm.pitch;
+        sm.rows_base = reinterpret_cast<float *>(base);
+        sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * sm.stage_floats);
+        sm.ids_base = reinterpret_cast<uint32_t *>(sm.alias_base + 64);
+        sm.walk = sm.ids_base + 2 * PIPE_SLOTS;
+        ring = reinterpret_cast<float *>(base + pipe_warp_bytes(K, p.chunks, L));
+    }
+    LaneView v;
+    v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
+    v.t1 = reinterpret_cast<const char *>(p.t1) + 16u * lane;
+    v.row_bytes = p.row_stride * 4u;
+    v.active = lane < p.chunks;
+    v.smem_chunk = 4u * (lane < p.chunks ? lane : p.chunks - 1u);
+    const uint32_t lower = (1u << lane) - 1u;
+    const uint32_t sentinel = 0xFFFFFF00u | lane;
+    float loss_acc = 0.0f;
+    unsigned long long n_pairs = 0, n_targets = 0;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(&p.counters->work_counter, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= p.n_walks) break;
+        const uint64_t wid = p.first_walk + w * p.walk_id_stride;
+        const uint32_t wid_lo = (uint32_t)wid, wid_hi = (uint32_t)(wid >> 32);
+        {
+            const uint32_t *src = p.walks + w * (uint64_t)L;
+            __syncwarp();
+            for (uint32_t t = lane; t < L; t += 32u) sm.walk[t] = __ldg(src + t);
+            stage_skip_mask(p, wid_lo, wid_hi, sm.walk, L, lane);
+            __syncwarp();
+        }
+        const uint32_t *walk = sm.walk;
+
+        auto draw = [&](uint32_t i, uint32_t a, uint32_t &idx, uint32_t &ry) {
+            idx = PAD;
+            ry = 0;
+            if (lane < K) {
+                const uint4 r = philox4x32_10(p.seed_lo, p.seed_hi, wid_lo, wid_hi,
+                                              (i << 16) | 0xFFFFu, (TAG_NEG << 24) | lane);
+                idx = __umulhi(r.x, p.n);
+                ry = r.y;
+                if (p.use_alias) cp_async8(sm.alias(a) + lane, p.alias + idx);
+            }
+        };
+        // ids of the negatives of centre i (token c), lane k = draw k: a draw that hits the centre,
+        // an earlier draw or a context token of the window is off (sentinel).  Lanes 0..15 hold
+        // the window, lanes 16..16+K-1 the draws: one MATCH answers both questions.
+        auto resolve = [&](uint32_t i, uint32_t c, uint32_t a, uint32_t idx, uint32_t ry, uint32_t &vmask) -> uint32_t {
+            uint32_t neg = idx;
+            if (p.use_alias && lane < K) {
+                const uint2 e = sm.alias(a)[lane];
+                neg = ry < e.x ? idx : e.y;
+            }
+            const uint32_t lo = i > W ? i - W : 0u;
+            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+            const uint32_t moved = __shfl_sync(FULL, neg, lane & 15u);
+            uint32_t key = sentinel;
+            if (lane < 16u) {
+                const uint32_t j = lo + lane;
+                if (j <= hi && j != i) {
+                    const uint32_t t = walk[j];
+                    if (t != PAD && t != c) key = t;
+                }
+            } else if (lane - 16u < K) {
+                key = moved;
+            }
+            const uint32_t same = __match_any_sync(FULL, key);
+            const bool valid = lane >= 16u && lane - 16u < K && moved != c && (same & 0xFFFFu) == 0u &&
+                               ((same >> 16) & ((1u << (lane - 16u)) - 1u)) == 0u;
+            vmask = __ballot_sync(FULL, valid) >> 16;
+            return ((vmask >> lane) & 1u) ? neg : sentinel;  // vmask has no bit at or above K
+        };
+        auto issue = [&](uint32_t stage, uint32_t ids, uint32_t vmask, uint32_t centre) {
+            if (vmask == full_mask) issue_rows<KT, true, true>(p, sm, v, stage, lane, ids, vmask, centre);
+            else issue_rows<KT, false, true>(p, sm, v, stage, lane, ids, vmask, centre);
+        };
+        uint32_t lo_at = 0, slot_lo = 0;  // ring slot of a walk position = position mod R, see cbow_pipe_kernel
+        auto slot_of = [&](uint32_t pos) -> uint32_t {
+            const uint32_t s = slot_lo + (pos - lo_at);
+            return s >= R ? s - R : s;
+        };
+        auto fetch = [&](uint32_t pos) {
+            const uint32_t t = walk[pos];
+            if (t != PAD && v.active) cp_async16(ring + slot_of(pos) * sm.pitch + 4u * lane, v.row1(t));
+        };
+
+        uint32_t c_cur = PAD, c_nxt = PAD, c_far = PAD;
+        uint32_t i_cur = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, 0, c_cur);
+        if (i_cur >= L) continue;
+        uint32_t stage = 0, slot_a = 0;
+        uint32_t idx_n = PAD, ry_n = 0, vmask_cur, ids_cur;
+        draw(i_cur, slot_a, idx_n, ry_n);
+        cp_async_commit();
+        cp_async_wait_all();
+        ids_cur = resolve(i_cur, c_cur, slot_a, idx_n, ry_n, vmask_cur);
+        issue(stage, ids_cur, vmask_cur, c_cur);
+        uint32_t resident = i_cur > W ? i_cur - W : 0u;  // positions < resident are in the ring (or are PAD)
+        lo_at = resident;
+        slot_lo = resident % R;
+        for (const uint32_t end = min(L, i_cur + W + 1u); resident < end; ++resident) fetch(resident);
+        uint32_t i_nxt = next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_cur + 1, c_nxt);
+        slot_a ^= 1u;
+        if (i_nxt < L) draw(i_nxt, slot_a, idx_n, ry_n);
+        cp_async_commit();
+
+        while (i_cur < L) {
+            cp_async_wait_all();
+            __syncwarp();  // inter-lane memory ordering, see skipgram_pipe_kernel
+            const uint32_t i = i_cur, c = c_cur;
+            const uint32_t lo = i > W ? i - W : 0u;
+            const uint32_t hi = i + W < L - 1 ? i + W : L - 1;
+            {
+                const uint32_t moved = lo - lo_at;
+                slot_lo = moved < R ? slot_lo + moved : (slot_lo + moved) % R;
+                if (slot_lo >= R) slot_lo -= R;
+                lo_at = lo;
+            }
+            if (resident <= hi) {  // the centre jumped (skipped centres): complete the window now
+                if (resident < lo) resident = lo;
+                for (; resident <= hi; ++resident) fetch(resident);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            // ---- the window of centre p: lane l looks at window slot l (2W + 1 <= 16) ----
+            const uint32_t j = lo + lane;
+            const uint32_t tok = j <= hi ? walk[j] : PAD;
+            const bool ctx = j <= hi && j != i && tok != PAD && tok != c;
+            const uint32_t cmask = __ballot_sync(FULL, ctx);
+            const uint32_t m = __popc(cmask);
+            const uint32_t my_ring = slot_of(lo + lane) * sm.pitch;
+            const uint32_t ctx_key = ctx ? tok : sentinel;
+
+            // ---- centre p+1: its negatives, its T0 row and the T1 row entering the window ----
+            uint32_t vmask_nxt = 0, ids_nxt = sentinel;
+            bool deferred = false, deferred_ring = false;
+            if (i_nxt < L) {
+                ids_nxt = resolve(i_nxt, c_nxt, slot_a, idx_n, ry_n, vmask_nxt);
+                uint32_t moved = __shfl_sync(FULL, ids_nxt, lane & 15u);
+                if (moved >= 0xFFFFFF00u) moved |= 16u;  // keep the two sentinel families apart
+                // a negative of p+1 that p is about to write: as one of its negatives, as a context row
+                const uint32_t hit_negs = __match_any_sync(FULL, lane < 16u ? ids_cur : moved);
+                const uint32_t hit_ctx = __match_any_sync(FULL, lane < 16u ? ctx_key : moved);
+                deferred = __ballot_sync(FULL, lane < 16u && ((hit_negs | hit_ctx) >> 16) != 0u) != 0u ||
+                           c_nxt == c;  // ... or the same centre token again (skipped centres between)
+                if (!deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt, c_nxt);
+                if (resident == hi + 1u && resident < L && resident <= i_nxt + W) {
+                    const uint32_t entering = walk[resident];
+                    deferred_ring = __ballot_sync(FULL, ctx_key == entering || ids_cur == entering) != 0u;
+                    if (!deferred_ring) fetch(resident);
+                    ++resident;
+                }
+            }
+            // ---- centre p+2: start its draw ----
+            const uint32_t i_far = i_nxt < L ? next_centre<true>(p, wid_lo, wid_hi, walk, L, W, i_nxt + 1, c_far) : L;
+            uint32_t idx_f = PAD, ry_f = 0;
+            if (i_far < L) draw(i_far, slot_a ^ 1u, idx_f, ry_f);
+            cp_async_commit();
+
+            // ---- centre p: every target is scored against h = T0[c] before anything is updated ----
+            const float lr = centre_lr(p, c);
+            float4 h = v.active ? lds128(sm.rows(stage) + 4u * lane + K * sm.pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float g_mine = 0.0f;
+            uint32_t pmask;  // bits 2s, 2s + 1: the context at window slot s is applied (not clipped)
+            {
+                float part[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    float d = 0.0f;
+                    if ((cmask >> s) & 1u) {
+                        const float4 r = lds128(ring + __shfl_sync(FULL, my_ring, s) + v.smem_chunk);
+                        d = __fmaf_rn(h.x, r.x, d);
+                        d = __fmaf_rn(h.y, r.y, d);
+                        d = __fmaf_rn(h.z, r.z, d);
+                        d = __fmaf_rn(h.w, r.w, d);
+                    }
+                    part[s] = d;
+                }
+                float f = reduce16(part, lane);  // lane l: score of window slot (l >> 1) & 15
+                if (p.scale_dot) f = __fmul_rn(f, p.inv_scale);
+                const bool my_on = (cmask >> ((lane >> 1) & 15u)) & 1u;
+                bool apply = false;
+                if (my_on && !(fabsf(f) > p.clip)) {
+                    const float e = exp_det(-f);
+                    const float sigmoid = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+                    g_mine = __fmul_rn(__fsub_rn(1.0f, sigmoid), lr);
+                    if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e);
+                    apply = true;
+                }
+                pmask = __ballot_sync(FULL, apply);
+            }
+            // the K negatives: each stands for the m pairs of this centre
+            const float fm = (float)m;
+            const float4 acc_n = vmask_cur == full_mask
+                ? train_site<KT, true, true>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc, fm)
+                : train_site<KT, false, true>(p, sm, v, stage, lane, vmask_cur, lr, h, loss_acc, fm);
+            // the contexts: T1[o] += g h, in the ring and (written through) in HBM; a token at k
+            // window positions receives k additions in each of its slots, its first position
+            // issues the k atomics
+            float4 acc_p = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                const uint32_t same = __match_any_sync(FULL, ctx_key);
+                const uint32_t leaders = __ballot_sync(FULL, ctx && (same & lower) == 0u);
+                const uint32_t mult = __popc(same);
+                const bool simple = leaders == cmask;  // every context token occurs once: the common case
+                for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
+                    const uint32_t q = __ffs(rem) - 1u;
+                    if (!((pmask >> (2u * q)) & 1u)) continue;
+                    const float g = __shfl_sync(FULL, g_mine, 2u * q);
+                    const uint32_t at = __shfl_sync(FULL, my_ring, q);
+                    const uint32_t t_id = __shfl_sync(FULL, tok, q);
+                    const uint32_t k = simple ? 1u : __shfl_sync(FULL, mult, q);
+                    if (v.active) {
+                        float *slot = ring + at + 4u * lane;
+                        float4 r = lds128(slot);
+                        acc_p.x = __fmaf_rn(g, r.x, acc_p.x);
+                        acc_p.y = __fmaf_rn(g, r.y, acc_p.y);
+                        acc_p.z = __fmaf_rn(g, r.z, acc_p.z);
+                        acc_p.w = __fmaf_rn(g, r.w, acc_p.w);
+                        const float4 delta = make_float4(__fmul_rn(g, h.x), __fmul_rn(g, h.y), __fmul_rn(g, h.z),
+                                                         __fmul_rn(g, h.w));
+                        for (uint32_t t = 0; t < k; ++t) add4(r, delta);
+                        *reinterpret_cast<float4 *>(slot) = r;
+                        if ((leaders >> q) & 1u)
+                            for (uint32_t t = 0; t < k; ++t)
+                                red_add4(reinterpret_cast<float *>(const_cast<char *>(v.row1(t_id))), delta);
+                    }
+                }
+            }
+            add4(acc_p, acc_n);
+            add4(h, acc_p);
+            if (v.active) *reinterpret_cast<float4 *>(const_cast<char *>(v.row0(c))) = h;
+            n_targets += __popc(vmask_cur) + m;
+            n_pairs += m;
+
+            if (deferred || deferred_ring) {
+                if (deferred) issue(stage ^ 1u, ids_nxt, vmask_nxt, c_nxt);
+                if (deferred_ring) fetch(resident - 1u);
+                cp_async_commit();
+            }
+            i_cur = i_nxt; c_cur = c_nxt; vmask_cur = vmask_nxt; ids_cur = ids_nxt;
+            i_nxt = i_far; c_nxt = c_far; idx_n = idx_f; ry_n = ry_f;
+            stage ^= 1u;
+            slot_a ^= 1u;
+        }
+    }
+    double loss = (double)loss_acc;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(FULL, loss, off);
+    if (lane == 0) {
+        atomicAdd(&p.counters->pairs, n_pairs);
+        atomicAdd(&p.counters->targets, n_targets);
+        atomicAdd(&p.counters->loss_sum, loss);
+    }
+}
+
+bool shared_negatives_supported(const TrainParams &p) {
+    return p.chunks <= 32u && p.negatives <= 15u && 2u * p.window + 1u <= 16u && p.walk_length <= 1024u;
+}
+
 bool pipe_supported(const TrainParams &p, uint32_t model) {
     if (p.chunks > 32u || p.negatives + 1u > PIPE_SLOTS || p.walk_length > 1024u) return false;
     return model == B2E_SKIPGRAM || 2u * p.window + 1u <= 32u;
@@ -759,6 +1052,15 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
                               uint64_t max_warps, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(&p.counters->work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
+    if (model == B2E_SKIPGRAM && p.shared_negatives) {
+        if (!shared_negatives_supported(p)) return cudaErrorInvalidValue;  // b2e_create refuses these
+        const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u;
+        switch (p.negatives) {
+            case 10: return launch_pipe(skipgram_shared_kernel<10>, p, deterministic, sm_count, max_warps, stream, ring);
+            case 5: return launch_pipe(skipgram_shared_kernel<5>, p, deterministic, sm_count, max_warps, stream, ring);
+            default: return launch_pipe(skipgram_shared_kernel<0>, p, deterministic, sm_count, max_warps, stream, ring);
+        }
+    }
     if (model == B2E_SKIPGRAM && p.bulk && p.negatives + 1u == 11u)  // B2E_BULK=1: the UBLKCP experiment
         return launch_pipe(skipgram_pipe_kernel<11, true>, p, deterministic, sm_count, max_warps, stream, 16);
     // CTAs per SM of the SkipGram kernel (B2E_SGD_OCC overrides).  Measured in pairs/s at 5 / 4 / 3 / 2:

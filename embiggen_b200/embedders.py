@@ -33,7 +33,7 @@ from .graph import as_csr, as_types
 _DTYPES = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
 # engine options that are not part of the reference's signature (keyword-only, defaulted)
 _B200_DEFAULTS = dict(negative_sampling_exponent=0.75, scale_by_sqrt_dim=False, deterministic=False,
-                      chunk_walks=0, max_concurrent_walks=0, sync_interval=4, device=None)
+                      shared_negatives=False, chunk_walks=0, max_concurrent_walks=0, sync_interval=4, device=None)
 
 
 @abstract_class
@@ -142,7 +142,7 @@ class Node2VecB200(B200Embedder):
             change_edge_type_weight=k.get("change_edge_type_weight", 1.0),
             stochastic_downsample_by_degree=bool(k.get("stochastic_downsample_by_degree", False)),
             scale_by_sqrt_dim=k["scale_by_sqrt_dim"], deterministic=k["deterministic"],
-            walklet_scale=scale,
+            shared_negatives=k["shared_negatives"], walklet_scale=scale,
             chunk_walks=k["chunk_walks"], max_concurrent_walks=k["max_concurrent_walks"],
             device=device)
 

@@ -53,6 +53,7 @@ KWARG_SCHEMA = {
     "verbose": "bool", "alpha": "float",
     # B200 extras
     "negative_sampling_exponent": "float", "scale_by_sqrt_dim": "bool", "deterministic": "bool",
+    "shared_negatives": "bool",
     "chunk_walks": "int", "max_concurrent_walks": "int", "sync_interval": "int", "device": ["int", "None"],
 }
 _TYPES = {"bool": bool, "int": int, "float": float, "str": str, "None": type(None)}

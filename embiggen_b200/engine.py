@@ -113,6 +113,7 @@ class Engine:
                  glove_alpha: float = 0.75,
                  stochastic_downsample_by_degree: bool = False,
                  scale_by_sqrt_dim: bool = False, walklet_scale: int = 0, deterministic: bool = False,
+                 shared_negatives: bool = False,
                  chunk_walks: int = 0, max_concurrent_walks: int = 0, device: int = 0):
         self._lib = _lib.load()
         self._handle = ctypes.c_void_p()
@@ -136,7 +137,7 @@ class Engine:
             change_edge_type_weight=change_edge_type_weight,
             stochastic_downsample_by_degree=int(bool(stochastic_downsample_by_degree)),
             scale_by_sqrt_dim=int(bool(scale_by_sqrt_dim)), walklet_scale=int(walklet_scale),
-            deterministic=int(bool(deterministic)),
+            deterministic=int(bool(deterministic)), shared_negatives=int(bool(shared_negatives)),
             chunk_walks=chunk_walks, max_concurrent_walks=max_concurrent_walks, device=device,
         )
         check(self._lib.b2e_create(ctypes.byref(self.config), ctypes.byref(self._handle)))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2E_ABI_VERSION 2
+#define B2E_ABI_VERSION 3
 #define B2E_PAD_TOKEN 0xFFFFFFFFu /* walk token after a dead end (directed graphs only) */
 #define B2E_MAX_WORLD 16          /* replicas one exchange step can average (GPUs of one node) */
 #define B2E_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
@@ -68,6 +68,10 @@ typedef struct {
     uint32_t scale_by_sqrt_dim;                 /* score = dot / sqrt(D) */
     uint32_t walklet_scale; /* k >= 2: Walklets (.../walklets.py), train on the k sub-walks made of
                                every k-th token, so that `window_size` counts in hops of k */
+    uint32_t shared_negatives; /* SkipGram, opt-in (north_star's shared-negative batching): one set of
+                                  negatives per CENTRE, shared by its pairs, each negative weighted by
+                                  the number of pairs it stands for; needs window_size <= 7,
+                                  number_of_negative_samples <= 15, embedding_size <= 128 */
     uint32_t deterministic; /* 1: one warp trains walks in ascending id order (bit-exact) */
     uint32_t chunk_walks;   /* walks per walk->SGD chunk, 0 = automatic */
     uint32_t max_concurrent_walks; /* walks trained concurrently (Hogwild), 0 = automatic */

@@ -48,6 +48,7 @@ class SgnsCfg(ctypes.Structure):
         ("scale_by_sqrt_dim", ctypes.c_uint32),
         ("downsample_bound", ctypes.c_uint32),
         ("fast_math", ctypes.c_uint32),
+        ("shared_negatives", ctypes.c_uint32),
     ]
 
 
@@ -304,9 +305,10 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
           thr: Optional[np.ndarray] = None, alias: Optional[np.ndarray] = None,
           indptr: Optional[np.ndarray] = None, normalize_learning_rate_by_degree: bool = False,
           scale_by_sqrt_dim: bool = False, stochastic_downsample_by_degree: bool = False,
-          fast_math: bool = False) -> dict:
+          fast_math: bool = False, shared_negatives: bool = False) -> dict:
     """Train in place over row-major walks; returns loss_sum / pairs / targets.  ``fast_math``
-    (vectorised dot, libm exp) is for timing the CPU baseline only, never for parity."""
+    (vectorised dot, libm exp) is for timing the CPU baseline only, never for parity.
+    ``shared_negatives`` (SkipGram): one set of negatives per centre, see sgns.c."""
     walk_array = np.ascontiguousarray(walk_array, dtype=np.uint32)
     assert t0.dtype == np.float32 and t1.dtype == np.float32
     assert t0.flags.c_contiguous and t1.flags.c_contiguous
@@ -323,6 +325,7 @@ def train(model: str, walk_array: np.ndarray, t0: np.ndarray, t1: np.ndarray, se
         normalize_learning_rate_by_degree=int(normalize_learning_rate_by_degree),
         scale_by_sqrt_dim=int(scale_by_sqrt_dim),
         fast_math=int(fast_math),
+        shared_negatives=int(shared_negatives),
     )
     if indptr is not None:
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)

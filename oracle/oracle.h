@@ -105,6 +105,8 @@ typedef struct {
     uint32_t scale_by_sqrt_dim;                 /* dot / sqrt(D)  (P)   */
     uint32_t downsample_bound; /* stochastic_downsample_by_degree: max degree + 1, 0 => off */
     uint32_t fast_math; /* 1: vectorised dot + libm expf: for timing the CPU baseline only (sgns.c) */
+    uint32_t shared_negatives; /* SkipGram only, opt-in: one set of negatives per CENTRE, shared by
+                                  its pairs (north_star's shared-negative batching; sgns.c)        */
 } orc_sgns_cfg;
 
 /*

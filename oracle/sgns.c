@@ -183,6 +183,81 @@ static void apply_targets(const orc_sgns_cfg *cfg, float lr, float inv_scale, co
     }
 }
 
+/*
+ * SkipGram with shared negatives (cfg->shared_negatives; north_star's opt-in "shared-negative
+ * batching"): the draw site is the CENTRE, not the pair.  One set of K negatives (the CBOW site
+ * key, (i << 16) | 0xFFFF) serves the m pairs of centre i, and all m + K targets are scored
+ * against the same h = T0[c] before anything is updated (batch semantics):
+ *   context at window position q:  g_q = (1 - sigmoid(f_q)) lr;  T1[o_q] += fl(g_q h)   (mul, then
+ *       add: the product is what the GPU hands to the L2 atomic adder); a token at k positions
+ *       receives its k additions one after the other;
+ *   negative s (valid: not the centre, not a repeat, not a context token of this window):
+ *       g_s = ((0 - sigmoid(f_s)) lr) m  -- it stands for the m pairs that would each have drawn
+ *       their own; T1[n_s] = fma(g_s, h, T1[n_s]);
+ *   T0[c] = h + (sum_q g_q T1[o_q] + sum_s g_s T1[n_s]), rows as they were before the update,
+ *       each sum accumulated with fma in the order written.
+ * Rows moved per pair fall from K + 1 (+ the centre's share) to (K + 2) / m: DESIGN.md section 5.
+ */
+static void train_centre_shared(const orc_sgns_cfg *cfg, float lr, float inv_scale, uint32_t c,
+                                const uint32_t *ctx, uint32_t m, uint64_t seed, uint64_t wid,
+                                uint32_t i, uint64_t n, const uint32_t *thr, const uint32_t *alias,
+                                float *t0, float *t1, float *h, float *acc, train_acc *out) {
+    const uint32_t stride = cfg->row_stride, K = cfg->negatives;
+    uint32_t neg[MAX_TARGETS];
+    int valid[MAX_TARGETS];
+    float fp[2 * 64], fn[MAX_TARGETS], gp[2 * 64];
+    float *crow = t0 + (uint64_t)c * stride;
+    memcpy(h, crow, stride * sizeof(float));
+    draw_negatives(cfg, seed, wid, (i << 16) | 0xFFFFu, n, thr, alias, c, c, neg, valid);
+    for (uint32_t k = 0; k < K; ++k)
+        for (uint32_t q = 0; q < m && valid[k]; ++q) valid[k] = neg[k] != ctx[q];
+    /* cfg->fast_math: vectorisable dot and libm exp, for timing the CPU baseline only (apply_targets) */
+    const int fast = cfg->fast_math != 0;
+    for (uint32_t q = 0; q < m; ++q) {
+        fp[q] = fast ? fast_dot(h, t1 + (uint64_t)ctx[q] * stride, stride)
+                     : orc_dot(h, t1 + (uint64_t)ctx[q] * stride, stride);
+        if (cfg->scale_by_sqrt_dim) fp[q] = fp[q] * inv_scale;
+    }
+    for (uint32_t k = 0; k < K; ++k) {
+        if (!valid[k]) continue;
+        fn[k] = fast ? fast_dot(h, t1 + (uint64_t)neg[k] * stride, stride)
+                     : orc_dot(h, t1 + (uint64_t)neg[k] * stride, stride);
+        if (cfg->scale_by_sqrt_dim) fn[k] = fn[k] * inv_scale;
+    }
+    const float fm = (float)m;
+    float *acc_p = acc, *acc_n = acc + stride;
+    memset(acc, 0, 2 * stride * sizeof(float));
+    for (uint32_t k = 0; k < K; ++k) {
+        if (!valid[k]) continue;
+        ++out->targets;
+        if (fabsf(fn[k]) > cfg->clipping_value) continue;
+        const float g = ((0.0f - (fast ? 1.0f / (1.0f + expf(-fn[k])) : orc_sigmoid(fn[k]))) * lr) * fm;
+        out->loss += (double)m * softplus((double)fn[k]);
+        float *row = t1 + (uint64_t)neg[k] * stride;
+        for (uint32_t e = 0; e < stride; ++e) {
+            const float old = row[e];
+            acc_n[e] = fmaf(g, old, acc_n[e]);
+            row[e] = fmaf(g, h[e], old);
+        }
+    }
+    for (uint32_t q = 0; q < m; ++q) { /* every sum over the rows as they were */
+        ++out->targets;
+        gp[q] = 0.0f;
+        if (fabsf(fp[q]) > cfg->clipping_value) continue;
+        gp[q] = (1.0f - (fast ? 1.0f / (1.0f + expf(-fp[q])) : orc_sigmoid(fp[q]))) * lr;
+        out->loss += softplus(-(double)fp[q]);
+        const float *row = t1 + (uint64_t)ctx[q] * stride;
+        for (uint32_t e = 0; e < stride; ++e) acc_p[e] = fmaf(gp[q], row[e], acc_p[e]);
+    }
+    for (uint32_t q = 0; q < m; ++q) {
+        if (fabsf(fp[q]) > cfg->clipping_value) continue;
+        float *row = t1 + (uint64_t)ctx[q] * stride;
+        for (uint32_t e = 0; e < stride; ++e) row[e] = row[e] + gp[q] * h[e];
+    }
+    for (uint32_t e = 0; e < stride; ++e) crow[e] = h[e] + (acc_p[e] + acc_n[e]);
+    out->pairs += m;
+}
+
 static void train_one_walk(const orc_sgns_cfg *cfg, const uint32_t *walk, uint64_t wid,
                            uint64_t seed, uint64_t n, const int64_t *indptr, const uint32_t *thr,
                            const uint32_t *alias, float *t0, float *t1, float *h, float *acc,
@@ -211,7 +286,16 @@ static void train_one_walk(const orc_sgns_cfg *cfg, const uint32_t *walk, uint64
         }
         const uint32_t lo = i > w ? i - w : 0;
         const uint32_t hi = i + w < L - 1 ? i + w : L - 1;
-        if (cfg->model == 0) {
+        if (cfg->model == 0 && cfg->shared_negatives) {
+            uint32_t ctx[2 * 64];
+            uint32_t m = 0;
+            for (uint32_t j = lo; j <= hi; ++j) {
+                const uint32_t o = walk[j];
+                if (j == i || o == ORC_PAD_TOKEN || o == c) continue;
+                ctx[m++] = o;
+            }
+            if (m) train_centre_shared(cfg, lr, inv_scale, c, ctx, m, seed, wid, i, n, thr, alias, t0, t1, h, acc, out);
+        } else if (cfg->model == 0) {
             float *crow = t0 + (uint64_t)c * stride;
             memcpy(h, crow, stride * sizeof(float));
             for (uint32_t j = lo; j <= hi; ++j) {
@@ -267,13 +351,14 @@ int orc_train(const orc_sgns_cfg *cfg, const uint32_t *walks, uint64_t n_walks,
         (cfg->row_stride & 3) || cfg->row_stride < cfg->embedding_size || n > 0xFFFFFFFFull)
         return -1;
     if (cfg->use_alias && (!thr || !alias)) return -1;
+    if (cfg->shared_negatives && cfg->model != 0) return -1;
     if ((cfg->normalize_learning_rate_by_degree || cfg->downsample_bound) && !indptr) return -1;
     train_acc total = {0.0, 0, 0};
     int failed = 0;
 #pragma omp parallel num_threads(g_threads) if (g_threads > 1)
     {
         float *h = (float *)malloc(cfg->row_stride * sizeof(float));
-        float *acc = (float *)malloc(cfg->row_stride * sizeof(float));
+        float *acc = (float *)malloc(2 * cfg->row_stride * sizeof(float)); /* two sums in the shared mode */
         train_acc local = {0.0, 0, 0};
         if (!h || !acc) {
 #pragma omp atomic write

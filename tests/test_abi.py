@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header_layout():
-    # 27 four-byte fields, no padding
-    assert ctypes.sizeof(_lib.B2EConfig) == 108
+    # 28 four-byte fields, no padding
+    assert ctypes.sizeof(_lib.B2EConfig) == 112
     assert ctypes.sizeof(_lib.B2ECounters) == 64
 
 
@@ -69,7 +69,7 @@ def test_integration_stub_lists_the_config_fields_in_header_order():
 
 def test_abi_version_and_error_channel():
     lib = _lib.load()
-    assert lib.b2e_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.b2e_abi_version() == _lib.ABI_VERSION == 3
     handle = ctypes.c_void_p()
     config = _lib.B2EConfig(struct_size=1)
     assert lib.b2e_create(ctypes.byref(config), ctypes.byref(handle)) == _lib.B2E_ERR_INVALID
