@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02v: the opt-in shared-negative SkipGram kernel: parity, sanitizers, C3 / C2 rates
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests/test_gpu_shared_negatives.py -q -x -s > gpurun_out/r02v_pytest.txt 2>&1
+timeout 500 python -m pytest tests/test_gpu_shared_negatives.py -q -s > gpurun_out/r02v_pytest.txt 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r02v_pytest.txt; grep -h "AUROC\|oracle loss" gpurun_out/r02v_pytest.txt
 ( time timeout 240 compute-sanitizer --tool memcheck python scripts/sanitize_shared.py ) > gpurun_out/r02v_memcheck.txt 2>&1
 tail -4 gpurun_out/r02v_memcheck.txt | head -3
