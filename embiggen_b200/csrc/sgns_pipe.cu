@@ -743,8 +743,15 @@ __global__ void __launch_bounds__(128, 3) cbow_pipe_kernel(const TrainParams p) 
 // early: such copies are issued after its stores, as in the kernels above.  Semantics and
 // floating point: oracle/sgns.c, train_centre_shared; the single-warp launch reproduces it bit
 // for bit.  Needs 2W + 1 <= 16 and K <= 15 (two id sets are compared in one MATCH).
-template <int KT>
-__global__ void __launch_bounds__(128, 3) skipgram_shared_kernel(const TrainParams p) {
+// a stage of the shared-negative kernel holds K + 1 rows, one fewer than a stage of the per-pair
+// kernels: with D = 100, K = 10, W = 4 four CTAs of four warps then fit an SM (54.6 KB each)
+__host__ __device__ __forceinline__ uint32_t shared_warp_bytes(uint32_t negatives, uint32_t chunks,
+                                                               uint32_t walk_length) {
+    return pipe_warp_bytes(negatives, chunks, walk_length) - 2u * chunks * 16u;
+}
+
+template <int KT, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) skipgram_shared_kernel(const TrainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t K = KT ? (uint32_t)KT : p.negatives;
@@ -754,14 +761,14 @@ __global__ void __launch_bounds__(128, 3) skipgram_shared_kernel(const TrainPara
     PipeSmem sm;
     float *ring;  // [R][pitch]: T1 rows of the walk positions around the centre
     {
-        unsigned char *base = smem_raw + warp * (pipe_warp_bytes(K, p.chunks, L) + R * p.chunks * 16u);
+        unsigned char *base = smem_raw + warp * (shared_warp_bytes(K, p.chunks, L) + R * p.chunks * 16u);
         sm.pitch = p.chunks * 4u;
-        sm.stage_floats = (K + 2u) * sm.pitch;
+        sm.stage_floats = (K + 1u) * sm.pitch;  // K negatives and the centre's T0 row
         sm.rows_base = reinterpret_cast<float *>(base);
         sm.alias_base = reinterpret_cast<uint2 *>(sm.rows_base + 2u * sm.stage_floats);
         sm.ids_base = reinterpret_cast<uint32_t *>(sm.alias_base + 64);
         sm.walk = sm.ids_base + 2 * PIPE_SLOTS;
-        ring = reinterpret_cast<float *>(base + pipe_warp_bytes(K, p.chunks, L));
+        ring = reinterpret_cast<float *>(base + shared_warp_bytes(K, p.chunks, L));
     }
     LaneView v;
     v.t0 = reinterpret_cast<const char *>(p.t0) + 16u * lane;
@@ -1054,9 +1061,13 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
     if (err != cudaSuccess) return err;
     if (model == B2E_SKIPGRAM && p.shared_negatives) {
         if (!shared_negatives_supported(p)) return cudaErrorInvalidValue;  // b2e_create refuses these
-        const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u;
+        // launch_pipe sizes a warp's slab as pipe_warp_bytes + extra: one row per stage less here
+        const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u - 2u * p.chunks * 16u;
         switch (p.negatives) {
-            case 10: return launch_pipe(skipgram_shared_kernel<10>, p, deterministic, sm_count, max_warps, stream, ring);
+            case 10:
+                if (p.sgd_occupancy == 4 && !deterministic)
+                    return launch_pipe(skipgram_shared_kernel<10, 4>, p, deterministic, sm_count, max_warps, stream, ring);
+                return launch_pipe(skipgram_shared_kernel<10>, p, deterministic, sm_count, max_warps, stream, ring);
             case 5: return launch_pipe(skipgram_shared_kernel<5>, p, deterministic, sm_count, max_warps, stream, ring);
             default: return launch_pipe(skipgram_shared_kernel<0>, p, deterministic, sm_count, max_warps, stream, ring);
         }
