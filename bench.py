@@ -579,7 +579,8 @@ def run_ours(args, name, cfg, note):
         f"<{K + 1}>"
     traffic, traffic_source = measured_traffic(name, chunk)
     if OPTIONS.get("shared_negatives"):
-        kernel_name, traffic, traffic_source = f"skipgram_shared_kernel<{K}>", None, "no ncu capture of this kernel"
+        kernel_name = f"skipgram_shared_kernel<{K}>"
+        traffic, traffic_source = measured_traffic(name + "_shared", chunk)
     result = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,

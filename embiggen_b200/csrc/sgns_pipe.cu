@@ -1065,7 +1065,10 @@ cudaError_t launch_train_pipe(const TrainParams &p, uint32_t model, bool determi
         const size_t ring = (size_t)cbow_ring_slots(p.window) * p.chunks * 16u - 2u * p.chunks * 16u;
         switch (p.negatives) {
             case 10:
-                if (p.sgd_occupancy == 4 && !deterministic)
+                // four CTAs per SM (128 registers, 54.6 KB each) unless B2E_SGD_OCC=3: the kernel is bound by
+                // the dependency chain of a warp, not by HBM -- C3 2.61 G against 2.20 G pairs/s, C5 2.51 G
+                // (profiles/r02x_*)
+                if (p.sgd_occupancy != 3 && !deterministic)
                     return launch_pipe(skipgram_shared_kernel<10, 4>, p, deterministic, sm_count, max_warps, stream, ring);
                 return launch_pipe(skipgram_shared_kernel<10>, p, deterministic, sm_count, max_warps, stream, ring);
             case 5: return launch_pipe(skipgram_shared_kernel<5>, p, deterministic, sm_count, max_warps, stream, ring);
