@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(128, MINB) skipgram_shared_kernel(const TrainP
             const float lr = centre_lr(p, c);
             float4 h = v.active ? lds128(sm.rows(stage) + 4u * lane + K * sm.pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
             float g_mine = 0.0f;
-            uint32_t pmask;  // bits 2s, 2s + 1: the context at window slot s is applied (not clipped)
+            uint32_t applied;  // bit s: the context at window slot s is applied (a context, not clipped)
             {
                 float part[16];
 #pragma unroll
@@ -953,7 +953,8 @@ __global__ void __launch_bounds__(128, MINB) skipgram_shared_kernel(const TrainP
                     if ((lane & 1u) == 0) loss_acc += __logf(1.0f + e);
                     apply = true;
                 }
-                pmask = __ballot_sync(FULL, apply);
+                // the decision for slot s sits on lanes 2s, 2s + 1: gather it to lane s
+                applied = __ballot_sync(FULL, __shfl_sync(FULL, (int)apply, (2u * lane) & 31u) != 0) & 0xFFFFu & cmask;
             }
             // the K negatives: each stands for the m pairs of this centre
             const float fm = (float)m;
@@ -968,14 +969,11 @@ __global__ void __launch_bounds__(128, MINB) skipgram_shared_kernel(const TrainP
                 const uint32_t same = __match_any_sync(FULL, ctx_key);
                 const uint32_t leaders = __ballot_sync(FULL, ctx && (same & lower) == 0u);
                 const uint32_t mult = __popc(same);
-                const bool simple = leaders == cmask;  // every context token occurs once: the common case
-                for (uint32_t rem = cmask; rem; rem &= rem - 1u) {
-                    const uint32_t q = __ffs(rem) - 1u;
-                    if (!((pmask >> (2u * q)) & 1u)) continue;
+                // one context row: acc_p += g * row (as it was), row += k times fl(g h) here and in HBM
+                auto push = [&](uint32_t q, uint32_t k, bool leader) {
                     const float g = __shfl_sync(FULL, g_mine, 2u * q);
                     const uint32_t at = __shfl_sync(FULL, my_ring, q);
                     const uint32_t t_id = __shfl_sync(FULL, tok, q);
-                    const uint32_t k = simple ? 1u : __shfl_sync(FULL, mult, q);
                     if (v.active) {
                         float *slot = ring + at + 4u * lane;
                         float4 r = lds128(slot);
@@ -985,11 +983,24 @@ __global__ void __launch_bounds__(128, MINB) skipgram_shared_kernel(const TrainP
                         acc_p.w = __fmaf_rn(g, r.w, acc_p.w);
                         const float4 delta = make_float4(__fmul_rn(g, h.x), __fmul_rn(g, h.y), __fmul_rn(g, h.z),
                                                          __fmul_rn(g, h.w));
-                        for (uint32_t t = 0; t < k; ++t) add4(r, delta);
+                        float *row = reinterpret_cast<float *>(const_cast<char *>(v.row1(t_id)));
+                        if (k == 1u) {
+                            add4(r, delta);
+                            red_add4(row, delta);
+                        } else {
+                            for (uint32_t t = 0; t < k; ++t) add4(r, delta);
+                            if (leader)
+                                for (uint32_t t = 0; t < k; ++t) red_add4(row, delta);
+                        }
                         *reinterpret_cast<float4 *>(slot) = r;
-                        if ((leaders >> q) & 1u)
-                            for (uint32_t t = 0; t < k; ++t)
-                                red_add4(reinterpret_cast<float *>(const_cast<char *>(v.row1(t_id))), delta);
+                    }
+                };
+                if (leaders == cmask) {  // every context token occurs once: the common case
+                    for (uint32_t rem = applied; rem; rem &= rem - 1u) push(__ffs(rem) - 1u, 1u, true);
+                } else {
+                    for (uint32_t rem = applied; rem; rem &= rem - 1u) {
+                        const uint32_t q = __ffs(rem) - 1u;
+                        push(q, __shfl_sync(FULL, mult, q), (leaders >> q) & 1u);
                     }
                 }
             }
