@@ -92,6 +92,14 @@ class Node2VecB200(B200Embedder):
         embedding_size = self._model_kwargs.pop("embedding_size")
         random_state = self._model_kwargs.pop("random_state")
         self._check_supported(self._model_kwargs)
+        if self._model_kwargs.get("shared_negatives"):  # the limits b2e_create enforces, at construction
+            if self.MODELS[self.model_name()] != "SkipGram":
+                raise ValueError("shared_negatives is a SkipGram option (CBOW draws its negatives per centre "
+                                 f"already, GloVe draws none); {self.model_name()!r} cannot use it.")
+            if self._model_kwargs.get("window_size", 1) > 7 or embedding_size > 128 or \
+                    self._model_kwargs.get("number_of_negative_samples", 0) > 15:
+                raise ValueError("shared_negatives needs window_size <= 7, number_of_negative_samples <= 15 "
+                                 "and embedding_size <= 128.")
         # Like the reference, which builds the Rust model here (node2vec.py:65-69), fail at
         # construction time when the native engine cannot run.
         _lib.load()

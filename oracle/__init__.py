@@ -380,7 +380,7 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
         clipping_value: float = 6.0, alpha: float = 0.75, use_scale_free_distribution: bool = True,
         normalize_learning_rate_by_degree: bool = False, chunk_walks: int = 1 << 16,
         stochastic_downsample_by_degree: bool = False, normalize_by_degree: bool = False,
-        walklet_scale: int = 0):
+        walklet_scale: int = 0, shared_negatives: bool = False):
     """Whole path: walks + SGD for ``epochs`` epochs in ascending walk-id order.
 
     Returns (t0, t1, epoch_mean_loss) with padded row stride.
@@ -407,7 +407,8 @@ def fit(model: str, indptr, indices, seed: int, embedding_size: int, epochs: int
                       negatives, float(lr), clipping_value=clipping_value,
                       first_walk=first, thr=thr, alias=alias, indptr=indptr,
                       normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
-                      stochastic_downsample_by_degree=stochastic_downsample_by_degree)
+                      stochastic_downsample_by_degree=stochastic_downsample_by_degree,
+                      shared_negatives=shared_negatives)
             loss_sum += r["loss_sum"]
             pairs += r["pairs"]
             done += count

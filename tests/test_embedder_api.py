@@ -93,6 +93,22 @@ def test_kwarg_coercion_and_rejection():
             Node2VecSkipGramB200(**invalid)
 
 
+def test_shared_negatives_is_an_opt_in_skipgram_keyword():
+    """B200 extra: off by default, survives the parameters() round trip and the smoke
+    conversion, refused at construction where the kernel does not apply."""
+    from embiggen_b200.embedders import Node2VecCBOWB200, DeepWalkSkipGramB200, Node2VecGloVeB200
+    assert Node2VecSkipGramB200().parameters()["shared_negatives"] is False
+    m = DeepWalkSkipGramB200(shared_negatives=True)
+    assert m.parameters()["shared_negatives"] is True
+    assert DeepWalkSkipGramB200(**m.parameters()).parameters() == m.parameters()
+    assert m.into_smoke_test().parameters()["shared_negatives"] is True
+    for model, kwargs in ((Node2VecCBOWB200, {}), (Node2VecGloVeB200, {}), (Node2VecSkipGramB200, dict(window_size=8)),
+                          (Node2VecSkipGramB200, dict(number_of_negative_samples=16)),
+                          (Node2VecSkipGramB200, dict(embedding_size=200))):
+        with pytest.raises(ValueError, match="shared_negatives"):
+            model(shared_negatives=True, **kwargs)
+
+
 @pytest.mark.parametrize("model", B200_EMBEDDERS)
 def test_smoke_test_conversion_and_random_state(model):
     m = model(epochs=7, walk_length=64)

@@ -70,13 +70,14 @@ def auroc(embedding, train_pos, test_pos, train_neg, test_neg):
     return roc_auc_score(y_test, model.decision_function(x_test / scale))
 
 
-def oracle_embedding(model, graph, seed, rw, ew, threads):
+def oracle_embedding(model, graph, seed, rw, ew, threads, shared_negatives=False):
     oracle.set_threads(threads)
     try:
         t0, t1, _ = oracle.fit(model, graph.indptr, graph.indices, seed, KW["embedding_size"], KW["epochs"],
                                KW["iterations"], KW["walk_length"], KW["window_size"],
                                KW["number_of_negative_samples"], KW["learning_rate"],
-                               KW["learning_rate_decay"], return_weight=rw, explore_weight=ew)
+                               KW["learning_rate_decay"], return_weight=rw, explore_weight=ew,
+                               shared_negatives=shared_negatives)
     finally:
         oracle.set_threads(1)
     D = KW["embedding_size"]
@@ -90,6 +91,19 @@ def test_oracle_embedding_predicts_held_out_edges():
     graph = csr_from_edges(train_pos[0], train_pos[1], n)
     embedding = oracle_embedding("SkipGram", graph, 42, 1.0, 1.0, threads=8)
     assert auroc(embedding, train_pos, test_pos, train_neg, test_neg) > 0.85
+
+
+def test_oracle_shared_negatives_embedding_predicts_held_out_edges():
+    """CPU only: the opt-in estimator with one set of negatives per centre (oracle/sgns.c:
+    train_centre_shared) learns the same planted structure, within 0.02 of the per-pair oracle."""
+    src, dst, n = block_model(0)
+    train_pos, test_pos, train_neg, test_neg = holdout(src, dst, n, 0)
+    graph = csr_from_edges(train_pos[0], train_pos[1], n)
+    plain = auroc(oracle_embedding("SkipGram", graph, 42, 1.0, 1.0, threads=8), train_pos, test_pos, train_neg, test_neg)
+    shared = auroc(oracle_embedding("SkipGram", graph, 42, 1.0, 1.0, threads=8, shared_negatives=True),
+                   train_pos, test_pos, train_neg, test_neg)
+    print("oracle AUROC: per-pair negatives", plain, "shared negatives", shared)
+    assert shared > 0.85 and shared > plain - 0.02
 
 
 @pytest.mark.gpu
