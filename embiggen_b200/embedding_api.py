@@ -17,6 +17,7 @@ half of ``AbstractModel`` is out of scope.
 """
 import gzip
 import hashlib
+import inspect
 import json
 import os
 import pickle
@@ -211,20 +212,110 @@ if not HAVE_EMBIGGEN:
             return EmbeddingResult(**cached)
 
     @abstract_class
+    def _declines(method) -> bool:
+        """abstract_model.py:16-23: a method counts as "not implemented" when its SOURCE TEXT holds
+        the raise -- which is why the capability methods of subclasses never spell it out."""
+        return "raise NotImplementedError" in inspect.getsource(method)
+
+    def _capability_family(name: str):
+        """`requires_<name>` / `can_use_<name>` / `is_using_<name>` with the defaults of
+        abstract_model.py:156-512: each answers from its sibling when the sibling settles the
+        question (cannot use => does not require; requires => can use and is using) and declines
+        otherwise, so that a subclass implements exactly the ones that carry information."""
+        requires, can_use, is_using = f"requires_{name}", f"can_use_{name}", f"is_using_{name}"
+
+        def requires_default(cls) -> bool:
+            try:
+                if not getattr(cls, can_use)():
+                    return False
+            except (NotImplementedError, RecursionError):
+                pass
+            raise NotImplementedError(f"The `{requires}` method must be implemented in the child classes of "
+                                      f"abstract model. It was not implemented in the class {cls.__name__}.")
+
+        def can_use_default(cls) -> bool:
+            try:
+                if not _declines(getattr(cls, requires)) and getattr(cls, requires)():
+                    return True
+            except (NotImplementedError, RecursionError):
+                pass
+            raise NotImplementedError(f"The `{can_use}` method must be implemented in the child classes of "
+                                      f"abstract model. It was not implemented in the class {cls.__name__}.")
+
+        def is_using_default(self) -> bool:
+            try:
+                if getattr(self, requires)():
+                    return True
+            except (NotImplementedError, RecursionError):
+                pass
+            raise NotImplementedError(f"The `{is_using}` method must be implemented in the child classes of "
+                                      f"abstract model. It was not implemented in the class "
+                                      f"{self.__class__.__name__}.")
+
+        for function, label in ((requires_default, requires), (can_use_default, can_use), (is_using_default, is_using)):
+            function.__name__ = function.__qualname__ = label
+        return {requires: classmethod(requires_default), can_use: classmethod(can_use_default),
+                is_using: is_using_default}
+
+    def _declined(name: str, instance_method: bool = False):
+        """A method the root class only declares (abstract_model.py: `task_involves_*`,
+        `is_topological`, `task_name`, `library_name`, `model_name`, `is_stocastic`, `clone`)."""
+        def method(cls_or_self):
+            owner = cls_or_self.__class__.__name__ if instance_method else cls_or_self.__name__
+            raise NotImplementedError(f"The `{name}` method must be implemented in the child classes of "
+                                      f"abstract model. It was not implemented in the class {owner}.")
+        method.__name__ = method.__qualname__ = name
+        return method if instance_method else classmethod(method)
+
     class AbstractModel:
-        """Registry + parameter plumbing of abstract_model.py, embedding half only."""
+        """abstract_model.py:27-750: registry, parameter plumbing, the capability vocabulary and the
+        constructor's cross-checks of it."""
 
         MODELS_LIBRARY: Dict[str, Dict[str, Dict[str, Type["AbstractModel"]]]] = {}
+        # the properties the constructor cross-checks (:86-92); node_type_features has the three
+        # methods as well (:419-464) but is not part of that loop
+        CHECKED_CAPABILITIES = ("edge_types", "node_types", "edge_weights", "edge_type_features", "edge_features")
 
         def __init__(self, random_state: Optional[int] = None):
+            names = (f"{self.model_name()} from library {self.library_name()} and task {self.task_name()}")
             if self.is_stocastic() and random_state is None:  # :41-48
                 raise ValueError(
                     "The provided model is stocastic, yet no random state was provided. Please do "
-                    f"provide a random state to the model {self.model_name()} from library "
-                    f"{self.library_name()} and task {self.task_name()}.")
+                    f"provide a random state to the model {names}.")
+            if not self.is_stocastic() and random_state is not None:  # :49-56
+                raise ValueError(
+                    f"The provided model is not stocastic, yet a random state of `{random_state}` was "
+                    f"provided. Please do not provide a random state to the model {names}.")
+
+            def useless(method: str, because: str) -> ValueError:
+                return ValueError(
+                    f"We have found an useless method in the class {self.__class__.__name__}, implementing "
+                    f"method {names}. It does not make sense to implement the `{method}` method when the "
+                    f"{because}, as it is already handled in the root abstract model class.")
+
+            if not _declines(self.can_use_edge_weights) and not self.can_use_edge_weights() and \
+                    not _declines(self.requires_positive_edge_weights):  # :58-76
+                raise useless("requires_positive_edge_weights", "`can_use_edge_weights` always returns False")
+            for capability in self.CHECKED_CAPABILITIES:  # :78-131
+                requires, can_use, is_using = (f"{prefix}_{capability}" for prefix in ("requires", "can_use", "is_using"))
+                requires_method, can_use_method = getattr(self, requires), getattr(self, can_use)
+                if _declines(requires_method) and _declines(can_use_method):
+                    raise ValueError(
+                        f"We have found a missing method implementation in the class {self.__class__.__name__}, "
+                        f"implementing method {names}. It is strictly necessary to implement either the "
+                        f"`{requires}` method or the {can_use} method in order to adhere to the model interface "
+                        "and facilitate the integration with the pipelines.")
+                if not _declines(requires_method) and requires_method():
+                    for method in (can_use, is_using):
+                        if not _declines(getattr(self, method)):
+                            raise useless(method, f"`{requires}` always returns True")
+                if not _declines(can_use_method) and not can_use_method():
+                    for method in (requires, is_using):
+                        if not _declines(getattr(self, method)):
+                            raise useless(method, f"`{can_use}` always returns False")
             self._random_state = random_state
 
-        def parameters(self) -> Dict[str, Any]:
+        def parameters(self) -> Dict[str, Any]:  # :146-150
             return {} if self._random_state is None else dict(random_state=self._random_state)
 
         @classmethod
@@ -249,31 +340,28 @@ if not HAVE_EMBIGGEN:
         def is_available() -> bool:
             return True
 
-        # requires_X defaults to False when the model says it cannot use X at all
-        # (abstract_model.py:156-171 and the node / edge type twins below it)
         @classmethod
-        def requires_edge_weights(cls) -> bool:
-            if not cls.can_use_edge_weights():
-                return False
-            raise NotImplementedError(f"`requires_edge_weights` is not implemented in {cls.__name__}.")
+        def requires_positive_edge_weights(cls) -> bool:  # :217-231
+            try:
+                if not cls.requires_edge_weights():
+                    return False
+            except (NotImplementedError, RecursionError):
+                pass
+            raise NotImplementedError(f"The `requires_positive_edge_weights` method must be implemented in the "
+                                      f"child classes of abstract model. It was not implemented in the class {cls.__name__}.")
 
-        @classmethod
-        def requires_node_types(cls) -> bool:
-            if not cls.can_use_node_types():
-                return False
-            raise NotImplementedError(f"`requires_node_types` is not implemented in {cls.__name__}.")
-
-        @classmethod
-        def requires_edge_types(cls) -> bool:
-            if not cls.can_use_edge_types():
-                return False
-            raise NotImplementedError(f"`requires_edge_types` is not implemented in {cls.__name__}.")
-
-        def is_using_node_types(self) -> bool:
-            return self.requires_node_types()
-
-        def is_using_edge_types(self) -> bool:
-            return self.requires_edge_types()
+        locals().update(_capability_family("edge_weights"))
+        locals().update(_capability_family("node_types"))
+        locals().update(_capability_family("edge_types"))
+        locals().update(_capability_family("edge_type_features"))
+        locals().update(_capability_family("node_type_features"))
+        locals().update(_capability_family("edge_features"))
+        for _name in ("task_involves_edge_weights", "task_involves_topology", "is_topological",
+                      "task_involves_node_types", "task_involves_edge_types", "task_name", "library_name",
+                      "model_name", "is_stocastic"):
+            locals()[_name] = _declined(_name)
+        clone = _declined("clone", instance_method=True)
+        del _name
 
         @staticmethod
         def register(model_class):  # :721-749

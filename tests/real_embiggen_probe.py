@@ -124,6 +124,12 @@ def main():
         names.append(model.model_name())
     report["models"] = names
 
+    # the capability cross-checks, probed with classes built to violate them one at a time
+    # (tests/capability_cases.py): what the REFERENCE's AbstractModel does with each
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import capability_cases
+    report["capability_cases"] = capability_cases.run_cases(AbstractModel)
+
     # the registry (abstract_model.py:640-749): the four models resolve under library "B200";
     # Walklets / GloVe were deliberately not registered
     for name in ("Node2Vec SkipGram", "Node2Vec CBOW", "DeepWalk SkipGram", "DeepWalk CBOW"):

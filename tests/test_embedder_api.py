@@ -93,6 +93,15 @@ def test_kwarg_coercion_and_rejection():
             Node2VecSkipGramB200(**invalid)
 
 
+def test_restated_abstract_model_cross_checks_its_capability_methods():
+    """abstract_model.py:32-133 and the requires_ / can_use_ / is_using_ defaults (:156-512), probed
+    with classes that break one rule each.  tests/test_real_embiggen_base.py runs the same cases
+    under the reference's own class and holds it to the same table."""
+    import capability_cases
+    from embiggen_b200.embedding_api import AbstractModel
+    assert capability_cases.run_cases(AbstractModel) == capability_cases.expected_outcomes()
+
+
 def test_shared_negatives_is_an_opt_in_skipgram_keyword():
     """B200 extra: off by default, survives the parameters() round trip and the smoke
     conversion, refused at construction where the kernel does not apply."""

@@ -32,3 +32,7 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     assert report["registered"] == ["DeepWalk CBOW", "DeepWalk SkipGram", "Node2Vec CBOW", "Node2Vec SkipGram"]
     assert "Walklets SkipGram" in report["models"] and "Node2Vec GloVe" in report["models"]
     assert "ensmallen" in report["stubs"]  # the engine behind the reference classes is what is absent
+    # the reference's constructor cross-checks and capability defaults, case by case: the outcomes
+    # the restatement is held to in tests/test_embedder_api.py are the reference's own
+    import capability_cases
+    assert report["capability_cases"] == capability_cases.expected_outcomes()

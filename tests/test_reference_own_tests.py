@@ -28,7 +28,8 @@ SHIM = {
         def get_available_models_for_edge_prediction():
             return pd.DataFrame(columns=["model_name", "task_name", "library_name", "available"])
     """,
-    "embiggen/utils/__init__.py": "from embiggen_b200.embedding_api import EmbeddingResult\n",
+    "embiggen/utils/__init__.py":
+        "from embiggen_b200.embedding_api import AbstractEmbeddingModel, AbstractModel, EmbeddingResult\n",
     "embiggen/utils/normalize_kwargs.py": "from embiggen_b200.embedding_api import normalize_kwargs\n",
     "embiggen/utils/abstract_models/__init__.py":
         "from embiggen_b200.embedding_api import AbstractEmbeddingModel, AbstractModel, EmbeddingResult\n",
@@ -57,6 +58,8 @@ SHIM = {
     ("test_embedding_result.py", None, 2),
     ("test_normalize_kwargs.py", "node_embedding", 1),
     ("test_node_embedding_pipelines.py", "model_recreation", 1),
+    # the constructor's capability cross-checks and the NotImplementedError defaults of AbstractModel
+    ("test_abstract_model.py", "implemented_methods", 2),
 ])
 def test_reference_test_file_passes_against_the_restatement(tmp_path, test_file, selection, expected):
     for relative, text in SHIM.items():
