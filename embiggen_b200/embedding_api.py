@@ -434,6 +434,19 @@ if not HAVE_EMBIGGEN:
             return "Node Embedding"
 
         @classmethod
+        def requires_nodes_sorted_by_decreasing_node_degree(cls) -> bool:  # :56-62
+            raise NotImplementedError("The `requires_nodes_sorted_by_decreasing_node_degree` method must be "
+                                      "implemented in the child classes of abstract model.")
+
+        @classmethod
+        def get_minimum_required_number_of_node_types(cls) -> int:  # :64-67
+            return 0
+
+        def _fit_transform(self, graph, return_dataframe: bool = True):  # :69-89
+            raise NotImplementedError("The `_fit_transform` method must be implemented in the child classes "
+                                      "of abstract model.")
+
+        @classmethod
         def can_use_edge_type_features(cls) -> bool:
             return False
 
@@ -445,9 +458,22 @@ if not HAVE_EMBIGGEN:
             name = graph.get_name()
             if not graph.has_nodes():
                 raise ValueError(f"The provided graph {name} is empty.")
+            if self.requires_nodes_sorted_by_decreasing_node_degree() and \
+                    not graph.has_nodes_sorted_by_decreasing_outbound_node_degree():  # :119-128
+                raise ValueError(
+                    f"The given graph {name} does not have the nodes sorted by decreasing order, therefore "
+                    "the negative sampling (which follows a scale free distribution) would not approximate "
+                    "well the Softmax.\nIn order to sort the given graph in such a way that the node IDs are "
+                    "sorted by decreasing outbound node degrees, you can use the Graph method "
+                    "`graph.sort_by_decreasing_outbound_node_degree()`.")
             if self.requires_node_types() and not graph.has_node_types():
                 raise ValueError(f"The provided graph {name} does not have node types, but the "
                                  f"{self.model_name()} requires node types.")
+            if self.requires_node_types() and graph.get_number_of_node_types() <= 1:  # :136-142
+                raise ValueError(
+                    f"The {self.model_name()} requires the graph to have at least "
+                    f"{self.get_minimum_required_number_of_node_types()} node types, but the provided one "
+                    f"has {graph.get_number_of_node_types()} node types.")
             if self.requires_edge_types() and not graph.has_edge_types():
                 raise ValueError(f"The provided graph {name} does not have edge types, but the "
                                  f"{self.model_name()} requires edge types.")

@@ -129,6 +129,9 @@ def main():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import capability_cases
     report["capability_cases"] = capability_cases.run_cases(AbstractModel)
+    # fit_transform's checks of the graph (abstract_embedding_model.py:114-198, 229-251), same idea
+    import validation_cases
+    report["validation_cases"] = validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult)
 
     # the registry (abstract_model.py:640-749): the four models resolve under library "B200";
     # Walklets / GloVe were deliberately not registered

@@ -102,6 +102,15 @@ def test_restated_abstract_model_cross_checks_its_capability_methods():
     assert capability_cases.run_cases(AbstractModel) == capability_cases.expected_outcomes()
 
 
+def test_restated_fit_transform_checks_the_graph_like_the_reference():
+    """abstract_embedding_model.py:114-198, 229-251: which check fires for which graph, in which
+    order, with which exception; the same table is asserted for the reference's own class in
+    tests/test_real_embiggen_base.py."""
+    import validation_cases
+    from embiggen_b200.embedding_api import AbstractEmbeddingModel, EmbeddingResult
+    assert validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult) == validation_cases.expected_outcomes()
+
+
 def test_shared_negatives_is_an_opt_in_skipgram_keyword():
     """B200 extra: off by default, survives the parameters() round trip and the smoke
     conversion, refused at construction where the kernel does not apply."""

@@ -36,3 +36,5 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     # the restatement is held to in tests/test_embedder_api.py are the reference's own
     import capability_cases
     assert report["capability_cases"] == capability_cases.expected_outcomes()
+    import validation_cases
+    assert report["validation_cases"] == validation_cases.expected_outcomes()
