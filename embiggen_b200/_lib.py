@@ -96,6 +96,7 @@ SIGNATURES = {
     "b2e_last_error": (ctypes.c_char_p, []),
     "b2e_abi_version": (ctypes.c_int, []),
     "b2e_device_count": (ctypes.c_int, []),
+    "b2e_select_device": (ctypes.c_int, [ctypes.c_int]),
     "b2e_create": (ctypes.c_int, [_P(B2EConfig), _P(_H)]),
     "b2e_destroy": (None, [_H]),
     "b2e_load_csr": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, _U64, _U64]),

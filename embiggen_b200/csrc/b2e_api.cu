@@ -49,6 +49,17 @@ extern "C" int b2e_device_count(void) {
     return usable;
 }
 
+extern "C" int b2e_select_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2E_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(B2E_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    return B2E_OK;
+}
+
 // accept thresholds of the typed-walk tests, [same type, changed type] (oracle/walks.c)
 static void type_thresholds(float change_weight, unsigned long long q[2]) {
     const double w = (double)change_weight, m = w > 1.0 ? w : 1.0;

@@ -283,6 +283,8 @@ class PerceptronEdgePredictionB200:
             config = self._config()
             size = ctypes.c_uint32()
             lib = _lib.load()
+            if features is None:  # no feature matrix to carry the device: say it
+                check(lib.b2e_select_device(int(self._device)))
             check(lib.b2e_edge_embedding_size(features.shape[1] if features else 0, *self._ids(),
                                               ctypes.byref(size)))
             params = np.empty(size.value + 1, dtype=np.float32)
@@ -312,6 +314,8 @@ class PerceptronEdgePredictionB200:
             _as_device_features(node_features, self._device)
         try:
             scores = np.empty(src.shape[0], dtype=np.float32)
+            if features is None:
+                check(_lib.load().b2e_select_device(int(self._device)))
             check(_lib.load().b2e_perceptron_predict(
                 features._handle if features else None, indptr.ctypes.data, indices.ctypes.data,
                 indptr.shape[0] - 1, indices.shape[0], src.ctypes.data, dst.ctypes.data, src.shape[0],

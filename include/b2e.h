@@ -96,6 +96,10 @@ const char *b2e_last_error(void);
 int b2e_abi_version(void);
 /* number of visible devices this library can run on (compute capability >= 10.0); 0 if none */
 int b2e_device_count(void);
+/* Make `device` the current CUDA device of the calling thread.  The handle-free entry points
+ * (b2e_edge_metrics, b2e_perceptron_fit / _predict without node features, the graph builders)
+ * run on the current device; handles and feature matrices carry their own. */
+int b2e_select_device(int device);
 
 int b2e_create(const b2e_config *config, b2e_handle **out);
 void b2e_destroy(b2e_handle *handle);

@@ -86,6 +86,13 @@ def test_no_cpu_fallback_without_device():
     from embiggen_b200.engine import Engine
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         Engine("SkipGram")
+    lib = _lib.load()
+    assert lib.b2e_select_device(0) == _lib.B2E_ERR_CUDA and b"no CUDA device" in lib.b2e_last_error()
+    # the feature-less perceptron names its device through that call: it fails here, loudly
+    from embiggen_b200.edge_prediction import PerceptronEdgePredictionB200
+    from embiggen_b200.graph import erdos_renyi
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        PerceptronEdgePredictionB200(edge_features="Degree", number_of_epochs=1).fit(erdos_renyi(50, 100, seed=1))
 
 
 def test_product_never_touches_the_oracle():
