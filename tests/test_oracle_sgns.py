@@ -412,3 +412,26 @@ def test_log_det_and_glove_step_against_float64(small_ppi):
     assert (t0[:, D:] == 0).all() and (t1[:, D:] == 0).all()
     _, _, losses = oracle.glove_fit(small_ppi.indptr, small_ppi.indices, 5, 16, 6, 32, 4, 0.75, 0.05, 0.9)
     assert losses[-1] < 0.8 * losses[0]
+
+
+def test_shared_negatives_mode_counts(small_ppi):
+    """The opt-in estimator sees the same (centre, context) pairs as the per-pair model and scores
+    at most one row per context position plus K negatives per centre; a centre with no valid
+    context draws nothing (the site key is the centre's, like CBOW's)."""
+    seed, L, w, K, D = 5, 24, 3, 6, 8
+    n = small_ppi.get_number_of_nodes()
+    walks, _ = oracle.walks(small_ppi.indptr, small_ppi.indices, seed, 0, 200, L, 2.0, 0.5)
+    thr, alias = oracle.alias_build(small_ppi.indptr, 0.75)
+    stats = {}
+    for shared in (False, True):
+        t0, t1 = oracle.init_tables(n, D, seed)
+        stats[shared] = oracle.train("SkipGram", walks, t0, t1, seed, n, D, w, K, 0.05, thr=thr, alias=alias,
+                                     shared_negatives=shared)
+        assert np.isfinite(t0).all() and np.isfinite(t1).all()
+    centres = int((walks != oracle.PAD_TOKEN).sum())
+    assert stats[True]["pairs"] == stats[False]["pairs"] > 0
+    assert stats[True]["pairs"] < stats[True]["targets"] <= stats[True]["pairs"] + K * centres
+    assert stats[True]["targets"] < stats[False]["targets"] / 2
+    with pytest.raises(ValueError):  # a SkipGram option
+        t0, t1 = oracle.init_tables(n, D, seed)
+        oracle.train("CBOW", walks, t0, t1, seed, n, D, w, K, 0.05, thr=thr, alias=alias, shared_negatives=True)
