@@ -595,7 +595,7 @@ def embed_graph(graph, embedding_model, repository: Optional[str] = None,
     re-raised as ValueError), defaulting to this library."""
     if isinstance(embedding_model, str):
         embedding_model = AbstractEmbeddingModel.get_model_from_library(
-            model_name=embedding_model, task_name="Node Embedding", library_name=library_name)(**kwargs)
+            model_name=embedding_model, library_name=library_name)(**kwargs)
     elif kwargs:
         raise ValueError("Please be advised that even though you have provided yourself the "
                          "embedding model, you have also provided the kwargs which would normally "
@@ -612,6 +612,9 @@ def embed_graph(graph, embedding_model, repository: Optional[str] = None,
                 "An exception was raised while trying to create a smoke test version of the model "
                 f"called {embedding_model.model_name()} from the library {library_name}. The body "
                 f"of the exception was: {e}.") from e
+    if embedding_model.requires_nodes_sorted_by_decreasing_node_degree() and \
+            hasattr(graph, "sort_by_decreasing_outbound_node_degree"):  # :93-94 (none of the B200 models asks)
+        graph = graph.sort_by_decreasing_outbound_node_degree()
     try:
         return embedding_model.fit_transform(graph, repository=repository, version=version,
                                              return_dataframe=return_dataframe)

@@ -277,20 +277,22 @@ if not HAVE_EMBIGGEN:
         CHECKED_CAPABILITIES = ("edge_types", "node_types", "edge_weights", "edge_type_features", "edge_features")
 
         def __init__(self, random_state: Optional[int] = None):
-            names = (f"{self.model_name()} from library {self.library_name()} and task {self.task_name()}")
+            def names() -> str:  # only ever evaluated inside an error message, as in the reference
+                return f"{self.model_name()} from library {self.library_name()} and task {self.task_name()}"
+
             if self.is_stocastic() and random_state is None:  # :41-48
                 raise ValueError(
                     "The provided model is stocastic, yet no random state was provided. Please do "
-                    f"provide a random state to the model {names}.")
+                    f"provide a random state to the model {names()}.")
             if not self.is_stocastic() and random_state is not None:  # :49-56
                 raise ValueError(
                     f"The provided model is not stocastic, yet a random state of `{random_state}` was "
-                    f"provided. Please do not provide a random state to the model {names}.")
+                    f"provided. Please do not provide a random state to the model {names()}.")
 
             def useless(method: str, because: str) -> ValueError:
                 return ValueError(
                     f"We have found an useless method in the class {self.__class__.__name__}, implementing "
-                    f"method {names}. It does not make sense to implement the `{method}` method when the "
+                    f"method {names()}. It does not make sense to implement the `{method}` method when the "
                     f"{because}, as it is already handled in the root abstract model class.")
 
             if not _declines(self.can_use_edge_weights) and not self.can_use_edge_weights() and \
@@ -302,7 +304,7 @@ if not HAVE_EMBIGGEN:
                 if _declines(requires_method) and _declines(can_use_method):
                     raise ValueError(
                         f"We have found a missing method implementation in the class {self.__class__.__name__}, "
-                        f"implementing method {names}. It is strictly necessary to implement either the "
+                        f"implementing method {names()}. It is strictly necessary to implement either the "
                         f"`{requires}` method or the {can_use} method in order to adhere to the model interface "
                         "and facilitate the integration with the pipelines.")
                 if not _declines(requires_method) and requires_method():
@@ -386,7 +388,16 @@ if not HAVE_EMBIGGEN:
         @classmethod
         def get_model_from_library(cls, model_name: str, task_name: Optional[str] = None,
                                    library_name: Optional[str] = None):  # :626-700
-            task_name = cls.task_name() if task_name is None else task_name
+            if task_name is None:  # :654-669: the class's own task, else the first registered under that name
+                try:
+                    task_name = cls.task_name()
+                except NotImplementedError as exception:
+                    tasks = [task for task, models in AbstractModel.MODELS_LIBRARY.items() if model_name in models]
+                    if not tasks:
+                        raise ValueError(
+                            f"The requested model `{model_name}` is not available. Please do provide a "
+                            "valid model name to resolve this ambiguity.") from exception
+                    task_name = tasks[0]
             task_data = AbstractModel.get_task_data(model_name, task_name)
             if library_name is None:
                 names = list(task_data)
@@ -428,10 +439,6 @@ if not HAVE_EMBIGGEN:
         def parameters(self) -> Dict[str, Any]:
             extra = {} if self._embedding_size is None else dict(embedding_size=self._embedding_size)
             return dict(**super().parameters(), **extra)
-
-        @classmethod
-        def task_name(cls) -> str:
-            return "Node Embedding"
 
         @classmethod
         def requires_nodes_sorted_by_decreasing_node_degree(cls) -> bool:  # :56-62

@@ -132,6 +132,13 @@ def main():
     # fit_transform's checks of the graph (abstract_embedding_model.py:114-198, 229-251), same idea
     import validation_cases
     report["validation_cases"] = validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult)
+    # the reference's embed_graph itself (graph_embedding_pipeline.py:10-106); its iterate_graphs
+    # wants instances of ensmallen.Graph, so the fake graph inherits from the stub class
+    import embed_graph_cases
+    import ensmallen as stub_ensmallen
+    from embiggen.embedders.graph_embedding_pipeline import embed_graph as real_embed_graph
+    report["embed_graph_cases"] = embed_graph_cases.run_cases(real_embed_graph, AbstractEmbeddingModel, EmbeddingResult,
+                                                              graph_base=stub_ensmallen.Graph)
 
     # the registry (abstract_model.py:640-749): the four models resolve under library "B200";
     # Walklets / GloVe were deliberately not registered

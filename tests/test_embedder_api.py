@@ -111,6 +111,14 @@ def test_restated_fit_transform_checks_the_graph_like_the_reference():
     assert validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult) == validation_cases.expected_outcomes()
 
 
+def test_embed_graph_accepts_converts_and_re_raises_like_the_reference():
+    """graph_embedding_pipeline.py:10-106; the same table holds for the reference's own function
+    (tests/test_real_embiggen_base.py)."""
+    import embed_graph_cases
+    from embiggen_b200.embedding_api import AbstractEmbeddingModel, EmbeddingResult
+    assert embed_graph_cases.run_cases(embed_graph, AbstractEmbeddingModel, EmbeddingResult) == embed_graph_cases.EXPECTED
+
+
 def test_shared_negatives_is_an_opt_in_skipgram_keyword():
     """B200 extra: off by default, survives the parameters() round trip and the smoke
     conversion, refused at construction where the kernel does not apply."""

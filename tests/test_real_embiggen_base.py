@@ -38,3 +38,5 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     assert report["capability_cases"] == capability_cases.expected_outcomes()
     import validation_cases
     assert report["validation_cases"] == validation_cases.expected_outcomes()
+    import embed_graph_cases
+    assert report["embed_graph_cases"] == embed_graph_cases.EXPECTED
