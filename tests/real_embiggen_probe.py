@@ -132,6 +132,8 @@ def main():
     # fit_transform's checks of the graph (abstract_embedding_model.py:114-198, 229-251), same idea
     import validation_cases
     report["validation_cases"] = validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult)
+    import embedding_result_cases
+    report["embedding_result_cases"] = embedding_result_cases.run_cases(EmbeddingResult)
     # the reference's embed_graph itself (graph_embedding_pipeline.py:10-106); its iterate_graphs
     # wants instances of ensmallen.Graph, so the fake graph inherits from the stub class
     import embed_graph_cases

@@ -111,6 +111,14 @@ def test_restated_fit_transform_checks_the_graph_like_the_reference():
     assert validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult) == validation_cases.expected_outcomes()
 
 
+def test_restated_embedding_result_behaves_like_the_reference():
+    """embedding_result.py:11-334, the cases its own test file leaves out; same table asserted for
+    the reference's class in tests/test_real_embiggen_base.py."""
+    import embedding_result_cases
+    from embiggen_b200.embedding_api import EmbeddingResult
+    assert embedding_result_cases.run_cases(EmbeddingResult) == embedding_result_cases.EXPECTED
+
+
 def test_embed_graph_accepts_converts_and_re_raises_like_the_reference():
     """graph_embedding_pipeline.py:10-106; the same table holds for the reference's own function
     (tests/test_real_embiggen_base.py)."""

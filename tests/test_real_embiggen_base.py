@@ -40,3 +40,5 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     assert report["validation_cases"] == validation_cases.expected_outcomes()
     import embed_graph_cases
     assert report["embed_graph_cases"] == embed_graph_cases.EXPECTED
+    import embedding_result_cases
+    assert report["embedding_result_cases"] == embedding_result_cases.EXPECTED
