@@ -399,11 +399,14 @@ def _walklets_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
                    contextual_nodes_embedding_path=None, normalize_by_degree=False,
                    stochastic_downsample_by_degree=False, normalize_learning_rate_by_degree=False,
                    use_scale_free_distribution=True, random_state=42, dtype="f32", ring_bell=False,
-                   enable_cache=False, verbose=True, **b200_kwargs):
-    """Signature and defaults of walklets_skipgram.py:9-33 (identical in walklets_cbow.py).  Like
-    walklets.py:112-113 the per-scale embedding size is ``embedding_size // window_size``."""
+                   enable_cache=False, **b200_kwargs):
+    """Signature and defaults of walklets_skipgram.py:9-33 (identical in walklets_cbow.py; no
+    ``verbose`` there).  Like walklets.py:112-113 the per-scale embedding size is
+    ``embedding_size // window_size``."""
     if central_nodes_embedding_path is not None or contextual_nodes_embedding_path is not None:
         raise NotImplementedError("Walklets return one embedding per scale; embedding paths are not supported.")
+    if "verbose" in b200_kwargs:  # the reference's Walklets constructors have no such keyword
+        raise TypeError(f"{type(self).__name__}.__init__() got an unexpected keyword argument 'verbose'")
     Node2VecB200.__init__(
         self, embedding_size=embedding_size // window_size, epochs=epochs,
         clipping_value=clipping_value, number_of_negative_samples=number_of_negative_samples,
@@ -413,8 +416,9 @@ def _walklets_init(self, embedding_size=100, epochs=30, clipping_value=6.0,
         normalize_by_degree=normalize_by_degree,
         stochastic_downsample_by_degree=stochastic_downsample_by_degree,
         normalize_learning_rate_by_degree=normalize_learning_rate_by_degree,
+        central_nodes_embedding_path=None, contextual_nodes_embedding_path=None,
         use_scale_free_distribution=use_scale_free_distribution, dtype=dtype,
-        random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=verbose,
+        random_state=random_state, ring_bell=ring_bell, enable_cache=enable_cache, verbose=False,
         **{**_B200_DEFAULTS, **b200_kwargs})
 
 
@@ -502,9 +506,7 @@ class WalkletsB200(Node2VecB200):
 
     def parameters(self) -> Dict[str, Any]:
         """walklets.py:137-141: the public embedding size is the per-scale size x window_size."""
-        parameters = {k: v for k, v in super().parameters().items()
-                      if k not in _NODE2VEC_HIDDEN + ("central_nodes_embedding_path",
-                                                      "contextual_nodes_embedding_path")}
+        parameters = {k: v for k, v in super().parameters().items() if k not in _NODE2VEC_HIDDEN + ("verbose",)}
         parameters["embedding_size"] = parameters["embedding_size"] * parameters["window_size"]
         return parameters
 

@@ -134,6 +134,23 @@ def main():
     report["validation_cases"] = validation_cases.run_cases(AbstractEmbeddingModel, EmbeddingResult)
     import embedding_result_cases
     report["embedding_result_cases"] = embedding_result_cases.run_cases(EmbeddingResult)
+    # the reference's adapter classes themselves, described as data (`ensmallen.models` is a stub:
+    # their constructors run, their engines do not exist)
+    import adapter_cases
+    import compress_json  # a stub: hand normalize_kwargs its real schema file (normalize_kwargs.py:90)
+    schema = json.load(open(os.path.join(REFERENCE, "embiggen", "utils", "normalization_schemas.json")))
+    compress_json.local_load = lambda name, use_cache=True: schema
+    from embiggen.embedders import ensmallen_embedders as reference_adapters
+    report["adapter_description"] = adapter_cases.describe({
+        "Node2Vec SkipGram": reference_adapters.Node2VecSkipGramEnsmallen,
+        "Node2Vec CBOW": reference_adapters.Node2VecCBOWEnsmallen,
+        "DeepWalk SkipGram": reference_adapters.DeepWalkSkipGramEnsmallen,
+        "DeepWalk CBOW": reference_adapters.DeepWalkCBOWEnsmallen,
+        "Walklets SkipGram": reference_adapters.WalkletsSkipGramEnsmallen,
+        "Walklets CBOW": reference_adapters.WalkletsCBOWEnsmallen,
+        "Node2Vec GloVe": reference_adapters.Node2VecGloVeEnsmallen,
+        "DeepWalk GloVe": reference_adapters.DeepWalkGloVeEnsmallen,
+    })
     # the reference's embed_graph itself (graph_embedding_pipeline.py:10-106); its iterate_graphs
     # wants instances of ensmallen.Graph, so the fake graph inherits from the stub class
     import embed_graph_cases

@@ -230,7 +230,7 @@ def test_walklets_deterministic_bit_exact(small_ppi, model, k, L):
 def test_walklets_embedder(small_ppi):
     from embiggen_b200.embedders import WalkletsSkipGramB200, WalkletsCBOWB200
     for cls in (WalkletsSkipGramB200, WalkletsCBOWB200):
-        model = cls(embedding_size=24, window_size=3, epochs=2, walk_length=32, iterations=2, verbose=False)
+        model = cls(embedding_size=24, window_size=3, epochs=2, walk_length=32, iterations=2)
         result = model.fit_transform(small_ppi, return_dataframe=False)
         tables = result.get_all_node_embedding()
         assert len(tables) == 6 and all(t.shape == (1064, 8) and np.isfinite(t).all() for t in tables)
@@ -247,7 +247,7 @@ def test_walklets_one_pass_equals_scale_by_scale(small_ppi_weighted, small_ppi):
     bit for bit.  A weighted graph takes the scale-by-scale path (same walks by weight)."""
     from embiggen_b200.embedders import WalkletsCBOWB200, WalkletsSkipGramB200
     for cls in (WalkletsSkipGramB200, WalkletsCBOWB200):
-        kw = dict(embedding_size=12, window_size=3, epochs=2, walk_length=20, iterations=1, verbose=False,
+        kw = dict(embedding_size=12, window_size=3, epochs=2, walk_length=20, iterations=1,
                   deterministic=True, chunk_walks=300, return_weight=2.0, explore_weight=0.5)
         one_pass = cls(**kw).fit_transform(small_ppi, return_dataframe=False).get_all_node_embedding()
         reference = []

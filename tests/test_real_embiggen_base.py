@@ -42,3 +42,19 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     assert report["embed_graph_cases"] == embed_graph_cases.EXPECTED
     import embedding_result_cases
     assert report["embedding_result_cases"] == embedding_result_cases.EXPECTED
+    # the adapter classes themselves: signature, defaults, parameters(), smoke conversion, names and
+    # capability answers of the reference's eight classes against ours (computed here, under the
+    # restated base classes), equal once the keyword-only B200 extras are left out
+    import adapter_cases
+    from embiggen_b200 import embedders
+    ours = adapter_cases.describe({
+        "Node2Vec SkipGram": embedders.Node2VecSkipGramB200, "Node2Vec CBOW": embedders.Node2VecCBOWB200,
+        "DeepWalk SkipGram": embedders.DeepWalkSkipGramB200, "DeepWalk CBOW": embedders.DeepWalkCBOWB200,
+        "Walklets SkipGram": embedders.WalkletsSkipGramB200, "Walklets CBOW": embedders.WalkletsCBOWB200,
+        "Node2Vec GloVe": embedders.Node2VecGloVeB200, "DeepWalk GloVe": embedders.DeepWalkGloVeB200,
+    }, drop=set(embedders._B200_DEFAULTS))
+    theirs = report["adapter_description"]
+    assert sorted(theirs) == sorted(ours)
+    for name in theirs:
+        for section in theirs[name]:
+            assert json.loads(json.dumps(ours[name][section])) == theirs[name][section], (name, section)
