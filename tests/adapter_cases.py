@@ -58,3 +58,19 @@ def describe(classes, drop=()):
             answers=_jsonable(answers),
         )
     return out
+
+
+def describe_perceptron(cls, drop=()):
+    """The edge-prediction perceptron (perceptron.py:15-300) the same way."""
+    signature = inspect.signature(cls.__init__).parameters
+    model = cls()
+    custom = cls(edge_features=["Degree", "AdamicAdar"], edge_embeddings="Hadamard", number_of_epochs=7,
+                 learning_rate=0.01, random_state=3)
+    return dict(
+        signature=[[p.name, _jsonable(p.default)] for p in signature.values()
+                   if p.name != "self" and p.name not in drop],
+        parameters=_jsonable({k: v for k, v in model.parameters().items() if k not in drop}),
+        custom_parameters=_jsonable({k: v for k, v in custom.parameters().items() if k not in drop}),
+        smoke_test_parameters=_jsonable(cls.smoke_test_parameters()),
+        names=[cls.model_name(), cls.task_name()],
+    )

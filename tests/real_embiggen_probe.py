@@ -83,16 +83,25 @@ def install_real_base_classes():
     sys.modules["ensmallen"] = ensmallen
     sys.path.insert(0, REFERENCE)
     sys.path.insert(0, ROOT)
+    import_discovering_stubs("embiggen.utils.abstract_models")
+    return sorted(StubFinder.roots)
+
+
+def import_discovering_stubs(module_name):
+    """Import a module of the reference, stubbing one missing third-party root per attempt."""
+    import importlib
     for _ in range(80):
         try:
-            import embiggen.utils.abstract_models  # noqa: F401
-            return sorted(StubFinder.roots)
+            return importlib.import_module(module_name)
         except ModuleNotFoundError as error:
             root = error.name.split(".")[0]
             if root == "embiggen" or root in StubFinder.roots:
                 raise
             StubFinder.roots.add(root)
-            for name in [m for m in sys.modules if m == "embiggen" or m.startswith("embiggen.")]:
+            # half-imported reference modules are dropped; the ones already bound by callers stay valid
+            for name in [m for m in sys.modules if (m == "embiggen" or m.startswith("embiggen."))
+                         and getattr(sys.modules[m], "__spec__", None) is not None
+                         and getattr(sys.modules[m].__spec__, "_initializing", False)]:
                 del sys.modules[name]
     raise RuntimeError("too many missing modules")
 
@@ -151,6 +160,9 @@ def main():
         "Node2Vec GloVe": reference_adapters.Node2VecGloVeEnsmallen,
         "DeepWalk GloVe": reference_adapters.DeepWalkGloVeEnsmallen,
     })
+    PerceptronEdgePrediction = import_discovering_stubs(
+        "embiggen.edge_prediction.edge_prediction_ensmallen.perceptron").PerceptronEdgePrediction
+    report["perceptron_description"] = adapter_cases.describe_perceptron(PerceptronEdgePrediction)
     # the reference's embed_graph itself (graph_embedding_pipeline.py:10-106); its iterate_graphs
     # wants instances of ensmallen.Graph, so the fake graph inherits from the stub class
     import embed_graph_cases

@@ -58,3 +58,7 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     for name in theirs:
         for section in theirs[name]:
             assert json.loads(json.dumps(ours[name][section])) == theirs[name][section], (name, section)
+    # ... and the edge-prediction perceptron of the step after the path (perceptron.py:15-300)
+    from embiggen_b200.edge_prediction import PerceptronEdgePredictionB200
+    ours = adapter_cases.describe_perceptron(PerceptronEdgePredictionB200, drop={"device"})
+    assert json.loads(json.dumps(ours)) == report["perceptron_description"]
