@@ -555,14 +555,37 @@ if not HAVE_EMBIGGEN:
             return result
 
 
+def get_model_metadata(model_class) -> Dict[str, Any]:
+    """One registry row (abstract_model.py:762-793): names, availability and the capability answers
+    with `can_use_X` widened by `requires_X`."""
+    try:
+        row = dict(model_name=model_class.model_name(), task_name=model_class.task_name(),
+                   library_name=model_class.library_name(), available=model_class.is_available())
+        for capability in ("node_types", "edge_types", "edge_type_features", "edge_features", "edge_weights"):
+            required = getattr(model_class, f"requires_{capability}")()
+            row[f"requires_{capability}"] = required
+            row[f"can_use_{capability}"] = required or getattr(model_class, f"can_use_{capability}")()
+        row["requires_positive_edge_weights"] = model_class.requires_positive_edge_weights()
+        return row
+    except NotImplementedError as exception:
+        raise NotImplementedError(
+            f"Some of the mandatory static methods were not implemented in model class "
+            f"{model_class.__name__}. The previous exception was: {exception}") from exception
+
+
+def get_models_dataframe() -> pd.DataFrame:
+    """Every registered model, available or not (abstract_model.py:796-805)."""
+    return pd.DataFrame([get_model_metadata(model_class)
+                         for tasks in AbstractModel.MODELS_LIBRARY.values()
+                         for libraries in tasks.values()
+                         for model_class in libraries.values()])
+
+
 def get_available_models_for_node_embedding() -> pd.DataFrame:
-    """One row per registered node-embedding model (reference: embiggen/utils/
-    abstract_models/abstract_model.py get_models_dataframe, as the reference tests iterate it,
-    tests/test_node_embedding_pipelines.py:19)."""
-    rows = []
-    for model_name, libraries in AbstractModel.MODELS_LIBRARY.get("Node Embedding", {}).items():
-        for library_name, model in libraries.items():
-            rows.append(dict(model_name=model_name, task_name="Node Embedding",
-                             library_name=library_name, available=model.is_available(),
-                             requires_edge_weights=model.requires_edge_weights()))
-    return pd.DataFrame(rows)
+    """abstract_model.py:808-811: the node-embedding models that can run HERE (for the B200 library:
+    libb2e.so built and a Blackwell device visible), as the reference's tests iterate them
+    (tests/test_node_embedding_pipelines.py:19)."""
+    frame = get_models_dataframe()
+    if frame.empty:
+        return frame
+    return frame[(frame.task_name == "Node Embedding") & frame.available]

@@ -180,6 +180,11 @@ def main():
     registered = AbstractModel.MODELS_LIBRARY["Node Embedding"]
     assert "B200" not in registered.get("Walklets SkipGram", {}) and "B200" not in registered.get("Node2Vec GloVe", {})
     report["registered"] = sorted(name for name, libraries in registered.items() if "B200" in libraries)
+    # the reference's own registry table (abstract_model.py:762-805) for our four classes
+    from embiggen.utils.abstract_models.abstract_model import get_models_dataframe
+    frame = get_models_dataframe()
+    frame = frame[frame.library_name == "B200"].sort_values("model_name")
+    report["registry_rows"] = json.loads(frame.to_json(orient="records"))
     try:
         AbstractEmbeddingModel.get_model_from_library(model_name="Node2Vec SkipGram", task_name="Node Embedding",
                                                       library_name="no such library")

@@ -17,7 +17,8 @@ from embiggen_b200 import embedders
 from embiggen_b200.embedders import (B200_EMBEDDERS, DeepWalkCBOWB200, DeepWalkSkipGramB200,
                                      Node2VecCBOWB200, Node2VecSkipGramB200, embed_graph)
 from embiggen_b200.embedding_api import (AbstractEmbeddingModel, AbstractModel, EmbeddingResult,
-                                         get_available_models_for_node_embedding, normalize_kwargs)
+                                         get_available_models_for_node_embedding, get_models_dataframe,
+                                         normalize_kwargs)
 
 # defaults of node2vec_skipgram.py:9-35 (Node2Vec) and deepwalk_skipgram.py:9-31 (DeepWalk)
 REFERENCE_DEFAULTS = dict(
@@ -175,8 +176,13 @@ def test_identity_and_capability_flags(model):
         assert "raise NotImplementedError" not in inspect.getsource(getattr(embedders.Node2VecB200, name))
 
 
-def test_registry():
-    frame = get_available_models_for_node_embedding()
+def test_registry(monkeypatch):
+    frame = get_models_dataframe()
+    # the "available" view is the same frame filtered (abstract_model.py:808-811)
+    monkeypatch.setattr(embedders.B200Embedder, "is_available", staticmethod(lambda: False))
+    assert get_available_models_for_node_embedding().empty
+    monkeypatch.setattr(embedders.B200Embedder, "is_available", staticmethod(lambda: True))
+    assert sorted(get_available_models_for_node_embedding().model_name) == sorted(frame.model_name)
     ours = frame[frame.library_name == "B200"]
     assert sorted(ours.model_name) == ["DeepWalk CBOW", "DeepWalk SkipGram", "Node2Vec CBOW", "Node2Vec SkipGram"]
     assert not ours.requires_edge_weights.any()
@@ -295,7 +301,7 @@ def test_walklets_classes_mirror_the_reference_surface():
         assert model._embedding_size == 25
         smoke = model.into_smoke_test()
         assert type(smoke) is cls
-    frame = get_available_models_for_node_embedding()
+    frame = get_models_dataframe()
     assert not any("Walklets" in name for name in frame.model_name)
     with pytest.raises(NotImplementedError):
         WalkletsSkipGramB200(central_nodes_embedding_path="x.npy")
@@ -318,7 +324,7 @@ def test_glove_classes_mirror_the_reference_surface():
     assert q["learning_rate_decay"] == 0.99 and "return_weight" not in q
     assert DeepWalkGloVeB200(**q).parameters() == q and d.model_name() == "DeepWalk GloVe"
     assert type(d.into_smoke_test()) is DeepWalkGloVeB200
-    frame = get_available_models_for_node_embedding()
+    frame = get_models_dataframe()
     assert not any("GloVe" in name for name in frame.model_name)
 
 

@@ -58,6 +58,11 @@ def test_embedders_satisfy_the_real_embiggen_base_classes():
     for name in theirs:
         for section in theirs[name]:
             assert json.loads(json.dumps(ours[name][section])) == theirs[name][section], (name, section)
+    # the registry table: the reference's get_models_dataframe over our classes against the restated one
+    from embiggen_b200.embedding_api import get_models_dataframe
+    frame = get_models_dataframe()
+    frame = frame[frame.library_name == "B200"].sort_values("model_name")
+    assert json.loads(frame.to_json(orient="records")) == report["registry_rows"] and len(frame) == 4
     # ... and the edge-prediction perceptron of the step after the path (perceptron.py:15-300)
     from embiggen_b200.edge_prediction import PerceptronEdgePredictionB200
     ours = adapter_cases.describe_perceptron(PerceptronEdgePredictionB200, drop={"device"})

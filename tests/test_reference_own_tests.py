@@ -24,6 +24,9 @@ SHIM = {
     "embiggen/__init__.py": """
         import pandas as pd
         import embiggen_b200.embedders  # registers the four B200 models
+        # no device in the build container: constructing and normalising need none, and the
+        # reference's tests iterate the AVAILABLE models
+        embiggen_b200.embedders.B200Embedder.is_available = staticmethod(lambda: True)
         from embiggen_b200.embedding_api import get_available_models_for_node_embedding
         def get_available_models_for_edge_prediction():
             return pd.DataFrame(columns=["model_name", "task_name", "library_name", "available"])
